@@ -1,0 +1,393 @@
+"""CPU oracle for the WaNN batched policy-net leaf-evaluation path (numpy).
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.  The product
+(wann_b200/) never does: it fails loudly when its CUDA library is missing.
+
+Every function restates a piece of the reference (paths relative to
+/root/reference) and cites the lines it follows.
+
+PARITY STATUS
+  * encode / move index / legal moves: PINNED.  Checked against (a) the literal
+    155-entry move tables tools/utils.pyx:71-113,126-141,300-315, (b) the compiled
+    reference itself (oracle/_ref, built by oracle/build_ref.py) on thousands of
+    play-out positions, (c) committed fixtures tests/golden/*.npz generated from the
+    compiled reference by tests/golden/make_golden.py.
+  * logits / probabilities: **PARITY UNPINNED**.  The arithmetic lives in TensorFlow
+    1.0.0 (model.meta meta_info_def.tensorflow_version), which is not vendored in
+    the reference tree, not installed and not installable here; the weight shard
+    policy_net_model/model.data-00000-of-00001 is absent (.MISSING_LARGE_BLOBS:1);
+    no reference test pins any logit.  forward_fp32() restates the published
+    semantics of tf.nn.conv2d(NHWC, SAME, stride 1) / bias_add / relu / reshape /
+    matmul / softmax at the reference's call sites
+    Breakthrough_Player/policy_net_utils.pyx:106-124,149-178,215-239.
+"""
+import numpy as np
+
+N_MOVES = 155          # tools/utils.pyx:605-641 (154 from-to moves + 'no-move')
+NO_MOVE = 154          # tools/utils.pyx:113
+MAX_LEGAL = 48         # 16 pieces x 3 directions
+EMPTY, WHITE, BLACK = 0, 1, 2
+FILES = "abcdefgh"
+
+# ----------------------------------------------------------------------------
+# Board type  (tools/utils.pyx:518-541, Breakthrough_Player/board_utils.pyx:18-30)
+# compact form: squares[64] int8, index = (rank-1)*8 + file, 0='e' 1='w' 2='b'
+# ----------------------------------------------------------------------------
+_CH2V = {"e": EMPTY, "w": WHITE, "b": BLACK}
+_V2CH = "ewb"
+
+
+def squares_from_board(board):
+    """Reference board dict {1..8:{'a'..'h':'w'|'b'|'e'}, 9:.., 10:..} -> int8[64]."""
+    sq = np.zeros(64, dtype=np.int8)
+    for rank in range(1, 9):
+        row = board[rank]
+        for f, ch in enumerate(FILES):
+            sq[(rank - 1) * 8 + f] = _CH2V[row[ch]]
+    return sq
+
+
+def board_from_squares(sq, white_to_move=1, last_mover=-1):
+    """Inverse of squares_from_board (keys 9/10 as in tools/utils.pyx:533-536)."""
+    board = {9: int(white_to_move), 10: int(last_mover)}
+    for rank in range(1, 9):
+        board[rank] = {ch: _V2CH[int(sq[(rank - 1) * 8 + f])] for f, ch in enumerate(FILES)}
+    return board
+
+
+def initial_squares():
+    """tools/utils.pyx:518-541 initial_game_board(): white ranks 1-2, black 7-8."""
+    sq = np.zeros(64, dtype=np.int8)
+    sq[0:16] = WHITE
+    sq[48:64] = BLACK
+    return sq
+
+
+def pov_squares(squares, black_to_move):
+    """Side-to-move point of view: values 0=empty 1=player 2=opponent.
+
+    tools/utils.pyx:563-600: for Black the board is rotated 180 degrees (column
+    mirror :566-584 + row swap :586-599), i.e. pov index = 63 - index; player/opponent
+    letters swap (:842-848).
+    squares [N,64] int8, black_to_move [N] -> [N,64] int8.
+    """
+    squares = np.asarray(squares, dtype=np.int8).reshape(-1, 64)
+    black = np.asarray(black_to_move).astype(bool).reshape(-1)
+    pov = np.where(black[:, None], squares[:, ::-1], squares)
+    # recolour: for white-to-move 1=w stays player, 2=b opponent; for black swap
+    swapped = np.where(pov == WHITE, 2, np.where(pov == BLACK, 1, 0)).astype(np.int8)
+    return np.where(black[:, None], swapped, pov).astype(np.int8)
+
+
+def encode_planes(squares, black_to_move):
+    """convert_board_to_2d_matrix_POEB (tools/utils.pyx:546-602) +
+    generate_binary_plane_POEB (:819-866).  -> int8 [N,8,8,4] planes
+    (Player, Opponent, Empty, Bias=1); row index 0 = side-to-move's home rank."""
+    pov = pov_squares(squares, black_to_move)
+    n = pov.shape[0]
+    planes = np.zeros((n, 64, 4), dtype=np.int8)
+    planes[:, :, 0] = pov == 1
+    planes[:, :, 1] = pov == 2
+    planes[:, :, 2] = pov == 0
+    planes[:, :, 3] = 1                       # utils.pyx:828 [[0,0,0,bias]]
+    return planes.reshape(n, 8, 8, 4)
+
+
+# ----------------------------------------------------------------------------
+# Move-index codec (tools/utils.pyx:69-114, 118-477, 480-516, 605-641)
+# ----------------------------------------------------------------------------
+def move_index(move, color=None):
+    """generate_transition_vector (tools/utils.pyx:605-641) closed form.
+    move like 'a2-a3'; colour inferred from direction when not given."""
+    move = move.lower()
+    if move == "no-move":
+        return NO_MOVE
+    fc, fr, tc, tr = ord(move[0]) - 97, int(move[1]), ord(move[3]) - 97, int(move[4])
+    if color is None:
+        color = "White" if tr > fr else "Black"
+    col_off = fc * 3
+    if color == "Black":
+        row_off = (tr - 1) * 22
+        assert row_off == (fr - 2) * 22       # utils.pyx:632
+        return 153 - ((tc - fc) + col_off + row_off)
+    row_off = (fr - 1) * 22
+    assert row_off == (tr - 2) * 22           # utils.pyx:637
+    return (tc - fc) + col_off + row_off
+
+
+def move_tables():
+    """generate_move_lookup (tools/utils.pyx:480-516): index -> move string for
+    White and Black (each 155 long, last entry 'no-move')."""
+    chars = FILES
+    white = []
+    for k in range(1, 8):
+        for i in range(8):
+            if i > 0:
+                white.append("%s%d-%s%d" % (chars[i], k, chars[i - 1], k + 1))
+            white.append("%s%d-%s%d" % (chars[i], k, chars[i], k + 1))
+            if i < 7:
+                white.append("%s%d-%s%d" % (chars[i], k, chars[i + 1], k + 1))
+    black = []
+    for k in range(8, 1, -1):
+        for i in range(7, -1, -1):
+            if i < 7:
+                black.append("%s%d-%s%d" % (chars[i], k, chars[i + 1], k - 1))
+            black.append("%s%d-%s%d" % (chars[i], k, chars[i], k - 1))
+            if i > 0:
+                black.append("%s%d-%s%d" % (chars[i], k, chars[i - 1], k - 1))
+    white.append("no-move")
+    black.append("no-move")
+    return white, black
+
+
+def pov_move_index(r, c, d):
+    """POV-frame closed form: piece on pov (r,c) moving to (r+1,c+d)."""
+    return 22 * r + 3 * c + d
+
+
+# ----------------------------------------------------------------------------
+# Legal moves (Breakthrough_Player/board_utils.pyx:293-400)
+# ----------------------------------------------------------------------------
+def legal_mask(squares, black_to_move):
+    """-> bool [N,155]: policy-net indices of the side-to-move's legal moves.
+
+    check_forward_move (:355-378): forward legal iff target == 'e'.
+    check_left/right_diagonal_move (:331-353, :380-400): diagonal legal iff
+    in-board and target != own piece.  Index by generate_transition_vector.
+    Pieces on the far rank generate nothing (board_utils.pyx:364,372: the game is
+    already over there)."""
+    pov = pov_squares(squares, black_to_move).reshape(-1, 8, 8)
+    n = pov.shape[0]
+    mask = np.zeros((n, N_MOVES), dtype=bool)
+    for r in range(7):
+        for c in range(8):
+            own = pov[:, r, c] == 1
+            for d in (-1, 0, 1):
+                cc = c + d
+                if cc < 0 or cc > 7:
+                    continue
+                tgt = pov[:, r + 1, cc]
+                ok = (tgt == 0) if d == 0 else (tgt != 1)
+                mask[:, 22 * r + 3 * c + d] = own & ok
+    return mask
+
+
+def game_over(squares):
+    """board_utils.pyx:408-422: white on rank 8 or black on rank 1."""
+    squares = np.asarray(squares).reshape(-1, 64)
+    return (squares[:, 56:64] == WHITE).any(1) | (squares[:, 0:8] == BLACK).any(1)
+
+
+# ----------------------------------------------------------------------------
+# Policy net forward (Breakthrough_Player/policy_net_utils.pyx:106-124,149-178,215-239
+#                     == policy_net_model/PolicyNet.py:38-114)
+# ----------------------------------------------------------------------------
+WEIGHT_NAMES = ["hidden_layer/%d/%s" % (i, k) for i in range(1, 6) for k in ("weights", "bias")] + \
+               ["output_layer/weights", "output_layer/bias"]
+
+
+def weight_shapes(final_kernel=3):
+    """model.index shapes: HWIO conv kernels, [64,155] FC."""
+    s = {}
+    cin = 4
+    for i in range(1, 6):
+        cout = 192 if i < 5 else 1
+        k = 3 if i < 5 else final_kernel
+        s["hidden_layer/%d/weights" % i] = (k, k, cin, cout)
+        s["hidden_layer/%d/bias" % i] = (cout,)
+        cin = cout
+    s["output_layer/weights"] = (64, 155)
+    s["output_layer/bias"] = (155,)
+    return s
+
+
+def synthetic_weights(preset="trained_like", seed=1, final_kernel=3):
+    """Deterministic stand-ins for the missing weight shard.
+
+    'ref_init'    : the reference's initialisers -- conv N(0, sqrt(2/prod(prev shape[1:])))
+                    (policy_net_utils.pyx:152,161), conv bias 0.01 (:166-167), FC Xavier
+                    uniform (:227), FC bias 0 (:233).
+    'trained_like': fan-in-correct He conv N(0, sqrt(2/(k*k*Cin))), small random conv
+                    biases, FC scaled so that logits have sigma ~ 2.5 (a peaked policy, so
+                    that top-1 agreement is a meaningful test)."""
+    rng = np.random.RandomState(seed)
+    w = {}
+    shapes = weight_shapes(final_kernel)
+    for i in range(1, 6):
+        shp = shapes["hidden_layer/%d/weights" % i]
+        k, _, cin, cout = shp
+        if preset == "ref_init":
+            std = np.sqrt(2.0 / (64 * cin))
+            b = np.full((cout,), 0.01, np.float32)
+        else:
+            std = np.sqrt(2.0 / (k * k * cin))
+            b = (0.05 * rng.standard_normal(cout)).astype(np.float32)
+        w["hidden_layer/%d/weights" % i] = (std * rng.standard_normal(shp)).astype(np.float32)
+        w["hidden_layer/%d/bias" % i] = b
+    if preset == "ref_init":
+        lim = np.sqrt(6.0 / (64 + 155))
+        w["output_layer/weights"] = rng.uniform(-lim, lim, (64, 155)).astype(np.float32)
+        w["output_layer/bias"] = np.zeros(155, np.float32)
+    else:
+        w["output_layer/weights"] = (0.9 * rng.standard_normal((64, 155))).astype(np.float32)
+        w["output_layer/bias"] = (0.1 * rng.standard_normal(155)).astype(np.float32)
+    return w
+
+
+def conv2d_same_nhwc(x, w_hwio, dtype=np.float32):
+    """tf.nn.conv2d(input NHWC, filter HWIO, strides 1, padding 'SAME')
+    (policy_net_utils.pyx:171-175): cross-correlation, symmetric zero pad (k-1)/2."""
+    n, h, wd, cin = x.shape
+    kh, kw, _, cout = w_hwio.shape
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    xp = np.zeros((n, h + 2 * ph, wd + 2 * pw, cin), dtype=dtype)
+    xp[:, ph:ph + h, pw:pw + wd, :] = x
+    cols = np.empty((n, h, wd, kh * kw * cin), dtype=dtype)
+    for i in range(kh):
+        for j in range(kw):
+            cols[..., (i * kw + j) * cin:(i * kw + j + 1) * cin] = xp[:, i:i + h, j:j + wd, :]
+    out = cols.reshape(n * h * wd, kh * kw * cin) @ w_hwio.reshape(kh * kw * cin, cout).astype(dtype)
+    return out.reshape(n, h, wd, cout)
+
+
+def forward_fp32(planes, weights, dtype=np.float32, return_all=False):
+    """build_policy_net (policy_net_utils.pyx:106-124): 5 x [conv3x3 SAME + bias_add + relu]
+    (hidden_layer_init :149-178; ReLU also on the 1-channel 5th map, default activation
+    :149), reshape [-1,64] (:216), matmul [64,155] + bias (:235-238), softmax (:217).
+    planes [N,8,8,4] any numeric dtype.  Returns (logits, probs) [N,155]."""
+    x = np.asarray(planes).astype(dtype)
+    acts = []
+    for i in range(1, 6):
+        x = conv2d_same_nhwc(x, weights["hidden_layer/%d/weights" % i], dtype)
+        x = np.maximum(x + weights["hidden_layer/%d/bias" % i].astype(dtype), 0)
+        acts.append(x)
+    h = x.reshape(-1, 64)
+    logits = h @ weights["output_layer/weights"].astype(dtype) + weights["output_layer/bias"].astype(dtype)
+    z = logits - logits.max(axis=1, keepdims=True)
+    e = np.exp(z)
+    probs = e / e.sum(axis=1, keepdims=True)
+    if return_all:
+        return logits, probs, acts
+    return logits, probs
+
+
+# ----------------------------------------------------------------------------
+# Prior gather + ranking (tree_search_utils.pyx:979-986, tree_builder.pyx:557,606-609;
+# board_utils.pyx:262-291)
+# ----------------------------------------------------------------------------
+def ranked_children(probs, mask):
+    """For each position: legal indices sorted by prior descending (prior =
+    softmax155[idx], NO renormalisation: tree_search_utils.pyx:983-986; sort
+    tree_builder.pyx:557).  Ties broken by ascending move index (the reference's tie
+    order depends on history-dependent piece-list order and is not a function of the
+    board; DESIGN.md 'tie-break').  Returns idx uint8 [N,48] (pad 255),
+    prior float32 [N,48] (pad 0), n_legal uint8 [N]."""
+    probs = np.asarray(probs, dtype=np.float32)
+    n = probs.shape[0]
+    idx = np.full((n, MAX_LEGAL), 255, np.uint8)
+    pri = np.zeros((n, MAX_LEGAL), np.float32)
+    cnt = np.zeros(n, np.uint8)
+    for i in range(n):
+        legal = np.nonzero(mask[i])[0]
+        order = np.lexsort((legal, -probs[i, legal]))     # primary -prob, secondary idx
+        legal = legal[order]
+        k = len(legal)
+        idx[i, :k] = legal
+        pri[i, :k] = probs[i, legal]
+        cnt[i] = k
+    return idx, pri, cnt
+
+
+def top1_legal(probs, mask):
+    """get_best_move (board_utils.pyx:262-277): first legal index in the descending
+    ranking == argmax of prior over legal indices."""
+    p = np.where(mask, probs, -1.0)
+    return p.argmax(axis=1)
+
+
+# ----------------------------------------------------------------------------
+# Position generator: seeded random legal play-outs
+# ----------------------------------------------------------------------------
+def apply_pov_move(squares, black, idx):
+    """Apply policy index idx for the side to move; returns new squares (absolute)."""
+    r, rem = divmod(int(idx), 22)
+    # invert 22r + 3c + d
+    c = (rem + 1) // 3
+    d = rem - 3 * c
+    frm, to = r * 8 + c, (r + 1) * 8 + c + d
+    if black:
+        frm, to = 63 - frm, 63 - to
+    sq = squares.copy()
+    sq[to] = sq[frm]
+    sq[frm] = EMPTY
+    return sq
+
+
+def random_positions(n, seed=20260601, balance=True):
+    """n non-terminal positions from seeded random play-outs from the opening; one
+    position sampled uniformly per play-out ply range.  -> squares int8 [n,64],
+    black_to_move uint8 [n]."""
+    rng = np.random.RandomState(seed)
+    out_sq, out_b = [], []
+    want_black = 0
+    while len(out_sq) < n:
+        sq = initial_squares()
+        black = 0
+        traj = []
+        for _ in range(200):
+            if game_over(sq)[0]:
+                break
+            m = np.nonzero(legal_mask(sq[None], [black])[0])[0]
+            if len(m) == 0:
+                break
+            traj.append((sq, black))
+            sq = apply_pov_move(sq, black, m[rng.randint(len(m))])
+            black ^= 1
+        if balance:
+            cand = [t for t in traj if t[1] == want_black]
+        else:
+            cand = traj
+        if not cand:
+            continue
+        s, b = cand[rng.randint(len(cand))]
+        out_sq.append(s)
+        out_b.append(b)
+        want_black ^= 1
+    return np.stack(out_sq).astype(np.int8), np.array(out_b, dtype=np.uint8)
+
+
+def random_positions_fast(n, seed=20260601):
+    """Vectorised variant for large suites: plays n games in lock-step for a random
+    number of plies each (uniform 0..59), keeping a game frozen once its target ply is
+    reached or the next move would end it.  Same distributional intent as
+    random_positions, much faster for n >= 1e4."""
+    rng = np.random.RandomState(seed)
+    sq = np.tile(initial_squares(), (n, 1))
+    black = np.zeros(n, dtype=np.uint8)
+    target = rng.randint(0, 60, size=n)
+    ply = np.zeros(n, dtype=np.int64)
+    active = ply < target
+    for _ in range(60):
+        if not active.any():
+            break
+        ids = np.nonzero(active)[0]
+        m = legal_mask(sq[ids], black[ids])
+        # choose a random legal move per active board
+        r = rng.random_sample(m.shape) * m
+        choice = r.argmax(axis=1)
+        has = m.any(axis=1)
+        for j, i in enumerate(ids):
+            if not has[j]:
+                active[i] = False
+                continue
+            nsq = apply_pov_move(sq[i], black[i], choice[j])
+            if game_over(nsq)[0]:
+                active[i] = False          # keep the pre-terminal position
+                continue
+            sq[i] = nsq
+            black[i] ^= 1
+            ply[i] += 1
+            if ply[i] >= target[i]:
+                active[i] = False
+    return sq.astype(np.int8), black
