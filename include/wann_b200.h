@@ -1,0 +1,144 @@
+/* wann_b200.h -- C ABI of the B200-native WaNN policy-net leaf evaluator.
+ *
+ * This library replaces, for ONE path, what the reference (TeoZosa/WaNN) does through a
+ * TensorFlow 1.0 CPU session:   board(s) -> feature planes -> 5-layer 3x3 conv stack ->
+ * FC-155 -> softmax -> (legal-move gather + descending sort).
+ * Citations are into /root/reference.  The reference has no C ABI of its own (it is
+ * Python/Cython calling `sess.run`); each entry point names the reference interface it
+ * stands in for.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / numpy types.
+ *   - every function returns 0 on success, a negative WANN_E_* code otherwise;
+ *     wann_last_error() returns a human-readable message for the calling thread.
+ *   - `mem` says where ALL data pointers of the call live: WANN_MEM_HOST (pageable or
+ *     pinned host memory; the call stages through the context's pinned buffers, runs the
+ *     kernels and returns when the outputs are in place) or WANN_MEM_DEVICE (device
+ *     pointers on the context's GPU; work is enqueued on `stream` -- a cudaStream_t passed
+ *     as void*, NULL = the context's own stream followed by a synchronize).
+ *   - board encoding ("squares"): int8[64] per position, index = (rank-1)*8 + file
+ *     (a1=0, b1=1, ..., h8=63), value 0 = empty 'e', 1 = white 'w', 2 = black 'b'
+ *     (the compact form of the dict-of-dicts board, tools/utils.pyx:518-541).
+ *     `black_to_move`: uint8 per position, 0 = White to move, 1 = Black to move
+ *     (the `player_color` / node['color'] argument, MCTS.pyx:98-102).
+ *   - move indices are the reference's 155-way alphabet (tools/utils.pyx:69-114,605-641),
+ *     in the side-to-move frame; 154 = 'no-move'.
+ *   - there is NO CPU fallback: without an sm_100 device wann_create fails.
+ *   - all entry points are re-entrant; concurrent callers (the reference calls evaluate
+ *     from 11 threads without a lock, tree_builder.pyx:186-189) run on separate lanes.
+ */
+#ifndef WANN_B200_H
+#define WANN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WANN_N_MOVES 155   /* tools/utils.pyx:605-641 */
+#define WANN_MAX_LEGAL 48  /* 16 pieces x 3 directions */
+
+enum wann_status {
+  WANN_OK = 0,
+  WANN_E_INVALID = -1,   /* bad argument */
+  WANN_E_NO_DEVICE = -2, /* no sm_100 GPU / CUDA failure at init */
+  WANN_E_CUDA = -3,      /* CUDA runtime error during a call */
+  WANN_E_KERNEL = -4     /* device-side watchdog tripped (see wann_last_error) */
+};
+
+enum wann_mode {
+  WANN_MODE_BF16 = 0, /* tcgen05 tensor-core path: bf16 operands, fp32 accumulate */
+  WANN_MODE_FP32 = 1  /* CUDA-core fp32 path (accuracy mode, validation) */
+};
+
+enum wann_mem { WANN_MEM_HOST = 0, WANN_MEM_DEVICE = 1 };
+
+enum wann_planes_dtype { WANN_PLANES_I8 = 0, WANN_PLANES_F32 = 1 };
+
+/* Weights in TensorFlow layout, fp32, HOST pointers (copied at wann_create).
+ * Names/shapes are those of policy_net_model/model.index:
+ *   hidden_layer/{1..5}/weights  HWIO [3,3,4,192] [3,3,192,192]x3 [k,k,192,1]
+ *   hidden_layer/{1..5}/bias     [192]x4, [1]
+ *   output_layer/weights [64,155], output_layer/bias [155]
+ * (Breakthrough_Player/policy_net_utils.pyx:106-124,149-178,215-239). */
+typedef struct wann_weights {
+  const float* conv_w[5];
+  const float* conv_b[5];
+  const float* fc_w;
+  const float* fc_b;
+  int final_kernel; /* 3 = shipped checkpoint; 1 = the `_128` variant (policy_net_utils.pyx:135) */
+} wann_weights;
+
+typedef struct wann_ctx wann_ctx;
+
+/* Replaces instantiate_session() / Saver.restore (policy_net_utils.pyx:64-76): uploads the
+ * weights to `device`, builds the tensor-core weight images, allocates lanes/workspaces. */
+int wann_create(const wann_weights* weights, int device, int mode, wann_ctx** out_ctx);
+
+/* Replaces sess.close() (MCTS.pyx:132-133). */
+int wann_destroy(wann_ctx* ctx);
+
+/* Message for the last failing call made by the calling thread ("" if none). */
+const char* wann_last_error(void);
+
+/* Replaces convert_board_to_2d_matrix_POEB + generate_binary_plane_POEB
+ * (tools/utils.pyx:546-602, 819-866): planes int8 [n][8][8][4] = {player, opponent, empty, 1}
+ * in the side-to-move frame.  Standalone (the eval entry points fuse this step). */
+int wann_encode(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n,
+                int8_t* planes, int mem, void* stream);
+
+/* Replaces enumerate_legal_moves + index_lookup_by_move
+ * (Breakthrough_Player/board_utils.pyx:293-400, tools/utils.pyx:69-114):
+ * mask uint8 [n][155], 1 where the move index is legal for the side to move. */
+int wann_legal_mask(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
+                    int64_t n, uint8_t* mask, int mem, void* stream);
+
+/* Replaces NeuralNetsCombined_128.evaluate on board inputs (MCTS.pyx:85-127):
+ * encode + sess.run(y_pred, {X: batch}).  probs float [n][155] (softmax over all 155,
+ * not renormalised over legal moves); logits float [n][155] optional (may be NULL). */
+int wann_eval_probs(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
+                    int64_t n, float* probs, float* logits, int mem, void* stream);
+
+/* Replaces sess.run(y_pred, feed_dict={X: planes}) for pre-encoded input
+ * (evaluate(..., already_converted=True), MCTS.pyx:103-104; call_policy_net,
+ * policy_net_utils.pyx:9-16).  planes [n][8][8][4], int8 or float32 per planes_dtype. */
+int wann_eval_planes(wann_ctx* ctx, const void* planes, int planes_dtype, int64_t n,
+                     float* probs, float* logits, int mem, void* stream);
+
+/* Replaces evaluate + the per-parent consumer: legal enumeration
+ * (board_utils.pyx:311-319), prior gather NN_output[child_index]
+ * (tree_search_utils.pyx:979-986) and the descending sort (tree_builder.pyx:557).
+ * For each position: idx uint8 [n][48] legal move indices, prior float [n][48] their
+ * softmax-155 probabilities, sorted by prior descending (ties: ascending index), padded
+ * with 255 / 0; n_legal uint8 [n].  idx[.][0] is the policy move of get_best_move
+ * (board_utils.pyx:262-277). */
+int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
+                   int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal, int mem,
+                   void* stream);
+
+/* Test/inspection hook: activations after hidden layer `layer` (1..5) as float
+ * [n][8][8][C] (C = 192, or 1 for layer 5), host or device per `mem`.  In BF16 mode the
+ * values are the bf16-rounded activations the next layer consumes (layer 5: fp32). */
+int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
+                           int64_t n, int layer, float* out, int mem);
+
+/* Pinned host buffers for callers that want copy/compute overlap on the HOST path. */
+int wann_host_alloc(void** ptr, uint64_t bytes);
+int wann_host_free(void* ptr);
+
+/* Counters since create: [0] positions evaluated, [1] kernel launches, [2] calls,
+ * [3] H2D bytes, [4] D2H bytes, [5..7] reserved. */
+int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]);
+
+/* Tunables (optional).  key: "chunk" (positions per internal chunk, default 16384),
+ * "variant" (debug: tensor-core descriptor variant bits). */
+int wann_set_option(wann_ctx* ctx, const char* key, int64_t value);
+
+/* Library/ABI version (major*100+minor). */
+int wann_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WANN_B200_H */

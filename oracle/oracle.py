@@ -391,3 +391,36 @@ def random_positions_fast(n, seed=20260601):
             if ply[i] >= target[i]:
                 active[i] = False
     return sq.astype(np.int8), black
+
+
+# ----------------------------------------------------------------------------
+# bf16 emulation of the tensor-core path (for tight per-layer checks of the CUDA kernel)
+# ----------------------------------------------------------------------------
+def bf16_round(a):
+    """Round-to-nearest-even float32 -> bfloat16 -> float32 (what cvt.rn.bf16.f32 does)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(a))
+
+
+def forward_bf16_emulated(planes, weights, return_all=False):
+    """Same graph as forward_fp32 but with the roundings the tcgen05 path applies: conv
+    weights and layer inputs rounded to bf16, fp32 accumulation, bias+ReLU in fp32, the
+    activations of layers 1-4 rounded to bf16 when stored; layer 5 and the FC/softmax in fp32."""
+    x = bf16_round(np.asarray(planes).astype(np.float32))
+    acts = []
+    for i in range(1, 6):
+        w = bf16_round(weights["hidden_layer/%d/weights" % i])
+        x = conv2d_same_nhwc(x, w, np.float32)
+        x = np.maximum(x + weights["hidden_layer/%d/bias" % i], 0).astype(np.float32)
+        if i < 5:
+            x = bf16_round(x)
+        acts.append(x)
+    h = x.reshape(-1, 64)
+    logits = h @ weights["output_layer/weights"] + weights["output_layer/bias"]
+    z = logits - logits.max(axis=1, keepdims=True)
+    e = np.exp(z)
+    probs = e / e.sum(axis=1, keepdims=True)
+    if return_all:
+        return logits, probs, acts
+    return logits, probs

@@ -1,0 +1,63 @@
+"""Host-side board and move-index helpers mirroring the reference's data types.
+
+Board dict (tools/utils.pyx:518-541): {1..8: {'a'..'h': 'w'|'b'|'e'}, 9: is_white, 10: last}.
+Compact form handed to the C ABI: int8[64], index (rank-1)*8+file, 0 'e', 1 'w', 2 'b'.
+Move alphabet (tools/utils.pyx:69-114, 118-477, 605-641): 154 from-to moves + 'no-move'."""
+import numpy as np
+
+FILES = "abcdefgh"
+_CH2V = {"e": 0, "w": 1, "b": 2}
+NO_MOVE = 154
+
+
+def board_to_squares(board, out=None):
+    sq = out if out is not None else np.empty(64, np.int8)
+    i = 0
+    for rank in range(1, 9):
+        row = board[rank]
+        for ch in FILES:
+            sq[i] = _CH2V[row[ch]]
+            i += 1
+    return sq
+
+
+def squares_to_board(sq, white_to_move=1, last_mover=-1):
+    board = {9: int(white_to_move), 10: int(last_mover)}
+    for rank in range(1, 9):
+        board[rank] = {ch: "ewb"[int(sq[(rank - 1) * 8 + f])] for f, ch in enumerate(FILES)}
+    return board
+
+
+def color_is_black(color):
+    """The reference passes 'White' / 'Black' strings (MCTS.pyx:98-102)."""
+    return 1 if str(color).lower().startswith("b") else 0
+
+
+def _tables():
+    white, black = [], []
+    for r in range(7):
+        for c in range(8):
+            for d in (-1, 0, 1):
+                if 0 <= c + d <= 7:
+                    # POV closed form idx = 22r + 3c + d; White frame = absolute,
+                    # Black frame = 180-degree rotation (tools/utils.pyx:629-638)
+                    white.append("%s%d-%s%d" % (FILES[c], r + 1, FILES[c + d], r + 2))
+                    black.append("%s%d-%s%d" % (FILES[7 - c], 8 - r, FILES[7 - c - d], 7 - r))
+    white.append("no-move")
+    black.append("no-move")
+    return white, black
+
+
+WHITE_MOVES, BLACK_MOVES = _tables()
+_INDEX = {m: i for i, m in enumerate(WHITE_MOVES)}
+_INDEX.update({m: i for i, m in enumerate(BLACK_MOVES)})
+
+
+def move_lookup_by_index(index, player_color):
+    """tools/utils.pyx:118-477."""
+    return (BLACK_MOVES if color_is_black(player_color) else WHITE_MOVES)[index]
+
+
+def index_lookup_by_move(move):
+    """tools/utils.pyx:69-114."""
+    return _INDEX[move.lower()]

@@ -1,0 +1,293 @@
+// Auxiliary sm_100a kernels of the WaNN leaf-evaluation path:
+//   encode_kernel      board -> int8 POEB planes        (tools/utils.pyx:546-602,819-866)
+//   legal_mask_kernel  board -> uint8[155] legality mask (board_utils.pyx:293-400, utils.pyx:605-641)
+//   tail_kernel        h5[64] -> FC-155 + bias -> softmax -> (legal gather + descending sort)
+//                      (policy_net_utils.pyx:215-239; tree_search_utils.pyx:979-986;
+//                       tree_builder.pyx:557; board_utils.pyx:262-291)
+//   conv3x3_f32_kernel / conv_small_f32_kernel / planes_to_f32_kernel
+//                      CUDA-core fp32 conv stack for WANN_MODE_FP32 (accuracy mode)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wann {
+
+constexpr int kMoves = 155;
+constexpr int kMaxLegal = 48;
+
+// side-to-move view of one square: 0 empty, 1 player, 2 opponent
+__device__ __forceinline__ int pov_square(const int8_t* sq64, int blk, int i) {
+  int s = sq64[blk ? 63 - i : i];
+  if (blk && s) s = 3 - s;
+  return s;
+}
+
+// One thread per square; writes 4 plane bytes (char4) -> fully coalesced 4 B stores.
+__global__ void encode_kernel(const int8_t* __restrict__ squares, const uint8_t* __restrict__ black,
+                              long long n, int8_t* __restrict__ planes) {
+  const long long total = n * 64;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long board = i >> 6;
+    const int s = pov_square(squares + board * 64, black[board], static_cast<int>(i & 63));
+    reinterpret_cast<char4*>(planes)[i] = make_char4(s == 1, s == 2, s == 0, 1);
+  }
+}
+
+// decode a move index into its POV (row, col, dcol); idx in [0,154)
+__device__ __forceinline__ void decode_move(int idx, int& r, int& c, int& d) {
+  r = idx / 22;
+  const int rem = idx - 22 * r;
+  c = (rem + 1) / 3;
+  d = rem - 3 * c;
+}
+
+__device__ __forceinline__ bool move_is_legal(const int8_t* pov, int idx) {
+  if (idx >= 154) return false;   // 'no-move' is never a legal child
+  int r, c, d;
+  decode_move(idx, r, c, d);
+  if (pov[r * 8 + c] != 1) return false;
+  const int t = pov[(r + 1) * 8 + c + d];
+  return d == 0 ? (t == 0) : (t != 1);
+}
+
+__global__ void legal_mask_kernel(const int8_t* __restrict__ squares,
+                                  const uint8_t* __restrict__ black, long long n,
+                                  uint8_t* __restrict__ mask) {
+  __shared__ int8_t pov[8][64];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long board = blockIdx.x * 8ll + w; board < n; board += gridDim.x * 8ll) {
+    const int blk = black[board];
+    pov[w][lane] = static_cast<int8_t>(pov_square(squares + board * 64, blk, lane));
+    pov[w][lane + 32] = static_cast<int8_t>(pov_square(squares + board * 64, blk, lane + 32));
+    __syncwarp();
+    for (int j = lane; j < kMoves; j += 32) mask[board * kMoves + j] = move_is_legal(pov[w], j);
+    __syncwarp();
+  }
+}
+
+struct TailParams {
+  const float* h5;          // [n][64]
+  const int8_t* squares;    // [n][64] or null (no legality -> no top-k)
+  const uint8_t* black;     // [n]
+  long long n;
+  const float* fc_w;        // [64][155]
+  const float* fc_b;        // [155]
+  float* probs;             // [n][155] or null
+  float* logits;            // [n][155] or null
+  uint8_t* idx;             // [n][48] or null
+  float* prior;             // [n][48]
+  uint8_t* n_legal;         // [n]
+};
+
+// One warp per board, 8 boards per CTA pass; FC weights resident in shared memory.
+constexpr int kTailWarps = 8;
+constexpr int kTailSmemBytes = (64 * kMoves + kMoves + 5) * 4 + kTailWarps * (64 * 4 + 160 * 4 + 64);
+
+__global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams p) {
+  extern __shared__ float tsm[];
+  float* w_s = tsm;                        // [64][155]
+  float* b_s = w_s + 64 * kMoves;          // [155] (+5 pad)
+  float* h_s = b_s + 160;                  // [warps][64]
+  float* pm_s = h_s + kTailWarps * 64;     // [warps][160] masked probs for ranking
+  int8_t* pov_s = reinterpret_cast<int8_t*>(pm_s + kTailWarps * 160);   // [warps][64]
+  for (int i = threadIdx.x; i < 64 * kMoves; i += blockDim.x) w_s[i] = p.fc_w[i];
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) b_s[i] = i < kMoves ? p.fc_b[i] : 0.f;
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* h = h_s + w * 64;
+  float* pm = pm_s + w * 160;
+  int8_t* pov = pov_s + w * 64;
+  for (long long board = blockIdx.x * static_cast<long long>(kTailWarps) + w; board < p.n;
+       board += static_cast<long long>(gridDim.x) * kTailWarps) {
+    h[lane] = p.h5[board * 64 + lane];
+    h[lane + 32] = p.h5[board * 64 + lane + 32];
+    if (p.squares != nullptr) {
+      const int blk = p.black[board];
+      pov[lane] = static_cast<int8_t>(pov_square(p.squares + board * 64, blk, lane));
+      pov[lane + 32] = static_cast<int8_t>(pov_square(p.squares + board * 64, blk, lane + 32));
+    }
+    __syncwarp();
+    // logits[j] = sum_q h[q] * W[q][j] + b[j]   (reshape [-1,64] row-major, matmul, bias_add)
+    float lg[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lg[k] = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 64; ++q) {
+      const float hq = h[q];
+      const float* wr = w_s + q * kMoves + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lg[k] = fmaf(hq, wr[32 * k], lg[k]);
+      if (lane < kMoves - 128) lg[4] = fmaf(hq, wr[128], lg[4]);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int j = lane + 32 * k;
+      if (j < kMoves) {
+        lg[k] += b_s[j];
+        mx = fmaxf(mx, lg[k]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float e[5], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int j = lane + 32 * k;
+      e[k] = (j < kMoves) ? expf(lg[k] - mx) : 0.f;
+      sum += e[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int j = lane + 32 * k;
+      if (j < kMoves) {
+        const float pr = e[k] / sum;
+        if (p.probs != nullptr) p.probs[board * kMoves + j] = pr;
+        if (p.logits != nullptr) p.logits[board * kMoves + j] = lg[k];
+        e[k] = pr;
+      }
+    }
+    if (p.idx != nullptr) {
+      // legal gather: prior_i = softmax155[idx_i] (no renormalisation), then rank sort
+      // descending by prior, ties by ascending index.
+      bool legal[5];
+      int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int j = lane + 32 * k;
+        legal[k] = (j < kMoves) && move_is_legal(pov, j);
+        if (j < 160) pm[j] = legal[k] ? e[k] : -1.f;
+        cnt += legal[k];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      __syncwarp();
+      for (int j = lane; j < kMaxLegal; j += 32) {
+        if (j >= cnt) {
+          p.idx[board * kMaxLegal + j] = 255;
+          p.prior[board * kMaxLegal + j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        if (!legal[k]) continue;
+        const int j = lane + 32 * k;
+        const float me = e[k];
+        int rank = 0;
+        for (int o = 0; o < kMoves - 1; ++o) {
+          const float other = pm[o];
+          rank += (other > me) || (other == me && o < j);
+        }
+        p.idx[board * kMaxLegal + rank] = static_cast<uint8_t>(j);
+        p.prior[board * kMaxLegal + rank] = me;
+      }
+      if (lane == 0) p.n_legal[board] = static_cast<uint8_t>(cnt);
+    }
+    __syncwarp();
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// fp32 accuracy mode (CUDA cores).  One CTA per board, 256 threads: warp = output row y,
+// lane -> output channels lane + 32*j.  Input board staged zero-padded in shared memory.
+// tf.nn.conv2d NHWC/HWIO SAME stride 1 + bias_add + relu (policy_net_utils.pyx:169-176).
+__global__ void planes_to_f32_kernel(const int8_t* __restrict__ squares,
+                                     const uint8_t* __restrict__ black,
+                                     const void* __restrict__ planes_in, int planes_f32,
+                                     long long n, float* __restrict__ out) {
+  const long long total = n * 64;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v;
+    if (squares != nullptr) {
+      const long long board = i >> 6;
+      const int s = pov_square(squares + board * 64, black[board], static_cast<int>(i & 63));
+      v = make_float4(s == 1, s == 2, s == 0, 1.f);
+    } else if (planes_f32) {
+      v = reinterpret_cast<const float4*>(planes_in)[i];
+    } else {
+      const char4 c = reinterpret_cast<const char4*>(planes_in)[i];
+      v = make_float4(c.x, c.y, c.z, c.w);
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restrict__ in,   // [n][64][CIN]
+                                                          const float* __restrict__ w,    // [3][3][CIN][192]
+                                                          const float* __restrict__ bias, // [192]
+                                                          float* __restrict__ out) {      // [n][64][192]
+  extern __shared__ float a_s[];   // [10][10][CIN]
+  const long long board = blockIdx.x;
+  for (int i = threadIdx.x; i < 100 * CIN; i += 256) a_s[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * CIN; i += 256) {
+    const int px = i / CIN, c = i - px * CIN;
+    a_s[((px / 8 + 1) * 10 + (px % 8) + 1) * CIN + c] = in[board * 64 * CIN + i];
+  }
+  __syncthreads();
+  const int y = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[8][6];
+#pragma unroll
+  for (int x = 0; x < 8; ++x)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[x][j] = 0.f;
+  for (int dy = 0; dy < 3; ++dy) {
+    for (int ci = 0; ci < CIN; ++ci) {
+      float a[10];
+#pragma unroll
+      for (int x = 0; x < 10; ++x) a[x] = a_s[((y + dy) * 10 + x) * CIN + ci];
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float* wr = w + (static_cast<size_t>(dy * 3 + dx) * CIN + ci) * 192 + lane;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const float wv = __ldg(wr + 32 * j);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) acc[x][j] = fmaf(a[x + dx], wv, acc[x][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float bv = bias[lane + 32 * j];
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+      out[(board * 64 + y * 8 + x) * 192 + lane + 32 * j] = fmaxf(acc[x][j] + bv, 0.f);
+  }
+}
+
+// 192 -> 1 channel conv (k = 3 or 1): one warp per output pixel, lanes split the channels.
+__global__ void __launch_bounds__(256) conv_small_f32_kernel(const float* __restrict__ in,  // [n][64][192]
+                                                             const float* __restrict__ w,   // [k][k][192][1]
+                                                             const float* __restrict__ bias, int k,
+                                                             float* __restrict__ h5) {      // [n][64]
+  const long long board = blockIdx.x;
+  const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = (k - 1) / 2;
+  for (int px = wp; px < 64; px += 8) {
+    const int y = px >> 3, x = px & 7;
+    float acc = 0.f;
+    for (int i = 0; i < k; ++i) {
+      const int yy = y + i - p;
+      if (yy < 0 || yy > 7) continue;
+      for (int j = 0; j < k; ++j) {
+        const int xx = x + j - p;
+        if (xx < 0 || xx > 7) continue;
+        const float* a = in + (board * 64 + yy * 8 + xx) * 192;
+        const float* wr = w + (i * k + j) * 192;
+        for (int c = lane; c < 192; c += 32) acc = fmaf(a[c], wr[c], acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) h5[board * 64 + px] = fmaxf(acc + bias[0], 0.f);
+  }
+}
+
+}  // namespace wann

@@ -1,0 +1,391 @@
+// conv_stack_tc: the WaNN policy-net conv stack (encode -> conv1..conv5) as ONE persistent,
+// warp-specialised sm_100a kernel.  Replaces the TF graph ops
+//   hidden_layer/{1..5}/{Conv2D,BiasAdd,Relu}   (Breakthrough_Player/policy_net_utils.pyx:149-178)
+// and the Python board->plane encoder (tools/utils.pyx:546-602,819-866) for batched leaf
+// positions.  Output: h5[n][64] fp32 = the post-ReLU 1-channel 5th feature map, which the tail
+// kernel (tail_kernels.cuh) turns into logits / softmax / ranked legal priors.
+//
+// Design (see DESIGN.md "K2"):
+//   * CTA pair (cluster of 2, tcgen05 cta_group::2).  A pair owns a "supertile" of 8 boards:
+//     each CTA holds 4 boards = two M=128 row tiles (2 boards x 64 squares each); one
+//     tcgen05.mma covers M=256 (128 rows in each CTA) x N=192 x K=16.
+//   * Activations NEVER leave the SM: a layer's bf16 output is written by the epilogue warps
+//     straight into the shared-memory layout the next layer's MMAs read as operand A.
+//     Layout per row tile ("A tile"):  [24 channel-chunks of 8][10 rows y=-1..8][2 boards]
+//     [9 cells x=-1..7][16 B], i.e. a zero-haloed board image whose 16-byte cells are the
+//     8x16B "core matrix" rows of a K-major SWIZZLE_NONE UMMA descriptor.  MMA row m of a tile
+//     is square (y = m/16, board = (m/8)%2, x = m%8), so an 8-row core-matrix group is one
+//     board row, the group stride (SBO) is one padded row = 144 B and the K-chunk stride (LBO)
+//     is 2896 B.  The 3x3 taps are then nothing but nine different descriptor START ADDRESSES
+//     ((dy+1)*288 + (dx+1)*16 bytes): implicit GEMM with zero im2col traffic, SAME padding
+//     supplied by the (never written) zero halo.
+//   * Weights (operand B) stream from L2 through a ring of shared-memory stages via
+//     cp.async.bulk (TMA engine, 1-D).  They are pre-arranged on the host into the exact
+//     shared-memory image of each stage (K-major SWIZZLE_NONE core matrices; each CTA of the
+//     pair holds its half of the 192 output channels), so no tensor map is needed.
+//   * conv1 (4->192) runs as 9 taps x K=16 (4 real channels), conv2-4 as 9 taps x 3 x K=64,
+//     conv5 (192->1, 3x3) as a 1x1 GEMM with N=16 whose columns are the 9 TAPS
+//     (P[pixel][tap] = <act4[pixel], w5[tap]>) followed by a 9-point stencil sum in the epilogue.
+//   * Warp roles per CTA (320 threads): warp 0 = weight producer, warp 1 = MMA issuer (leader
+//     CTA) / full-barrier relay (peer CTA), warps 2..9 = epilogue (TMEM -> +bias, ReLU, bf16 ->
+//     shared memory A tile of the next layer).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace wann {
+
+// ---- geometry ------------------------------------------------------------------------------
+constexpr int kC = 192;                       // hidden channels
+constexpr int kKChunks = kC / 8;              // 24 chunks of 8 channels (16 B of bf16)
+constexpr int kCell = 16;                     // bytes per (pixel, channel-chunk) cell
+constexpr int kRowStride = 9 * kCell;         // 144 B: x = -1..7 (x = 8 halo is next row's x = -1)
+constexpr int kYStride = 2 * kRowStride;      // 288 B: two boards interleaved per y
+constexpr int kChunkStride = 10 * kYStride + kCell;  // 2896 B: y = -1..8, + trailing halo cell
+constexpr int kATileBytes = kKChunks * kChunkStride;  // 69504 B per 128-row tile
+constexpr int kTilesPerCta = 2;
+constexpr int kABytes = kTilesPerCta * kATileBytes;   // 139008 B
+constexpr int kBoardsPerCta = 4;
+constexpr int kBoardsPerPair = 8;
+
+constexpr int kStageBytes = 96 * 64 * 2;      // 12288 B: half of [192 x 64] bf16
+constexpr int kStageBytesL5 = 8 * 64 * 2;     // 1024 B: half of [16 x 64] bf16
+constexpr int kStages = 7;
+constexpr int kLboB = 96 / 8 * 128;           // 1536 B between K-chunks of a stage
+constexpr int kLboB5 = 8 / 8 * 128;           // 128 B
+constexpr int kSboB = 128;
+
+constexpr int kKbL1 = 3, kKbMid = 27, kKbL5 = 3;
+constexpr int kImgBytesPerRank = (kKbL1 + 3 * kKbMid) * kStageBytes + kKbL5 * kStageBytesL5;
+
+constexpr int kNumEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kNumEpiWarps);   // 320
+constexpr int kBiasFloats = 4 * kC + 4;
+
+// shared memory carve-up (bytes from the 128-aligned base)
+constexpr int kOffA = 0;
+constexpr int kOffB = kOffA + kABytes;
+constexpr int kOffBias = kOffB + kStages * kStageBytes;
+constexpr int kOffBar = kOffBias + kBiasFloats * 4;
+constexpr int kNumBars = 3 * kStages + 2;
+constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemSlot + 16 + 128;   // +128 for base alignment slack
+
+constexpr uint32_t kIdescN192 = ptx::make_idesc_bf16(256, 192);
+constexpr uint32_t kIdescN16 = ptx::make_idesc_bf16(256, 16);
+
+constexpr long long kWatchdogCycles = 1ll << 29;
+
+struct TcParams {
+  const int8_t* squares;     // [n][64] or null
+  const uint8_t* black;      // [n]
+  const void* planes;        // [n][8][8][4] int8/f32 or null
+  int planes_f32;
+  long long n;
+  const uint8_t* wimg;       // [2][kImgBytesPerRank]
+  const float* bias;         // [4][192] conv1..4 bias, then b5
+  float* h5;                 // [n][64]
+  float* dbg;                // optional activation dump [n][64][192] (layer 1..4)
+  int dbg_layer;
+  int variant;               // bit0: swap A LBO/SBO, bit1: swap B LBO/SBO, bit2: swap B halves
+  int* err;                  // [8] watchdog record
+};
+
+// bounded mbarrier wait: returns false (and records who/where) instead of hanging the GPU
+__device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity, bool cluster_scope,
+                                         int* err, int code) {
+  if (cluster_scope ? ptx::mbar_try_wait_cluster(bar, parity) : ptx::mbar_try_wait(bar, parity))
+    return true;
+  long long t0 = clock64();
+  while (true) {
+    if (cluster_scope ? ptx::mbar_try_wait_cluster(bar, parity) : ptx::mbar_try_wait(bar, parity))
+      return true;
+    if (clock64() - t0 > kWatchdogCycles) {
+      if (atomicCAS(err, 0, code) == 0) {
+        err[1] = static_cast<int>(blockIdx.x);
+        err[2] = static_cast<int>(parity);
+      }
+      return false;
+    }
+  }
+}
+
+// write the conv1 input cell (planes P,O,E,1 as bf16 + 4 zero channels) of one square
+__device__ __forceinline__ void write_input_cell(const TcParams& p, long long board, int y, int x,
+                                                 uint32_t cell0) {
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (board < p.n) {
+    const int sq = y * 8 + x;
+    if (p.squares != nullptr) {
+      // tools/utils.pyx:563-600 (Black: 180-degree rotation) + :842-865 (P/O/E/bias planes)
+      const int blk = p.black[board];
+      int s = p.squares[board * 64 + (blk ? 63 - sq : sq)];
+      if (blk && s) s = 3 - s;
+      const uint32_t one = 0x3F80u;  // bf16 1.0
+      v.x = (s == 1 ? one : 0u) | ((s == 2 ? one : 0u) << 16);
+      v.y = (s == 0 ? one : 0u) | (one << 16);
+    } else if (p.planes_f32) {
+      const float4 f = reinterpret_cast<const float4*>(p.planes)[board * 64 + sq];
+      __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+      v.x = *reinterpret_cast<uint32_t*>(&lo);
+      v.y = *reinterpret_cast<uint32_t*>(&hi);
+    } else {
+      const char4 c = reinterpret_cast<const char4*>(p.planes)[board * 64 + sq];
+      __nv_bfloat162 lo = __floats2bfloat162_rn(float(c.x), float(c.y));
+      __nv_bfloat162 hi = __floats2bfloat162_rn(float(c.z), float(c.w));
+      v.x = *reinterpret_cast<uint32_t*>(&lo);
+      v.y = *reinterpret_cast<uint32_t*>(&hi);
+    }
+  }
+  ptx::st_shared_v4(cell0, v);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_stack_tc_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t a_base = smem_base + kOffA;
+  const uint32_t b_base = smem_base + kOffB;
+  const uint32_t bias_addr = smem_base + kOffBias;
+  const uint32_t bar_base = smem_base + kOffBar;
+  const uint32_t slot_addr = smem_base + kOffTmemSlot;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const float* bias_s = reinterpret_cast<const float*>(smem_gen + kOffBias);
+
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_peer_full = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  const uint32_t bar_acc_full = bar_base + 8u * (3 * kStages);
+  const uint32_t bar_a_ready = bar_base + 8u * (3 * kStages + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const long long total_st = (p.n + kBoardsPerPair - 1) / kBoardsPerPair;
+
+  // ---- one-time setup ---------------------------------------------------------------------
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(bar_full(s), 1);
+      ptx::mbar_init(bar_peer_full(s), 1);
+      ptx::mbar_init(bar_empty(s), 1);
+    }
+    ptx::mbar_init(bar_acc_full, 1);
+    ptx::mbar_init(bar_a_ready, 2);   // one arrival per CTA of the pair
+    ptx::fence_mbar_init();
+  }
+  // zero the activation tiles (the halo cells stay zero for the whole kernel)
+  for (int i = tid; i < kABytes / 16; i += kThreads)
+    ptx::st_shared_v4(a_base + 16u * i, make_uint4(0u, 0u, 0u, 0u));
+  for (int i = tid; i < kBiasFloats; i += kThreads)
+    reinterpret_cast<float*>(smem_gen + kOffBias)[i] = (i < 4 * kC + 1) ? p.bias[i] : 0.f;
+  ptx::fence_proxy_async_smem();
+  if (warp == 0) {
+    ptx::tmem_alloc<2>(slot_addr, 512);
+    ptx::tmem_relinquish<2>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kOffTmemSlot);
+  (void)bias_addr;
+
+  // ---- roles -------------------------------------------------------------------------------
+  if (warp == 0) {
+    // ===== weight producer: stream this CTA's half of every weight stage ====================
+    if (lane == 0) {
+      const uint32_t img_rank = (p.variant & 4) ? (rank ^ 1u) : rank;
+      const uint8_t* img = p.wimg + static_cast<size_t>(img_rank) * kImgBytesPerRank;
+      uint32_t it = 0;
+      bool ok = true;
+      for (long long st = pair; st < total_st && ok; st += npairs) {
+        size_t off = 0;
+        for (int layer = 0; layer < 5 && ok; ++layer) {
+          const int nkb = (layer == 0) ? kKbL1 : (layer == 4 ? kKbL5 : kKbMid);
+          const uint32_t bytes = (layer == 4) ? kStageBytesL5 : kStageBytes;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1u;
+            if (!wait_bar(bar_empty(s), ph ^ 1u, false, p.err, 100 + s)) { ok = false; break; }
+            ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
+            ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes, bar_full(s));
+            off += bytes;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===== MMA issuer (leader CTA, one thread) ===========================================
+      if (lane == 0) {
+        const bool swapA = p.variant & 1, swapB = p.variant & 2;
+        uint32_t it = 0, lstep = 0;
+        bool ok = true;
+        for (long long st = pair; st < total_st && ok; st += npairs) {
+          for (int layer = 0; layer < 5 && ok; ++layer, ++lstep) {
+            if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 200 + layer)) { ok = false; break; }
+            ptx::tc_fence_after();
+            const int nkb = (layer == 0) ? kKbL1 : (layer == 4 ? kKbL5 : kKbMid);
+            const uint32_t idesc = (layer == 4) ? kIdescN16 : kIdescN192;
+            const uint32_t lbo_b = (layer == 4) ? kLboB5 : kLboB;
+            uint32_t accumulate = 0;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+              const int s = it % kStages;
+              const uint32_t ph = (it / kStages) & 1u;
+              if (!wait_bar(bar_full(s), ph, false, p.err, 300 + s) ||
+                  !wait_bar(bar_peer_full(s), ph, true, p.err, 400 + s)) { ok = false; break; }
+              ptx::tc_fence_after();
+              const uint32_t bst = b_base + s * kStageBytes;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                int tap, kc0;
+                if (layer == 0) {
+                  tap = kb * 4 + ks; kc0 = 0;
+                  if (tap >= 9) continue;
+                } else if (layer == 4) {
+                  tap = 4; kc0 = kb * 8 + ks * 2;
+                } else {
+                  tap = kb / 3; kc0 = (kb % 3) * 8 + ks * 2;
+                }
+                const uint32_t a_off = kc0 * kChunkStride + (tap / 3) * kYStride + (tap % 3) * kCell;
+                const uint64_t bdesc = swapB ? ptx::make_desc(bst + ks * 2 * lbo_b, kSboB, lbo_b)
+                                             : ptx::make_desc(bst + ks * 2 * lbo_b, lbo_b, kSboB);
+#pragma unroll
+                for (int t = 0; t < kTilesPerCta; ++t) {
+                  const uint32_t aaddr = a_base + t * kATileBytes + a_off;
+                  const uint64_t adesc = swapA ? ptx::make_desc(aaddr, kRowStride, kChunkStride)
+                                               : ptx::make_desc(aaddr, kChunkStride, kRowStride);
+                  ptx::umma_bf16<2>(tmem_base + t * kC, adesc, bdesc, idesc, accumulate);
+                }
+                accumulate = 1;
+              }
+              ptx::umma_commit<2>(bar_empty(s), 3);   // frees the stage in BOTH CTAs
+            }
+            if (ok) ptx::umma_commit<2>(bar_acc_full, 3);  // accumulators ready, both CTAs
+          }
+        }
+      }
+    } else {
+      // ===== relay (peer CTA): forward "my half of stage s has landed" to the leader =========
+      if (lane == 0) {
+        uint32_t it = 0;
+        bool ok = true;
+        for (long long st = pair; st < total_st && ok; st += npairs) {
+          for (int kb = 0; kb < kKbL1 + 3 * kKbMid + kKbL5; ++kb, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1u;
+            if (!wait_bar(bar_full(s), ph, false, p.err, 500 + s)) { ok = false; break; }
+            ptx::mbar_arrive_cluster(ptx::mapa(bar_peer_full(s), 0));
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps ====================================================================
+    const int ew = warp - 2;
+    const int tile = ew >> 2;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // MMA row inside the tile
+    const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
+    const uint32_t cell0 = a_base + tile * kATileBytes + ((y + 1) * 2 + b) * kRowStride + (x + 1) * kCell;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tile * kC;
+    const int board_in_pair = static_cast<int>(rank) * kBoardsPerCta + tile * 2 + b;
+    const bool signaller = (tid == 64);
+    const uint32_t a_ready_leader = ptx::mapa(bar_a_ready, 0);
+
+    auto signal_a_ready = [&]() {
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+      if (signaller) ptx::mbar_arrive_cluster(a_ready_leader);
+    };
+
+    long long st = pair;
+    if (st < total_st) {
+      write_input_cell(p, st * kBoardsPerPair + board_in_pair, y, x, cell0);
+      signal_a_ready();
+    }
+    uint32_t lstep = 0;
+    bool ok = true;
+    for (; st < total_st && ok; st += npairs) {
+      const long long board = st * kBoardsPerPair + board_in_pair;
+      for (int layer = 0; layer < 5; ++layer, ++lstep) {
+        if (!wait_bar(bar_acc_full, lstep & 1u, true, p.err, 600 + layer)) { ok = false; break; }
+        ptx::tc_fence_after();
+        if (layer < 4) {
+          const float* bs = bias_s + layer * kC;
+          float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < p.n)
+                           ? p.dbg + (board * 64 + y * 8 + x) * kC : nullptr;
+#pragma unroll 1
+          for (int ch = 0; ch < 6; ++ch) {
+            uint32_t v[32];
+            ptx::tmem_ld_x32(taddr + ch * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8 + 4);
+              uint4 o;
+              o.x = ptx::pack_relu_bf16x2(__uint_as_float(v[kc * 8 + 0]) + b0.x,
+                                          __uint_as_float(v[kc * 8 + 1]) + b0.y);
+              o.y = ptx::pack_relu_bf16x2(__uint_as_float(v[kc * 8 + 2]) + b0.z,
+                                          __uint_as_float(v[kc * 8 + 3]) + b0.w);
+              o.z = ptx::pack_relu_bf16x2(__uint_as_float(v[kc * 8 + 4]) + b1.x,
+                                          __uint_as_float(v[kc * 8 + 5]) + b1.y);
+              o.w = ptx::pack_relu_bf16x2(__uint_as_float(v[kc * 8 + 6]) + b1.z,
+                                          __uint_as_float(v[kc * 8 + 7]) + b1.w);
+              ptx::st_shared_v4(cell0 + (ch * 4 + kc) * kChunkStride, o);
+              if (dbg != nullptr) {
+                const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  dbg[ch * 32 + kc * 8 + 2 * i] = __uint_as_float(w[i] << 16);
+                  dbg[ch * 32 + kc * 8 + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+                }
+              }
+            }
+          }
+        } else {
+          // conv5: column t of the accumulator is P[pixel][tap t]; out = 9-point stencil sum.
+          uint32_t v[16];
+          ptx::tmem_ld_x16(taddr, v);
+          ptx::tmem_ld_wait();
+          // scratch = cells of channel-chunks 2..4 at this pixel (fp32 x 4 per cell); halo = 0
+          ptx::st_shared_v4(cell0 + 2 * kChunkStride, make_uint4(v[0], v[1], v[2], v[3]));
+          ptx::st_shared_v4(cell0 + 3 * kChunkStride, make_uint4(v[4], v[5], v[6], v[7]));
+          ptx::st_shared_v4(cell0 + 4 * kChunkStride, make_uint4(v[8], 0u, 0u, 0u));
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory");
+          float acc = 0.f;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            acc += ptx::ld_shared_f32(cell0 + (2 + tap / 4) * kChunkStride + dy * kYStride +
+                                      dx * kCell + (tap % 4) * 4);
+          }
+          const float h = fmaxf(acc + bias_s[4 * kC], 0.f);
+          if (board < p.n) p.h5[board * 64 + y * 8 + x] = h;
+          // all stencil reads must finish before anyone overwrites the scratch / input cells
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory");
+          if (st + npairs < total_st)
+            write_input_cell(p, (st + npairs) * kBoardsPerPair + board_in_pair, y, x, cell0);
+        }
+        signal_a_ready();
+      }
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 0) ptx::tmem_dealloc<2>(tmem_base, 512);
+}
+
+}  // namespace wann

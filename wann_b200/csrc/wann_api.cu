@@ -1,0 +1,687 @@
+// C-ABI + host runtime of the B200-native WaNN policy-net leaf evaluator (include/wann_b200.h).
+// Host logic only: weight upload / tensor-core weight image construction, lanes (streams +
+// workspaces) for re-entrant concurrent callers, chunking, copy/compute overlap, error
+// reporting.  All arithmetic is in the kernels (conv_stack_tc.cuh, aux_kernels.cuh).
+// There is NO CPU fallback: every entry point either runs the CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/wann_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_stack_tc.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(WANN_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),    \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+uint16_t f32_to_bf16(float f) {   // round-to-nearest-even, like cvt.rn.bf16.f32
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x7FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  bool busy = false;
+  int8_t* d_squares = nullptr;
+  uint8_t* d_black = nullptr;
+  void* d_planes = nullptr;
+  float* d_h5 = nullptr;
+  float* d_probs = nullptr;
+  float* d_logits = nullptr;
+  uint8_t* d_idx = nullptr;
+  float* d_prior = nullptr;
+  uint8_t* d_nlegal = nullptr;
+  int8_t* d_planes_out = nullptr;
+  uint8_t* d_mask = nullptr;
+  int* d_err = nullptr;
+  int* h_err = nullptr;     // pinned
+  float* d_act0 = nullptr;  // fp32 mode ping-pong activations
+  float* d_act1 = nullptr;
+  long long cap = 0;        // positions
+};
+
+struct Lane {
+  Slot slot[2];
+  bool in_use = false;
+  cudaEvent_t last = nullptr;   // completion of the last async (device/stream) call
+  bool last_valid = false;
+};
+
+constexpr int kLanes = 4;
+
+}  // namespace
+
+struct wann_ctx {
+  int device = 0;
+  int mode = WANN_MODE_BF16;
+  int sm_count = 0;
+  int final_kernel = 3;
+  long long chunk = 16384;
+  int variant = 0;
+  // weights on device
+  float* d_conv_w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* d_conv_b[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* d_fc_w = nullptr;
+  float* d_fc_b = nullptr;
+  uint8_t* d_wimg = nullptr;   // tensor-core weight stage images, [2][kImgBytesPerRank]
+  float* d_bias_tc = nullptr;  // [4*192 + 1]
+  Lane lanes[kLanes];
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<uint64_t> stats[8];
+};
+
+namespace {
+
+using namespace wann;
+
+// Build the shared-memory stage images of operand B (see conv_stack_tc.cuh).
+// Element (n, k) of a stage lives at (k/8)*LBO + (n/8)*128 + (n%8)*16 + (k%8)*2 bytes.
+void build_weight_image(const wann_weights& w, std::vector<uint8_t>& img) {
+  img.assign(2 * static_cast<size_t>(kImgBytesPerRank), 0);
+  for (int rank = 0; rank < 2; ++rank) {
+    uint8_t* base = img.data() + static_cast<size_t>(rank) * kImgBytesPerRank;
+    size_t off = 0;
+    auto put = [&](uint8_t* stage, int lbo, int n, int k, float v) {
+      const uint16_t h = f32_to_bf16(v);
+      memcpy(stage + (k / 8) * lbo + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2, &h, 2);
+    };
+    // conv1: k-block kb holds taps 4kb..4kb+3, 16 k per tap (4 real input planes)
+    for (int kb = 0; kb < kKbL1; ++kb, off += kStageBytes)
+      for (int ks = 0; ks < 4; ++ks) {
+        const int tap = kb * 4 + ks;
+        if (tap >= 9) continue;
+        for (int c = 0; c < 4; ++c)
+          for (int nl = 0; nl < 96; ++nl) {
+            const int co = rank * 96 + nl;
+            put(base + off, kLboB, nl, ks * 16 + c, w.conv_w[0][(tap * 4 + c) * 192 + co]);
+          }
+      }
+    // conv2..4: k-block kb = tap*3 + j holds input channels 64j..64j+63 of tap
+    for (int layer = 1; layer <= 3; ++layer)
+      for (int kb = 0; kb < kKbMid; ++kb, off += kStageBytes) {
+        const int tap = kb / 3, j = kb % 3;
+        for (int k = 0; k < 64; ++k)
+          for (int nl = 0; nl < 96; ++nl) {
+            const int co = rank * 96 + nl, ci = j * 64 + k;
+            put(base + off, kLboB, nl, k, w.conv_w[layer][(static_cast<size_t>(tap) * 192 + ci) * 192 + co]);
+          }
+      }
+    // conv5 as a 1x1 GEMM whose N index is the TAP: row n = tap (9 real of 16)
+    for (int j = 0; j < kKbL5; ++j, off += kStageBytesL5)
+      for (int nl = 0; nl < 8; ++nl) {
+        const int tap = rank * 8 + nl;
+        for (int k = 0; k < 64; ++k) {
+          const int ci = j * 64 + k;
+          float v = 0.f;
+          if (w.final_kernel == 3) {
+            if (tap < 9) v = w.conv_w[4][tap * 192 + ci];
+          } else if (tap == 4) {
+            v = w.conv_w[4][ci];
+          }
+          put(base + off, kLboB5, nl, k, v);
+        }
+      }
+  }
+}
+
+int alloc_slot(Slot& s, long long cap, int mode) {
+  s.cap = cap;
+  CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  CU(cudaMalloc(&s.d_squares, cap * 64));
+  CU(cudaMalloc(&s.d_black, cap));
+  CU(cudaMalloc(&s.d_planes, cap * 256 * 4));
+  CU(cudaMalloc(&s.d_h5, cap * 64 * 4));
+  CU(cudaMalloc(&s.d_probs, cap * kMoves * 4));
+  CU(cudaMalloc(&s.d_logits, cap * kMoves * 4));
+  CU(cudaMalloc(&s.d_idx, cap * kMaxLegal));
+  CU(cudaMalloc(&s.d_prior, cap * kMaxLegal * 4));
+  CU(cudaMalloc(&s.d_nlegal, cap));
+  CU(cudaMalloc(&s.d_planes_out, cap * 256));
+  CU(cudaMalloc(&s.d_mask, cap * kMoves));
+  CU(cudaMalloc(&s.d_err, 8 * sizeof(int)));
+  CU(cudaMemset(s.d_err, 0, 8 * sizeof(int)));
+  CU(cudaMallocHost(&s.h_err, 8 * sizeof(int)));
+  memset(s.h_err, 0, 8 * sizeof(int));
+  if (mode == WANN_MODE_FP32) {
+    CU(cudaMalloc(&s.d_act0, cap * 64 * 192 * 4));
+    CU(cudaMalloc(&s.d_act1, cap * 64 * 192 * 4));
+  }
+  return WANN_OK;
+}
+
+void free_slot(Slot& s) {
+  if (s.stream) cudaStreamDestroy(s.stream);
+  if (s.done) cudaEventDestroy(s.done);
+  cudaFree(s.d_squares); cudaFree(s.d_black); cudaFree(s.d_planes); cudaFree(s.d_h5);
+  cudaFree(s.d_probs); cudaFree(s.d_logits); cudaFree(s.d_idx); cudaFree(s.d_prior);
+  cudaFree(s.d_nlegal); cudaFree(s.d_planes_out); cudaFree(s.d_mask); cudaFree(s.d_err);
+  if (s.h_err) cudaFreeHost(s.h_err);
+  cudaFree(s.d_act0); cudaFree(s.d_act1);
+  s = Slot();
+}
+
+// lanes are allocated lazily (first use) so that idle lanes cost no HBM
+int acquire_lane(wann_ctx* ctx, Lane** out) {
+  std::unique_lock<std::mutex> lk(ctx->mu);
+  while (true) {
+    for (int i = 0; i < kLanes; ++i) {
+      Lane& l = ctx->lanes[i];
+      if (!l.in_use) {
+        l.in_use = true;
+        lk.unlock();
+        if (l.slot[0].stream == nullptr) {
+          const long long cap = (ctx->mode == WANN_MODE_FP32) ? std::min<long long>(ctx->chunk, 2048)
+                                                               : ctx->chunk;
+          for (int k = 0; k < 2; ++k) {
+            int rc = alloc_slot(l.slot[k], cap, ctx->mode);
+            if (rc != WANN_OK) {
+              std::lock_guard<std::mutex> g(ctx->mu);
+              l.in_use = false;
+              ctx->cv.notify_one();
+              return rc;
+            }
+          }
+          cudaEventCreateWithFlags(&l.last, cudaEventDisableTiming);
+        }
+        if (l.last_valid) {
+          cudaEventSynchronize(l.last);
+          l.last_valid = false;
+        }
+        *out = &l;
+        return WANN_OK;
+      }
+    }
+    ctx->cv.wait(lk);
+  }
+}
+
+void release_lane(wann_ctx* ctx, Lane* l) {
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    l->in_use = false;
+  }
+  ctx->cv.notify_one();
+}
+
+struct ChunkIO {   // device pointers for one chunk
+  const int8_t* squares = nullptr;
+  const uint8_t* black = nullptr;
+  const void* planes = nullptr;
+  int planes_f32 = 0;
+  float* probs = nullptr;
+  float* logits = nullptr;
+  uint8_t* idx = nullptr;
+  float* prior = nullptr;
+  uint8_t* nlegal = nullptr;
+  float* dbg = nullptr;
+  int dbg_layer = 0;
+};
+
+// Enqueue encode -> conv stack -> tail for `n` positions on `stream`, using `ws` workspaces.
+int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io, long long n) {
+  if (n <= 0) return WANN_OK;
+  uint64_t launches = 0;
+  if (ctx->mode == WANN_MODE_BF16) {
+    TcParams p;
+    p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
+    p.n = n; p.wimg = ctx->d_wimg; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
+    p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err;
+    const long long total_st = (n + kBoardsPerPair - 1) / kBoardsPerPair;
+    const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
+    conv_stack_tc_kernel<<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
+    ++launches;
+  } else {
+    const int blocks = static_cast<int>(std::min<long long>((n * 64 + 255) / 256, 65535));
+    planes_to_f32_kernel<<<blocks, 256, 0, stream>>>(io.squares, io.black, io.planes, io.planes_f32, n,
+                                                     ws.d_act1);
+    conv3x3_f32_kernel<4><<<static_cast<unsigned>(n), 256, 100 * 4 * 4, stream>>>(
+        ws.d_act1, ctx->d_conv_w[0], ctx->d_conv_b[0], ws.d_act0);
+    float* cur = ws.d_act0;
+    float* nxt = ws.d_act1;
+    for (int l = 1; l <= 3; ++l) {
+      if (io.dbg != nullptr && io.dbg_layer == l)
+        CU(cudaMemcpyAsync(io.dbg, cur, n * 64 * 192 * 4, cudaMemcpyDeviceToDevice, stream));
+      conv3x3_f32_kernel<192><<<static_cast<unsigned>(n), 256, 100 * 192 * 4, stream>>>(
+          cur, ctx->d_conv_w[l], ctx->d_conv_b[l], nxt);
+      std::swap(cur, nxt);
+    }
+    if (io.dbg != nullptr && io.dbg_layer == 4)
+      CU(cudaMemcpyAsync(io.dbg, cur, n * 64 * 192 * 4, cudaMemcpyDeviceToDevice, stream));
+    conv_small_f32_kernel<<<static_cast<unsigned>(n), 256, 0, stream>>>(
+        cur, ctx->d_conv_w[4], ctx->d_conv_b[4], ctx->final_kernel, ws.d_h5);
+    launches += 6;
+  }
+  if (io.dbg != nullptr && io.dbg_layer == 5)
+    CU(cudaMemcpyAsync(io.dbg, ws.d_h5, n * 64 * 4, cudaMemcpyDeviceToDevice, stream));
+  if (io.probs != nullptr || io.logits != nullptr || io.idx != nullptr) {
+    TailParams t;
+    t.h5 = ws.d_h5; t.squares = io.squares; t.black = io.black; t.n = n;
+    t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
+    t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal;
+    const int blocks = static_cast<int>(
+        std::min<long long>((n + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
+    tail_kernel<<<blocks, kTailWarps * 32, kTailSmemBytes, stream>>>(t);
+    ++launches;
+  }
+  CU(cudaGetLastError());
+  ctx->stats[0] += static_cast<uint64_t>(n);
+  ctx->stats[1] += launches;
+  return WANN_OK;
+}
+
+int check_device_err(Slot& s) {
+  if (s.h_err[0] != 0) {
+    const int code = s.h_err[0], blk = s.h_err[1], par = s.h_err[2];
+    memset(s.h_err, 0, 8 * sizeof(int));
+    cudaMemset(s.d_err, 0, 8 * sizeof(int));
+    return fail(WANN_E_KERNEL, "conv_stack_tc watchdog: wait site %d timed out (block %d, parity %d)",
+                code, blk, par);
+  }
+  return WANN_OK;
+}
+
+struct EvalArgs {
+  const int8_t* squares = nullptr;
+  const uint8_t* black = nullptr;
+  const void* planes = nullptr;
+  int planes_dtype = 0;
+  float* probs = nullptr;
+  float* logits = nullptr;
+  uint8_t* idx = nullptr;
+  float* prior = nullptr;
+  uint8_t* nlegal = nullptr;
+  float* dbg = nullptr;
+  int dbg_layer = 0;
+};
+
+int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void* stream_v) {
+  const long long cap = lane->slot[0].cap;
+  const size_t plane_elt = a.planes_dtype == WANN_PLANES_F32 ? 4 : 1;
+  const long long dbg_c = (a.dbg_layer == 5) ? 1 : 192;
+  Slot& ws = lane->slot[0];
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ws.stream;
+  for (long long off = 0; off < n; off += cap) {
+    const long long m = std::min(cap, n - off);
+    ChunkIO io;
+    io.squares = a.squares ? a.squares + off * 64 : nullptr;
+    io.black = a.black ? a.black + off : nullptr;
+    io.planes = a.planes ? static_cast<const uint8_t*>(a.planes) + off * 256 * plane_elt : nullptr;
+    io.planes_f32 = a.planes_dtype == WANN_PLANES_F32;
+    io.probs = a.probs ? a.probs + off * kMoves : nullptr;
+    io.logits = a.logits ? a.logits + off * kMoves : nullptr;
+    io.idx = a.idx ? a.idx + off * kMaxLegal : nullptr;
+    io.prior = a.prior ? a.prior + off * kMaxLegal : nullptr;
+    io.nlegal = a.nlegal ? a.nlegal + off : nullptr;
+    io.dbg = a.dbg ? a.dbg + off * 64 * dbg_c : nullptr;
+    io.dbg_layer = a.dbg_layer;
+    int rc = enqueue_eval(ctx, ws, stream, io, m);
+    if (rc != WANN_OK) return rc;
+  }
+  if (stream_v == nullptr) {
+    CU(cudaMemcpyAsync(ws.h_err, ws.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return check_device_err(ws);
+  }
+  // caller's stream: the lane's workspace stays reserved until this event has fired
+  CU(cudaEventRecord(lane->last, stream));
+  lane->last_valid = true;
+  return WANN_OK;
+}
+
+// HOST memory: chunked, double-buffered over the lane's two slots so that the H2D copy of
+// chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
+int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
+  const long long cap = lane->slot[0].cap;
+  const size_t plane_elt = a.planes_dtype == WANN_PLANES_F32 ? 4 : 1;
+  const long long dbg_c = (a.dbg_layer == 5) ? 1 : 192;
+  uint64_t h2d = 0, d2h = 0;
+  long long ci = 0;
+  for (long long off = 0; off < n; off += cap, ++ci) {
+    const long long m = std::min(cap, n - off);
+    Slot& s = lane->slot[ci & 1];
+    if (s.busy) {
+      s.busy = false;
+      CU(cudaEventSynchronize(s.done));
+      int rc = check_device_err(s);
+      if (rc != WANN_OK) return rc;
+    }
+    ChunkIO io;
+    if (a.squares) {
+      CU(cudaMemcpyAsync(s.d_squares, a.squares + off * 64, m * 64, cudaMemcpyHostToDevice, s.stream));
+      CU(cudaMemcpyAsync(s.d_black, a.black + off, m, cudaMemcpyHostToDevice, s.stream));
+      h2d += m * 65;
+      io.squares = s.d_squares; io.black = s.d_black;
+    } else {
+      CU(cudaMemcpyAsync(s.d_planes, static_cast<const uint8_t*>(a.planes) + off * 256 * plane_elt,
+                         m * 256 * plane_elt, cudaMemcpyHostToDevice, s.stream));
+      h2d += m * 256 * plane_elt;
+      io.planes = s.d_planes; io.planes_f32 = a.planes_dtype == WANN_PLANES_F32;
+    }
+    io.probs = a.probs ? s.d_probs : nullptr;
+    io.logits = a.logits ? s.d_logits : nullptr;
+    if (a.idx) { io.idx = s.d_idx; io.prior = s.d_prior; io.nlegal = s.d_nlegal; }
+    float* d_dbg = nullptr;
+    if (a.dbg) {
+      CU(cudaMalloc(&d_dbg, m * 64 * dbg_c * 4));
+      io.dbg = d_dbg; io.dbg_layer = a.dbg_layer;
+    }
+    int rc = enqueue_eval(ctx, s, s.stream, io, m);
+    if (rc == WANN_OK) {
+      cudaError_t e = cudaSuccess;
+      auto D2H = [&](void* h, const void* d, size_t bytes) {
+        d2h += bytes;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s.stream);
+      };
+      if (a.probs) D2H(a.probs + off * kMoves, s.d_probs, m * kMoves * 4);
+      if (a.logits) D2H(a.logits + off * kMoves, s.d_logits, m * kMoves * 4);
+      if (a.idx) {
+        D2H(a.idx + off * kMaxLegal, s.d_idx, m * kMaxLegal);
+        D2H(a.prior + off * kMaxLegal, s.d_prior, m * kMaxLegal * 4);
+        D2H(a.nlegal + off, s.d_nlegal, m);
+      }
+      if (a.dbg) D2H(a.dbg + off * 64 * dbg_c, d_dbg, m * 64 * dbg_c * 4);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s.h_err, s.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+      if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
+      if (e == cudaSuccess) s.busy = true;
+      else rc = fail(WANN_E_CUDA, "D2H enqueue: %s", cudaGetErrorString(e));
+    }
+    if (d_dbg) { cudaStreamSynchronize(s.stream); cudaFree(d_dbg); }
+    if (rc != WANN_OK) return rc;
+  }
+  int rc = WANN_OK;
+  for (int k = 0; k < 2; ++k) {
+    Slot& s = lane->slot[k];
+    if (s.busy) {
+      s.busy = false;
+      cudaError_t e = cudaEventSynchronize(s.done);
+      if (e != cudaSuccess && rc == WANN_OK) rc = fail(WANN_E_CUDA, "event sync: %s", cudaGetErrorString(e));
+      if (rc == WANN_OK) rc = check_device_err(s);
+    }
+  }
+  ctx->stats[3] += h2d;
+  ctx->stats[4] += d2h;
+  return rc;
+}
+
+// The one driver behind wann_eval_probs / _planes / _topk / _debug_activations.
+int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* stream_v) {
+  if (ctx == nullptr) return fail(WANN_E_INVALID, "null context");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
+  if (n == 0) return WANN_OK;
+  if (mem != WANN_MEM_HOST && mem != WANN_MEM_DEVICE) return fail(WANN_E_INVALID, "bad mem kind %d", mem);
+  if (a.squares == nullptr && a.planes == nullptr) return fail(WANN_E_INVALID, "no input");
+  if (a.squares != nullptr && a.black == nullptr) return fail(WANN_E_INVALID, "black_to_move is null");
+  if (a.idx != nullptr && (a.squares == nullptr || a.prior == nullptr || a.nlegal == nullptr))
+    return fail(WANN_E_INVALID, "top-k needs squares, prior and n_legal");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats[2] += 1;
+  Lane* lane = nullptr;
+  int rc = acquire_lane(ctx, &lane);
+  if (rc != WANN_OK) return rc;
+  rc = (mem == WANN_MEM_DEVICE) ? eval_device(ctx, lane, a, n, stream_v) : eval_host(ctx, lane, a, n);
+  if (rc != WANN_OK) {   // drain whatever is still in flight on this lane before handing it back
+    for (int k = 0; k < 2; ++k) { cudaStreamSynchronize(lane->slot[k].stream); lane->slot[k].busy = false; }
+  }
+  release_lane(ctx, lane);
+  return rc;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int wann_version(void) { return 100; }
+
+const char* wann_last_error(void) { return g_err.c_str(); }
+
+int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx) {
+  if (out_ctx == nullptr || w == nullptr) return fail(WANN_E_INVALID, "null argument");
+  *out_ctx = nullptr;
+  if (mode != WANN_MODE_BF16 && mode != WANN_MODE_FP32) return fail(WANN_E_INVALID, "bad mode %d", mode);
+  if (w->final_kernel != 3 && w->final_kernel != 1)
+    return fail(WANN_E_INVALID, "final_kernel must be 3 or 1");
+  for (int i = 0; i < 5; ++i)
+    if (!w->conv_w[i] || !w->conv_b[i]) return fail(WANN_E_INVALID, "null conv weight %d", i + 1);
+  if (!w->fc_w || !w->fc_b) return fail(WANN_E_INVALID, "null output_layer weights");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(WANN_E_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(WANN_E_NO_DEVICE, "device %d out of range (%d)", device, count);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(WANN_E_NO_DEVICE, "cannot query device");
+  if (prop.major != 10)
+    return fail(WANN_E_NO_DEVICE, "device %d is sm_%d%d; this library is sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  CU(cudaSetDevice(device));
+  wann_ctx* ctx = new wann_ctx();
+  for (auto& s : ctx->stats) s = 0;
+  ctx->device = device;
+  ctx->mode = mode;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->final_kernel = w->final_kernel;
+  const size_t k5 = static_cast<size_t>(w->final_kernel) * w->final_kernel;
+  const size_t wsz[5] = {9 * 4 * 192, 9 * 192 * 192, 9 * 192 * 192, 9 * 192 * 192, k5 * 192};
+  const size_t bsz[5] = {192, 192, 192, 192, 1};
+  auto up = [&](float** d, const float* h, size_t nfl) -> int {
+    CU(cudaMalloc(d, nfl * 4));
+    CU(cudaMemcpy(*d, h, nfl * 4, cudaMemcpyHostToDevice));
+    return WANN_OK;
+  };
+  int rc = WANN_OK;
+  for (int i = 0; i < 5 && rc == WANN_OK; ++i) {
+    rc = up(&ctx->d_conv_w[i], w->conv_w[i], wsz[i]);
+    if (rc == WANN_OK) rc = up(&ctx->d_conv_b[i], w->conv_b[i], bsz[i]);
+  }
+  if (rc == WANN_OK) rc = up(&ctx->d_fc_w, w->fc_w, 64 * kMoves);
+  if (rc == WANN_OK) rc = up(&ctx->d_fc_b, w->fc_b, kMoves);
+  if (rc == WANN_OK) {
+    std::vector<uint8_t> img;
+    build_weight_image(*w, img);
+    e = cudaMalloc(&ctx->d_wimg, img.size());
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice);
+    std::vector<float> bias(4 * 192 + 4, 0.f);
+    for (int l = 0; l < 4; ++l) memcpy(bias.data() + l * 192, w->conv_b[l], 192 * 4);
+    bias[4 * 192] = w->conv_b[4][0];
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_bias_tc, bias.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_bias_tc, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_f32_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               100 * 192 * 4);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes);
+    if (e != cudaSuccess) rc = fail(WANN_E_CUDA, "weight upload / kernel attributes: %s", cudaGetErrorString(e));
+  }
+  if (rc != WANN_OK) {
+    wann_destroy(ctx);
+    return rc;
+  }
+  *out_ctx = ctx;
+  return WANN_OK;
+}
+
+int wann_destroy(wann_ctx* ctx) {
+  if (ctx == nullptr) return WANN_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& l : ctx->lanes) {
+    free_slot(l.slot[0]);
+    free_slot(l.slot[1]);
+    if (l.last) cudaEventDestroy(l.last);
+  }
+  for (int i = 0; i < 5; ++i) { cudaFree(ctx->d_conv_w[i]); cudaFree(ctx->d_conv_b[i]); }
+  cudaFree(ctx->d_fc_w); cudaFree(ctx->d_fc_b); cudaFree(ctx->d_wimg); cudaFree(ctx->d_bias_tc);
+  delete ctx;
+  return WANN_OK;
+}
+
+int wann_eval_probs(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, float* probs,
+                    float* logits, int mem, void* stream) {
+  if (probs == nullptr && logits == nullptr) return fail(WANN_E_INVALID, "no output buffer");
+  EvalArgs a;
+  a.squares = squares; a.black = black; a.probs = probs; a.logits = logits;
+  if (squares == nullptr && n > 0) return fail(WANN_E_INVALID, "squares is null");
+  return run_eval(ctx, a, n, mem, stream);
+}
+
+int wann_eval_planes(wann_ctx* ctx, const void* planes, int planes_dtype, int64_t n, float* probs,
+                     float* logits, int mem, void* stream) {
+  if (probs == nullptr && logits == nullptr) return fail(WANN_E_INVALID, "no output buffer");
+  if (planes == nullptr && n > 0) return fail(WANN_E_INVALID, "planes is null");
+  if (planes_dtype != WANN_PLANES_I8 && planes_dtype != WANN_PLANES_F32)
+    return fail(WANN_E_INVALID, "bad planes dtype");
+  EvalArgs a;
+  a.planes = planes; a.planes_dtype = planes_dtype; a.probs = probs; a.logits = logits;
+  return run_eval(ctx, a, n, mem, stream);
+}
+
+int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, uint8_t* idx,
+                   float* prior, uint8_t* n_legal, int mem, void* stream) {
+  if ((idx == nullptr || prior == nullptr || n_legal == nullptr) && n > 0)
+    return fail(WANN_E_INVALID, "null output buffer");
+  if (squares == nullptr && n > 0) return fail(WANN_E_INVALID, "squares is null");
+  EvalArgs a;
+  a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
+  return run_eval(ctx, a, n, mem, stream);
+}
+
+int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, int layer,
+                           float* out, int mem) {
+  if (layer < 1 || layer > 5) return fail(WANN_E_INVALID, "layer must be 1..5");
+  if ((squares == nullptr || out == nullptr) && n > 0) return fail(WANN_E_INVALID, "null buffer");
+  EvalArgs a;
+  a.squares = squares; a.black = black; a.dbg = out; a.dbg_layer = layer;
+  return run_eval(ctx, a, n, mem, nullptr);
+}
+
+// encode / legal mask: standalone byte kernels (parity surface of tools.utils / board_utils)
+static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, void* out,
+                     int out_per_pos, bool is_mask, int mem, void* stream_v) {
+  if (ctx == nullptr) return fail(WANN_E_INVALID, "null context");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
+  if (n == 0) return WANN_OK;
+  if (!squares || !black || !out) return fail(WANN_E_INVALID, "null buffer");
+  CU(cudaSetDevice(ctx->device));
+  Lane* lane = nullptr;
+  int rc = acquire_lane(ctx, &lane);
+  if (rc != WANN_OK) return rc;
+  Slot& s = lane->slot[0];
+  cudaStream_t stream = (mem == WANN_MEM_DEVICE && stream_v) ? static_cast<cudaStream_t>(stream_v) : s.stream;
+  auto body = [&]() -> int {
+    for (long long off = 0; off < n; off += s.cap) {
+      const long long m = std::min<long long>(s.cap, n - off);
+      const int8_t* dsq = squares + off * 64;
+      const uint8_t* dbl = black + off;
+      uint8_t* dout = static_cast<uint8_t*>(out) + off * out_per_pos;
+      if (mem == WANN_MEM_HOST) {
+        CU(cudaMemcpyAsync(s.d_squares, dsq, m * 64, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(s.d_black, dbl, m, cudaMemcpyHostToDevice, stream));
+        dsq = s.d_squares; dbl = s.d_black;
+        dout = is_mask ? s.d_mask : reinterpret_cast<uint8_t*>(s.d_planes_out);
+      }
+      if (is_mask) {
+        const int blocks = static_cast<int>(std::min<long long>((m + 7) / 8, 8ll * ctx->sm_count));
+        legal_mask_kernel<<<blocks, 256, 0, stream>>>(dsq, dbl, m, dout);
+      } else {
+        const int blocks = static_cast<int>(std::min<long long>((m * 64 + 255) / 256, 16ll * ctx->sm_count));
+        encode_kernel<<<blocks, 256, 0, stream>>>(dsq, dbl, m, reinterpret_cast<int8_t*>(dout));
+      }
+      CU(cudaGetLastError());
+      ctx->stats[1] += 1;
+      if (mem == WANN_MEM_HOST) {
+        CU(cudaMemcpyAsync(static_cast<uint8_t*>(out) + off * out_per_pos, dout,
+                           static_cast<size_t>(m) * out_per_pos, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+      }
+    }
+    if (mem == WANN_MEM_DEVICE) {
+      if (stream_v == nullptr) CU(cudaStreamSynchronize(stream));
+      else { cudaEventRecord(lane->last, stream); lane->last_valid = true; }
+    }
+    return WANN_OK;
+  };
+  rc = body();
+  release_lane(ctx, lane);
+  return rc;
+}
+
+int wann_encode(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, int8_t* planes, int mem,
+                void* stream) {
+  return run_bytes(ctx, squares, black, n, planes, 256, false, mem, stream);
+}
+
+int wann_legal_mask(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, uint8_t* mask,
+                    int mem, void* stream) {
+  return run_bytes(ctx, squares, black, n, mask, kMoves, true, mem, stream);
+}
+
+int wann_host_alloc(void** ptr, uint64_t bytes) {
+  if (ptr == nullptr) return fail(WANN_E_INVALID, "null ptr");
+  CU(cudaMallocHost(ptr, bytes));
+  return WANN_OK;
+}
+
+int wann_host_free(void* ptr) {
+  CU(cudaFreeHost(ptr));
+  return WANN_OK;
+}
+
+int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]) {
+  if (ctx == nullptr || stats == nullptr) return fail(WANN_E_INVALID, "null argument");
+  for (int i = 0; i < 8; ++i) stats[i] = ctx->stats[i].load();
+  return WANN_OK;
+}
+
+int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
+  if (ctx == nullptr || key == nullptr) return fail(WANN_E_INVALID, "null argument");
+  if (strcmp(key, "variant") == 0) { ctx->variant = static_cast<int>(value); return WANN_OK; }
+  if (strcmp(key, "chunk") == 0) {
+    if (value < 8 || value > (1 << 20)) return fail(WANN_E_INVALID, "chunk out of range");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    for (auto& l : ctx->lanes)
+      if (l.in_use || l.slot[0].stream != nullptr)
+        return fail(WANN_E_INVALID, "chunk must be set before the first evaluation");
+    ctx->chunk = value;
+    return WANN_OK;
+  }
+  return fail(WANN_E_INVALID, "unknown option %s", key);
+}
+
+}  // extern "C"

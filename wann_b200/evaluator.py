@@ -1,0 +1,156 @@
+"""PolicyEvaluator: Python handle on a wann_ctx (one GPU, one set of weights).
+
+numpy arrays go through the HOST path of the C ABI (copies inside the call);
+torch CUDA tensors go through the DEVICE path on torch's current stream (no copies,
+asynchronous; outputs are torch tensors).  torch is used for buffers/streams only."""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+from . import weights as W
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class PolicyEvaluator(object):
+    def __init__(self, weights=None, device=0, mode="bf16", final_kernel=3, chunk=None):
+        lib = L.load()
+        w = W.validate(weights if weights is not None else W.default_weights(), final_kernel)
+        self._keep = w
+        cw = L.WannWeights()
+        for i in range(5):
+            cw.conv_w[i] = w["hidden_layer/%d/weights" % (i + 1)].ctypes.data
+            cw.conv_b[i] = w["hidden_layer/%d/bias" % (i + 1)].ctypes.data
+        cw.fc_w = w["output_layer/weights"].ctypes.data
+        cw.fc_b = w["output_layer/bias"].ctypes.data
+        cw.final_kernel = final_kernel
+        self.mode = {"bf16": L.MODE_BF16, "fp32": L.MODE_FP32}[mode] if isinstance(mode, str) else int(mode)
+        self.device = int(device)
+        ctx = ctypes.c_void_p()
+        L.check(lib.wann_create(ctypes.byref(cw), self.device, self.mode, ctypes.byref(ctx)))
+        self._ctx = ctx
+        self._lib = lib
+        if chunk is not None:
+            self.set_option("chunk", chunk)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.wann_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, key, value):
+        L.check(self._lib.wann_set_option(self._ctx, key.encode(), int(value)))
+
+    def stats(self):
+        arr = (ctypes.c_uint64 * 8)()
+        L.check(self._lib.wann_get_stats(self._ctx, ctypes.byref(arr)))
+        keys = ["positions", "kernel_launches", "calls", "h2d_bytes", "d2h_bytes"]
+        return dict(zip(keys, list(arr)[:5]))
+
+    @staticmethod
+    def _np_in(squares, black):
+        sq = np.ascontiguousarray(squares, dtype=np.int8).reshape(-1, 64)
+        bl = np.ascontiguousarray(black, dtype=np.uint8).reshape(-1)
+        if bl.shape[0] != sq.shape[0]:
+            raise ValueError("squares/black_to_move length mismatch")
+        return sq, bl
+
+    @staticmethod
+    def _torch_stream(t):
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    # ------------------------------------------------------------------ byte kernels
+    def encode(self, squares, black):
+        sq, bl = self._np_in(squares, black)
+        out = np.empty((sq.shape[0], 8, 8, 4), np.int8)
+        L.check(self._lib.wann_encode(self._ctx, sq.ctypes.data, bl.ctypes.data, sq.shape[0],
+                                      out.ctypes.data, L.MEM_HOST, None))
+        return out
+
+    def legal_mask(self, squares, black):
+        sq, bl = self._np_in(squares, black)
+        out = np.empty((sq.shape[0], L.N_MOVES), np.uint8)
+        L.check(self._lib.wann_legal_mask(self._ctx, sq.ctypes.data, bl.ctypes.data, sq.shape[0],
+                                          out.ctypes.data, L.MEM_HOST, None))
+        return out.astype(bool)
+
+    # ------------------------------------------------------------------ evaluation
+    def eval_probs(self, squares, black, return_logits=False, out=None):
+        if _is_torch(squares):
+            import torch
+            n = squares.shape[0]
+            probs = out if out is not None else torch.empty((n, L.N_MOVES), dtype=torch.float32, device=squares.device)
+            logits = torch.empty_like(probs) if return_logits else None
+            L.check(self._lib.wann_eval_probs(self._ctx, squares.data_ptr(), black.data_ptr(), n,
+                                              probs.data_ptr(), logits.data_ptr() if return_logits else None,
+                                              L.MEM_DEVICE, self._torch_stream(squares)))
+            return (probs, logits) if return_logits else probs
+        sq, bl = self._np_in(squares, black)
+        n = sq.shape[0]
+        probs = out if out is not None else np.empty((n, L.N_MOVES), np.float32)
+        logits = np.empty((n, L.N_MOVES), np.float32) if return_logits else None
+        L.check(self._lib.wann_eval_probs(self._ctx, sq.ctypes.data, bl.ctypes.data, n, probs.ctypes.data,
+                                          logits.ctypes.data if return_logits else None, L.MEM_HOST, None))
+        return (probs, logits) if return_logits else probs
+
+    def eval_planes(self, planes, return_logits=False):
+        p = np.asarray(planes)
+        if p.dtype == np.int8:
+            dt = L.PLANES_I8
+        else:
+            p = p.astype(np.float32, copy=False)
+            dt = L.PLANES_F32
+        p = np.ascontiguousarray(p).reshape(-1, 8, 8, 4)
+        n = p.shape[0]
+        probs = np.empty((n, L.N_MOVES), np.float32)
+        logits = np.empty((n, L.N_MOVES), np.float32) if return_logits else None
+        L.check(self._lib.wann_eval_planes(self._ctx, p.ctypes.data, dt, n, probs.ctypes.data,
+                                           logits.ctypes.data if return_logits else None, L.MEM_HOST, None))
+        return (probs, logits) if return_logits else probs
+
+    def eval_topk(self, squares, black, out=None):
+        """-> idx uint8 [n,48], prior float32 [n,48], n_legal uint8 [n] (sorted, descending)."""
+        if _is_torch(squares):
+            import torch
+            n = squares.shape[0]
+            dev = squares.device
+            if out is None:
+                out = (torch.empty((n, L.MAX_LEGAL), dtype=torch.uint8, device=dev),
+                       torch.empty((n, L.MAX_LEGAL), dtype=torch.float32, device=dev),
+                       torch.empty((n,), dtype=torch.uint8, device=dev))
+            idx, pri, cnt = out
+            L.check(self._lib.wann_eval_topk(self._ctx, squares.data_ptr(), black.data_ptr(), n, idx.data_ptr(),
+                                             pri.data_ptr(), cnt.data_ptr(), L.MEM_DEVICE,
+                                             self._torch_stream(squares)))
+            return idx, pri, cnt
+        sq, bl = self._np_in(squares, black)
+        n = sq.shape[0]
+        if out is None:
+            out = (np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL), np.float32),
+                   np.empty(n, np.uint8))
+        idx, pri, cnt = out
+        L.check(self._lib.wann_eval_topk(self._ctx, sq.ctypes.data, bl.ctypes.data, n, idx.ctypes.data,
+                                         pri.ctypes.data, cnt.ctypes.data, L.MEM_HOST, None))
+        return idx, pri, cnt
+
+    def debug_activations(self, squares, black, layer):
+        sq, bl = self._np_in(squares, black)
+        n = sq.shape[0]
+        c = 1 if layer == 5 else 192
+        out = np.empty((n, 8, 8, c), np.float32)
+        L.check(self._lib.wann_debug_activations(self._ctx, sq.ctypes.data, bl.ctypes.data, n, int(layer),
+                                                 out.ctypes.data, L.MEM_HOST))
+        return out

@@ -1,0 +1,159 @@
+"""Drop-in call surface of the reference's TensorFlow session for the policy net.
+
+Mirrors (names, argument meaning, return types) of
+  monte_carlo_tree_search/MCTS.pyx:76-133          class NeuralNetsCombined_128
+  Breakthrough_Player/policy_net_utils.pyx:9-16    call_policy_net
+  Breakthrough_Player/policy_net_utils.pyx:19-104  instantiate_session*()  -> (sess, y_pred, X)
+  policy_net_model/PolicyNet.py:16-36              PolicyNet.call_policy_net / instantiate_session
+so that MCTS.pyx, expansion_MCTS_functions.pyx / tree_builder.pyx (policy_net.evaluate(...))
+and policy_net_utils.pyx (sess.run(y_pred, feed_dict={X: batch})) work unchanged on top of the
+B200 kernels.  Documented divergence: inputs longer than 16,384 return the correct [N,155]
+array (the reference's multi-chunk concatenation, MCTS.pyx:124, is broken)."""
+import numpy as np
+
+from . import boards
+from . import weights as W
+from .evaluator import PolicyEvaluator
+
+
+class _Endpoint(object):
+    """Stands in for a TF tensor handle (y_pred / X): identifies a net inside a Session."""
+
+    def __init__(self, net, kind):
+        self.net, self.kind = net, kind
+
+    def __repr__(self):
+        return "<wann_b200 %s of net %r>" % (self.kind, self.net)
+
+
+class Session(object):
+    """tf.Session-shaped object: run(y_pred, feed_dict={X: batch}) and close()."""
+
+    def __init__(self, evaluators):
+        self._nets = evaluators          # name -> PolicyEvaluator
+        self._closed = False
+
+    def run(self, fetches, feed_dict=None):
+        if self._closed:
+            raise RuntimeError("Attempted to use a closed Session.")
+        if not isinstance(fetches, _Endpoint) or fetches.kind != "y_pred":
+            raise TypeError("fetches must be a y_pred endpoint returned by instantiate_session*()")
+        feed_dict = feed_dict or {}
+        X = None
+        for k, v in feed_dict.items():
+            if isinstance(k, _Endpoint) and k.kind == "X" and k.net == fetches.net:
+                X = v
+        if X is None:
+            raise ValueError("feed_dict has no value for the input placeholder of net %r" % fetches.net)
+        planes = np.asarray(X)
+        if planes.ndim == 3:
+            planes = planes[None]
+        if planes.shape[1:] != (8, 8, 4):
+            raise ValueError("Cannot feed value of shape %s for placeholder of shape (?, 8, 8, 4)"
+                             % (planes.shape,))
+        return self._nets[fetches.net].eval_planes(planes)
+
+    def evaluator(self, net):
+        return self._nets[net]
+
+    def close(self):
+        if not self._closed:
+            for ev in set(self._nets.values()):
+                ev.close()
+            self._closed = True
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def _make(weights, device, mode, final_kernel):
+    return PolicyEvaluator(weights if weights is not None else W.default_weights(), device=device,
+                           mode=mode, final_kernel=final_kernel)
+
+
+def instantiate_session(weights=None, device=0, mode="bf16"):
+    """policy_net_utils.pyx:64-76 / PolicyNet.py:25-36 -> (sess, y_pred, X)."""
+    sess = Session({"policy": _make(weights, device, mode, 3)})
+    return sess, _Endpoint("policy", "y_pred"), _Endpoint("policy", "X")
+
+
+def _both(weights_white, weights_black, device, mode, final_kernel):
+    white = _make(weights_white, device, mode, final_kernel)
+    black = white if weights_black is None and weights_white is None else \
+        _make(weights_black if weights_black is not None else weights_white, device, mode, final_kernel)
+    sess = Session({"white_net": white, "black_net": black})
+    return (sess, _Endpoint("white_net", "y_pred"), _Endpoint("white_net", "X"),
+            _Endpoint("black_net", "y_pred"), _Endpoint("black_net", "X"))
+
+
+def instantiate_session_both(weights_white=None, weights_black=None, device=0, mode="bf16"):
+    """policy_net_utils.pyx:19-39 -> (sess, y_pred_white, X_white, y_pred_black, X_black)."""
+    return _both(weights_white, weights_black, device, mode, 3)
+
+
+def instantiate_session_both_128(weights_white=None, weights_black=None, device=0, mode="bf16",
+                                 final_kernel=1):
+    """policy_net_utils.pyx:40-60: the `_128` nets (last conv 1x1, :135)."""
+    return _both(weights_white, weights_black, device, mode, final_kernel)
+
+
+def call_policy_net(board_representation, weights=None):
+    """policy_net_utils.pyx:9-16 (deprecated one-shot call)."""
+    sess, y_pred, X = instantiate_session(weights)
+    try:
+        if isinstance(board_representation, list):
+            return sess.run(y_pred, feed_dict={X: board_representation})
+        return sess.run(y_pred, feed_dict={X: [board_representation]})
+    finally:
+        sess.close()
+
+
+class NeuralNetsCombined_128(object):
+    """MCTS.pyx:76-133.  evaluate() keeps the reference signature and its three input forms."""
+
+    BATCH_SIZE = 16384   # MCTS.pyx:96 (kept as the internal chunk size)
+
+    def __init__(self, weights_white=None, weights_black=None, device=0, mode="bf16", final_kernel=1):
+        (self.sess, self.output_white, self.input_white,
+         self.output_black, self.input_black) = instantiate_session_both_128(
+            weights_white, weights_black, device, mode, final_kernel)
+
+    def _net(self, is_player):
+        # MCTS.pyx:111-116: is_player -> the 'white' (winner) net, else the 'black' net
+        return self.sess.evaluator("white_net" if is_player else "black_net")
+
+    def evaluate(self, game_nodes, player_color=None, is_player=True, already_converted=False):
+        ev = self._net(is_player)
+        if already_converted:                                   # MCTS.pyx:103-104
+            return ev.eval_planes(np.asarray(game_nodes))
+        if player_color is not None:                            # MCTS.pyx:98-99: one board + colour
+            sq = boards.board_to_squares(game_nodes)[None]
+            bl = np.array([boards.color_is_black(player_color)], np.uint8)
+        else:                                                   # MCTS.pyx:100-102: list of nodes
+            n = len(game_nodes)
+            sq = np.empty((n, 64), np.int8)
+            bl = np.empty(n, np.uint8)
+            for i, node in enumerate(game_nodes):
+                boards.board_to_squares(node['game_board'], sq[i])
+                bl[i] = boards.color_is_black(node['color'])
+        return ev.eval_probs(sq, bl)
+
+    def evaluate_children(self, game_nodes, is_player=True):
+        """Fused variant for callers that only need the ranked legal priors
+        (what enumerate_update_and_prune consumes, tree_builder.pyx:428-445)."""
+        n = len(game_nodes)
+        sq = np.empty((n, 64), np.int8)
+        bl = np.empty(n, np.uint8)
+        for i, node in enumerate(game_nodes):
+            boards.board_to_squares(node['game_board'], sq[i])
+            bl[i] = boards.color_is_black(node['color'])
+        return self._net(is_player).eval_topk(sq, bl)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        self.sess.close()                                       # MCTS.pyx:132-133
