@@ -123,6 +123,12 @@ int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to
 int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
                            int64_t n, int layer, float* out, int mem);
 
+/* Test/inspection hook (tensor-core mode): clock64 stamps of CTA pair 0 for its first 64
+ * layer-steps: [0][k] MMA issue start, [1][k] MMA issue end, [2][k] epilogue start,
+ * [3][k] epilogue end.  Host pointers; n <= chunk. */
+int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
+                       int64_t n, int64_t* stamps);
+
 /* Pinned host buffers for callers that want copy/compute overlap on the HOST path. */
 int wann_host_alloc(void** ptr, uint64_t bytes);
 int wann_host_free(void* ptr);

@@ -16,6 +16,7 @@ N_MOVES, MAX_LEGAL = 155, 48
 EXPORTS = [
     "wann_create", "wann_destroy", "wann_last_error", "wann_encode", "wann_legal_mask",
     "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_debug_activations",
+    "wann_debug_profile",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
 ]
 
@@ -52,6 +53,7 @@ def load():
     lib.wann_eval_planes.argtypes = [vp, vp, ci, i64, vp, vp, ci, vp]
     lib.wann_eval_topk.argtypes = [vp, vp, vp, i64, vp, vp, vp, ci, vp]
     lib.wann_debug_activations.argtypes = [vp, vp, vp, i64, ci, vp, ci]
+    lib.wann_debug_profile.argtypes = [vp, vp, vp, i64, vp]
     lib.wann_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_uint64]
     lib.wann_host_free.argtypes = [vp]
     lib.wann_get_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 8)]

@@ -90,9 +90,11 @@ struct TcParams {
   float* h5;                 // [n][64]
   float* dbg;                // optional activation dump [n][64][192] (layer 1..4)
   int dbg_layer;
-  int variant;               // bit0: swap A LBO/SBO, bit1: swap B LBO/SBO, bit2: swap B halves
+  int variant;               // debug: bit2 = swap the B halves between the CTAs of a pair
   int* err;                  // [8] watchdog record
+  long long* prof;           // optional [4][kProfSteps] clock64 stamps of pair 0 (debug)
 };
+constexpr int kProfSteps = 64;
 
 // bounded mbarrier wait: returns false (and records who/where) instead of hanging the GPU
 __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity, bool cluster_scope,
@@ -223,55 +225,93 @@ conv_stack_tc_kernel(const TcParams p) {
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      // ===== MMA issuer (leader CTA, one thread) ===========================================
-      if (lane == 0) {
-        const bool swapA = p.variant & 1, swapB = p.variant & 2;
-        uint32_t it = 0, lstep = 0;
-        bool ok = true;
-        for (long long st = pair; st < total_st && ok; st += npairs) {
-          for (int layer = 0; layer < 5 && ok; ++layer, ++lstep) {
-            if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 200 + layer)) { ok = false; break; }
-            ptx::tc_fence_after();
-            const int nkb = (layer == 0) ? kKbL1 : (layer == 4 ? kKbL5 : kKbMid);
-            const uint32_t idesc = (layer == 4) ? kIdescN16 : kIdescN192;
-            const uint32_t lbo_b = (layer == 4) ? kLboB5 : kLboB;
-            uint32_t accumulate = 0;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-              const int s = it % kStages;
-              const uint32_t ph = (it / kStages) & 1u;
-              if (!wait_bar(bar_full(s), ph, false, p.err, 300 + s) ||
-                  !wait_bar(bar_peer_full(s), ph, true, p.err, 400 + s)) { ok = false; break; }
-              ptx::tc_fence_after();
-              const uint32_t bst = b_base + s * kStageBytes;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                int tap, kc0;
-                if (layer == 0) {
-                  tap = kb * 4 + ks; kc0 = 0;
-                  if (tap >= 9) continue;
-                } else if (layer == 4) {
-                  tap = 4; kc0 = kb * 8 + ks * 2;
-                } else {
-                  tap = kb / 3; kc0 = (kb % 3) * 8 + ks * 2;
-                }
-                const uint32_t a_off = kc0 * kChunkStride + (tap / 3) * kYStride + (tap % 3) * kCell;
-                const uint64_t bdesc = swapB ? ptx::make_desc(bst + ks * 2 * lbo_b, kSboB, lbo_b)
-                                             : ptx::make_desc(bst + ks * 2 * lbo_b, lbo_b, kSboB);
-#pragma unroll
-                for (int t = 0; t < kTilesPerCta; ++t) {
-                  const uint32_t aaddr = a_base + t * kATileBytes + a_off;
-                  const uint64_t adesc = swapA ? ptx::make_desc(aaddr, kRowStride, kChunkStride)
-                                               : ptx::make_desc(aaddr, kChunkStride, kRowStride);
-                  ptx::umma_bf16<2>(tmem_base + t * kC, adesc, bdesc, idesc, accumulate);
-                }
-                accumulate = 1;
-              }
-              ptx::umma_commit<2>(bar_empty(s), 3);   // frees the stage in BOTH CTAs
-            }
-            if (ok) ptx::umma_commit<2>(bar_acc_full, 3);  // accumulators ready, both CTAs
-          }
-        }
+      // ===== MMA issuer (leader CTA).  The WHOLE warp runs the loop with uniform control flow
+      // (so the descriptors live in uniform registers); one elected lane issues the tcgen05 ops.
+      // The issue path is kept to a handful of instructions per MMA: the 64-bit descriptors are
+      // {lo = start>>4 | LBO<<16, hi = SBO | version} and only `lo` changes (one add).
+      const uint32_t issuer = ptx::elect_one();
+      const uint32_t a_hi = (kRowStride >> 4) | (1u << 14);
+      const uint32_t b_hi = (kSboB >> 4) | (1u << 14);
+      const uint32_t a_lo0 = (a_base >> 4) | ((kChunkStride >> 4) << 16);
+      const uint32_t a_lo1 = ((a_base + kATileBytes) >> 4) | ((kChunkStride >> 4) << 16);
+      const uint32_t b_lo_mid = (b_base >> 4) | ((kLboB >> 4) << 16);
+      const uint32_t b_lo_l5 = (b_base >> 4) | ((kLboB5 >> 4) << 16);
+      const uint32_t tmem0 = tmem_base, tmem1 = tmem_base + kC;
+      constexpr uint32_t kChunk16 = kChunkStride >> 4;          // 181
+      constexpr uint32_t kStage16 = kStageBytes >> 4;           // 768
+      uint32_t s = 0, ph = 0, lstep = 0;
+      bool ok = true;
+      const bool prof = (p.prof != nullptr && pair == 0);
+      // one K-block: wait for the stage, 4 (or fewer) K=16 steps x 2 row tiles, free the stage
+#define WANN_KBLOCK(NKS, A_OFF16_OF_KS, B_LO, B_KS16, IDESC, ACC_FIRST)                          \
+      {                                                                                           \
+        if (!wait_bar(bar_full(s), ph, false, p.err, 300 + s) ||                                 \
+            !wait_bar(bar_peer_full(s), ph, true, p.err, 400 + s)) { ok = false; break; }       \
+        ptx::tc_fence_after();                                                                    \
+        const uint32_t blo = (B_LO) + s * kStage16;                                               \
+        _Pragma("unroll") for (int ks = 0; ks < (NKS); ++ks) {                                   \
+          const uint32_t ao = (A_OFF16_OF_KS);                                                    \
+          const uint32_t acc = ((ACC_FIRST) && ks == 0) ? 0u : 1u;                                \
+          if (issuer) {                                                                           \
+            ptx::umma_bf16_2cta(tmem0, a_lo0 + ao, a_hi, blo + ks * (B_KS16), b_hi, (IDESC), acc); \
+            ptx::umma_bf16_2cta(tmem1, a_lo1 + ao, a_hi, blo + ks * (B_KS16), b_hi, (IDESC), acc); \
+          }                                                                                       \
+        }                                                                                         \
+        if (issuer) ptx::umma_commit<2>(bar_empty(s), 3);   /* frees the stage in BOTH CTAs */    \
+        if (++s == kStages) { s = 0; ph ^= 1u; }                                                  \
       }
+      for (long long st = pair; st < total_st && ok; st += npairs) {
+        // ---- conv1: 9 taps x K=16 (4 real planes); K-block kb holds taps 4kb..4kb+3
+        do {
+          if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 200)) { ok = false; break; }
+          ptx::tc_fence_after();
+          if (prof && lstep < kProfSteps && issuer) p.prof[lstep] = clock64();
+          constexpr uint32_t kTap16[12] = {0, 1, 2, 18, 19, 20, 36, 37, 38, 0, 0, 0};
+          WANN_KBLOCK(4, kTap16[ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, true)
+          WANN_KBLOCK(4, kTap16[4 + ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
+          WANN_KBLOCK(1, kTap16[8 + ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
+          if (issuer) ptx::umma_commit<2>(bar_acc_full, 3);
+          if (prof && lstep < kProfSteps && issuer) p.prof[kProfSteps + lstep] = clock64();
+          ++lstep;
+        } while (false);
+        // ---- conv2..4: K-block (tap, j) = input channels 64j..64j+63 of tap
+        for (int layer = 1; layer <= 3 && ok; ++layer) {
+          if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 200 + layer)) { ok = false; break; }
+          ptx::tc_fence_after();
+          if (prof && lstep < kProfSteps && issuer) p.prof[lstep] = clock64();
+          uint32_t first = 1;
+          for (uint32_t ty = 0; ty < 3 && ok; ++ty)
+            for (uint32_t tx = 0; tx < 3 && ok; ++tx) {
+              const uint32_t tap16 = ty * (kYStride >> 4) + tx;
+              for (uint32_t j = 0; j < 3; ++j) {
+                const uint32_t ao0 = j * 8 * kChunk16 + tap16;
+                WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_mid, (2 * kLboB) >> 4, kIdescN192, first)
+                first = 0;
+              }
+            }
+          if (!ok) break;
+          if (issuer) ptx::umma_commit<2>(bar_acc_full, 3);   // accumulators ready, both CTAs
+          if (prof && lstep < kProfSteps && issuer) p.prof[kProfSteps + lstep] = clock64();
+          ++lstep;
+        }
+        if (!ok) break;
+        // ---- conv5 as a 1x1 GEMM over the centre tap with N = 16 (columns = the 9 taps)
+        do {
+          if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 204)) { ok = false; break; }
+          ptx::tc_fence_after();
+          if (prof && lstep < kProfSteps && issuer) p.prof[lstep] = clock64();
+          constexpr uint32_t kCentre16 = (kYStride >> 4) + 1;
+          for (uint32_t j = 0; j < 3; ++j) {
+            const uint32_t ao0 = j * 8 * kChunk16 + kCentre16;
+            WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_l5, (2 * kLboB5) >> 4, kIdescN16, j == 0)
+          }
+          if (!ok) break;
+          if (issuer) ptx::umma_commit<2>(bar_acc_full, 3);
+          if (prof && lstep < kProfSteps && issuer) p.prof[kProfSteps + lstep] = clock64();
+          ++lstep;
+        } while (false);
+      }
+#undef WANN_KBLOCK
     } else {
       // ===== relay (peer CTA): forward "my half of stage s has landed" to the leader =========
       if (lane == 0) {
@@ -319,6 +359,8 @@ conv_stack_tc_kernel(const TcParams p) {
       for (int layer = 0; layer < 5; ++layer, ++lstep) {
         if (!wait_bar(bar_acc_full, lstep & 1u, true, p.err, 600 + layer)) { ok = false; break; }
         ptx::tc_fence_after();
+        if (p.prof != nullptr && blockIdx.x == 0 && signaller && lstep < kProfSteps)
+          p.prof[2 * kProfSteps + lstep] = clock64();
         if (layer < 4) {
           const float* bs = bias_s + layer * kC;
           float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < p.n)
@@ -377,6 +419,8 @@ conv_stack_tc_kernel(const TcParams p) {
             write_input_cell(p, (st + npairs) * kBoardsPerPair + board_in_pair, y, x, cell0);
         }
         signal_a_ready();
+        if (p.prof != nullptr && blockIdx.x == 0 && signaller && lstep < kProfSteps)
+          p.prof[3 * kProfSteps + lstep] = clock64();
       }
     }
   }

@@ -142,6 +142,31 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         : "memory");
 }
 
+// Same, 2-CTA form, with the two descriptors given as their 32-bit halves (cheap to update).
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                               uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// returns 1 in exactly one (converged) lane of the warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+
 // Make `bar` (same smem offset in every CTA of cta_mask) complete one arrival when all
 // tcgen05.mma previously issued by this thread have finished.
 template <int kCtaGroup>

@@ -247,6 +247,7 @@ struct ChunkIO {   // device pointers for one chunk
   uint8_t* nlegal = nullptr;
   float* dbg = nullptr;
   int dbg_layer = 0;
+  long long* prof = nullptr;
 };
 
 // Enqueue encode -> conv stack -> tail for `n` positions on `stream`, using `ws` workspaces.
@@ -257,7 +258,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
     TcParams p;
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
     p.n = n; p.wimg = ctx->d_wimg; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
-    p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err;
+    p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
     const long long total_st = (n + kBoardsPerPair - 1) / kBoardsPerPair;
     const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
     conv_stack_tc_kernel<<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
@@ -650,6 +651,39 @@ int wann_encode(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int6
 int wann_legal_mask(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, uint8_t* mask,
                     int mem, void* stream) {
   return run_bytes(ctx, squares, black, n, mask, kMoves, true, mem, stream);
+}
+
+int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n,
+                       int64_t* stamps /* [4][64] */) {
+  if (ctx == nullptr || !squares || !black || !stamps || n <= 0) return fail(WANN_E_INVALID, "bad argument");
+  if (ctx->mode != WANN_MODE_BF16) return fail(WANN_E_INVALID, "profile needs the tensor-core mode");
+  CU(cudaSetDevice(ctx->device));
+  Lane* lane = nullptr;
+  int rc = acquire_lane(ctx, &lane);
+  if (rc != WANN_OK) return rc;
+  Slot& s = lane->slot[0];
+  auto body = [&]() -> int {
+    if (n > s.cap) return fail(WANN_E_INVALID, "n exceeds the chunk size");
+    long long* d_prof = nullptr;
+    CU(cudaMalloc(&d_prof, 4 * kProfSteps * 8));
+    CU(cudaMemsetAsync(d_prof, 0, 4 * kProfSteps * 8, s.stream));
+    CU(cudaMemcpyAsync(s.d_squares, squares, n * 64, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.d_black, black, n, cudaMemcpyHostToDevice, s.stream));
+    ChunkIO io;
+    io.squares = s.d_squares; io.black = s.d_black; io.prof = d_prof;
+    io.idx = s.d_idx; io.prior = s.d_prior; io.nlegal = s.d_nlegal;
+    int r = enqueue_eval(ctx, s, s.stream, io, n);
+    if (r == WANN_OK) {
+      cudaMemcpyAsync(stamps, d_prof, 4 * kProfSteps * 8, cudaMemcpyDeviceToHost, s.stream);
+      cudaError_t e = cudaStreamSynchronize(s.stream);
+      if (e != cudaSuccess) r = fail(WANN_E_CUDA, "sync: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_prof);
+    return r;
+  };
+  rc = body();
+  release_lane(ctx, lane);
+  return rc;
 }
 
 int wann_host_alloc(void** ptr, uint64_t bytes) {
