@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- policy-net leaf evaluations per second (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+  python bench.py --impl reference [...]                       # CPU arm: the oracle port on host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...            # one rank per GPU (driver does this)
+
+A "step" = one pass of the hot path (encode -> conv stack -> FC-155 -> softmax -> legal gather +
+sort -> ranked child priors) over one batch of synthetic leaf positions per GPU.
+Workload = BASELINE.json configs[3] (the batch sweep the metric is quoted on) at its top batch,
+65,536 positions per GPU per step, leaf batches sharded one slice per GPU (weak scaling, no
+collective on the data path).  The smaller configs (1 / 256 / 1024 positions) are parity-test
+cases; their throughput is listed under "sweep" for information.
+
+`value`  : whole-job positions/s, inputs resident in HBM, device pointers through the C ABI.
+`e2e`    : same metric through the public host-buffer API (wann_eval_topk with pinned host
+           arrays): every step copies its 65 B/position inputs H2D and its 241 B/position ranked
+           priors D2H inside the timed region.
+`roofline`: conv_stack_tc kernel, algorithmic FLOPs per launch / CUDA-event time of the launch,
+           against the measured cuBLAS bf16 peak in MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_POS_CONV = 2 * (442368 + 3 * 21233664 + 110592)      # conv1..conv5, SURVEY 8(d)
+FLOP_PER_POS_ALL = FLOP_PER_POS_CONV + 2 * 9920                # + FC-155 = 128,527,744
+BATCH = 65536
+POOL_SETS = 32                                                 # 32 x (4.3 MB in + 15.8 MB out) > L2
+IN_BYTES, OUT_BYTES = 65, 48 + 48 * 4 + 1
+METRIC, UNIT = "policy_net_leaf_evals_per_sec", "positions/s"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+def make_positions(n, seed):
+    """Synthetic leaf positions: seeded random legal play-out positions, tiled."""
+    from wann_b200 import synthetic
+    base_sq, base_bl = synthetic.random_positions(4096, seed=seed)
+    reps = (n + 4095) // 4096
+    rng = np.random.RandomState(seed)
+    perm = rng.permutation(reps * 4096)[:n]
+    return np.tile(base_sq, (reps, 1))[perm], np.tile(base_bl, reps)[perm]
+
+
+def cpu_arm(sample_seconds=15.0):
+    """The oracle port timed on the host cores: encode -> fp32 forward -> legal mask -> rank.
+    Returns (positions/s, cores, kind, sample description)."""
+    from oracle import c_oracle as C
+    from oracle import oracle as O
+    w = O.synthetic_weights("trained_like", 1)
+    sq, bl = O.random_positions_fast(2048, seed=99)
+    sq, bl = np.tile(sq, (32, 1)), np.tile(bl, 32)              # up to 65,536 positions to draw from
+
+    def run_numpy(s, b):
+        pl = O.encode_planes(s, b)
+        _, pr = O.forward_fp32(pl, w)
+        return O.ranked_children(pr, O.legal_mask(s, b))
+
+    def run_c(s, b):
+        pl = C.encode(s, b)
+        _, pr = C.forward(pl, w)
+        return C.rank(pr, C.legal_mask(s, b))
+
+    best, best_name = None, None
+    for name, fn in (("numpy+OpenBLAS", run_numpy), ("C+OpenMP", run_c)):
+        try:
+            fn(sq[:64], bl[:64])
+            t0 = time.perf_counter()
+            fn(sq[:256], bl[:256])
+            rate = 256 / (time.perf_counter() - t0)
+        except Exception:  # noqa: BLE001
+            continue
+        if best is None or rate > best:
+            best, best_name, best_fn = rate, name, fn
+    n = int(min(len(sq), max(256, best * sample_seconds)))
+    t0 = time.perf_counter()
+    best_fn(sq[:n], bl[:n])
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    return n / dt, cores, "port", "%d positions, oracle port (%s, fp32), %.1f s" % (n, best_name, dt)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, cores, kind, sample = cpu_arm(sample_seconds=max(2.0, min(15.0, 120.0 / (args.warmup + args.steps))))
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[3] batch sweep, top batch: 65536 positions per GPU per step "
+                                   "(CPU arm: bounded sample of the same workload per step)",
+                       "weights": "synthetic trained_like seed 1 (reference shard absent)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "note": "CPU stand-in for the TF-1.0 session (TensorFlow is not installable here)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3 if args.impl == "ours" else 0)
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import wann_b200
+    from wann_b200 import weights as W
+    from wann_b200.sharding import gather_counters, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world if world > 1 else 1
+    if args.gpus != n_gpus and rank == 0:
+        print("note: --gpus %d but WORLD_SIZE=%d; running on %d GPU(s)" % (args.gpus, world, n_gpus),
+              file=sys.stderr)
+
+    B = args.batch
+    ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode=args.mode)
+    # whole-job pool of leaf positions, this rank's contiguous slice (weak scaling: B per GPU)
+    pool_n = POOL_SETS * B
+    lo, hi = shard_range(pool_n * n_gpus, rank, n_gpus)
+    sq_np, bl_np = make_positions(B * 4, seed=20260601 + rank)
+    sq_pool = torch.from_numpy(np.tile(sq_np, (POOL_SETS // 4, 1))).to(dev)
+    bl_pool = torch.from_numpy(np.tile(bl_np, POOL_SETS // 4)).to(dev)
+    assert sq_pool.shape[0] == hi - lo == pool_n
+    outs = [(torch.empty((B, 48), dtype=torch.uint8, device=dev),
+             torch.empty((B, 48), dtype=torch.float32, device=dev),
+             torch.empty((B,), dtype=torch.uint8, device=dev)) for _ in range(POOL_SETS)]
+
+    def step(i):
+        k = i % POOL_SETS
+        ev.eval_topk(sq_pool[k * B:(k + 1) * B], bl_pool[k * B:(k + 1) * B], out=outs[k])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) --------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev.set_option("time_kernels", 1)
+    ev.kernel_times()
+    launches0 = ev.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = ev.stats()["kernel_launches"] - launches0
+    conv_ms, conv_launches = ev.kernel_times()
+    ev.set_option("time_kernels", 0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n_gpus * B * args.steps / (ms_max * 1e-3)
+
+    # ---------------- end to end through the host-buffer API (`e2e`) ----------------------
+    h_sq = torch.from_numpy(sq_np[:B].copy()).pin_memory()
+    h_bl = torch.from_numpy(bl_np[:B].copy()).pin_memory()
+    h_out = (torch.empty((B, 48), dtype=torch.uint8).pin_memory(),
+             torch.empty((B, 48), dtype=torch.float32).pin_memory(),
+             torch.empty((B,), dtype=torch.uint8).pin_memory())
+    h_args = (h_sq.numpy(), h_bl.numpy(), tuple(x.numpy() for x in h_out))
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        ev.eval_topk(h_args[0], h_args[1], out=h_args[2])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ev.eval_topk(h_args[0], h_args[1], out=h_args[2])      # returns when the priors are on the host
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * B * e2e_steps / float(t.item())
+
+    # ---------------- optional: counters gathered with NCCL, sweep, CPU baseline ----------
+    counters = gather_counters([B * args.steps, int(ms * 1e6)], device=dev)
+    sweep = {}
+    if rank == 0 and not args.no_sweep:
+        for nb in (1, 256, 1024, 8192, 65536):
+            o = tuple(x[:nb] for x in outs[0])
+            for _ in range(3):
+                ev.eval_topk(sq_pool[:nb], bl_pool[:nb], out=o)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            a.record()
+            for r in range(reps):
+                off = ((r * 4099) % (pool_n - nb)) if nb < pool_n else 0
+                ev.eval_topk(sq_pool[off:off + nb], bl_pool[off:off + nb], out=o)
+            b.record()
+            torch.cuda.synchronize()
+            sweep[str(nb)] = round(nb * reps / (a.elapsed_time(b) * 1e-3), 1)
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        burst, sustained, src = peaks()
+        per_launch_pos = B * args.steps / max(conv_launches, 1)
+        achieved = FLOP_PER_POS_CONV * per_launch_pos / (conv_ms / max(conv_launches, 1) * 1e-3) / 1e12
+        traffic = None
+        summ = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        if os.path.exists(summ):
+            traffic = json.load(open(summ)).get("conv_stack_tc", {}).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+            "config": {"workload": "configs[3] batch sweep, top batch: %d positions per GPU per step, "
+                                   "full path encode->conv stack->FC->softmax->legal gather+sort "
+                                   "(ranked child priors out)" % B,
+                       "weights": "synthetic trained_like seed 1 (reference weight shard absent)",
+                       "positions": "seeded random legal play-out positions",
+                       "l2": "inputs/outputs rotate over %d buffer sets (%.0f MB) > 126 MB L2; 2 MB of "
+                             "weights stay L2-resident by design" % (POOL_SETS, POOL_SETS * B * (IN_BYTES + OUT_BYTES) / 1e6),
+                       "parallelism": "replicas x%d, leaf batches sharded per GPU, no collective" % n_gpus},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * IN_BYTES,
+                    "d2h_bytes_per_step": B * OUT_BYTES, "api": "wann_eval_topk(WANN_MEM_HOST), pinned buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv_stack_tc_kernel", "achieved": achieved,
+                         "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                         "peak_kind": "%s cuBLAS bf16, sustained (kernel timed inside a long step)" % src,
+                         "frac_of_burst_peak": achieved / burst, "burst_peak": burst,
+                         "flop_per_position": FLOP_PER_POS_CONV, "positions_per_launch": per_launch_pos,
+                         "kernel_ms_per_launch": conv_ms / max(conv_launches, 1),
+                         "kernel_share_of_step": conv_ms / ms, "traffic": traffic},
+            "sweep_positions_per_s_1gpu": sweep,
+            "per_rank_counters": counters.tolist(),
+        }
+        if not args.no_cpu_baseline:
+            v, cores, kind, sample = cpu_arm()
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                                    "note": "CPU stand-in for the reference's TF-1.0 session "
+                                            "(TensorFlow/weights not available); reported baseline only"}
+        print(json.dumps(line), flush=True)
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -49,7 +49,9 @@ enum wann_status {
 
 enum wann_mode {
   WANN_MODE_BF16 = 0, /* tcgen05 tensor-core path: bf16 operands, fp32 accumulate */
-  WANN_MODE_FP32 = 1  /* CUDA-core fp32 path (accuracy mode, validation) */
+  WANN_MODE_FP32 = 1, /* CUDA-core fp32 path (accuracy mode, validation) */
+  WANN_MODE_FP16 = 2  /* tcgen05 path with fp16 operands (same speed as BF16, 3 more mantissa
+                         bits; activations saturate at 65504) */
 };
 
 enum wann_mem { WANN_MEM_HOST = 0, WANN_MEM_DEVICE = 1 };
@@ -129,6 +131,11 @@ int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* 
 int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
                        int64_t n, int64_t* stamps);
 
+/* Measurement hook: with option "time_kernels" = 1 every conv-stack kernel launch is bracketed
+ * by CUDA events on its own stream; this call synchronises the device and returns
+ * out[0] = summed kernel milliseconds, out[1] = number of launches since the last call. */
+int wann_kernel_times(wann_ctx* ctx, double out[2]);
+
 /* Pinned host buffers for callers that want copy/compute overlap on the HOST path. */
 int wann_host_alloc(void** ptr, uint64_t bytes);
 int wann_host_free(void* ptr);
@@ -138,7 +145,7 @@ int wann_host_free(void* ptr);
 int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]);
 
 /* Tunables (optional).  key: "chunk" (positions per internal chunk, default 16384),
- * "variant" (debug: tensor-core descriptor variant bits). */
+ * "variant" (debug bits), "time_kernels" (0/1, see wann_kernel_times). */
 int wann_set_option(wann_ctx* ctx, const char* key, int64_t value);
 
 /* Library/ABI version (major*100+minor). */

@@ -424,3 +424,30 @@ def forward_bf16_emulated(planes, weights, return_all=False):
     if return_all:
         return logits, probs, acts
     return logits, probs
+
+
+def f16_round(a):
+    """Round-to-nearest-even float32 -> float16 -> float32, saturating at +-65504."""
+    return np.clip(np.asarray(a, np.float32), -65504.0, 65504.0).astype(np.float16).astype(np.float32)
+
+
+def forward_16bit_emulated(planes, weights, fmt="bf16", return_all=False):
+    """forward_bf16_emulated generalised to the operand format of the tensor-core mode
+    ('bf16' or 'fp16')."""
+    rnd = bf16_round if fmt == "bf16" else f16_round
+    x = rnd(np.asarray(planes).astype(np.float32))
+    acts = []
+    for i in range(1, 6):
+        x = conv2d_same_nhwc(x, rnd(weights["hidden_layer/%d/weights" % i]), np.float32)
+        x = np.maximum(x + weights["hidden_layer/%d/bias" % i], 0).astype(np.float32)
+        if i < 5:
+            x = rnd(x)
+        acts.append(x)
+    h = x.reshape(-1, 64)
+    logits = h @ weights["output_layer/weights"] + weights["output_layer/bias"]
+    z = logits - logits.max(axis=1, keepdims=True)
+    e = np.exp(z)
+    probs = e / e.sum(axis=1, keepdims=True)
+    if return_all:
+        return logits, probs, acts
+    return logits, probs

@@ -1,0 +1,333 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes), against the
+oracle on the same seeded inputs, against the committed reference-made golden fixtures, and --
+at BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances (written here, derived from north_star and the physics of the operand formats):
+  planes / legal masks / move indices / ranked indices ...... bit-exact
+  fp32 mode   logits, probs vs fp32 oracle ................. 1e-5 (max |d| / max |ref|)
+  fp16 mode   logits vs fp32 oracle ........................ 2e-3   (north_star's 1e-3 class)
+  bf16 mode   logits vs fp32 oracle ........................ 2e-2   (bf16 has 8 mantissa bits;
+              a 5-layer K=1728 stack cannot reach 1e-3 with bf16 operands -- DESIGN.md)
+  fp16/bf16   vs the oracle's emulation of the SAME roundings  5e-3 / 5e-3 (tight check of the kernel)
+Logits/probabilities have no reference-made golden values (PARITY UNPINNED, see oracle/oracle.py)."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def nerr(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def weights():
+    from wann_b200 import weights as W
+    return W.synthetic("trained_like", 1)
+
+
+@pytest.fixture(scope="module")
+def suite():
+    sq, bl = O.random_positions_fast(1024, seed=20260601)     # BASELINE config 2 size
+    return sq, bl
+
+
+@pytest.fixture(scope="module")
+def ref1k(suite, weights):
+    sq, bl = suite
+    planes = O.encode_planes(sq, bl)
+    lg, pr, acts = O.forward_fp32(planes, weights, return_all=True)
+    return dict(planes=planes, logits=lg, probs=pr, acts=acts, mask=O.legal_mask(sq, bl))
+
+
+@pytest.fixture(scope="module")
+def ev_bf16(weights):
+    import wann_b200
+    ev = wann_b200.PolicyEvaluator(weights, mode="bf16")
+    yield ev
+    ev.close()
+
+
+@pytest.fixture(scope="module")
+def ev_fp16(weights):
+    import wann_b200
+    ev = wann_b200.PolicyEvaluator(weights, mode="fp16")
+    yield ev
+    ev.close()
+
+
+@pytest.fixture(scope="module")
+def ev_fp32(weights):
+    import wann_b200
+    ev = wann_b200.PolicyEvaluator(weights, mode="fp32")
+    yield ev
+    ev.close()
+
+
+# ------------------------------------------------------------------ bit-exact byte/index work
+def test_encode_and_legal_mask_bit_exact_vs_reference_golden(ev_bf16, golden):
+    assert (ev_bf16.encode(golden["squares"], golden["black"]) == golden["planes"]).all()
+    assert (ev_bf16.legal_mask(golden["squares"], golden["black"]) == golden["legal"].astype(bool)).all()
+
+
+def test_encode_and_legal_mask_bit_exact_vs_oracle(ev_bf16, suite, ref1k):
+    sq, bl = suite
+    assert (ev_bf16.encode(sq, bl) == ref1k["planes"]).all()
+    assert (ev_bf16.legal_mask(sq, bl) == ref1k["mask"]).all()
+
+
+def test_opening_position_config1(ev_fp32, ev_bf16, weights):
+    # BASELINE config 1: batch = 1 on the opening position, both colours
+    sq = np.stack([O.initial_squares()] * 2)
+    bl = np.array([0, 1], np.uint8)
+    lg_ref, pr_ref = O.forward_fp32(O.encode_planes(sq, bl), weights)
+    for i in range(2):
+        pr = ev_fp32.eval_probs(sq[i:i + 1], bl[i:i + 1])
+        assert pr.shape == (1, 155) and nerr(pr, pr_ref[i:i + 1]) < 1e-5
+        idx, pri, cnt = ev_bf16.eval_topk(sq[i:i + 1], bl[i:i + 1])
+        assert cnt[0] == 22 and sorted(idx[0, :22]) == list(range(22, 44))
+    # the opening is colour-symmetric in the side-to-move frame
+    assert np.array_equal(ev_fp32.eval_probs(sq[:1], bl[:1]), ev_fp32.eval_probs(sq[1:], bl[1:]))
+
+
+# ------------------------------------------------------------------ floating point
+def test_fp32_mode_matches_oracle_1e5(ev_fp32, suite, ref1k):
+    sq, bl = suite
+    for layer in (1, 3, 5):
+        a = ev_fp32.debug_activations(sq[:64], bl[:64], layer)
+        assert nerr(a, ref1k["acts"][layer - 1][:64]) < 1e-5
+    pr, lg = ev_fp32.eval_probs(sq, bl, return_logits=True)
+    assert nerr(lg, ref1k["logits"]) < 1e-5
+    assert nerr(pr, ref1k["probs"]) < 1e-5
+    assert np.abs(pr.sum(1) - 1).max() < 1e-5
+
+
+@pytest.mark.parametrize("mode,tol_emu,tol_fp32", [("bf16", 5e-3, 2e-2), ("fp16", 5e-3, 2e-3)])
+def test_tensor_core_modes(mode, tol_emu, tol_fp32, ev_bf16, ev_fp16, suite, ref1k, weights):
+    ev = ev_bf16 if mode == "bf16" else ev_fp16
+    sq, bl = suite
+    n = 256                                                    # BASELINE config 3 size
+    lg_e, pr_e, acts_e = O.forward_16bit_emulated(ref1k["planes"][:n], weights, mode, return_all=True)
+    a1 = ev.debug_activations(sq[:n], bl[:n], 1)
+    assert np.array_equal(a1, acts_e[0])                       # conv1 of 0/1 planes is exact
+    for layer in (2, 4, 5):
+        a = ev.debug_activations(sq[:n], bl[:n], layer)
+        assert nerr(a, acts_e[layer - 1]) < tol_emu            # 1 ulp rounding flips at most
+    pr, lg = ev.eval_probs(sq, bl, return_logits=True)
+    assert nerr(lg[:n], lg_e) < tol_emu
+    assert nerr(lg, ref1k["logits"]) < tol_fp32
+    assert nerr(pr, ref1k["probs"]) < 2 * tol_fp32
+    assert np.abs(pr.sum(1) - 1).max() < 1e-5
+
+
+def test_top1_agreement_vs_fp32_oracle(ev_bf16, ev_fp16, suite, ref1k):
+    sq, bl = suite
+    top_ref = O.top1_legal(ref1k["probs"], ref1k["mask"])
+    # margin (in logit units) between the oracle's best and second-best legal move
+    lg = np.where(ref1k["mask"], ref1k["logits"], -np.inf)
+    srt = np.sort(lg, axis=1)
+    margin = srt[:, -1] - srt[:, -2]
+    for ev, raw_min, tol in ((ev_bf16, 0.97, 0.20), (ev_fp16, 0.995, 0.03)):
+        idx, pri, cnt = ev.eval_topk(sq, bl)
+        agree = idx[:, 0] == top_ref
+        assert agree.mean() >= raw_min
+        # every disagreement is a near-tie of the oracle itself (margin below the mode's
+        # logit tolerance): agreement modulo ties is 100 %
+        assert (margin[~agree] < tol).all()
+
+
+def test_topk_ranking_is_exactly_the_oracle_ranking_of_gpu_probs(ev_bf16, suite, ref1k):
+    sq, bl = suite
+    pr = ev_bf16.eval_probs(sq, bl)
+    idx, pri, cnt = ev_bf16.eval_topk(sq, bl)
+    ridx, rpri, rcnt = O.ranked_children(pr, ref1k["mask"])
+    assert np.array_equal(idx, ridx) and np.array_equal(cnt, rcnt) and np.array_equal(pri, rpri)
+
+
+def test_planes_input_paths(ev_bf16, ev_fp32, suite, ref1k):
+    sq, bl = suite
+    for ev in (ev_bf16, ev_fp32):
+        base = ev.eval_probs(sq[:200], bl[:200])
+        assert np.array_equal(ev.eval_planes(ref1k["planes"][:200]), base)                   # int8
+        assert np.array_equal(ev.eval_planes(ref1k["planes"][:200].astype(np.float32)), base)  # f32
+
+
+def test_final_kernel_1_variant(weights):
+    import wann_b200
+    from wann_b200 import weights as W
+    w = W.synthetic("trained_like", 5, final_kernel=1)
+    sq, bl = O.random_positions_fast(64, seed=8)
+    lg_ref, pr_ref = O.forward_fp32(O.encode_planes(sq, bl), w)
+    for mode, tol in (("fp32", 1e-5), ("fp16", 2e-3), ("bf16", 2e-2)):
+        with wann_b200.PolicyEvaluator(w, mode=mode, final_kernel=1) as ev:
+            pr, lg = ev.eval_probs(sq, bl, return_logits=True)
+            assert nerr(lg, lg_ref) < tol
+
+
+# ------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 8, 9, 15, 17, 63, 65, 255, 300])
+def test_ragged_batch_sizes(ev_bf16, suite, n):
+    sq, bl = suite
+    full = ev_bf16.eval_probs(sq[:304], bl[:304])
+    pr = ev_bf16.eval_probs(sq[:n], bl[:n])
+    assert pr.shape == (n, 155) and np.array_equal(pr, full[:n])   # row i <-> input i, batch-invariant
+    idx, pri, cnt = ev_bf16.eval_topk(sq[:n], bl[:n])
+    assert idx.shape == (n, 48) and cnt.shape == (n,)
+
+
+def test_batch_larger_than_chunk_and_many_pairs(weights):
+    import wann_b200
+    sq, bl = O.random_positions_fast(512, seed=77)
+    sq = np.tile(sq, (9, 1))[:4500]
+    bl = np.tile(bl, 9)[:4500]
+    with wann_b200.PolicyEvaluator(weights, mode="bf16", chunk=1024) as ev:   # 5 chunks, last ragged
+        pr = ev.eval_probs(sq, bl)
+    with wann_b200.PolicyEvaluator(weights, mode="bf16") as ev:
+        ref = ev.eval_probs(sq, bl)
+    assert np.array_equal(pr, ref)
+    assert np.array_equal(pr[:512], pr[512:1024])            # same inputs -> same outputs (any tile slot)
+
+
+def test_extreme_boards(ev_bf16, ev_fp32):
+    # maximum legal-move fan-out and minimal material
+    sq = np.zeros((3, 64), np.int8)
+    sq[0, 8:24] = 1; sq[0, 56:64] = 2           # 16 white pieces with free squares ahead
+    sq[1, 27] = 1; sq[1, 36] = 2                # lone pieces
+    sq[2, 0:8] = 1; sq[2, 8:16] = 1; sq[2, 16:24] = 2   # fully blocked front: forward illegal, captures legal
+    bl = np.zeros(3, np.uint8)
+    mask = O.legal_mask(sq, bl)
+    assert (ev_bf16.legal_mask(sq, bl) == mask).all()
+    idx, pri, cnt = ev_fp32.eval_topk(sq, bl)
+    assert list(cnt) == list(mask.sum(1))
+    for i in range(3):
+        assert set(idx[i, :cnt[i]]) == set(np.nonzero(mask[i])[0])
+
+
+def test_errors_are_reported_not_swallowed(ev_bf16):
+    import wann_b200
+    with pytest.raises(wann_b200.WannError):
+        ev_bf16.debug_activations(np.zeros((1, 64), np.int8), np.zeros(1, np.uint8), 9)
+    with pytest.raises(ValueError):
+        ev_bf16.eval_probs(np.zeros((2, 64), np.int8), np.zeros(3, np.uint8))
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_full_size_properties_65536(ev_bf16):
+    import torch
+    sq0, bl0 = O.random_positions_fast(4096, seed=31)
+    n = 65536                                                   # BASELINE config 4 top of sweep
+    sq = torch.from_numpy(np.tile(sq0, (16, 1))).cuda()
+    bl = torch.from_numpy(np.tile(bl0, 16)).cuda()
+    probs = ev_bf16.eval_probs(sq, bl)
+    idx, pri, cnt = ev_bf16.eval_topk(sq, bl)
+    torch.cuda.synchronize()
+    probs, idx, pri, cnt = probs.cpu().numpy(), idx.cpu().numpy(), pri.cpu().numpy(), cnt.cpu().numpy()
+    assert np.isfinite(probs).all() and np.abs(probs.sum(1) - 1).max() < 1e-5      # softmax
+    assert np.array_equal(probs[:4096], probs[n - 4096:])                          # determinism / tile-slot invariance
+    mask = O.legal_mask(sq0, bl0)
+    assert np.array_equal(cnt[:4096], mask.sum(1).astype(np.uint8))                # legality
+    k = np.arange(48)[None, :] < cnt[:, None]
+    assert (np.diff(pri, axis=1)[k[:, 1:]] <= 0).all()                             # sortedness
+    rows = np.arange(n)[:, None].repeat(48, 1)
+    assert np.array_equal(pri[k], probs[rows[k], idx[k]])                          # gather, no renormalisation
+    assert (idx[~k] == 255).all() and (pri[~k] == 0).all()
+    # colour symmetry: a position and its 180-degree rotated, colour-swapped twin are the
+    # same input in the side-to-move frame -> identical outputs
+    sq_t = np.where(sq0[:, ::-1] == 1, 2, np.where(sq0[:, ::-1] == 2, 1, 0)).astype(np.int8)
+    p_a = ev_bf16.eval_probs(sq0, bl0)
+    p_b = ev_bf16.eval_probs(sq_t, (1 - bl0).astype(np.uint8))
+    assert np.array_equal(p_a, p_b)
+
+
+# ------------------------------------------------------------------ the reference-facing surface
+def test_session_shim_is_a_drop_in(weights, suite, ref1k):
+    import wann_b200
+    from wann_b200 import boards
+    sq, bl = suite
+    w1 = wann_b200.weights.synthetic("trained_like", 1, final_kernel=1)
+    nodes = [{"game_board": boards.squares_to_board(sq[i], 0 if bl[i] else 1),
+              "color": "Black" if bl[i] else "White"} for i in range(40)]
+    with wann_b200.NeuralNetsCombined_128(w1, mode="fp32") as net:
+        out = net.evaluate(nodes, is_player=True)                      # tree_builder.pyx:189
+        assert isinstance(out, np.ndarray) and out.shape == (40, 155) and out.dtype == np.float32
+        one = net.evaluate(nodes[3]["game_board"], nodes[3]["color"])  # MCTS.pyx:57 (Policy mode)
+        assert np.array_equal(one[0], out[3])
+        conv = net.evaluate(ref1k["planes"][:40], already_converted=True)   # policy_net_metrics.py:101
+        assert np.array_equal(conv, out)
+        assert np.array_equal(net.evaluate([nodes[5]])[0], out[5])     # tree_builder.pyx:830
+        idx, pri, cnt = net.evaluate_children(nodes)
+        assert np.array_equal(idx[:, 0], O.top1_legal(out, ref1k["mask"][:40]))
+    sess, y_pred, X = wann_b200.instantiate_session(weights, mode="fp32")    # policy_net_utils.pyx:64
+    got = sess.run(y_pred, feed_dict={X: [p for p in ref1k["planes"][:16]]})
+    assert nerr(got, ref1k["probs"][:16]) < 1e-5
+    sess.close()
+    with pytest.raises(RuntimeError):
+        sess.run(y_pred, feed_dict={X: ref1k["planes"][:1]})
+
+
+def test_concurrent_callers_are_reentrant(ev_bf16, suite):
+    # the reference calls evaluate from 11 threads without a lock (tree_builder.pyx:186-189)
+    sq, bl = suite
+    ref = ev_bf16.eval_probs(sq, bl)
+    errs = []
+
+    def worker(t):
+        try:
+            for k in range(20):
+                i = (37 * t + 11 * k) % 1000
+                n = 1 + (t + k) % 9
+                out = ev_bf16.eval_probs(sq[i:i + n], bl[i:i + n])
+                if not np.array_equal(out, ref[i:i + n]):
+                    errs.append((t, k))
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(11)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", ".built")),
+                    reason="compiled reference (oracle/_ref) not shipped")
+def test_unmodified_reference_tree_code_runs_on_our_evaluator(weights):
+    """Drive the reference's own compiled expand_descendants_to_depth_wrt_NN through the real
+    boundary (policy_net.evaluate) with our evaluator standing in for the TF session."""
+    import time
+    import wann_b200
+    from oracle.ref_loader import load_ref
+    ref = load_ref()
+    tb = ref.module("monte_carlo_tree_search.tree_builder")
+    TreeNode = ref.module("monte_carlo_tree_search.TreeNode").TreeNode
+    w1 = wann_b200.weights.synthetic("trained_like", 1, final_kernel=1)
+    calls = []
+    with wann_b200.NeuralNetsCombined_128(w1, mode="fp32") as net:
+        class Spy(object):
+            def evaluate(self, nodes, **kw):
+                out = net.evaluate(nodes, **kw)
+                calls.append((len(nodes), out))
+                return out
+        board = ref.utils.initial_game_board()
+        wp, bp = ref.board_utils.initial_piece_arrays()
+        root = TreeNode(board, wp, bp, "White", 0, None, 0)
+        sim_info = {"root": root, "time_to_think": 0.3, "start_time": time.time(), "game_tree": [],
+                    "main_pid": "not-this-thread", "do_eval": False, "counter": 0, "prev_game_tree_size": 0,
+                    "game_num": 0, "eval_times": []}
+        tb.expand_descendants_to_depth_wrt_NN([root], 0, 1, sim_info, threading.Lock(), Spy())
+    assert calls and calls[0][0] == 1
+    kids = root["children"]
+    assert kids is not None and len(kids) == 22                  # all legal moves kept
+    pri = [k["UCT_multiplier"] for k in kids]
+    assert pri == sorted(pri, reverse=True)                      # tree_builder.pyx:557
+    sq = O.initial_squares()[None]
+    want = O.ranked_children(calls[0][1], O.legal_mask(sq, [0]))
+    got_idx = [k["index"] for k in kids]
+    assert got_idx == want[0][0, :22].tolist()                   # same children, same order
+    assert abs((pri[0] - 1) - want[1][0, 0]) < 1e-6              # 1 + NN_output[idx], tree_search_utils.pyx:986

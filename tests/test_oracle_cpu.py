@@ -1,0 +1,245 @@
+"""CPU suite (-m "not gpu"): pins the ORACLE against the reference's golden vectors and
+checks host logic + that the C-ABI library loads and exports every declared symbol.
+No compute call on the CUDA library happens here (there is no GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as C
+from oracle import oracle as O
+from oracle.ref_loader import load_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- golden vectors (reference-made)
+def test_move_tables_match_reference_literals(golden):
+    white, black = O.move_tables()
+    assert list(golden["white_moves"]) == white       # tools/utils.pyx:126-141
+    assert list(golden["black_moves"]) == black       # tools/utils.pyx:300-315
+    assert list(golden["gen_white"]) == white         # tools/utils.pyx:480-516
+    assert list(golden["gen_black"]) == black
+    for i in range(155):
+        assert O.move_index(white[i], "White") == i   # tools/utils.pyx:605-641
+        assert O.move_index(black[i], "Black") == i
+
+
+def test_encode_matches_reference_planes(golden):
+    planes = O.encode_planes(golden["squares"], golden["black"])
+    assert planes.dtype == np.int8 and (planes == golden["planes"]).all()
+    assert (C.encode(golden["squares"], golden["black"]) == golden["planes"]).all()
+    # one-hot invariant (self_play_logs_to_data_structures.py:292-293) + bias plane
+    assert (planes[..., :3].sum(-1) == 1).all() and (planes[..., 3] == 1).all()
+
+
+def test_legal_mask_matches_reference(golden):
+    m = O.legal_mask(golden["squares"], golden["black"])
+    assert (m == golden["legal"].astype(bool)).all()
+    assert (m == golden["legal_pa"].astype(bool)).all()
+    assert (C.legal_mask(golden["squares"], golden["black"]) == m).all()
+    assert not m[:, 154].any()                         # 'no-move' is never enumerated
+
+
+def test_known_answers_opening_and_debug_board(golden):
+    # SURVEY 8c KATs: opening has 22 legal moves = indices 22..43 for either colour;
+    # planes identical for both colours; debug board has 28 legal moves each side.
+    sq, bl = golden["squares"], golden["black"]
+    for k in (0, 1):
+        assert list(np.nonzero(golden["legal"][k])[0]) == list(range(22, 44))
+    assert (golden["planes"][0] == golden["planes"][1]).all()
+    white_dbg = {110, 111, 93, 95, 68, 69, 80, 82, 58, 83, 84, 85, 30, 31, 32, 8, 10, 5, 6, 2, 3, 4,
+                 14, 15, 16, 17, 18, 19}
+    black_dbg = {19, 18, 16, 14, 7, 6, 5, 4, 3, 2, 38, 36, 60, 58, 54, 53, 51, 49, 47, 46, 73, 71,
+                 104, 103, 102, 120, 119, 118}
+    assert set(np.nonzero(O.legal_mask(sq[2:3], bl[2:3])[0])[0]) == white_dbg
+    assert set(np.nonzero(O.legal_mask(sq[3:4], bl[3:4])[0])[0]) == black_dbg
+    # Black planes == 180-degree rotation of White planes with P/O swapped
+    pw, pb = golden["planes"][2], golden["planes"][3]
+    rot = pw[::-1, ::-1]
+    assert (pb[..., 0] == rot[..., 1]).all() and (pb[..., 1] == rot[..., 0]).all()
+
+
+@pytest.mark.skipif(load_ref() is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_against_live_compiled_reference():
+    ref = load_ref()
+    sq, bl = O.random_positions(60, seed=123)
+    planes = O.encode_planes(sq, bl)
+    mask = O.legal_mask(sq, bl)
+    for i in range(len(sq)):
+        color = "Black" if bl[i] else "White"
+        board = O.board_from_squares(sq[i], white_to_move=0 if bl[i] else 1)
+        assert (ref.utils.convert_board_to_2d_matrix_POEB(board, color) == planes[i]).all()
+        idx = sorted(ref.utils.index_lookup_by_move(m)
+                     for m in ref.board_utils.enumerate_legal_moves(board, color))
+        assert idx == list(np.nonzero(mask[i])[0])
+        # get_best_move (board_utils.pyx:262-277) == argmax of prior over legal indices
+        probs = np.random.RandomState(i).dirichlet(np.ones(155)).astype(np.float32)[None]
+        mv = ref.board_utils.get_best_move(board, probs)
+        assert ref.utils.index_lookup_by_move(mv) == O.top1_legal(probs, mask[i:i + 1])[0]
+
+
+# ---------------------------------------------------------------- forward restatement
+def test_forward_numpy_vs_c_oracle_and_explicit_conv():
+    sq, bl = O.random_positions_fast(24, seed=3)
+    w = O.synthetic_weights("trained_like", 2)
+    planes = O.encode_planes(sq, bl)
+    lg, pr = O.forward_fp32(planes, w)
+    lg_c, pr_c = C.forward(planes, w)
+    assert np.abs(lg - lg_c).max() < 2e-4 and np.abs(pr - pr_c).max() < 1e-5
+    assert np.allclose(pr.sum(1), 1, atol=1e-5)
+    # explicit NHWC/HWIO cross-correlation for one output element (SAME = zero pad 1)
+    x = planes[:1].astype(np.float64)
+    k = w["hidden_layer/1/weights"].astype(np.float64)
+    y, xx, co = 0, 7, 5
+    acc = 0.0
+    for i in range(3):
+        for j in range(3):
+            yy, xj = y + i - 1, xx + j - 1
+            if 0 <= yy < 8 and 0 <= xj < 8:
+                acc += (x[0, yy, xj] * k[i, j, :, co]).sum()
+    ref = max(acc + w["hidden_layer/1/bias"][co], 0)
+    got = O.forward_fp32(planes[:1], w, return_all=True)[2][0][0, y, xx, co]
+    assert abs(got - ref) < 1e-5
+
+
+def test_forward_final_kernel_1_variant():
+    sq, bl = O.random_positions_fast(8, seed=4)
+    w = O.synthetic_weights("trained_like", 3, final_kernel=1)
+    planes = O.encode_planes(sq, bl)
+    lg, _ = O.forward_fp32(planes, w)
+    lg_c, _ = C.forward(planes, w, final_k=1)
+    assert np.abs(lg - lg_c).max() < 2e-4
+
+
+def test_ranked_children_semantics():
+    sq, bl = O.random_positions_fast(16, seed=9)
+    mask = O.legal_mask(sq, bl)
+    probs = np.random.RandomState(0).dirichlet(np.ones(155), size=16).astype(np.float32)
+    probs[:, 30] = probs[:, 31]                      # force exact ties -> ascending index
+    idx, pri, cnt = O.ranked_children(probs, mask)
+    idx_c, pri_c, cnt_c = C.rank(probs, mask)
+    assert (idx == idx_c).all() and (pri == pri_c).all() and (cnt == cnt_c).all()
+    for i in range(16):
+        k = cnt[i]
+        assert k == mask[i].sum() and (idx[i, k:] == 255).all()
+        assert set(idx[i, :k]) == set(np.nonzero(mask[i])[0])
+        assert (np.diff(pri[i, :k]) <= 0).all()                       # descending, no renorm
+        assert (pri[i, :k] == probs[i, idx[i, :k]]).all()
+        assert idx[i, 0] == O.top1_legal(probs[i:i + 1], mask[i:i + 1])[0]
+
+
+def test_bf16_round_matches_torch():
+    import torch
+    x = np.random.RandomState(0).standard_normal(4096).astype(np.float32) * 3
+    assert (O.bf16_round(x) == torch.tensor(x).bfloat16().float().numpy()).all()
+
+
+# ---------------------------------------------------------------- host logic / boundary
+def test_library_loads_and_exports_every_declared_symbol(lib_built):
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "wann_b200.h")).read()
+    declared = set(re.findall(r"\b(wann_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"wann_ctx", "wann_weights"}
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(lib_built)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "library does not export %s" % name
+    from wann_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+    assert _lib.load().wann_version() >= 100
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "wann_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_no_cpu_fallback_without_gpu(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import wann_b200
+    with pytest.raises(wann_b200.WannError):
+        wann_b200.PolicyEvaluator()
+    with pytest.raises(wann_b200.WannError):
+        wann_b200.NeuralNetsCombined_128()
+
+
+def test_board_helpers_and_move_tables(golden):
+    from wann_b200 import boards
+    assert boards.WHITE_MOVES == list(golden["white_moves"])
+    assert boards.BLACK_MOVES == list(golden["black_moves"])
+    for i in (0, 21, 22, 77, 153, 154):
+        for color in ("White", "Black"):
+            mv = boards.move_lookup_by_index(i, color)
+            assert boards.index_lookup_by_move(mv) == i
+    sq = golden["squares"][2]
+    board = boards.squares_to_board(sq)
+    assert (boards.board_to_squares(board) == sq).all()
+    assert boards.color_is_black("Black") == 1 and boards.color_is_black("White") == 0
+
+
+def test_weight_presets_and_validation():
+    from wann_b200 import weights as W
+    w = W.synthetic("trained_like", 1)
+    o = O.synthetic_weights("trained_like", 1)
+    for k in W.NAMES:
+        assert (w[k] == o[k]).all()                  # product preset == oracle preset (same seed)
+    assert sum(v.size for v in w.values()) == 1014812      # SURVEY 8a.a7 parameter count
+    W.validate(w)
+    bad = dict(w)
+    bad["hidden_layer/2/weights"] = bad["hidden_layer/2/weights"][:, :, :10]
+    with pytest.raises(ValueError):
+        W.validate(bad)
+    with pytest.raises(KeyError):
+        W.validate({})
+
+
+def test_shard_range_partition():
+    from wann_b200.sharding import shard_range, tree_owner
+    for n in (0, 1, 7, 8, 1024, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert [tree_owner(t, 8) for t in range(10)] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wann_b200.sharding import gather_counters, shard_range
+    sq, bl = O.random_positions_fast(101, seed=1)
+    lo, hi = shard_range(len(sq), rank, world)
+    # each rank works on its own slice only (no data-path collective); stand-in work = the
+    # oracle's legal-move count, then the end-of-run counter gather
+    local = int(O.legal_mask(sq[lo:hi], bl[lo:hi]).sum())
+    g = gather_counters([hi - lo, local])
+    q.put((rank, g.tolist(), int(O.legal_mask(sq, bl).sum())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_counter_gather():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, g, total in res:
+        assert len(g) == 2 and g[0][0] + g[1][0] == 101       # every unit owned exactly once
+        assert g[0][1] + g[1][1] == total                     # sharded work == whole-job work

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwann_b200.so")
 
-MODE_BF16, MODE_FP32 = 0, 1
+MODE_BF16, MODE_FP32, MODE_FP16 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 PLANES_I8, PLANES_F32 = 0, 1
 N_MOVES, MAX_LEGAL = 155, 48
@@ -16,7 +16,7 @@ N_MOVES, MAX_LEGAL = 155, 48
 EXPORTS = [
     "wann_create", "wann_destroy", "wann_last_error", "wann_encode", "wann_legal_mask",
     "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_debug_activations",
-    "wann_debug_profile",
+    "wann_debug_profile", "wann_kernel_times",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
 ]
 
@@ -54,6 +54,7 @@ def load():
     lib.wann_eval_topk.argtypes = [vp, vp, vp, i64, vp, vp, vp, ci, vp]
     lib.wann_debug_activations.argtypes = [vp, vp, vp, i64, ci, vp, ci]
     lib.wann_debug_profile.argtypes = [vp, vp, vp, i64, vp]
+    lib.wann_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 2)]
     lib.wann_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_uint64]
     lib.wann_host_free.argtypes = [vp]
     lib.wann_get_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 8)]

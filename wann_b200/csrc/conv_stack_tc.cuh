@@ -31,6 +31,7 @@
 //     shared memory A tile of the next layer).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -74,8 +75,6 @@ constexpr int kNumBars = 3 * kStages + 2;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16 + 128;   // +128 for base alignment slack
 
-constexpr uint32_t kIdescN192 = ptx::make_idesc_bf16(256, 192);
-constexpr uint32_t kIdescN16 = ptx::make_idesc_bf16(256, 16);
 
 constexpr long long kWatchdogCycles = 1ll << 29;
 
@@ -115,7 +114,19 @@ __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity, bool clu
   }
 }
 
-// write the conv1 input cell (planes P,O,E,1 as bf16 + 4 zero channels) of one square
+// two floats -> packed 16-bit pair in the operand format (bf16 or fp16), lo = a
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (kF16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// write the conv1 input cell (planes P,O,E,1 in the operand format + 4 zero channels) of one square
+template <bool kF16>
 __device__ __forceinline__ void write_input_cell(const TcParams& p, long long board, int y, int x,
                                                  uint32_t cell0) {
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -126,27 +137,27 @@ __device__ __forceinline__ void write_input_cell(const TcParams& p, long long bo
       const int blk = p.black[board];
       int s = p.squares[board * 64 + (blk ? 63 - sq : sq)];
       if (blk && s) s = 3 - s;
-      const uint32_t one = 0x3F80u;  // bf16 1.0
+      const uint32_t one = kF16 ? 0x3C00u : 0x3F80u;  // 1.0 in fp16 / bf16
       v.x = (s == 1 ? one : 0u) | ((s == 2 ? one : 0u) << 16);
       v.y = (s == 0 ? one : 0u) | (one << 16);
     } else if (p.planes_f32) {
       const float4 f = reinterpret_cast<const float4*>(p.planes)[board * 64 + sq];
-      __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
-      v.x = *reinterpret_cast<uint32_t*>(&lo);
-      v.y = *reinterpret_cast<uint32_t*>(&hi);
+      v.x = pack2<kF16>(f.x, f.y);
+      v.y = pack2<kF16>(f.z, f.w);
     } else {
       const char4 c = reinterpret_cast<const char4*>(p.planes)[board * 64 + sq];
-      __nv_bfloat162 lo = __floats2bfloat162_rn(float(c.x), float(c.y));
-      __nv_bfloat162 hi = __floats2bfloat162_rn(float(c.z), float(c.w));
-      v.x = *reinterpret_cast<uint32_t*>(&lo);
-      v.y = *reinterpret_cast<uint32_t*>(&hi);
+      v.x = pack2<kF16>(float(c.x), float(c.y));
+      v.y = pack2<kF16>(float(c.z), float(c.w));
     }
   }
   ptx::st_shared_v4(cell0, v);
 }
 
+template <bool kF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_stack_tc_kernel(const TcParams p) {
+  constexpr uint32_t kIdescN192 = ptx::make_idesc_16bit(256, 192, kF16);
+  constexpr uint32_t kIdescN16 = ptx::make_idesc_16bit(256, 16, kF16);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t a_base = smem_base + kOffA;
@@ -349,7 +360,7 @@ conv_stack_tc_kernel(const TcParams p) {
 
     long long st = pair;
     if (st < total_st) {
-      write_input_cell(p, st * kBoardsPerPair + board_in_pair, y, x, cell0);
+      write_input_cell<kF16>(p, st * kBoardsPerPair + board_in_pair, y, x, cell0);
       signal_a_ready();
     }
     uint32_t lstep = 0;
@@ -375,21 +386,21 @@ conv_stack_tc_kernel(const TcParams p) {
               const float4 b0 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8 + 4);
               uint4 o;
-              o.x = ptx::pack_relu_bf16x2(__uint_as_float(v[kc * 8 + 0]) + b0.x,
+              o.x = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 0]) + b0.x,
                                           __uint_as_float(v[kc * 8 + 1]) + b0.y);
-              o.y = ptx::pack_relu_bf16x2(__uint_as_float(v[kc * 8 + 2]) + b0.z,
+              o.y = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 2]) + b0.z,
                                           __uint_as_float(v[kc * 8 + 3]) + b0.w);
-              o.z = ptx::pack_relu_bf16x2(__uint_as_float(v[kc * 8 + 4]) + b1.x,
+              o.z = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 4]) + b1.x,
                                           __uint_as_float(v[kc * 8 + 5]) + b1.y);
-              o.w = ptx::pack_relu_bf16x2(__uint_as_float(v[kc * 8 + 6]) + b1.z,
+              o.w = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
                                           __uint_as_float(v[kc * 8 + 7]) + b1.w);
               ptx::st_shared_v4(cell0 + (ch * 4 + kc) * kChunkStride, o);
               if (dbg != nullptr) {
                 const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  dbg[ch * 32 + kc * 8 + 2 * i] = __uint_as_float(w[i] << 16);
-                  dbg[ch * 32 + kc * 8 + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+                  dbg[ch * 32 + kc * 8 + 2 * i] = ptx::unpack16<kF16>(w[i] & 0xFFFFu);
+                  dbg[ch * 32 + kc * 8 + 2 * i + 1] = ptx::unpack16<kF16>(w[i] >> 16);
                 }
               }
             }
@@ -416,7 +427,7 @@ conv_stack_tc_kernel(const TcParams p) {
           // all stencil reads must finish before anyone overwrites the scratch / input cells
           asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory");
           if (st + npairs < total_st)
-            write_input_cell(p, (st + npairs) * kBoardsPerPair + board_in_pair, y, x, cell0);
+            write_input_cell<kF16>(p, (st + npairs) * kBoardsPerPair + board_in_pair, y, x, cell0);
         }
         signal_a_ready();
         if (p.prof != nullptr && blockIdx.x == 0 && signaller && lstep < kProfSteps)

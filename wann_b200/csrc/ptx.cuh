@@ -2,6 +2,7 @@
 // form), tcgen05 (alloc / mma / commit / ld / fences), cluster helpers.
 // Only what the WaNN conv-stack kernel needs; no CUTLASS dependency.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -224,17 +225,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;         // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
 
-// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, dense.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16 (format 1) or fp16 (format 0),
+// both K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc_16bit(int m, int n, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// two fp32 -> packed bf16x2 with fused ReLU (lo = a, hi = b)
-__device__ __forceinline__ uint32_t pack_relu_bf16x2(float a, float b) {
+// two fp32 -> packed bf16x2 / f16x2 with fused ReLU (lo = a, hi = b); fp16 saturates to finite
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_relu(float a, float b) {
   uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  if (kF16)
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+template <bool kF16>
+__device__ __forceinline__ float unpack16(uint32_t bits16) {
+  if (kF16) return __half2float(__ushort_as_half(static_cast<unsigned short>(bits16)));
+  return __uint_as_float(bits16 << 16);
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),

@@ -3,6 +3,7 @@
 // workspaces) for re-entrant concurrent callers, chunking, copy/compute overlap, error
 // reporting.  All arithmetic is in the kernels (conv_stack_tc.cuh, aux_kernels.cuh).
 // There is NO CPU fallback: every entry point either runs the CUDA kernels or fails.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -46,6 +47,15 @@ uint16_t f32_to_bf16(float f) {   // round-to-nearest-even, like cvt.rn.bf16.f32
   if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x7FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);
   u += 0x7FFFu + ((u >> 16) & 1u);
   return static_cast<uint16_t>(u >> 16);
+}
+
+uint16_t f32_to_f16(float f) {    // round-to-nearest-even, saturating to the largest finite fp16
+  if (f > 65504.f) f = 65504.f;
+  if (f < -65504.f) f = -65504.f;
+  const __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
 }
 
 struct Slot {
@@ -99,6 +109,10 @@ struct wann_ctx {
   std::mutex mu;
   std::condition_variable cv;
   std::atomic<uint64_t> stats[8];
+  // optional CUDA-event timing of the conv-stack kernel (bench.py roofline)
+  bool time_kernels = false;
+  std::mutex ev_mu;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
 };
 
 namespace {
@@ -107,13 +121,13 @@ using namespace wann;
 
 // Build the shared-memory stage images of operand B (see conv_stack_tc.cuh).
 // Element (n, k) of a stage lives at (k/8)*LBO + (n/8)*128 + (n%8)*16 + (k%8)*2 bytes.
-void build_weight_image(const wann_weights& w, std::vector<uint8_t>& img) {
+void build_weight_image(const wann_weights& w, bool f16, std::vector<uint8_t>& img) {
   img.assign(2 * static_cast<size_t>(kImgBytesPerRank), 0);
   for (int rank = 0; rank < 2; ++rank) {
     uint8_t* base = img.data() + static_cast<size_t>(rank) * kImgBytesPerRank;
     size_t off = 0;
     auto put = [&](uint8_t* stage, int lbo, int n, int k, float v) {
-      const uint16_t h = f32_to_bf16(v);
+      const uint16_t h = f16 ? f32_to_f16(v) : f32_to_bf16(v);
       memcpy(stage + (k / 8) * lbo + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2, &h, 2);
     };
     // conv1: k-block kb holds taps 4kb..4kb+3, 16 k per tap (4 real input planes)
@@ -254,14 +268,28 @@ struct ChunkIO {   // device pointers for one chunk
 int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io, long long n) {
   if (n <= 0) return WANN_OK;
   uint64_t launches = 0;
-  if (ctx->mode == WANN_MODE_BF16) {
+  if (ctx->mode != WANN_MODE_FP32) {
     TcParams p;
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
     p.n = n; p.wimg = ctx->d_wimg; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
     const long long total_st = (n + kBoardsPerPair - 1) / kBoardsPerPair;
     const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
-    conv_stack_tc_kernel<<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ctx->time_kernels) {
+      CU(cudaEventCreate(&t0));
+      CU(cudaEventCreate(&t1));
+      CU(cudaEventRecord(t0, stream));
+    }
+    if (ctx->mode == WANN_MODE_FP16)
+      conv_stack_tc_kernel<true><<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
+    else
+      conv_stack_tc_kernel<false><<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
+    if (t0 != nullptr) {
+      CU(cudaEventRecord(t1, stream));
+      std::lock_guard<std::mutex> g(ctx->ev_mu);
+      ctx->ev_pairs.emplace_back(t0, t1);
+    }
     ++launches;
   } else {
     const int blocks = static_cast<int>(std::min<long long>((n * 64 + 255) / 256, 65535));
@@ -472,7 +500,7 @@ const char* wann_last_error(void) { return g_err.c_str(); }
 int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx) {
   if (out_ctx == nullptr || w == nullptr) return fail(WANN_E_INVALID, "null argument");
   *out_ctx = nullptr;
-  if (mode != WANN_MODE_BF16 && mode != WANN_MODE_FP32) return fail(WANN_E_INVALID, "bad mode %d", mode);
+  if (mode != WANN_MODE_BF16 && mode != WANN_MODE_FP32 && mode != WANN_MODE_FP16) return fail(WANN_E_INVALID, "bad mode %d", mode);
   if (w->final_kernel != 3 && w->final_kernel != 1)
     return fail(WANN_E_INVALID, "final_kernel must be 3 or 1");
   for (int i = 0; i < 5; ++i)
@@ -513,7 +541,7 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
   if (rc == WANN_OK) rc = up(&ctx->d_fc_b, w->fc_b, kMoves);
   if (rc == WANN_OK) {
     std::vector<uint8_t> img;
-    build_weight_image(*w, img);
+    build_weight_image(*w, mode == WANN_MODE_FP16, img);
     e = cudaMalloc(&ctx->d_wimg, img.size());
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice);
     std::vector<float> bias(4 * 192 + 4, 0.f);
@@ -522,7 +550,11 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_bias_tc, bias.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_bias_tc, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_stack_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      e = cudaFuncSetAttribute(conv_stack_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_stack_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_f32_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                100 * 192 * 4);
@@ -656,7 +688,7 @@ int wann_legal_mask(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, 
 int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n,
                        int64_t* stamps /* [4][64] */) {
   if (ctx == nullptr || !squares || !black || !stamps || n <= 0) return fail(WANN_E_INVALID, "bad argument");
-  if (ctx->mode != WANN_MODE_BF16) return fail(WANN_E_INVALID, "profile needs the tensor-core mode");
+  if (ctx->mode == WANN_MODE_FP32) return fail(WANN_E_INVALID, "profile needs a tensor-core mode");
   CU(cudaSetDevice(ctx->device));
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);
@@ -686,6 +718,24 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
   return rc;
 }
 
+int wann_kernel_times(wann_ctx* ctx, double out[2]) {
+  if (ctx == nullptr || out == nullptr) return fail(WANN_E_INVALID, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> g(ctx->ev_mu);
+  double ms = 0;
+  for (auto& pr : ctx->ev_pairs) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) ms += t;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  out[0] = ms;
+  out[1] = static_cast<double>(ctx->ev_pairs.size());
+  ctx->ev_pairs.clear();
+  return WANN_OK;
+}
+
 int wann_host_alloc(void** ptr, uint64_t bytes) {
   if (ptr == nullptr) return fail(WANN_E_INVALID, "null ptr");
   CU(cudaMallocHost(ptr, bytes));
@@ -706,6 +756,7 @@ int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]) {
 int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
   if (ctx == nullptr || key == nullptr) return fail(WANN_E_INVALID, "null argument");
   if (strcmp(key, "variant") == 0) { ctx->variant = static_cast<int>(value); return WANN_OK; }
+  if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
   if (strcmp(key, "chunk") == 0) {
     if (value < 8 || value > (1 << 20)) return fail(WANN_E_INVALID, "chunk out of range");
     std::lock_guard<std::mutex> g(ctx->mu);

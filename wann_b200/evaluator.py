@@ -18,7 +18,7 @@ def _is_torch(x):
 class PolicyEvaluator(object):
     def __init__(self, weights=None, device=0, mode="bf16", final_kernel=3, chunk=None):
         lib = L.load()
-        w = W.validate(weights if weights is not None else W.default_weights(), final_kernel)
+        w = W.validate(weights if weights is not None else W.default_weights(final_kernel=final_kernel), final_kernel)
         self._keep = w
         cw = L.WannWeights()
         for i in range(5):
@@ -27,7 +27,7 @@ class PolicyEvaluator(object):
         cw.fc_w = w["output_layer/weights"].ctypes.data
         cw.fc_b = w["output_layer/bias"].ctypes.data
         cw.final_kernel = final_kernel
-        self.mode = {"bf16": L.MODE_BF16, "fp32": L.MODE_FP32}[mode] if isinstance(mode, str) else int(mode)
+        self.mode = {"bf16": L.MODE_BF16, "fp32": L.MODE_FP32, "fp16": L.MODE_FP16}[mode] if isinstance(mode, str) else int(mode)
         self.device = int(device)
         ctx = ctypes.c_void_p()
         L.check(lib.wann_create(ctypes.byref(cw), self.device, self.mode, ctypes.byref(ctx)))
@@ -162,3 +162,9 @@ class PolicyEvaluator(object):
         L.check(self._lib.wann_debug_profile(self._ctx, sq.ctypes.data, bl.ctypes.data, sq.shape[0],
                                              out.ctypes.data))
         return out
+
+    def kernel_times(self):
+        """(summed conv-stack kernel ms, launches) since the last call; needs option time_kernels=1."""
+        out = (ctypes.c_double * 2)()
+        L.check(self._lib.wann_kernel_times(self._ctx, ctypes.byref(out)))
+        return float(out[0]), int(out[1])

@@ -70,7 +70,7 @@ class Session(object):
 
 
 def _make(weights, device, mode, final_kernel):
-    return PolicyEvaluator(weights if weights is not None else W.default_weights(), device=device,
+    return PolicyEvaluator(weights if weights is not None else W.default_weights(final_kernel=final_kernel), device=device,
                            mode=mode, final_kernel=final_kernel)
 
 

@@ -65,7 +65,7 @@ def validate(w, final_kernel=3):
     return out
 
 
-def default_weights(scope=""):
+def default_weights(scope="", final_kernel=3):
     """Weights used when the reference-shaped constructors are called with no arguments
     (the reference hard-codes its checkpoint path, policy_net_utils.pyx:69).  Order:
     $WANN_B200_CHECKPOINT (TF-V2 bundle prefix, CRC-verified) else the synthetic
@@ -73,5 +73,5 @@ def default_weights(scope=""):
     prefix = os.environ.get("WANN_B200_CHECKPOINT")
     if prefix:
         from . import tf_bundle
-        return tf_bundle.load_policy_weights(prefix, scope=scope)
-    return synthetic("trained_like", int(os.environ.get("WANN_B200_SEED", "1")))
+        return tf_bundle.load_policy_weights(prefix, scope=scope, final_kernel=final_kernel)
+    return synthetic("trained_like", int(os.environ.get("WANN_B200_SEED", "1")), final_kernel)
