@@ -136,6 +136,10 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
  * out[0] = summed kernel milliseconds, out[1] = number of launches since the last call. */
 int wann_kernel_times(wann_ctx* ctx, double out[2]);
 
+/* CRC-32C (Castagnoli) of a host buffer, continuing from `seed` (0 to start): the checksum
+ * TF-V2 checkpoint bundles store per tensor (policy_net_model/model.index).  Host utility. */
+uint32_t wann_crc32c(const void* data, uint64_t bytes, uint32_t seed);
+
 /* Pinned host buffers for callers that want copy/compute overlap on the HOST path. */
 int wann_host_alloc(void** ptr, uint64_t bytes);
 int wann_host_free(void* ptr);

@@ -243,3 +243,50 @@ def test_two_rank_gloo_sharding_and_counter_gather():
     for rank, g, total in res:
         assert len(g) == 2 and g[0][0] + g[1][0] == 101       # every unit owned exactly once
         assert g[0][1] + g[1][1] == total                     # sharded work == whole-job work
+
+
+# ---------------------------------------------------------------- TF-V2 bundle I/O (host only)
+SURVEY_INDEX = {   # (offset, size, masked CRC32C) decoded from policy_net_model/model.index
+    "hidden_layer/1/bias": (8, 768, 0x5104bcb9), "hidden_layer/1/weights": (2312, 27648, 0x6f2c5271),
+    "hidden_layer/2/bias": (85256, 768, 0xa8156cc6), "hidden_layer/2/weights": (87560, 1327104, 0xc0bd8ad7),
+    "hidden_layer/3/bias": (4068872, 768, 0xbeb65717), "hidden_layer/3/weights": (4071176, 1327104, 0x24038a77),
+    "hidden_layer/4/bias": (8052488, 768, 0xd96d363a), "hidden_layer/4/weights": (8054792, 1327104, 0x2b93de69),
+    "hidden_layer/5/bias": (12036104, 4, 0xc1d762cd), "hidden_layer/5/weights": (12036116, 6912, 0xdc238e50),
+    "output_layer/bias": (12056852, 620, 0xf13a2743), "output_layer/weights": (12058712, 39680, 0xa72e0fa6),
+}
+
+
+def test_tf_bundle_roundtrip_and_crc(lib_built, tmp_path):
+    from wann_b200 import tf_bundle as T
+    from wann_b200 import weights as W
+    assert T.crc32c(b"123456789") == 0xE3069283               # CRC-32C check value
+    assert T.crc32c(b"") == 0
+    w = W.synthetic("trained_like", 4)
+    prefix = str(tmp_path / "model")
+    T.save_policy_weights(prefix, w)
+    r = T.load_policy_weights(prefix)
+    assert all((r[k] == w[k]).all() for k in W.NAMES)
+    idx = T.read_index(prefix + ".index")
+    assert idx["hidden_layer/2/weights"]["shape"] == (3, 3, 192, 192)
+    raw = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    raw[123456] ^= 0x40
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        T.load_policy_weights(prefix)                          # corruption is detected, not loaded
+    T.save_policy_weights(prefix, w, scope="white_net/")
+    assert (T.load_policy_weights(prefix, scope="white_net/")["output_layer/bias"] == w["output_layer/bias"]).all()
+    with pytest.raises(KeyError):
+        T.load_policy_weights(prefix)                          # un-scoped names are absent now
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/policy_net_model/model.index"),
+                    reason="reference tree not present")
+def test_tf_bundle_reads_the_reference_index(lib_built):
+    from wann_b200 import tf_bundle as T
+    e = T.read_index("/root/reference/policy_net_model/model.index")
+    assert len(e) == 38                                        # 12 params + 24 Adam slots + 2 beta powers
+    for name, (off, size, crc) in SURVEY_INDEX.items():
+        assert (e[name]["offset"], e[name]["size"], e[name]["crc32c"]) == (off, size, crc)
+    assert max(v["offset"] + v["size"] for v in e.values()) == 12177752
+    with pytest.raises(FileNotFoundError):                     # the shard itself is not shipped
+        T.load_policy_weights("/root/reference/policy_net_model/model")

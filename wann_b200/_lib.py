@@ -16,7 +16,7 @@ N_MOVES, MAX_LEGAL = 155, 48
 EXPORTS = [
     "wann_create", "wann_destroy", "wann_last_error", "wann_encode", "wann_legal_mask",
     "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_debug_activations",
-    "wann_debug_profile", "wann_kernel_times",
+    "wann_debug_profile", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
 ]
 
@@ -55,6 +55,8 @@ def load():
     lib.wann_debug_activations.argtypes = [vp, vp, vp, i64, ci, vp, ci]
     lib.wann_debug_profile.argtypes = [vp, vp, vp, i64, vp]
     lib.wann_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 2)]
+    lib.wann_crc32c.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint32]
+    lib.wann_crc32c.restype = ctypes.c_uint32
     lib.wann_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_uint64]
     lib.wann_host_free.argtypes = [vp]
     lib.wann_get_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64 * 8)]

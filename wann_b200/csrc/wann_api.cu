@@ -736,6 +736,35 @@ int wann_kernel_times(wann_ctx* ctx, double out[2]) {
   return WANN_OK;
 }
 
+// CRC-32C (Castagnoli), the checksum of TF-V2 checkpoint bundles (model.index entries).
+uint32_t wann_crc32c(const void* data, uint64_t bytes, uint32_t seed) {
+  static uint32_t table[8][256];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xFF];
+  });
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~seed;
+  while (bytes >= 8) {   // slicing-by-8
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = table[7][lo & 0xFF] ^ table[6][(lo >> 8) & 0xFF] ^ table[5][(lo >> 16) & 0xFF] ^ table[4][lo >> 24] ^
+        table[3][hi & 0xFF] ^ table[2][(hi >> 8) & 0xFF] ^ table[1][(hi >> 16) & 0xFF] ^ table[0][hi >> 24];
+    p += 8;
+    bytes -= 8;
+  }
+  while (bytes--) c = table[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return ~c;
+}
+
 int wann_host_alloc(void** ptr, uint64_t bytes) {
   if (ptr == nullptr) return fail(WANN_E_INVALID, "null ptr");
   CU(cudaMallocHost(ptr, bytes));
