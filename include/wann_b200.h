@@ -126,8 +126,8 @@ int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* 
                            int64_t n, int layer, float* out, int mem);
 
 /* Test/inspection hook (tensor-core mode): clock64 stamps of CTA pair 0 for its first 64
- * layer-steps: [0][k] MMA issue start, [1][k] MMA issue end, [2][k] epilogue start,
- * [3][k] epilogue end.  Host pointers; n <= chunk. */
+ * layer-steps: for half h (0/1): [4h][k] MMA issue start, [4h+1][k] MMA issue end, [4h+2][k] epilogue start,
+ * [4h+3][k] epilogue end (int64 [8][64]).  Host pointers; n <= chunk. */
 int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
                        int64_t n, int64_t* stamps);
 

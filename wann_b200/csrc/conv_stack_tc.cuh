@@ -3,32 +3,38 @@
 //   hidden_layer/{1..5}/{Conv2D,BiasAdd,Relu}   (Breakthrough_Player/policy_net_utils.pyx:149-178)
 // and the Python board->plane encoder (tools/utils.pyx:546-602,819-866) for batched leaf
 // positions.  Output: h5[n][64] fp32 = the post-ReLU 1-channel 5th feature map, which the tail
-// kernel (tail_kernels.cuh) turns into logits / softmax / ranked legal priors.
+// kernel (aux_kernels.cuh) turns into logits / softmax / ranked legal priors.
 //
 // Design (see DESIGN.md "K2"):
 //   * CTA pair (cluster of 2, tcgen05 cta_group::2).  A pair owns a "supertile" of 8 boards:
 //     each CTA holds 4 boards = two M=128 row tiles (2 boards x 64 squares each); one
-//     tcgen05.mma covers M=256 (128 rows in each CTA) x N=192 x K=16.
-//   * Activations NEVER leave the SM: a layer's bf16 output is written by the epilogue warps
+//     tcgen05.mma covers M=256 (the same tile index in both CTAs = a "half") x N=192 x K=16.
+//   * Activations NEVER leave the SM: a layer's 16-bit output is written by the epilogue warps
 //     straight into the shared-memory layout the next layer's MMAs read as operand A.
-//     Layout per row tile ("A tile"):  [24 channel-chunks of 8][10 rows y=-1..8][2 boards]
+//     Layout per row tile ("A tile"):  [24 channel-chunks of 8][9 rows y=-1..7][2 boards]
 //     [9 cells x=-1..7][16 B], i.e. a zero-haloed board image whose 16-byte cells are the
-//     8x16B "core matrix" rows of a K-major SWIZZLE_NONE UMMA descriptor.  MMA row m of a tile
-//     is square (y = m/16, board = (m/8)%2, x = m%8), so an 8-row core-matrix group is one
-//     board row, the group stride (SBO) is one padded row = 144 B and the K-chunk stride (LBO)
-//     is 2896 B.  The 3x3 taps are then nothing but nine different descriptor START ADDRESSES
-//     ((dy+1)*288 + (dx+1)*16 bytes): implicit GEMM with zero im2col traffic, SAME padding
-//     supplied by the (never written) zero halo.
+//     8x16B "core matrix" rows of a K-major SWIZZLE_NONE UMMA descriptor.  (The y=8 halo row of
+//     a chunk IS the y=-1 row of the next chunk, the x=8 halo cell of a row IS the x=-1 cell
+//     of the next row.)  MMA row m of a tile is square (y = m/16, board = (m/8)%2, x = m%8), so
+//     an 8-row core-matrix group is one board row, the group stride (SBO) is one padded row =
+//     144 B and the K-chunk stride (LBO) is 2592 B.  The 3x3 taps are then nothing but nine
+//     descriptor START ADDRESSES ((dy+1)*288 + (dx+1)*16 bytes): implicit GEMM with zero im2col
+//     traffic, SAME padding supplied by the (never written) zero halo.
 //   * Weights (operand B) stream from L2 through a ring of shared-memory stages via
 //     cp.async.bulk (TMA engine, 1-D).  They are pre-arranged on the host into the exact
 //     shared-memory image of each stage (K-major SWIZZLE_NONE core matrices; each CTA of the
 //     pair holds its half of the 192 output channels), so no tensor map is needed.
+//   * The two halves (row tile 0 / row tile 1) are issued by TWO MMA warps and consume every
+//     weight stage one after the other: a stage is freed when BOTH have used it.  Because the
+//     eight epilogue warps serve the halves alternately, half 1 settles a few K-blocks behind
+//     half 0, and each half's epilogue (TMEM -> +bias, ReLU, 16-bit -> shared memory) runs while
+//     the tensor core works on the other half: the epilogue is off the critical path.
 //   * conv1 (4->192) runs as 9 taps x K=16 (4 real channels), conv2-4 as 9 taps x 3 x K=64,
 //     conv5 (192->1, 3x3) as a 1x1 GEMM with N=16 whose columns are the 9 TAPS
 //     (P[pixel][tap] = <act4[pixel], w5[tap]>) followed by a 9-point stencil sum in the epilogue.
-//   * Warp roles per CTA (320 threads): warp 0 = weight producer, warp 1 = MMA issuer (leader
-//     CTA) / full-barrier relay (peer CTA), warps 2..9 = epilogue (TMEM -> +bias, ReLU, bf16 ->
-//     shared memory A tile of the next layer).
+//   * Warp roles per CTA (352 threads): warp 0 = weight producer, warps 1/2 = MMA issuers of
+//     half 0/1 (leader CTA; in the peer CTA warp 1 relays "my half of the stage has landed"),
+//     warps 3..10 = epilogue.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -41,42 +47,45 @@ namespace wann {
 
 // ---- geometry ------------------------------------------------------------------------------
 constexpr int kC = 192;                       // hidden channels
-constexpr int kKChunks = kC / 8;              // 24 chunks of 8 channels (16 B of bf16)
+constexpr int kKChunks = kC / 8;              // 24 chunks of 8 channels (16 B of bf16/fp16)
 constexpr int kCell = 16;                     // bytes per (pixel, channel-chunk) cell
 constexpr int kRowStride = 9 * kCell;         // 144 B: x = -1..7 (x = 8 halo is next row's x = -1)
 constexpr int kYStride = 2 * kRowStride;      // 288 B: two boards interleaved per y
-constexpr int kChunkStride = 10 * kYStride + kCell;  // 2896 B: y = -1..8, + trailing halo cell
-constexpr int kATileBytes = kKChunks * kChunkStride;  // 69504 B per 128-row tile
+constexpr int kChunkStride = 9 * kYStride;    // 2592 B: y = -1..7 (y = 8 halo is next chunk's y = -1)
+constexpr int kATileBytes = kKChunks * kChunkStride;  // 62208 B per 128-row tile
 constexpr int kTilesPerCta = 2;
-constexpr int kABytes = kTilesPerCta * kATileBytes;   // 139008 B
+constexpr int kABytes = kTilesPerCta * kATileBytes + kYStride + kCell;   // + trailing halo row
 constexpr int kBoardsPerCta = 4;
 constexpr int kBoardsPerPair = 8;
 
-constexpr int kStageBytes = 96 * 64 * 2;      // 12288 B: half of [192 x 64] bf16
-constexpr int kStageBytesL5 = 8 * 64 * 2;     // 1024 B: half of [16 x 64] bf16
-constexpr int kStages = 7;
+constexpr int kStageBytes = 96 * 64 * 2;      // 12288 B: half of [192 x 64] 16-bit
+constexpr int kStageBytesL5 = 8 * 64 * 2;     // 1024 B: half of [16 x 64] 16-bit
+constexpr int kStages = 8;
 constexpr int kLboB = 96 / 8 * 128;           // 1536 B between K-chunks of a stage
 constexpr int kLboB5 = 8 / 8 * 128;           // 128 B
 constexpr int kSboB = 128;
 
 constexpr int kKbL1 = 3, kKbMid = 27, kKbL5 = 3;
+constexpr int kKbPerSupertile = kKbL1 + 3 * kKbMid + kKbL5;
 constexpr int kImgBytesPerRank = (kKbL1 + 3 * kKbMid) * kStageBytes + kKbL5 * kStageBytesL5;
 
 constexpr int kNumEpiWarps = 8;
-constexpr int kThreads = 32 * (2 + kNumEpiWarps);   // 320
+constexpr int kFirstEpiWarp = 3;
+constexpr int kThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);   // 352
 constexpr int kBiasFloats = 4 * kC + 4;
 
 // shared memory carve-up (bytes from the 128-aligned base)
 constexpr int kOffA = 0;
-constexpr int kOffB = kOffA + kABytes;
+constexpr int kOffB = (kOffA + kABytes + 127) / 128 * 128;
 constexpr int kOffBias = kOffB + kStages * kStageBytes;
 constexpr int kOffBar = kOffBias + kBiasFloats * 4;
-constexpr int kNumBars = 3 * kStages + 2;
+constexpr int kNumBars = 3 * kStages + 4;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16 + 128;   // +128 for base alignment slack
-
+static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB) exceeded");
 
 constexpr long long kWatchdogCycles = 1ll << 29;
+constexpr int kProfSteps = 64;
 
 struct TcParams {
   const int8_t* squares;     // [n][64] or null
@@ -84,16 +93,18 @@ struct TcParams {
   const void* planes;        // [n][8][8][4] int8/f32 or null
   int planes_f32;
   long long n;
-  const uint8_t* wimg;       // [2][kImgBytesPerRank]
+  const uint8_t* wimg;       // [wimg_copies][2][kImgBytesPerRank]; pair p reads copy p % wimg_copies
+  int wimg_copies;
   const float* bias;         // [4][192] conv1..4 bias, then b5
   float* h5;                 // [n][64]
   float* dbg;                // optional activation dump [n][64][192] (layer 1..4)
   int dbg_layer;
   int variant;               // debug: bit2 = swap the B halves between the CTAs of a pair
   int* err;                  // [8] watchdog record
-  long long* prof;           // optional [4][kProfSteps] clock64 stamps of pair 0 (debug)
+  long long* prof;           // optional [8][kProfSteps] clock64 stamps of pair 0 (debug):
+                             // half h: [4h+0] MMA start, [4h+1] MMA issue end,
+                             //         [4h+2] epilogue start, [4h+3] epilogue end
 };
-constexpr int kProfSteps = 64;
 
 // bounded mbarrier wait: returns false (and records who/where) instead of hanging the GPU
 __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity, bool cluster_scope,
@@ -162,7 +173,6 @@ conv_stack_tc_kernel(const TcParams p) {
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t a_base = smem_base + kOffA;
   const uint32_t b_base = smem_base + kOffB;
-  const uint32_t bias_addr = smem_base + kOffBias;
   const uint32_t bar_base = smem_base + kOffBar;
   const uint32_t slot_addr = smem_base + kOffTmemSlot;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -171,8 +181,8 @@ conv_stack_tc_kernel(const TcParams p) {
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
   auto bar_peer_full = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto bar_empty = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  const uint32_t bar_acc_full = bar_base + 8u * (3 * kStages);
-  const uint32_t bar_a_ready = bar_base + 8u * (3 * kStages + 1);
+  auto bar_acc_full = [&](int h) { return bar_base + 8u * (3 * kStages + h); };
+  auto bar_a_ready = [&](int h) { return bar_base + 8u * (3 * kStages + 2 + h); };
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -181,16 +191,19 @@ conv_stack_tc_kernel(const TcParams p) {
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
   const long long total_st = (p.n + kBoardsPerPair - 1) / kBoardsPerPair;
+  const uint32_t nst = kStages - ((p.variant >> 4) & 7);   // debug: use a shallower weight ring
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(bar_full(s), 1);
       ptx::mbar_init(bar_peer_full(s), 1);
-      ptx::mbar_init(bar_empty(s), 1);
+      ptx::mbar_init(bar_empty(s), 2);      // freed when BOTH halves' MMAs on the stage are done
     }
-    ptx::mbar_init(bar_acc_full, 1);
-    ptx::mbar_init(bar_a_ready, 2);   // one arrival per CTA of the pair
+    for (int h = 0; h < 2; ++h) {
+      ptx::mbar_init(bar_acc_full(h), 1);
+      ptx::mbar_init(bar_a_ready(h), 2);    // one arrival per CTA of the pair
+    }
     ptx::fence_mbar_init();
   }
   // zero the activation tiles (the halo cells stay zero for the whole kernel)
@@ -208,52 +221,72 @@ conv_stack_tc_kernel(const TcParams p) {
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kOffTmemSlot);
-  (void)bias_addr;
 
   // ---- roles -------------------------------------------------------------------------------
   if (warp == 0) {
     // ===== weight producer: stream this CTA's half of every weight stage ====================
     if (lane == 0) {
       const uint32_t img_rank = (p.variant & 4) ? (rank ^ 1u) : rank;
-      const uint8_t* img = p.wimg + static_cast<size_t>(img_rank) * kImgBytesPerRank;
-      uint32_t it = 0;
+      const uint8_t* img = p.wimg + (static_cast<size_t>(pair % p.wimg_copies) * 2 + img_rank) * kImgBytesPerRank;
+      uint32_t s = 0, ph = 0;
       bool ok = true;
       for (long long st = pair; st < total_st && ok; st += npairs) {
         size_t off = 0;
-        for (int layer = 0; layer < 5 && ok; ++layer) {
-          const int nkb = (layer == 0) ? kKbL1 : (layer == 4 ? kKbL5 : kKbMid);
-          const uint32_t bytes = (layer == 4) ? kStageBytesL5 : kStageBytes;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1u;
-            if (!wait_bar(bar_empty(s), ph ^ 1u, false, p.err, 100 + s)) { ok = false; break; }
+        for (int kb = 0; kb < kKbPerSupertile; ++kb) {
+          const uint32_t bytes = (kb >= kKbPerSupertile - kKbL5) ? kStageBytesL5 : kStageBytes;
+          if (!wait_bar(bar_empty(s), ph ^ 1u, false, p.err, 100 + s)) { ok = false; break; }
+          if (p.variant & 256) {            // timing experiment: half the bytes per stage
+            ptx::mbar_arrive_expect_tx(bar_full(s), bytes / 2);
+            ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes / 2, bar_full(s));
+          } else if (p.variant & 512) {     // experiment: 4 concurrent copies per stage
+            ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
+            for (uint32_t q = 0; q < 4; ++q)
+              ptx::bulk_g2s(b_base + s * kStageBytes + q * (bytes / 4), img + off + q * (bytes / 4), bytes / 4,
+                            bar_full(s));
+          } else {
             ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
             ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes, bar_full(s));
-            off += bytes;
           }
+          off += bytes;
+          if (++s == nst) { s = 0; ph ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank != 0) {
+    // ===== relay (peer CTA): forward "my half of stage s has landed" to the leader ===========
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      bool ok = true;
+      for (long long st = pair; st < total_st && ok; st += npairs) {
+        for (int kb = 0; kb < kKbPerSupertile; ++kb) {
+          if (!wait_bar(bar_full(s), ph, false, p.err, 500 + s)) { ok = false; break; }
+          ptx::mbar_arrive_cluster(ptx::mapa(bar_peer_full(s), 0));
+          if (++s == nst) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp <= 2) {
     if (rank == 0) {
-      // ===== MMA issuer (leader CTA).  The WHOLE warp runs the loop with uniform control flow
-      // (so the descriptors live in uniform registers); one elected lane issues the tcgen05 ops.
-      // The issue path is kept to a handful of instructions per MMA: the 64-bit descriptors are
-      // {lo = start>>4 | LBO<<16, hi = SBO | version} and only `lo` changes (one add).
+      // ===== MMA issuer of half h = warp - 1 (leader CTA).  The WHOLE warp runs the loop with
+      // uniform control flow (descriptors live in uniform registers); one elected lane issues
+      // the tcgen05 ops.  The 64-bit descriptors are {lo = start>>4 | LBO<<16, hi = SBO |
+      // version}; only `lo` changes from MMA to MMA (one add).
+      const int h = warp - 1;
       const uint32_t issuer = ptx::elect_one();
+      const bool skip_mma = p.variant & 8;        // timing experiment: weight stream only
       const uint32_t a_hi = (kRowStride >> 4) | (1u << 14);
       const uint32_t b_hi = (kSboB >> 4) | (1u << 14);
-      const uint32_t a_lo0 = (a_base >> 4) | ((kChunkStride >> 4) << 16);
-      const uint32_t a_lo1 = ((a_base + kATileBytes) >> 4) | ((kChunkStride >> 4) << 16);
+      const uint32_t a_lo = ((a_base + h * kATileBytes) >> 4) | ((kChunkStride >> 4) << 16);
       const uint32_t b_lo_mid = (b_base >> 4) | ((kLboB >> 4) << 16);
       const uint32_t b_lo_l5 = (b_base >> 4) | ((kLboB5 >> 4) << 16);
-      const uint32_t tmem0 = tmem_base, tmem1 = tmem_base + kC;
-      constexpr uint32_t kChunk16 = kChunkStride >> 4;          // 181
+      const uint32_t tmem_d = tmem_base + h * kC;
+      const uint32_t acc_bar = bar_acc_full(h), ready_bar = bar_a_ready(h);
+      constexpr uint32_t kChunk16 = kChunkStride >> 4;          // 162
       constexpr uint32_t kStage16 = kStageBytes >> 4;           // 768
       uint32_t s = 0, ph = 0, lstep = 0;
       bool ok = true;
-      const bool prof = (p.prof != nullptr && pair == 0);
-      // one K-block: wait for the stage, 4 (or fewer) K=16 steps x 2 row tiles, free the stage
+      long long* prof = (p.prof != nullptr && pair == 0) ? p.prof + 4 * h * kProfSteps : nullptr;
+      // one K-block: wait for the stage, 4 (or fewer) K=16 steps, release my claim on the stage
 #define WANN_KBLOCK(NKS, A_OFF16_OF_KS, B_LO, B_KS16, IDESC, ACC_FIRST)                          \
       {                                                                                           \
         if (!wait_bar(bar_full(s), ph, false, p.err, 300 + s) ||                                 \
@@ -263,33 +296,31 @@ conv_stack_tc_kernel(const TcParams p) {
         _Pragma("unroll") for (int ks = 0; ks < (NKS); ++ks) {                                   \
           const uint32_t ao = (A_OFF16_OF_KS);                                                    \
           const uint32_t acc = ((ACC_FIRST) && ks == 0) ? 0u : 1u;                                \
-          if (issuer) {                                                                           \
-            ptx::umma_bf16_2cta(tmem0, a_lo0 + ao, a_hi, blo + ks * (B_KS16), b_hi, (IDESC), acc); \
-            ptx::umma_bf16_2cta(tmem1, a_lo1 + ao, a_hi, blo + ks * (B_KS16), b_hi, (IDESC), acc); \
-          }                                                                                       \
+          if (issuer && !skip_mma)                                                                \
+            ptx::umma_bf16_2cta(tmem_d, a_lo + ao, a_hi, blo + ks * (B_KS16), b_hi, (IDESC), acc); \
         }                                                                                         \
-        if (issuer) ptx::umma_commit<2>(bar_empty(s), 3);   /* frees the stage in BOTH CTAs */    \
-        if (++s == kStages) { s = 0; ph ^= 1u; }                                                  \
+        if (issuer) ptx::umma_commit<2>(bar_empty(s), 3);   /* my claim, in BOTH CTAs */          \
+        if (++s == nst) { s = 0; ph ^= 1u; }                                                  \
       }
       for (long long st = pair; st < total_st && ok; st += npairs) {
         // ---- conv1: 9 taps x K=16 (4 real planes); K-block kb holds taps 4kb..4kb+3
         do {
-          if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 200)) { ok = false; break; }
+          if (!wait_bar(ready_bar, lstep & 1u, true, p.err, 200 + 10 * h)) { ok = false; break; }
           ptx::tc_fence_after();
-          if (prof && lstep < kProfSteps && issuer) p.prof[lstep] = clock64();
+          if (prof && lstep < kProfSteps && issuer) prof[lstep] = clock64();
           constexpr uint32_t kTap16[12] = {0, 1, 2, 18, 19, 20, 36, 37, 38, 0, 0, 0};
           WANN_KBLOCK(4, kTap16[ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, true)
           WANN_KBLOCK(4, kTap16[4 + ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
           WANN_KBLOCK(1, kTap16[8 + ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
-          if (issuer) ptx::umma_commit<2>(bar_acc_full, 3);
-          if (prof && lstep < kProfSteps && issuer) p.prof[kProfSteps + lstep] = clock64();
+          if (issuer) ptx::umma_commit<2>(acc_bar, 3);
+          if (prof && lstep < kProfSteps && issuer) prof[kProfSteps + lstep] = clock64();
           ++lstep;
         } while (false);
         // ---- conv2..4: K-block (tap, j) = input channels 64j..64j+63 of tap
         for (int layer = 1; layer <= 3 && ok; ++layer) {
-          if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 200 + layer)) { ok = false; break; }
+          if (!wait_bar(ready_bar, lstep & 1u, true, p.err, 200 + 10 * h + layer)) { ok = false; break; }
           ptx::tc_fence_after();
-          if (prof && lstep < kProfSteps && issuer) p.prof[lstep] = clock64();
+          if (prof && lstep < kProfSteps && issuer) prof[lstep] = clock64();
           uint32_t first = 1;
           for (uint32_t ty = 0; ty < 3 && ok; ++ty)
             for (uint32_t tx = 0; tx < 3 && ok; ++tx) {
@@ -301,137 +332,129 @@ conv_stack_tc_kernel(const TcParams p) {
               }
             }
           if (!ok) break;
-          if (issuer) ptx::umma_commit<2>(bar_acc_full, 3);   // accumulators ready, both CTAs
-          if (prof && lstep < kProfSteps && issuer) p.prof[kProfSteps + lstep] = clock64();
+          if (issuer) ptx::umma_commit<2>(acc_bar, 3);   // this half's accumulators ready, both CTAs
+          if (prof && lstep < kProfSteps && issuer) prof[kProfSteps + lstep] = clock64();
           ++lstep;
         }
         if (!ok) break;
         // ---- conv5 as a 1x1 GEMM over the centre tap with N = 16 (columns = the 9 taps)
         do {
-          if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 204)) { ok = false; break; }
+          if (!wait_bar(ready_bar, lstep & 1u, true, p.err, 204 + 10 * h)) { ok = false; break; }
           ptx::tc_fence_after();
-          if (prof && lstep < kProfSteps && issuer) p.prof[lstep] = clock64();
+          if (prof && lstep < kProfSteps && issuer) prof[lstep] = clock64();
           constexpr uint32_t kCentre16 = (kYStride >> 4) + 1;
           for (uint32_t j = 0; j < 3; ++j) {
             const uint32_t ao0 = j * 8 * kChunk16 + kCentre16;
             WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_l5, (2 * kLboB5) >> 4, kIdescN16, j == 0)
           }
           if (!ok) break;
-          if (issuer) ptx::umma_commit<2>(bar_acc_full, 3);
-          if (prof && lstep < kProfSteps && issuer) p.prof[kProfSteps + lstep] = clock64();
+          if (issuer) ptx::umma_commit<2>(acc_bar, 3);
+          if (prof && lstep < kProfSteps && issuer) prof[kProfSteps + lstep] = clock64();
           ++lstep;
         } while (false);
       }
 #undef WANN_KBLOCK
-    } else {
-      // ===== relay (peer CTA): forward "my half of stage s has landed" to the leader =========
-      if (lane == 0) {
-        uint32_t it = 0;
-        bool ok = true;
-        for (long long st = pair; st < total_st && ok; st += npairs) {
-          for (int kb = 0; kb < kKbL1 + 3 * kKbMid + kKbL5; ++kb, ++it) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1u;
-            if (!wait_bar(bar_full(s), ph, false, p.err, 500 + s)) { ok = false; break; }
-            ptx::mbar_arrive_cluster(ptx::mapa(bar_peer_full(s), 0));
-          }
-        }
-      }
     }
   } else {
-    // ===== epilogue warps ====================================================================
-    const int ew = warp - 2;
-    const int tile = ew >> 2;
+    // ===== epilogue warps: all 8 serve half 0, then half 1, alternately =======================
+    const int ew = warp - kFirstEpiWarp;       // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int chalf = ew >> 2;                 // which 96 of the 192 accumulator columns
     const int row = quad * 32 + lane;          // MMA row inside the tile
     const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
-    const uint32_t cell0 = a_base + tile * kATileBytes + ((y + 1) * 2 + b) * kRowStride + (x + 1) * kCell;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tile * kC;
-    const int board_in_pair = static_cast<int>(rank) * kBoardsPerCta + tile * 2 + b;
-    const bool signaller = (tid == 64);
-    const uint32_t a_ready_leader = ptx::mapa(bar_a_ready, 0);
+    const uint32_t cell_in_tile = ((y + 1) * 2 + b) * kRowStride + (x + 1) * kCell;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const bool signaller = (tid == kFirstEpiWarp * 32);
+    const uint32_t a_ready_leader0 = ptx::mapa(bar_a_ready(0), 0);
+    const uint32_t a_ready_leader1 = ptx::mapa(bar_a_ready(1), 0);
+    const bool profiler = (p.prof != nullptr && blockIdx.x == 0 && signaller);
 
-    auto signal_a_ready = [&]() {
+    auto signal_a_ready = [&](int h) {
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
-      if (signaller) ptx::mbar_arrive_cluster(a_ready_leader);
+      if (signaller) ptx::mbar_arrive_cluster(h ? a_ready_leader1 : a_ready_leader0);
+    };
+    auto board_of = [&](long long st, int h) {
+      return st * kBoardsPerPair + static_cast<int>(rank) * kBoardsPerCta + h * 2 + b;
     };
 
     long long st = pair;
     if (st < total_st) {
-      write_input_cell<kF16>(p, st * kBoardsPerPair + board_in_pair, y, x, cell0);
-      signal_a_ready();
+      for (int h = 0; h < 2; ++h) {
+        if (chalf == 0) write_input_cell<kF16>(p, board_of(st, h), y, x, a_base + h * kATileBytes + cell_in_tile);
+        signal_a_ready(h);
+      }
     }
     uint32_t lstep = 0;
     bool ok = true;
     for (; st < total_st && ok; st += npairs) {
-      const long long board = st * kBoardsPerPair + board_in_pair;
-      for (int layer = 0; layer < 5; ++layer, ++lstep) {
-        if (!wait_bar(bar_acc_full, lstep & 1u, true, p.err, 600 + layer)) { ok = false; break; }
-        ptx::tc_fence_after();
-        if (p.prof != nullptr && blockIdx.x == 0 && signaller && lstep < kProfSteps)
-          p.prof[2 * kProfSteps + lstep] = clock64();
-        if (layer < 4) {
-          const float* bs = bias_s + layer * kC;
-          float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < p.n)
-                           ? p.dbg + (board * 64 + y * 8 + x) * kC : nullptr;
+      for (int layer = 0; layer < 5 && ok; ++layer, ++lstep) {
+        for (int h = 0; h < 2; ++h) {
+          const long long board = board_of(st, h);
+          const uint32_t cell0 = a_base + h * kATileBytes + cell_in_tile;
+          const uint32_t taddr = lane_taddr + h * kC;
+          if (!wait_bar(bar_acc_full(h), lstep & 1u, true, p.err, 600 + 10 * h + layer)) { ok = false; break; }
+          ptx::tc_fence_after();
+          if (profiler && lstep < kProfSteps) p.prof[(4 * h + 2) * kProfSteps + lstep] = clock64();
+          if (layer < 4) {
+            const float* bs = bias_s + layer * kC + chalf * 96;
+            float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < p.n)
+                             ? p.dbg + (board * 64 + y * 8 + x) * kC + chalf * 96 : nullptr;
 #pragma unroll 1
-          for (int ch = 0; ch < 6; ++ch) {
-            uint32_t v[32];
-            ptx::tmem_ld_x32(taddr + ch * 32, v);
-            ptx::tmem_ld_wait();
+            for (int ch = 0; ch < 3; ++ch) {
+              uint32_t v[32];
+              ptx::tmem_ld_x32(taddr + chalf * 96 + ch * 32, v);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8 + 4);
-              uint4 o;
-              o.x = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 0]) + b0.x,
-                                          __uint_as_float(v[kc * 8 + 1]) + b0.y);
-              o.y = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 2]) + b0.z,
-                                          __uint_as_float(v[kc * 8 + 3]) + b0.w);
-              o.z = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 4]) + b1.x,
-                                          __uint_as_float(v[kc * 8 + 5]) + b1.y);
-              o.w = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
-                                          __uint_as_float(v[kc * 8 + 7]) + b1.w);
-              ptx::st_shared_v4(cell0 + (ch * 4 + kc) * kChunkStride, o);
-              if (dbg != nullptr) {
-                const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+              for (int kc = 0; kc < 4; ++kc) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8 + 4);
+                uint4 o;
+                o.x = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 0]) + b0.x,
+                                           __uint_as_float(v[kc * 8 + 1]) + b0.y);
+                o.y = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 2]) + b0.z,
+                                           __uint_as_float(v[kc * 8 + 3]) + b0.w);
+                o.z = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 4]) + b1.x,
+                                           __uint_as_float(v[kc * 8 + 5]) + b1.y);
+                o.w = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
+                                           __uint_as_float(v[kc * 8 + 7]) + b1.w);
+                ptx::st_shared_v4(cell0 + (chalf * 12 + ch * 4 + kc) * kChunkStride, o);
+                if (dbg != nullptr) {
+                  const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  dbg[ch * 32 + kc * 8 + 2 * i] = ptx::unpack16<kF16>(w[i] & 0xFFFFu);
-                  dbg[ch * 32 + kc * 8 + 2 * i + 1] = ptx::unpack16<kF16>(w[i] >> 16);
+                  for (int i = 0; i < 4; ++i) {
+                    dbg[ch * 32 + kc * 8 + 2 * i] = ptx::unpack16<kF16>(w[i] & 0xFFFFu);
+                    dbg[ch * 32 + kc * 8 + 2 * i + 1] = ptx::unpack16<kF16>(w[i] >> 16);
+                  }
                 }
               }
             }
-          }
-        } else {
-          // conv5: column t of the accumulator is P[pixel][tap t]; out = 9-point stencil sum.
-          uint32_t v[16];
-          ptx::tmem_ld_x16(taddr, v);
-          ptx::tmem_ld_wait();
-          // scratch = cells of channel-chunks 2..4 at this pixel (fp32 x 4 per cell); halo = 0
-          ptx::st_shared_v4(cell0 + 2 * kChunkStride, make_uint4(v[0], v[1], v[2], v[3]));
-          ptx::st_shared_v4(cell0 + 3 * kChunkStride, make_uint4(v[4], v[5], v[6], v[7]));
-          ptx::st_shared_v4(cell0 + 4 * kChunkStride, make_uint4(v[8], 0u, 0u, 0u));
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory");
-          float acc = 0.f;
+          } else if (chalf == 0) {
+            // conv5: column t of the accumulator is P[pixel][tap t]; out = 9-point stencil sum.
+            uint32_t v[16];
+            ptx::tmem_ld_x16(taddr, v);
+            ptx::tmem_ld_wait();
+            // scratch = cells of channel-chunks 2..4 at this pixel (fp32 x 4 per cell); halo = 0
+            ptx::st_shared_v4(cell0 + 2 * kChunkStride, make_uint4(v[0], v[1], v[2], v[3]));
+            ptx::st_shared_v4(cell0 + 3 * kChunkStride, make_uint4(v[4], v[5], v[6], v[7]));
+            ptx::st_shared_v4(cell0 + 4 * kChunkStride, make_uint4(v[8], 0u, 0u, 0u));
+            asm volatile("bar.sync 2, 128;" ::: "memory");        // the 4 chalf==0 warps
+            float acc = 0.f;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            acc += ptx::ld_shared_f32(cell0 + (2 + tap / 4) * kChunkStride + dy * kYStride +
-                                      dx * kCell + (tap % 4) * 4);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              acc += ptx::ld_shared_f32(cell0 + (2 + tap / 4) * kChunkStride + dy * kYStride +
+                                        dx * kCell + (tap % 4) * 4);
+            }
+            const float hval = fmaxf(acc + bias_s[4 * kC], 0.f);
+            if (board < p.n) p.h5[board * 64 + y * 8 + x] = hval;
+            if (st + npairs < total_st)
+              write_input_cell<kF16>(p, board_of(st + npairs, h), y, x, cell0);
           }
-          const float h = fmaxf(acc + bias_s[4 * kC], 0.f);
-          if (board < p.n) p.h5[board * 64 + y * 8 + x] = h;
-          // all stencil reads must finish before anyone overwrites the scratch / input cells
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + tile) : "memory");
-          if (st + npairs < total_st)
-            write_input_cell<kF16>(p, (st + npairs) * kBoardsPerPair + board_in_pair, y, x, cell0);
+          signal_a_ready(h);
+          if (profiler && lstep < kProfSteps) p.prof[(4 * h + 3) * kProfSteps + lstep] = clock64();
         }
-        signal_a_ready();
-        if (p.prof != nullptr && blockIdx.x == 0 && signaller && lstep < kProfSteps)
-          p.prof[3 * kProfSteps + lstep] = clock64();
       }
     }
   }

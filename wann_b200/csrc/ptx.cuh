@@ -47,8 +47,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // arrive on a barrier that lives in another CTA of the cluster (address from mapa)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr)
-               : "memory");
+  // default semantics (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): a
+  // `.release.cluster` arrive costs a MEMBAR.ALL.GPU per call (measured: ~870 cycles per
+  // weight stage in the relay loop, which then paced the whole kernel).
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -66,7 +68,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)

@@ -88,6 +88,7 @@ struct Lane {
 };
 
 constexpr int kLanes = 4;
+constexpr int kMaxWimgCopies = 32;
 
 }  // namespace
 
@@ -98,6 +99,7 @@ struct wann_ctx {
   int final_kernel = 3;
   long long chunk = 16384;
   int variant = 0;
+  int wimg_copies = 8;         // replicas of the weight image in use (spreads L2 hot lines)
   // weights on device
   float* d_conv_w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* d_conv_b[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -271,7 +273,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   if (ctx->mode != WANN_MODE_FP32) {
     TcParams p;
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
-    p.n = n; p.wimg = ctx->d_wimg; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
+    p.n = n; p.wimg = ctx->d_wimg; p.wimg_copies = ctx->wimg_copies; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
     const long long total_st = (n + kBoardsPerPair - 1) / kBoardsPerPair;
     const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
@@ -542,8 +544,9 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
   if (rc == WANN_OK) {
     std::vector<uint8_t> img;
     build_weight_image(*w, mode == WANN_MODE_FP16, img);
-    e = cudaMalloc(&ctx->d_wimg, img.size());
-    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice);
+    e = cudaMalloc(&ctx->d_wimg, img.size() * kMaxWimgCopies);
+    for (int c = 0; c < kMaxWimgCopies && e == cudaSuccess; ++c)
+      e = cudaMemcpy(ctx->d_wimg + c * img.size(), img.data(), img.size(), cudaMemcpyHostToDevice);
     std::vector<float> bias(4 * 192 + 4, 0.f);
     for (int l = 0; l < 4; ++l) memcpy(bias.data() + l * 192, w->conv_b[l], 192 * 4);
     bias[4 * 192] = w->conv_b[4][0];
@@ -697,8 +700,8 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
   auto body = [&]() -> int {
     if (n > s.cap) return fail(WANN_E_INVALID, "n exceeds the chunk size");
     long long* d_prof = nullptr;
-    CU(cudaMalloc(&d_prof, 4 * kProfSteps * 8));
-    CU(cudaMemsetAsync(d_prof, 0, 4 * kProfSteps * 8, s.stream));
+    CU(cudaMalloc(&d_prof, 8 * kProfSteps * 8));
+    CU(cudaMemsetAsync(d_prof, 0, 8 * kProfSteps * 8, s.stream));
     CU(cudaMemcpyAsync(s.d_squares, squares, n * 64, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.d_black, black, n, cudaMemcpyHostToDevice, s.stream));
     ChunkIO io;
@@ -706,7 +709,7 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
     io.idx = s.d_idx; io.prior = s.d_prior; io.nlegal = s.d_nlegal;
     int r = enqueue_eval(ctx, s, s.stream, io, n);
     if (r == WANN_OK) {
-      cudaMemcpyAsync(stamps, d_prof, 4 * kProfSteps * 8, cudaMemcpyDeviceToHost, s.stream);
+      cudaMemcpyAsync(stamps, d_prof, 8 * kProfSteps * 8, cudaMemcpyDeviceToHost, s.stream);
       cudaError_t e = cudaStreamSynchronize(s.stream);
       if (e != cudaSuccess) r = fail(WANN_E_CUDA, "sync: %s", cudaGetErrorString(e));
     }
@@ -785,6 +788,11 @@ int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]) {
 int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
   if (ctx == nullptr || key == nullptr) return fail(WANN_E_INVALID, "null argument");
   if (strcmp(key, "variant") == 0) { ctx->variant = static_cast<int>(value); return WANN_OK; }
+  if (strcmp(key, "wimg_copies") == 0) {
+    if (value < 1 || value > kMaxWimgCopies) return fail(WANN_E_INVALID, "wimg_copies out of range");
+    ctx->wimg_copies = static_cast<int>(value);
+    return WANN_OK;
+  }
   if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
   if (strcmp(key, "chunk") == 0) {
     if (value < 8 || value > (1 << 20)) return fail(WANN_E_INVALID, "chunk out of range");

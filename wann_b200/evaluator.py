@@ -158,7 +158,7 @@ class PolicyEvaluator(object):
     def debug_profile(self, squares, black):
         """clock64 stamps [4,64] of CTA pair 0 (MMA start/end, epilogue start/end per layer-step)."""
         sq, bl = self._np_in(squares, black)
-        out = np.zeros((4, 64), np.int64)
+        out = np.zeros((8, 64), np.int64)
         L.check(self._lib.wann_debug_profile(self._ctx, sq.ctypes.data, bl.ctypes.data, sq.shape[0],
                                              out.ctypes.data))
         return out
