@@ -116,6 +116,8 @@ def cpu_arm(sample_seconds=15.0):
     Returns (positions/s, cores, kind, sample description)."""
     from oracle import c_oracle as C
     from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    C.set_threads(cores)           # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     w = O.synthetic_weights("trained_like", 1)
     sq, bl = O.random_positions_fast(2048, seed=99)
     sq, bl = np.tile(sq, (32, 1)), np.tile(bl, 32)              # up to 65,536 positions to draw from
@@ -145,7 +147,6 @@ def cpu_arm(sample_seconds=15.0):
     t0 = time.perf_counter()
     best_fn(sq[:n], bl[:n])
     dt = time.perf_counter() - t0
-    cores = os.cpu_count() or 1
     return n / dt, cores, "port", "%d positions, oracle port (%s, fp32), %.1f s" % (n, best_name, dt)
 
 
@@ -169,11 +170,25 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                              "note": "CPU stand-in for the TF-1.0 session (TensorFlow is not installable here)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings
+    written by C libraries to fd 1) has been redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -335,12 +350,12 @@ def main():
             "sweep_positions_per_s_1gpu": sweep,
             "per_rank_counters": counters.tolist(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and n_gpus == 1:
             v, cores, kind, sample = cpu_arm()
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                                     "note": "CPU stand-in for the reference's TF-1.0 session "
                                             "(TensorFlow/weights not available); reported baseline only"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ev.close()
     if world > 1:
         dist.destroy_process_group()

@@ -82,3 +82,12 @@ def rank(probs, mask):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_threads(n):
+    lib().oracle_set_threads(ctypes.c_int(int(n)))
+    try:                                    # numpy's OpenBLAS pool, when threadpoolctl is around
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=int(n))
+    except Exception:  # noqa: BLE001
+        pass

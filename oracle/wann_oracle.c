@@ -171,6 +171,14 @@ void oracle_rank(const float *probs, const uint8_t *mask, int64_t n, uint8_t *id
     }
 }
 
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

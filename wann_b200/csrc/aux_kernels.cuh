@@ -80,111 +80,157 @@ struct TailParams {
   uint8_t* n_legal;         // [n]
 };
 
-// One warp per board, 8 boards per CTA pass; FC weights resident in shared memory.
+// One warp handles 4 boards per pass (each FC weight read from shared memory feeds 4 FMAs);
+// softmax by warp shuffles; legality from a per-CTA move table; ranking = compact the <= 48
+// legal candidates (ascending move index), then each lane counts how many candidates beat its
+// own (prior greater, or equal with a smaller index) -> its output slot.
 constexpr int kTailWarps = 8;
-constexpr int kTailSmemBytes = (64 * kMoves + kMoves + 5) * 4 + kTailWarps * (64 * 4 + 160 * 4 + 64);
+constexpr int kTailBoards = 4;                 // boards per warp per pass
+constexpr int kTailWarpFloats = kTailBoards * 64 + 64;   // h[4][64] + compact priors[48] (+pad)
+constexpr int kTailSmemBytes = (64 * kMoves + 160) * 4 + 160 * 2 +
+                               kTailWarps * (kTailWarpFloats * 4 + kTailBoards * 64 + 64);
 
 __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams p) {
   extern __shared__ float tsm[];
-  float* w_s = tsm;                        // [64][155]
-  float* b_s = w_s + 64 * kMoves;          // [155] (+5 pad)
-  float* h_s = b_s + 160;                  // [warps][64]
-  float* pm_s = h_s + kTailWarps * 64;     // [warps][160] masked probs for ranking
-  int8_t* pov_s = reinterpret_cast<int8_t*>(pm_s + kTailWarps * 160);   // [warps][64]
+  float* w_s = tsm;                                   // [64][155]
+  float* b_s = w_s + 64 * kMoves;                     // [160]
+  uint16_t* mv_s = reinterpret_cast<uint16_t*>(b_s + 160);   // [160] from | to<<6 | fwd<<12
+  float* warp_f = reinterpret_cast<float*>(mv_s + 160);
+  uint8_t* warp_b = reinterpret_cast<uint8_t*>(warp_f + kTailWarps * kTailWarpFloats);
   for (int i = threadIdx.x; i < 64 * kMoves; i += blockDim.x) w_s[i] = p.fc_w[i];
-  for (int i = threadIdx.x; i < 160; i += blockDim.x) b_s[i] = i < kMoves ? p.fc_b[i] : 0.f;
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) {
+    b_s[i] = i < kMoves ? p.fc_b[i] : 0.f;
+    int r = 0, c = 0, d = 0;
+    if (i < 154) decode_move(i, r, c, d);
+    mv_s[i] = static_cast<uint16_t>((r * 8 + c) | (((r + 1) * 8 + c + d) << 6) | ((d == 0) << 12));
+  }
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* h = h_s + w * 64;
-  float* pm = pm_s + w * 160;
-  int8_t* pov = pov_s + w * 64;
-  for (long long board = blockIdx.x * static_cast<long long>(kTailWarps) + w; board < p.n;
-       board += static_cast<long long>(gridDim.x) * kTailWarps) {
-    h[lane] = p.h5[board * 64 + lane];
-    h[lane + 32] = p.h5[board * 64 + lane + 32];
+  float* h = warp_f + w * kTailWarpFloats;            // [4][64]
+  float* cp = h + kTailBoards * 64;                   // [48] compact priors
+  int8_t* pov = reinterpret_cast<int8_t*>(warp_b + w * (kTailBoards * 64 + 64));   // [4][64]
+  uint8_t* cj = reinterpret_cast<uint8_t*>(pov + kTailBoards * 64);                // [48] compact indices
+  const long long ngroups = (p.n + kTailBoards - 1) / kTailBoards;
+  for (long long g = blockIdx.x * static_cast<long long>(kTailWarps) + w; g < ngroups;
+       g += static_cast<long long>(gridDim.x) * kTailWarps) {
+    const long long board0 = g * kTailBoards;
+    const int nb = static_cast<int>(min(static_cast<long long>(kTailBoards), p.n - board0));
+#pragma unroll
+    for (int t = 0; t < kTailBoards * 2; ++t) {        // 4 boards x 64 floats, coalesced
+      const int i = t * 32 + lane;
+      h[i] = (i >> 6) < nb ? p.h5[board0 * 64 + i] : 0.f;
+    }
     if (p.squares != nullptr) {
-      const int blk = p.black[board];
-      pov[lane] = static_cast<int8_t>(pov_square(p.squares + board * 64, blk, lane));
-      pov[lane + 32] = static_cast<int8_t>(pov_square(p.squares + board * 64, blk, lane + 32));
+#pragma unroll
+      for (int t = 0; t < kTailBoards; ++t)
+        if (t < nb) {
+          const int blk = p.black[board0 + t];
+          const int8_t* sq = p.squares + (board0 + t) * 64;
+          pov[t * 64 + lane] = static_cast<int8_t>(pov_square(sq, blk, lane));
+          pov[t * 64 + lane + 32] = static_cast<int8_t>(pov_square(sq, blk, lane + 32));
+        }
     }
     __syncwarp();
-    // logits[j] = sum_q h[q] * W[q][j] + b[j]   (reshape [-1,64] row-major, matmul, bias_add)
-    float lg[5];
+    // logits[t][j] = sum_q h[t][q] * W[q][j] + b[j]   (reshape [-1,64] row-major, matmul, bias_add)
+    float lg[kTailBoards][5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) lg[k] = 0.f;
-#pragma unroll 8
+    for (int t = 0; t < kTailBoards; ++t)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) lg[t][k] = 0.f;
+#pragma unroll 4
     for (int q = 0; q < 64; ++q) {
-      const float hq = h[q];
       const float* wr = w_s + q * kMoves + lane;
+      float wv[5];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) lg[k] = fmaf(hq, wr[32 * k], lg[k]);
-      if (lane < kMoves - 128) lg[4] = fmaf(hq, wr[128], lg[4]);
-    }
-    float mx = -INFINITY;
+      for (int k = 0; k < 4; ++k) wv[k] = wr[32 * k];
+      wv[4] = (lane < kMoves - 128) ? wr[128] : 0.f;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int j = lane + 32 * k;
-      if (j < kMoves) {
-        lg[k] += b_s[j];
-        mx = fmaxf(mx, lg[k]);
+      for (int t = 0; t < kTailBoards; ++t) {
+        const float hq = h[t * 64 + q];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) lg[t][k] = fmaf(hq, wv[k], lg[t][k]);
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float e[5], sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int j = lane + 32 * k;
-      e[k] = (j < kMoves) ? expf(lg[k] - mx) : 0.f;
-      sum += e[k];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int j = lane + 32 * k;
-      if (j < kMoves) {
-        const float pr = e[k] / sum;
-        if (p.probs != nullptr) p.probs[board * kMoves + j] = pr;
-        if (p.logits != nullptr) p.logits[board * kMoves + j] = lg[k];
-        e[k] = pr;
-      }
-    }
-    if (p.idx != nullptr) {
-      // legal gather: prior_i = softmax155[idx_i] (no renormalisation), then rank sort
-      // descending by prior, ties by ascending index.
-      bool legal[5];
-      int cnt = 0;
+    for (int t = 0; t < kTailBoards; ++t) {
+      if (t >= nb) break;
+      const long long board = board0 + t;
+      float e[5];
+      float mx = -INFINITY;
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const int j = lane + 32 * k;
-        legal[k] = (j < kMoves) && move_is_legal(pov, j);
-        if (j < 160) pm[j] = legal[k] ? e[k] : -1.f;
-        cnt += legal[k];
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      __syncwarp();
-      for (int j = lane; j < kMaxLegal; j += 32) {
-        if (j >= cnt) {
-          p.idx[board * kMaxLegal + j] = 255;
-          p.prior[board * kMaxLegal + j] = 0.f;
+        if (j < kMoves) {
+          e[k] = lg[t][k] + b_s[j];
+          mx = fmaxf(mx, e[k]);
+        } else {
+          e[k] = -INFINITY;
         }
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f, pr[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        if (!legal[k]) continue;
-        const int j = lane + 32 * k;
-        const float me = e[k];
-        int rank = 0;
-        for (int o = 0; o < kMoves - 1; ++o) {
-          const float other = pm[o];
-          rank += (other > me) || (other == me && o < j);
-        }
-        p.idx[board * kMaxLegal + rank] = static_cast<uint8_t>(j);
-        p.prior[board * kMaxLegal + rank] = me;
+        pr[k] = (lane + 32 * k < kMoves) ? expf(e[k] - mx) : 0.f;
+        sum += pr[k];
       }
-      if (lane == 0) p.n_legal[board] = static_cast<uint8_t>(cnt);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int j = lane + 32 * k;
+        pr[k] = pr[k] / sum;
+        if (j < kMoves) {
+          if (p.probs != nullptr) p.probs[board * kMoves + j] = pr[k];
+          if (p.logits != nullptr) p.logits[board * kMoves + j] = e[k];
+        }
+      }
+      if (p.idx != nullptr) {
+        // legal gather: prior_i = softmax155[idx_i] (no renormalisation); compact in ascending
+        // index order, then rank: descending by prior, ties by ascending index.
+        const int8_t* pv = pov + t * 64;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int j = lane + 32 * k;
+          bool legal = false;
+          if (j < 154) {
+            const uint32_t m = mv_s[j];
+            const int tgt = pv[(m >> 6) & 63];
+            legal = pv[m & 63] == 1 && ((m >> 12) ? tgt == 0 : tgt != 1);
+          }
+          const uint32_t mask = __ballot_sync(0xffffffffu, legal);
+          if (legal) {
+            const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+            cp[pos] = pr[k];
+            cj[pos] = static_cast<uint8_t>(j);
+          }
+          cnt += __popc(mask);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c = lane + 32 * half;
+          if (c < kMaxLegal) {
+            if (c < cnt) {
+              const float me = cp[c];
+              int rank = 0;
+              for (int o = 0; o < cnt; ++o) {
+                const float other = cp[o];
+                rank += (other > me) || (other == me && o < c);
+              }
+              p.idx[board * kMaxLegal + rank] = cj[c];
+              p.prior[board * kMaxLegal + rank] = me;
+            } else {
+              p.idx[board * kMaxLegal + c] = 255;
+              p.prior[board * kMaxLegal + c] = 0.f;
+            }
+          }
+        }
+        if (lane == 0) p.n_legal[board] = static_cast<uint8_t>(cnt);
+        __syncwarp();
+      }
     }
     __syncwarp();
   }

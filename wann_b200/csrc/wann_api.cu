@@ -321,8 +321,9 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
     t.h5 = ws.d_h5; t.squares = io.squares; t.black = io.black; t.n = n;
     t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
     t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal;
+    const long long groups = (n + kTailBoards - 1) / kTailBoards;
     const int blocks = static_cast<int>(
-        std::min<long long>((n + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
+        std::min<long long>((groups + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
     tail_kernel<<<blocks, kTailWarps * 32, kTailSmemBytes, stream>>>(t);
     ++launches;
   }
