@@ -145,11 +145,15 @@ int wann_host_alloc(void** ptr, uint64_t bytes);
 int wann_host_free(void* ptr);
 
 /* Counters since create: [0] positions evaluated, [1] kernel launches, [2] calls,
- * [3] H2D bytes, [4] D2H bytes, [5..7] reserved. */
+ * [3] H2D bytes, [4] D2H bytes, [5] merged launches made by the coalescer, [6] calls they
+ * served, [7] reserved. */
 int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]);
 
 /* Tunables (optional).  key: "chunk" (positions per internal chunk, default 16384),
- * "variant" (debug bits), "time_kernels" (0/1, see wann_kernel_times). */
+ * "coalesce" (0/1: merge concurrent HOST calls of <= 256 positions into one launch -- flat
+ * combining, no added latency for a lone caller; the reference calls evaluate with batch 1 from
+ * 11 threads), "wimg_copies" (1..32 replicas of the weight image), "variant" (debug bits),
+ * "time_kernels" (0/1, see wann_kernel_times). */
 int wann_set_option(wann_ctx* ctx, const char* key, int64_t value);
 
 /* Library/ABI version (major*100+minor). */

@@ -331,3 +331,43 @@ def test_unmodified_reference_tree_code_runs_on_our_evaluator(weights):
     got_idx = [k["index"] for k in kids]
     assert got_idx == want[0][0, :22].tolist()                   # same children, same order
     assert abs((pri[0] - 1) - want[1][0, 0]) < 1e-6              # 1 + NN_output[idx], tree_search_utils.pyx:986
+
+
+def test_coalescer_merges_concurrent_small_calls(weights, suite):
+    """11 threads x batch-1 calls (the reference's pattern): results identical to direct calls,
+    and fewer launches than calls (flat combining in the C++ runtime)."""
+    import wann_b200
+    sq, bl = suite
+    with wann_b200.PolicyEvaluator(weights, mode="bf16") as ev:
+        ref_p = ev.eval_probs(sq[:512], bl[:512])
+        ref_i, ref_r, ref_c = ev.eval_topk(sq[:512], bl[:512])
+    with wann_b200.PolicyEvaluator(weights, mode="bf16", coalesce=True) as ev:
+        assert np.array_equal(ev.eval_probs(sq[:3], bl[:3]), ref_p[:3])      # lone caller
+        errs = []
+
+        def worker(t):
+            try:
+                for k in range(40):
+                    i = (41 * t + 13 * k) % 500
+                    n = 1 + (k % 3 == 0) * (t % 5)
+                    if k % 2:
+                        out = ev.eval_probs(sq[i:i + n], bl[i:i + n])
+                        ok = np.array_equal(out, ref_p[i:i + n])
+                    else:
+                        a, b, c = ev.eval_topk(sq[i:i + n], bl[i:i + n])
+                        ok = np.array_equal(a, ref_i[i:i + n]) and np.array_equal(b, ref_r[i:i + n]) and \
+                            np.array_equal(c, ref_c[i:i + n])
+                    if not ok:
+                        errs.append((t, k))
+            except Exception as e:  # noqa: BLE001
+                errs.append(repr(e))
+
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(11)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        st = ev.stats()
+        assert not errs
+        assert st["merged_calls"] == 1 + 11 * 40
+        assert st["merged_launches"] < st["merged_calls"]     # concurrency was actually merged
+        big = ev.eval_probs(sq[:400], bl[:400])                # > 256 positions bypasses the combiner
+        assert np.array_equal(big, ref_p[:400]) and ev.stats()["merged_calls"] == st["merged_calls"]

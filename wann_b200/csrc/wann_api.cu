@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -88,6 +89,15 @@ struct Lane {
 };
 
 constexpr int kLanes = 4;
+constexpr long long kCombineMaxCall = 256;    // host calls up to this many positions may be merged
+constexpr long long kCombineMaxBatch = 4096;  // positions per merged launch
+
+// One small host call waiting to be merged with its concurrent siblings (flat combining).
+struct CombineReq {
+  const int8_t* squares; const uint8_t* black; long long n;
+  float* probs; float* logits; uint8_t* idx; float* prior; uint8_t* nlegal;
+  int rc = 0; std::string err; bool done = false;
+};
 constexpr int kMaxWimgCopies = 32;
 
 }  // namespace
@@ -111,6 +121,16 @@ struct wann_ctx {
   std::mutex mu;
   std::condition_variable cv;
   std::atomic<uint64_t> stats[8];
+  // flat-combining coalescer for concurrent small HOST calls (the reference calls evaluate with
+  // batch 1 from 11 threads, tree_builder.pyx:186-189): whoever finds the combiner idle becomes
+  // the leader, merges every queued request into ONE launch and hands the results back.
+  bool coalesce = false;
+  std::mutex cmu;
+  std::condition_variable ccv;
+  std::deque<CombineReq*> cq;
+  bool cbusy = false;
+  int8_t* c_sq = nullptr; uint8_t* c_bl = nullptr; float* c_probs = nullptr; float* c_logits = nullptr;
+  uint8_t* c_idx = nullptr; float* c_prior = nullptr; uint8_t* c_nlegal = nullptr;   // pinned staging
   // optional CUDA-event timing of the conv-stack kernel (bench.py roofline)
   bool time_kernels = false;
   std::mutex ev_mu;
@@ -468,10 +488,88 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
   return rc;
 }
 
+int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* stream_v);
+
+int combine_alloc(wann_ctx* ctx) {
+  if (ctx->c_sq != nullptr) return WANN_OK;
+  const long long m = kCombineMaxBatch;
+  CU(cudaMallocHost(&ctx->c_sq, m * 64));
+  CU(cudaMallocHost(&ctx->c_bl, m));
+  CU(cudaMallocHost(&ctx->c_probs, m * kMoves * 4));
+  CU(cudaMallocHost(&ctx->c_logits, m * kMoves * 4));
+  CU(cudaMallocHost(&ctx->c_idx, m * kMaxLegal));
+  CU(cudaMallocHost(&ctx->c_prior, m * kMaxLegal * 4));
+  CU(cudaMallocHost(&ctx->c_nlegal, m));
+  return WANN_OK;
+}
+
+// Flat combining: enqueue; if nobody is processing, become the leader, take a batch of queued
+// requests (FIFO, up to kCombineMaxBatch positions), evaluate them as ONE host-path call on the
+// pinned staging buffers, scatter the results and wake the owners.  A lone caller therefore pays
+// no hand-off latency; concurrent callers share launches.
+int run_combined(wann_ctx* ctx, const EvalArgs& a, long long n) {
+  CombineReq req;
+  req.squares = a.squares; req.black = a.black; req.n = n; req.probs = a.probs; req.logits = a.logits;
+  req.idx = a.idx; req.prior = a.prior; req.nlegal = a.nlegal;
+  std::unique_lock<std::mutex> lk(ctx->cmu);
+  ctx->cq.push_back(&req);
+  while (!req.done) {
+    if (ctx->cbusy) { ctx->ccv.wait(lk); continue; }
+    ctx->cbusy = true;
+    std::vector<CombineReq*> batch;
+    long long total = 0;
+    while (!ctx->cq.empty() && total + ctx->cq.front()->n <= kCombineMaxBatch) {
+      batch.push_back(ctx->cq.front());
+      total += ctx->cq.front()->n;
+      ctx->cq.pop_front();
+    }
+    lk.unlock();
+    int rc = combine_alloc(ctx);
+    EvalArgs m;
+    if (rc == WANN_OK) {
+      long long off = 0;
+      for (CombineReq* r : batch) {
+        memcpy(ctx->c_sq + off * 64, r->squares, r->n * 64);
+        memcpy(ctx->c_bl + off, r->black, r->n);
+        if (r->probs) m.probs = ctx->c_probs;
+        if (r->logits) m.logits = ctx->c_logits;
+        if (r->idx) { m.idx = ctx->c_idx; m.prior = ctx->c_prior; m.nlegal = ctx->c_nlegal; }
+        off += r->n;
+      }
+      m.squares = ctx->c_sq; m.black = ctx->c_bl;
+      rc = run_eval(ctx, m, -total, WANN_MEM_HOST, nullptr);   // negative n: bypass the combiner
+    }
+    const std::string err = g_err;
+    long long off = 0;
+    for (CombineReq* r : batch) {
+      if (rc == WANN_OK) {
+        if (r->probs) memcpy(r->probs, ctx->c_probs + off * kMoves, r->n * kMoves * 4);
+        if (r->logits) memcpy(r->logits, ctx->c_logits + off * kMoves, r->n * kMoves * 4);
+        if (r->idx) {
+          memcpy(r->idx, ctx->c_idx + off * kMaxLegal, r->n * kMaxLegal);
+          memcpy(r->prior, ctx->c_prior + off * kMaxLegal, r->n * kMaxLegal * 4);
+          memcpy(r->nlegal, ctx->c_nlegal + off, r->n);
+        }
+      }
+      off += r->n;
+    }
+    ctx->stats[5] += 1;                                   // merged launches
+    ctx->stats[6] += static_cast<uint64_t>(batch.size()); // requests served by them
+    lk.lock();
+    for (CombineReq* r : batch) { r->rc = rc; r->err = err; r->done = true; }
+    ctx->cbusy = false;
+    ctx->ccv.notify_all();
+  }
+  lk.unlock();
+  if (req.rc != WANN_OK) g_err = req.err;
+  return req.rc;
+}
+
 // The one driver behind wann_eval_probs / _planes / _topk / _debug_activations.
 int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* stream_v) {
+  bool bypass = false;
+  if (n < 0) { n = -n; bypass = true; }
   if (ctx == nullptr) return fail(WANN_E_INVALID, "null context");
-  if (n < 0) return fail(WANN_E_INVALID, "negative n");
   if (n == 0) return WANN_OK;
   if (mem != WANN_MEM_HOST && mem != WANN_MEM_DEVICE) return fail(WANN_E_INVALID, "bad mem kind %d", mem);
   if (a.squares == nullptr && a.planes == nullptr) return fail(WANN_E_INVALID, "no input");
@@ -479,7 +577,10 @@ int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* strea
   if (a.idx != nullptr && (a.squares == nullptr || a.prior == nullptr || a.nlegal == nullptr))
     return fail(WANN_E_INVALID, "top-k needs squares, prior and n_legal");
   CU(cudaSetDevice(ctx->device));
-  ctx->stats[2] += 1;
+  if (!bypass) ctx->stats[2] += 1;
+  if (!bypass && ctx->coalesce && mem == WANN_MEM_HOST && a.squares != nullptr && a.dbg == nullptr &&
+      n <= kCombineMaxCall)
+    return run_combined(ctx, a, n);
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);
   if (rc != WANN_OK) return rc;
@@ -583,6 +684,10 @@ int wann_destroy(wann_ctx* ctx) {
     free_slot(l.slot[1]);
     if (l.last) cudaEventDestroy(l.last);
   }
+  if (ctx->c_sq) {
+    cudaFreeHost(ctx->c_sq); cudaFreeHost(ctx->c_bl); cudaFreeHost(ctx->c_probs); cudaFreeHost(ctx->c_logits);
+    cudaFreeHost(ctx->c_idx); cudaFreeHost(ctx->c_prior); cudaFreeHost(ctx->c_nlegal);
+  }
   for (int i = 0; i < 5; ++i) { cudaFree(ctx->d_conv_w[i]); cudaFree(ctx->d_conv_b[i]); }
   cudaFree(ctx->d_fc_w); cudaFree(ctx->d_fc_b); cudaFree(ctx->d_wimg); cudaFree(ctx->d_bias_tc);
   delete ctx;
@@ -592,6 +697,7 @@ int wann_destroy(wann_ctx* ctx) {
 int wann_eval_probs(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, float* probs,
                     float* logits, int mem, void* stream) {
   if (probs == nullptr && logits == nullptr) return fail(WANN_E_INVALID, "no output buffer");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
   EvalArgs a;
   a.squares = squares; a.black = black; a.probs = probs; a.logits = logits;
   if (squares == nullptr && n > 0) return fail(WANN_E_INVALID, "squares is null");
@@ -604,6 +710,7 @@ int wann_eval_planes(wann_ctx* ctx, const void* planes, int planes_dtype, int64_
   if (planes == nullptr && n > 0) return fail(WANN_E_INVALID, "planes is null");
   if (planes_dtype != WANN_PLANES_I8 && planes_dtype != WANN_PLANES_F32)
     return fail(WANN_E_INVALID, "bad planes dtype");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
   EvalArgs a;
   a.planes = planes; a.planes_dtype = planes_dtype; a.probs = probs; a.logits = logits;
   return run_eval(ctx, a, n, mem, stream);
@@ -614,6 +721,7 @@ int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, i
   if ((idx == nullptr || prior == nullptr || n_legal == nullptr) && n > 0)
     return fail(WANN_E_INVALID, "null output buffer");
   if (squares == nullptr && n > 0) return fail(WANN_E_INVALID, "squares is null");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
   EvalArgs a;
   a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
   return run_eval(ctx, a, n, mem, stream);
@@ -623,6 +731,7 @@ int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* 
                            float* out, int mem) {
   if (layer < 1 || layer > 5) return fail(WANN_E_INVALID, "layer must be 1..5");
   if ((squares == nullptr || out == nullptr) && n > 0) return fail(WANN_E_INVALID, "null buffer");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
   EvalArgs a;
   a.squares = squares; a.black = black; a.dbg = out; a.dbg_layer = layer;
   return run_eval(ctx, a, n, mem, nullptr);
@@ -794,6 +903,7 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
     ctx->wimg_copies = static_cast<int>(value);
     return WANN_OK;
   }
+  if (strcmp(key, "coalesce") == 0) { ctx->coalesce = value != 0; return WANN_OK; }
   if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
   if (strcmp(key, "chunk") == 0) {
     if (value < 8 || value > (1 << 20)) return fail(WANN_E_INVALID, "chunk out of range");

@@ -16,7 +16,7 @@ def _is_torch(x):
 
 
 class PolicyEvaluator(object):
-    def __init__(self, weights=None, device=0, mode="bf16", final_kernel=3, chunk=None):
+    def __init__(self, weights=None, device=0, mode="bf16", final_kernel=3, chunk=None, coalesce=False):
         lib = L.load()
         w = W.validate(weights if weights is not None else W.default_weights(final_kernel=final_kernel), final_kernel)
         self._keep = w
@@ -35,6 +35,8 @@ class PolicyEvaluator(object):
         self._lib = lib
         if chunk is not None:
             self.set_option("chunk", chunk)
+        if coalesce:
+            self.set_option("coalesce", 1)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -56,8 +58,9 @@ class PolicyEvaluator(object):
     def stats(self):
         arr = (ctypes.c_uint64 * 8)()
         L.check(self._lib.wann_get_stats(self._ctx, ctypes.byref(arr)))
-        keys = ["positions", "kernel_launches", "calls", "h2d_bytes", "d2h_bytes"]
-        return dict(zip(keys, list(arr)[:5]))
+        keys = ["positions", "kernel_launches", "calls", "h2d_bytes", "d2h_bytes", "merged_launches",
+                "merged_calls"]
+        return dict(zip(keys, list(arr)[:7]))
 
     @staticmethod
     def _np_in(squares, black):

@@ -70,8 +70,11 @@ class Session(object):
 
 
 def _make(weights, device, mode, final_kernel):
+    # coalesce=True: the reference calls evaluate concurrently from its ThreadPool(10) + main
+    # thread, each with a single node (expansion_MCTS_functions.pyx:105-119); concurrent small
+    # calls are merged into one launch inside the C++ runtime.
     return PolicyEvaluator(weights if weights is not None else W.default_weights(final_kernel=final_kernel), device=device,
-                           mode=mode, final_kernel=final_kernel)
+                           mode=mode, final_kernel=final_kernel, coalesce=True)
 
 
 def instantiate_session(weights=None, device=0, mode="bf16"):
