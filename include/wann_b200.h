@@ -119,6 +119,18 @@ int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to
                    int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal, int mem,
                    void* stream);
 
+/* wann_eval_topk + child construction in one call (no host round trip between them): for every
+ * ranked legal move k < n_legal the child board after the move, child_squares int8 [n][48][64]
+ * (absolute frame, same encoding as `squares`; the child is to be moved by the OTHER colour) and
+ * child_flags uint8 [n][48]: bit0 = the move reaches the far rank (index > 131: game over, won
+ * by the mover), bit1 = capture.  Pad slots are zero.  Replaces get_child /
+ * init_unique_child_node_and_board / get_child_attributes (tree_builder.pyx:530-537,623-658),
+ * move_piece_update_piece_arrays (board_utils.pyx:90-131) and check_for_winning_move
+ * (tree_builder.pyx:902-905). */
+int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
+                     int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal,
+                     int8_t* child_squares, uint8_t* child_flags, int mem, void* stream);
+
 /* Test/inspection hook: activations after hidden layer `layer` (1..5) as float
  * [n][8][8][C] (C = 192, or 1 for layer 5), host or device per `mem`.  In BF16 mode the
  * values are the bf16-rounded activations the next layer consumes (layer 5: fp32). */

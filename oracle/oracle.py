@@ -451,3 +451,45 @@ def forward_16bit_emulated(planes, weights, fmt="bf16", return_all=False):
     if return_all:
         return logits, probs, acts
     return logits, probs
+
+
+# ----------------------------------------------------------------------------
+# Child construction: get_child / get_child_attributes
+# (monte_carlo_tree_search/tree_builder.pyx:530-537, 623-658),
+# move_piece_update_piece_arrays (Breakthrough_Player/board_utils.pyx:90-131),
+# check_for_winning_move (tree_builder.pyx:902-905)
+# ----------------------------------------------------------------------------
+FLAG_WIN, FLAG_CAPTURE = 1, 2
+
+
+def expand_children(squares, black_to_move, idx, n_legal):
+    """For each position and each listed move index (policy alphabet, side-to-move frame) build
+    the child board: the piece moves from->to, the origin becomes empty (board_utils.pyx:119-120);
+    a diagonal move onto an opponent piece is a capture (:124-130); a move index > 131 reaches
+    the far rank = game over, won by the mover (tree_builder.pyx:902-905).
+    idx uint8 [N,48] (255 = pad), n_legal [N] -> child_squares int8 [N,48,64] (absolute frame,
+    zeros for pads), flags uint8 [N,48] (bit0 win, bit1 capture).  The child is to be moved by
+    the other colour (get_opponent_color, tree_builder.pyx:646)."""
+    squares = np.asarray(squares, np.int8).reshape(-1, 64)
+    n = squares.shape[0]
+    out = np.zeros((n, MAX_LEGAL, 64), np.int8)
+    flags = np.zeros((n, MAX_LEGAL), np.uint8)
+    for i in range(n):
+        blk = int(black_to_move[i])
+        for k in range(int(n_legal[i])):
+            j = int(idx[i, k])
+            r, rem = divmod(j, 22)
+            c = (rem + 1) // 3
+            d = rem - 3 * c
+            frm, to = r * 8 + c, (r + 1) * 8 + c + d
+            if blk:
+                frm, to = 63 - frm, 63 - to
+            child = squares[i].copy()
+            f = FLAG_WIN if j > 131 else 0
+            if child[to] != 0:
+                f |= FLAG_CAPTURE
+            child[to] = child[frm]
+            child[frm] = 0
+            out[i, k] = child
+            flags[i, k] = f
+    return out, flags

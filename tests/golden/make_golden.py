@@ -11,6 +11,10 @@ Contents (all produced by reference code, not by the oracle):
   legal[N,155] uint8                      board_utils.enumerate_legal_moves ->
                                           tools.utils.index_lookup_by_move
   legal_pa[N,155] uint8                   same via enumerate_legal_moves_using_piece_arrays
+  child_squares[64,48,64] int8,           for the first 64 cases, every legal move in ascending
+  child_flags[64,48] uint8                index order: board_utils.move_piece_update_piece_arrays
+                                          (bit1 = remove_opponent_piece) and the win rule
+                                          index > 131 of tree_builder.check_for_winning_move (bit0)
   white_moves[155], black_moves[155]      tools.utils.move_lookup_by_index
   gen_white[155], gen_black[155]          tools.utils.generate_move_lookup
 """
@@ -94,12 +98,21 @@ def main():
         pieces = [c + str(r) for r in range(1, 9) for c in FILES if board[r][c] == me]
         for m in B.enumerate_legal_moves_using_piece_arrays(color, board, pieces):
             legal_pa[k, U.index_lookup_by_move(m)] = 1
+    child_squares = np.zeros((64, 48, 64), np.int8)
+    child_flags = np.zeros((64, 48), np.uint8)
+    for k, (board, color) in enumerate(cases[:64]):
+        for slot, j in enumerate(np.nonzero(legal[k])[0]):
+            mv = U.move_lookup_by_index(int(j), color)
+            nb, add, rem, cap = B.move_piece_update_piece_arrays(board, mv, color)
+            child_squares[k, slot] = to_squares(nb)
+            child_flags[k, slot] = (1 if (j > 131 and j != 154) else 0) | (2 if cap else 0)
+            assert nb[9] == (0 if color == "White" else 1)      # the other colour moves next
     wm = np.array([U.move_lookup_by_index(i, "White") for i in range(155)])
     bm = np.array([U.move_lookup_by_index(i, "Black") for i in range(155)])
     gw, gb = U.generate_move_lookup()
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_golden.npz")
     np.savez_compressed(out, squares=squares, black=black, planes=planes, legal=legal,
-                        legal_pa=legal_pa, white_moves=wm, black_moves=bm,
+                        legal_pa=legal_pa, child_squares=child_squares, child_flags=child_flags, white_moves=wm, black_moves=bm,
                         gen_white=np.array(gw), gen_black=np.array(gb),
                         n_readme=np.int64(n_readme))
     print("wrote", out, "cases", n, "readme plies", n_readme, "black share", black.mean(),

@@ -371,3 +371,31 @@ def test_coalescer_merges_concurrent_small_calls(weights, suite):
         assert st["merged_launches"] < st["merged_calls"]     # concurrency was actually merged
         big = ev.eval_probs(sq[:400], bl[:400])                # > 256 positions bypasses the combiner
         assert np.array_equal(big, ref_p[:400]) and ev.stats()["merged_calls"] == st["merged_calls"]
+
+
+def test_child_construction_bit_exact(ev_fp32, ev_bf16, golden, suite):
+    """children of every ranked legal move, against reference-made golden children
+    (board_utils.move_piece_update_piece_arrays) and the oracle."""
+    sq, bl = golden["squares"][:64], golden["black"][:64]
+    idx, pri, cnt, kids, flg = ev_fp32.eval_expand(sq, bl)
+    # golden children are stored in ascending move-index order; ours come in ranked order
+    for i in range(64):
+        order = np.argsort(idx[i, :cnt[i]], kind="stable")
+        assert np.array_equal(kids[i, :cnt[i]][order], golden["child_squares"][i, :cnt[i]])
+        assert np.array_equal(flg[i, :cnt[i]][order], golden["child_flags"][i, :cnt[i]])
+        assert not kids[i, cnt[i]:].any() and not flg[i, cnt[i]:].any()
+    sq, bl = suite
+    idx, pri, cnt, kids, flg = ev_bf16.eval_expand(sq, bl)
+    okids, oflg = O.expand_children(sq, bl, idx, cnt)
+    assert np.array_equal(kids, okids) and np.array_equal(flg, oflg)
+    i2, p2, c2 = ev_bf16.eval_topk(sq, bl)
+    assert np.array_equal(idx, i2) and np.array_equal(pri, p2) and np.array_equal(cnt, c2)
+    # children are valid positions for the other colour: material changes only by captures
+    mat = (sq != 0).sum(1)[:, None] - ((flg & 2) != 0)
+    k = np.arange(48)[None, :] < cnt[:, None]
+    assert np.array_equal((kids != 0).sum(2)[k], mat[k])
+    # device-resident path gives the same children (ready to be the next leaf batch)
+    import torch
+    out = ev_bf16.eval_expand(torch.from_numpy(sq).cuda(), torch.from_numpy(bl).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(out[3].cpu().numpy(), kids) and np.array_equal(out[4].cpu().numpy(), flg)

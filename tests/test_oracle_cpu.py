@@ -290,3 +290,17 @@ def test_tf_bundle_reads_the_reference_index(lib_built):
     assert max(v["offset"] + v["size"] for v in e.values()) == 12177752
     with pytest.raises(FileNotFoundError):                     # the shard itself is not shipped
         T.load_policy_weights("/root/reference/policy_net_model/model")
+
+
+def test_child_construction_oracle_vs_reference_golden(golden):
+    """the oracle's child boards / capture / win flags equal the reference's
+    move_piece_update_piece_arrays + check_for_winning_move on every legal move of 64 cases."""
+    sq, bl = golden["squares"][:64], golden["black"][:64]
+    m = golden["legal"][:64].astype(bool)
+    idx = np.full((64, 48), 255, np.uint8)
+    cnt = m.sum(1).astype(np.uint8)
+    for i in range(64):
+        idx[i, :cnt[i]] = np.nonzero(m[i])[0]
+    kids, flg = O.expand_children(sq, bl, idx, cnt)
+    assert np.array_equal(kids, golden["child_squares"]) and np.array_equal(flg, golden["child_flags"])
+    assert (flg & O.FLAG_CAPTURE).any() and (flg & O.FLAG_WIN).any()

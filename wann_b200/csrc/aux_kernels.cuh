@@ -236,6 +236,55 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
   }
 }
 
+// Child construction for every ranked legal move of every position:
+// get_child_attributes (tree_builder.pyx:641-658) + move_piece_update_piece_arrays
+// (board_utils.pyx:90-131) + check_for_winning_move (tree_builder.pyx:902-905).
+// One warp per board; 4 lanes build one 64-byte child (16 B each), 8 children per pass, so every
+// store is a coalesced 16-byte vector.  flags: bit0 = move reaches the far rank (index > 131),
+// bit1 = capture.  Pad slots (>= n_legal) get zero boards / zero flags.
+__global__ void __launch_bounds__(256) expand_children_kernel(const int8_t* __restrict__ squares,
+                                                              const uint8_t* __restrict__ black,
+                                                              const uint8_t* __restrict__ idx,
+                                                              const uint8_t* __restrict__ n_legal,
+                                                              long long n, int8_t* __restrict__ children,
+                                                              uint8_t* __restrict__ flags) {
+  __shared__ __align__(16) int8_t brd[8][64];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  for (long long board = blockIdx.x * 8ll + w; board < n; board += gridDim.x * 8ll) {
+    reinterpret_cast<uint16_t*>(brd[w])[lane] = reinterpret_cast<const uint16_t*>(squares + board * 64)[lane];
+    const int blk = black[board];
+    const int cnt = n_legal[board];
+    __syncwarp();
+    const uint4 base = reinterpret_cast<const uint4*>(brd[w])[q];
+#pragma unroll 1
+    for (int k0 = 0; k0 < kMaxLegal; k0 += 8) {
+      const int k = k0 + g;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t f = 0;
+      if (k < cnt) {
+        const int j = idx[board * kMaxLegal + k];
+        int r, c, d;
+        decode_move(j, r, c, d);
+        int frm = r * 8 + c, to = (r + 1) * 8 + c + d;
+        if (blk) { frm = 63 - frm; to = 63 - to; }
+        const uint32_t mover = static_cast<uint32_t>(brd[w][frm]) & 0xFFu;
+        f = (j > 131 ? 1u : 0u) | (brd[w][to] != 0 ? 2u : 0u);
+        uint32_t wd[4] = {base.x, base.y, base.z, base.w};
+        if ((frm >> 4) == q) wd[(frm >> 2) & 3] &= ~(0xFFu << ((frm & 3) * 8));
+        if ((to >> 4) == q) {
+          const int sh = (to & 3) * 8;
+          wd[(to >> 2) & 3] = (wd[(to >> 2) & 3] & ~(0xFFu << sh)) | (mover << sh);
+        }
+        v = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      }
+      reinterpret_cast<uint4*>(children + (board * kMaxLegal + k) * 64)[q] = v;
+      if (q == 0) flags[board * kMaxLegal + k] = static_cast<uint8_t>(f);
+    }
+    __syncwarp();
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // fp32 accuracy mode (CUDA cores).  One CTA per board, 256 threads: warp = output row y,
 // lane -> output channels lane + 32*j.  Input board staged zero-padded in shared memory.

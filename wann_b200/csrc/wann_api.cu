@@ -74,6 +74,8 @@ struct Slot {
   uint8_t* d_nlegal = nullptr;
   int8_t* d_planes_out = nullptr;
   uint8_t* d_mask = nullptr;
+  int8_t* d_children = nullptr;   // [cap][48][64], allocated on first use
+  uint8_t* d_cflags = nullptr;    // [cap][48]
   int* d_err = nullptr;
   int* h_err = nullptr;     // pinned
   float* d_act0 = nullptr;  // fp32 mode ping-pong activations
@@ -224,7 +226,7 @@ void free_slot(Slot& s) {
   cudaFree(s.d_probs); cudaFree(s.d_logits); cudaFree(s.d_idx); cudaFree(s.d_prior);
   cudaFree(s.d_nlegal); cudaFree(s.d_planes_out); cudaFree(s.d_mask); cudaFree(s.d_err);
   if (s.h_err) cudaFreeHost(s.h_err);
-  cudaFree(s.d_act0); cudaFree(s.d_act1);
+  cudaFree(s.d_act0); cudaFree(s.d_act1); cudaFree(s.d_children); cudaFree(s.d_cflags);
   s = Slot();
 }
 
@@ -284,6 +286,8 @@ struct ChunkIO {   // device pointers for one chunk
   float* dbg = nullptr;
   int dbg_layer = 0;
   long long* prof = nullptr;
+  int8_t* children = nullptr;
+  uint8_t* cflags = nullptr;
 };
 
 // Enqueue encode -> conv stack -> tail for `n` positions on `stream`, using `ws` workspaces.
@@ -346,6 +350,12 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
         std::min<long long>((groups + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
     tail_kernel<<<blocks, kTailWarps * 32, kTailSmemBytes, stream>>>(t);
     ++launches;
+    if (io.children != nullptr) {
+      const int eb = static_cast<int>(std::min<long long>((n + 7) / 8, 16ll * ctx->sm_count));
+      expand_children_kernel<<<eb, 256, 0, stream>>>(io.squares, io.black, io.idx, io.nlegal, n, io.children,
+                                                     io.cflags);
+      ++launches;
+    }
   }
   CU(cudaGetLastError());
   ctx->stats[0] += static_cast<uint64_t>(n);
@@ -365,6 +375,8 @@ int check_device_err(Slot& s) {
 }
 
 struct EvalArgs {
+  int8_t* children = nullptr;     // [n][48][64] optional (needs idx)
+  uint8_t* cflags = nullptr;      // [n][48]
   const int8_t* squares = nullptr;
   const uint8_t* black = nullptr;
   const void* planes = nullptr;
@@ -398,6 +410,8 @@ int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void*
     io.nlegal = a.nlegal ? a.nlegal + off : nullptr;
     io.dbg = a.dbg ? a.dbg + off * 64 * dbg_c : nullptr;
     io.dbg_layer = a.dbg_layer;
+    io.children = a.children ? a.children + off * kMaxLegal * 64 : nullptr;
+    io.cflags = a.cflags ? a.cflags + off * kMaxLegal : nullptr;
     int rc = enqueue_eval(ctx, ws, stream, io, m);
     if (rc != WANN_OK) return rc;
   }
@@ -444,6 +458,13 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
     io.probs = a.probs ? s.d_probs : nullptr;
     io.logits = a.logits ? s.d_logits : nullptr;
     if (a.idx) { io.idx = s.d_idx; io.prior = s.d_prior; io.nlegal = s.d_nlegal; }
+    if (a.children) {
+      if (s.d_children == nullptr) {
+        CU(cudaMalloc(&s.d_children, s.cap * kMaxLegal * 64));
+        CU(cudaMalloc(&s.d_cflags, s.cap * kMaxLegal));
+      }
+      io.children = s.d_children; io.cflags = s.d_cflags;
+    }
     float* d_dbg = nullptr;
     if (a.dbg) {
       CU(cudaMalloc(&d_dbg, m * 64 * dbg_c * 4));
@@ -462,6 +483,10 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
         D2H(a.idx + off * kMaxLegal, s.d_idx, m * kMaxLegal);
         D2H(a.prior + off * kMaxLegal, s.d_prior, m * kMaxLegal * 4);
         D2H(a.nlegal + off, s.d_nlegal, m);
+      }
+      if (a.children) {
+        D2H(a.children + off * kMaxLegal * 64, s.d_children, m * kMaxLegal * 64);
+        D2H(a.cflags + off * kMaxLegal, s.d_cflags, m * kMaxLegal);
       }
       if (a.dbg) D2H(a.dbg + off * 64 * dbg_c, d_dbg, m * 64 * dbg_c * 4);
       if (e == cudaSuccess)
@@ -579,7 +604,7 @@ int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* strea
   CU(cudaSetDevice(ctx->device));
   if (!bypass) ctx->stats[2] += 1;
   if (!bypass && ctx->coalesce && mem == WANN_MEM_HOST && a.squares != nullptr && a.dbg == nullptr &&
-      n <= kCombineMaxCall)
+      a.children == nullptr && n <= kCombineMaxCall)
     return run_combined(ctx, a, n);
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);
@@ -724,6 +749,20 @@ int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, i
   if (n < 0) return fail(WANN_E_INVALID, "negative n");
   EvalArgs a;
   a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
+  return run_eval(ctx, a, n, mem, stream);
+}
+
+int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, uint8_t* idx,
+                     float* prior, uint8_t* n_legal, int8_t* child_squares, uint8_t* child_flags, int mem,
+                     void* stream) {
+  if ((idx == nullptr || prior == nullptr || n_legal == nullptr || child_squares == nullptr ||
+       child_flags == nullptr) && n > 0)
+    return fail(WANN_E_INVALID, "null output buffer");
+  if (squares == nullptr && n > 0) return fail(WANN_E_INVALID, "squares is null");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
+  EvalArgs a;
+  a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
+  a.children = child_squares; a.cflags = child_flags;
   return run_eval(ctx, a, n, mem, stream);
 }
 

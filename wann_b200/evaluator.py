@@ -149,6 +149,35 @@ class PolicyEvaluator(object):
                                          pri.ctypes.data, cnt.ctypes.data, L.MEM_HOST, None))
         return idx, pri, cnt
 
+    def eval_expand(self, squares, black):
+        """eval_topk + device-side child construction.  -> idx, prior, n_legal, child_squares int8
+        [n,48,64], child_flags uint8 [n,48] (bit0 win, bit1 capture).  numpy in -> numpy out,
+        torch CUDA tensors in -> torch CUDA tensors out (children stay on the device, ready to be
+        the next leaf batch)."""
+        if _is_torch(squares):
+            import torch
+            n, dev = squares.shape[0], squares.device
+            idx = torch.empty((n, L.MAX_LEGAL), dtype=torch.uint8, device=dev)
+            pri = torch.empty((n, L.MAX_LEGAL), dtype=torch.float32, device=dev)
+            cnt = torch.empty((n,), dtype=torch.uint8, device=dev)
+            kids = torch.empty((n, L.MAX_LEGAL, 64), dtype=torch.int8, device=dev)
+            flg = torch.empty((n, L.MAX_LEGAL), dtype=torch.uint8, device=dev)
+            L.check(self._lib.wann_eval_expand(self._ctx, squares.data_ptr(), black.data_ptr(), n, idx.data_ptr(),
+                                               pri.data_ptr(), cnt.data_ptr(), kids.data_ptr(), flg.data_ptr(),
+                                               L.MEM_DEVICE, self._torch_stream(squares)))
+            return idx, pri, cnt, kids, flg
+        sq, bl = self._np_in(squares, black)
+        n = sq.shape[0]
+        idx = np.empty((n, L.MAX_LEGAL), np.uint8)
+        pri = np.empty((n, L.MAX_LEGAL), np.float32)
+        cnt = np.empty(n, np.uint8)
+        kids = np.empty((n, L.MAX_LEGAL, 64), np.int8)
+        flg = np.empty((n, L.MAX_LEGAL), np.uint8)
+        L.check(self._lib.wann_eval_expand(self._ctx, sq.ctypes.data, bl.ctypes.data, n, idx.ctypes.data,
+                                           pri.ctypes.data, cnt.ctypes.data, kids.ctypes.data, flg.ctypes.data,
+                                           L.MEM_HOST, None))
+        return idx, pri, cnt, kids, flg
+
     def debug_activations(self, squares, black, layer):
         sq, bl = self._np_in(squares, black)
         n = sq.shape[0]
