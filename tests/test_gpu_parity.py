@@ -399,3 +399,22 @@ def test_child_construction_bit_exact(ev_fp32, ev_bf16, golden, suite):
     out = ev_bf16.eval_expand(torch.from_numpy(sq).cuda(), torch.from_numpy(bl).cuda())
     torch.cuda.synchronize()
     assert np.array_equal(out[3].cpu().numpy(), kids) and np.array_equal(out[4].cpu().numpy(), flg)
+
+
+def test_malformed_boards_do_not_corrupt_memory(ev_bf16, suite):
+    """Boards that cannot occur in Breakthrough (random squares, > 16 pieces a side, > 48 'legal'
+    moves) are outside the reference's domain; the kernels must stay memory-safe: the mask is still
+    the rule-based mask, the ranking is truncated to 48 entries, neighbours are unaffected."""
+    rng = np.random.RandomState(5)
+    bad = rng.randint(0, 3, size=(64, 64)).astype(np.int8)
+    bl = rng.randint(0, 2, size=64).astype(np.uint8)
+    assert (ev_bf16.legal_mask(bad, bl) == O.legal_mask(bad, bl)).all()
+    assert (ev_bf16.encode(bad, bl) == O.encode_planes(bad, bl)).all()
+    sq, b2 = suite
+    mix_sq = np.concatenate([sq[:64], bad, sq[64:128]])
+    mix_bl = np.concatenate([b2[:64], bl, b2[64:128]])
+    idx, pri, cnt, kids, flg = ev_bf16.eval_expand(mix_sq, mix_bl)
+    assert cnt.max() <= 48 and np.isfinite(pri).all()
+    ref = ev_bf16.eval_expand(np.concatenate([sq[:64], sq[64:128]]), np.concatenate([b2[:64], b2[64:128]]))
+    for got, want in zip((idx, pri, cnt, kids, flg), ref):
+        assert np.array_equal(np.concatenate([got[:64], got[128:]]), want)

@@ -203,11 +203,14 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
           const uint32_t mask = __ballot_sync(0xffffffffu, legal);
           if (legal) {
             const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-            cp[pos] = pr[k];
-            cj[pos] = static_cast<uint8_t>(j);
+            if (pos < kMaxLegal) {   // a real position has <= 48 legal moves (16 pieces x 3);
+              cp[pos] = pr[k];       // malformed boards are truncated to the 48 lowest indices
+              cj[pos] = static_cast<uint8_t>(j);
+            }
           }
           cnt += __popc(mask);
         }
+        cnt = min(cnt, kMaxLegal);
         __syncwarp();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {

@@ -100,7 +100,7 @@ struct CombineReq {
   float* probs; float* logits; uint8_t* idx; float* prior; uint8_t* nlegal;
   int rc = 0; std::string err; bool done = false;
 };
-constexpr int kMaxWimgCopies = 32;
+constexpr int kMaxWimgCopies = 8;
 
 }  // namespace
 
@@ -111,7 +111,7 @@ struct wann_ctx {
   int final_kernel = 3;
   long long chunk = 16384;
   int variant = 0;
-  int wimg_copies = 8;         // replicas of the weight image in use (spreads L2 hot lines)
+  int wimg_copies = 1;         // replicas of the weight image in use (experiment knob; measured: no effect)
   // weights on device
   float* d_conv_w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* d_conv_b[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
