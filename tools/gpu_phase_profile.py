@@ -13,8 +13,8 @@ sq = np.tile(sq, (reps, 1))[:n]; bl = np.tile(bl, reps)[:n]
 ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), mode="bf16")
 for variant in [int(v) for v in os.environ.get("VARIANTS", "0").split(",")]:
   ev.set_option("variant", variant & 0xFFFF)
-  ev.set_option("wimg_copies", max(1, variant >> 16))
-  print("==== variant", variant & 0xFFFF, "wimg_copies", max(1, variant >> 16))
+  ev.set_option("skew", variant >> 16)
+  print("==== variant", variant & 0xFFFF, "skew", variant >> 16)
   for _ in range(2):
     st = ev.debug_profile(sq, bl)
   t0 = st[st > 0].min()

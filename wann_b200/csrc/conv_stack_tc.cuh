@@ -100,6 +100,7 @@ struct TcParams {
   float* dbg;                // optional activation dump [n][64][192] (layer 1..4)
   int dbg_layer;
   int variant;               // debug: bit2 = swap the B halves between the CTAs of a pair
+  int skew;                  // weight stages by which half 1 trails the stream (0 = free-running)
   int* err;                  // [8] watchdog record
   long long* prof;           // optional [8][kProfSteps] clock64 stamps of pair 0 (debug):
                              // half h: [4h+0] MMA start, [4h+1] MMA issue end,
@@ -136,19 +137,22 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// write the conv1 input cell (planes P,O,E,1 in the operand format + 4 zero channels) of one square
+// The conv1 input cell of one square = planes P,O,E,1 in the operand format + 4 zero channels
+// (tools/utils.pyx:563-600: Black sees the board rotated by 180 degrees; :842-865: P/O/E/bias
+// planes).  Split into a global-memory load (issued early, during the conv4 epilogue, so that its
+// latency is off the conv5 -> conv1 critical chain) and the shared-memory store.
 template <bool kF16>
-__device__ __forceinline__ void write_input_cell(const TcParams& p, long long board, int y, int x,
-                                                 uint32_t cell0) {
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+__device__ __forceinline__ uint2 load_input_cell(const TcParams& p, long long board, int y, int x) {
+  uint2 v = make_uint2(0u, 0u);
   if (board < p.n) {
     const int sq = y * 8 + x;
     if (p.squares != nullptr) {
-      // tools/utils.pyx:563-600 (Black: 180-degree rotation) + :842-865 (P/O/E/bias planes)
+      const int8_t* b64 = p.squares + board * 64;
+      const int s_w = b64[sq], s_b = b64[63 - sq];       // both candidates: no dependent load
       const int blk = p.black[board];
-      int s = p.squares[board * 64 + (blk ? 63 - sq : sq)];
+      int s = blk ? s_b : s_w;
       if (blk && s) s = 3 - s;
-      const uint32_t one = kF16 ? 0x3C00u : 0x3F80u;  // 1.0 in fp16 / bf16
+      const uint32_t one = kF16 ? 0x3C00u : 0x3F80u;      // 1.0 in fp16 / bf16
       v.x = (s == 1 ? one : 0u) | ((s == 2 ? one : 0u) << 16);
       v.y = (s == 0 ? one : 0u) | (one << 16);
     } else if (p.planes_f32) {
@@ -161,7 +165,10 @@ __device__ __forceinline__ void write_input_cell(const TcParams& p, long long bo
       v.y = pack2<kF16>(float(c.z), float(c.w));
     }
   }
-  ptx::st_shared_v4(cell0, v);
+  return v;
+}
+__device__ __forceinline__ void store_input_cell(uint32_t cell0, uint2 v) {
+  ptx::st_shared_v4(cell0, make_uint4(v.x, v.y, 0u, 0u));
 }
 
 template <bool kF16>
@@ -285,10 +292,21 @@ conv_stack_tc_kernel(const TcParams p) {
       constexpr uint32_t kStage16 = kStageBytes >> 4;           // 768
       uint32_t s = 0, ph = 0, lstep = 0;
       bool ok = true;
+      // half 1 may be held `lookahead` weight stages behind the stream so that it still has MMAs
+      // to run while half 0 sits in its epilogue (and vice versa at the start of the next layer)
+      const uint32_t lookahead = (h == 1) ? min(static_cast<uint32_t>(p.skew), nst - 2u) : 0u;
+      long long kb_left = 0;
+      for (long long st = pair; st < total_st; st += npairs) kb_left += kKbPerSupertile;
       long long* prof = (p.prof != nullptr && pair == 0) ? p.prof + 4 * h * kProfSteps : nullptr;
       // one K-block: wait for the stage, 4 (or fewer) K=16 steps, release my claim on the stage
 #define WANN_KBLOCK(NKS, A_OFF16_OF_KS, B_LO, B_KS16, IDESC, ACC_FIRST)                          \
       {                                                                                           \
+        if (lookahead != 0 && kb_left > lookahead) {   /* half 1 trails the stream by d stages */ \
+          const uint32_t s2 = (s + lookahead >= nst) ? s + lookahead - nst : s + lookahead;       \
+          const uint32_t ph2 = (s + lookahead >= nst) ? ph ^ 1u : ph;                             \
+          if (!wait_bar(bar_full(s2), ph2, false, p.err, 700 + s2)) { ok = false; break; }        \
+        }                                                                                         \
+        --kb_left;                                                                                \
         if (!wait_bar(bar_full(s), ph, false, p.err, 300 + s) ||                                 \
             !wait_bar(bar_peer_full(s), ph, true, p.err, 400 + s)) { ok = false; break; }       \
         ptx::tc_fence_after();                                                                    \
@@ -382,12 +400,14 @@ conv_stack_tc_kernel(const TcParams p) {
     long long st = pair;
     if (st < total_st) {
       for (int h = 0; h < 2; ++h) {
-        if (chalf == 0) write_input_cell<kF16>(p, board_of(st, h), y, x, a_base + h * kATileBytes + cell_in_tile);
+        if (chalf == 0)
+          store_input_cell(a_base + h * kATileBytes + cell_in_tile, load_input_cell<kF16>(p, board_of(st, h), y, x));
         signal_a_ready(h);
       }
     }
     uint32_t lstep = 0;
     bool ok = true;
+    uint2 next_in[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
     for (; st < total_st && ok; st += npairs) {
       for (int layer = 0; layer < 5 && ok; ++layer, ++lstep) {
         for (int h = 0; h < 2; ++h) {
@@ -398,6 +418,8 @@ conv_stack_tc_kernel(const TcParams p) {
           ptx::tc_fence_after();
           if (profiler && lstep < kProfSteps) p.prof[(4 * h + 2) * kProfSteps + lstep] = clock64();
           if (layer < 4) {
+            if (layer == 3 && chalf == 0 && st + npairs < total_st)   // prefetch next supertile's input
+              next_in[h] = load_input_cell<kF16>(p, board_of(st + npairs, h), y, x);
             const float* bs = bias_s + layer * kC + chalf * 96;
             float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < p.n)
                              ? p.dbg + (board * 64 + y * 8 + x) * kC + chalf * 96 : nullptr;
@@ -449,8 +471,7 @@ conv_stack_tc_kernel(const TcParams p) {
             }
             const float hval = fmaxf(acc + bias_s[4 * kC], 0.f);
             if (board < p.n) p.h5[board * 64 + y * 8 + x] = hval;
-            if (st + npairs < total_st)
-              write_input_cell<kF16>(p, board_of(st + npairs, h), y, x, cell0);
+            if (st + npairs < total_st) store_input_cell(cell0, next_in[h]);
           }
           signal_a_ready(h);
           if (profiler && lstep < kProfSteps) p.prof[(4 * h + 3) * kProfSteps + lstep] = clock64();

@@ -111,6 +111,7 @@ struct wann_ctx {
   int final_kernel = 3;
   long long chunk = 16384;
   int variant = 0;
+  int skew = 4;                // conv_stack_tc: stages by which half 1 trails the weight stream (0..6)
   int wimg_copies = 1;         // replicas of the weight image in use (experiment knob; measured: no effect)
   // weights on device
   float* d_conv_w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -297,7 +298,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   if (ctx->mode != WANN_MODE_FP32) {
     TcParams p;
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
-    p.n = n; p.wimg = ctx->d_wimg; p.wimg_copies = ctx->wimg_copies; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
+    p.n = n; p.wimg = ctx->d_wimg; p.wimg_copies = ctx->wimg_copies; p.skew = ctx->skew; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
     const long long total_st = (n + kBoardsPerPair - 1) / kBoardsPerPair;
     const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
@@ -940,6 +941,11 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "wimg_copies") == 0) {
     if (value < 1 || value > kMaxWimgCopies) return fail(WANN_E_INVALID, "wimg_copies out of range");
     ctx->wimg_copies = static_cast<int>(value);
+    return WANN_OK;
+  }
+  if (strcmp(key, "skew") == 0) {
+    if (value < 0 || value > 6) return fail(WANN_E_INVALID, "skew out of range");
+    ctx->skew = static_cast<int>(value);
     return WANN_OK;
   }
   if (strcmp(key, "coalesce") == 0) { ctx->coalesce = value != 0; return WANN_OK; }
