@@ -418,3 +418,29 @@ def test_malformed_boards_do_not_corrupt_memory(ev_bf16, suite):
     ref = ev_bf16.eval_expand(np.concatenate([sq[:64], sq[64:128]]), np.concatenate([b2[:64], b2[64:128]]))
     for got, want in zip((idx, pri, cnt, kids, flg), ref):
         assert np.array_equal(np.concatenate([got[:64], got[128:]]), want)
+
+
+def test_treefarm_steady_state_plays_legal_games(ev_bf16):
+    """BASELINE config 5 in miniature: device-resident games, one leaf per game per step; every move
+    taken is a legal move of the position it was taken in (oracle), finished games restart."""
+    import torch
+    from wann_b200.treefarm import TreeFarm
+    farm = TreeFarm(ev_bf16, 256, seed=3)
+    finished = 0
+    for step in range(70):
+        sq_before = farm.sq.cpu().numpy()
+        bl_before = farm.black.cpu().numpy()
+        idx, pri, cnt, k = farm.step()
+        idx, cnt, k = idx.cpu().numpy(), cnt.cpu().numpy(), k.cpu().numpy()
+        mask = O.legal_mask(sq_before, bl_before)
+        chosen = idx[np.arange(256), k]
+        assert (k < cnt).all() and mask[np.arange(256), chosen].all()
+        kids, flg = O.expand_children(sq_before, bl_before, chosen[:, None].astype(np.uint8), np.ones(256, np.uint8))
+        reset = farm.last_reset.cpu().numpy()
+        assert np.array_equal(reset, (flg[:, 0] & 1).astype(bool))
+        after = farm.sq.cpu().numpy()
+        assert np.array_equal(after[~reset], kids[~reset, 0])
+        assert (after[reset] == O.initial_squares()).all()
+        assert not O.game_over(after).any()
+        finished += int(reset.sum())
+    assert finished > 0                          # random games of Breakthrough end within ~60 plies
