@@ -88,6 +88,7 @@ struct Lane {
   bool in_use = false;
   cudaEvent_t last = nullptr;   // completion of the last async (device/stream) call
   bool last_valid = false;
+  cudaStream_t last_stream = nullptr;   // stream `last` was recorded on
 };
 
 constexpr int kLanes = 4;
@@ -254,16 +255,19 @@ int acquire_lane(wann_ctx* ctx, Lane** out) {
           }
           cudaEventCreateWithFlags(&l.last, cudaEventDisableTiming);
         }
-        if (l.last_valid) {
-          cudaEventSynchronize(l.last);
-          l.last_valid = false;
-        }
         *out = &l;
         return WANN_OK;
       }
     }
     ctx->cv.wait(lk);
   }
+}
+
+// A lane's workspaces may still be in use by an earlier asynchronous (device-pointer) call.
+// Work enqueued on the SAME stream is ordered behind it already; any other stream is made to
+// wait on the recorded event.  No host synchronisation: back-to-back small calls pipeline.
+void lane_wait(Lane* lane, cudaStream_t stream) {
+  if (lane->last_valid && lane->last_stream != stream) cudaStreamWaitEvent(stream, lane->last, 0);
 }
 
 void release_lane(wann_ctx* ctx, Lane* l) {
@@ -397,6 +401,7 @@ int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void*
   const long long dbg_c = (a.dbg_layer == 5) ? 1 : 192;
   Slot& ws = lane->slot[0];
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ws.stream;
+  lane_wait(lane, stream);
   for (long long off = 0; off < n; off += cap) {
     const long long m = std::min(cap, n - off);
     ChunkIO io;
@@ -419,11 +424,13 @@ int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void*
   if (stream_v == nullptr) {
     CU(cudaMemcpyAsync(ws.h_err, ws.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
+    lane->last_valid = false;
     return check_device_err(ws);
   }
-  // caller's stream: the lane's workspace stays reserved until this event has fired
+  // caller's stream: later users of this lane on OTHER streams wait for this event
   CU(cudaEventRecord(lane->last, stream));
   lane->last_valid = true;
+  lane->last_stream = stream;
   return WANN_OK;
 }
 
@@ -435,6 +442,9 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
   const long long dbg_c = (a.dbg_layer == 5) ? 1 : 192;
   uint64_t h2d = 0, d2h = 0;
   long long ci = 0;
+  lane_wait(lane, lane->slot[0].stream);
+  lane_wait(lane, lane->slot[1].stream);
+  lane->last_valid = false;          // this call ends with host synchronisation of both slots
   for (long long off = 0; off < n; off += cap, ++ci) {
     const long long m = std::min(cap, n - off);
     Slot& s = lane->slot[ci & 1];
@@ -790,6 +800,7 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
   if (rc != WANN_OK) return rc;
   Slot& s = lane->slot[0];
   cudaStream_t stream = (mem == WANN_MEM_DEVICE && stream_v) ? static_cast<cudaStream_t>(stream_v) : s.stream;
+  lane_wait(lane, stream);
   auto body = [&]() -> int {
     for (long long off = 0; off < n; off += s.cap) {
       const long long m = std::min<long long>(s.cap, n - off);
@@ -819,7 +830,7 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
     }
     if (mem == WANN_MEM_DEVICE) {
       if (stream_v == nullptr) CU(cudaStreamSynchronize(stream));
-      else { cudaEventRecord(lane->last, stream); lane->last_valid = true; }
+      else { cudaEventRecord(lane->last, stream); lane->last_valid = true; lane->last_stream = stream; }
     }
     return WANN_OK;
   };
@@ -847,6 +858,7 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
   int rc = acquire_lane(ctx, &lane);
   if (rc != WANN_OK) return rc;
   Slot& s = lane->slot[0];
+  lane_wait(lane, s.stream);
   auto body = [&]() -> int {
     if (n > s.cap) return fail(WANN_E_INVALID, "n exceeds the chunk size");
     long long* d_prof = nullptr;

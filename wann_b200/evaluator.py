@@ -73,7 +73,11 @@ class PolicyEvaluator(object):
     @staticmethod
     def _torch_stream(t):
         import torch
-        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        # torch's default stream has handle 0, which the C ABI reads as "no stream: use the
+        # context's own stream and synchronise"; name the legacy default stream explicitly
+        # (cudaStreamLegacy == 0x1) so that the call stays asynchronous.
+        h = torch.cuda.current_stream(t.device).cuda_stream
+        return ctypes.c_void_p(h if h else 1)
 
     # ------------------------------------------------------------------ byte kernels
     def encode(self, squares, black):
