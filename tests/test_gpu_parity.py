@@ -444,3 +444,41 @@ def test_treefarm_steady_state_plays_legal_games(ev_bf16):
         assert not O.game_over(after).any()
         finished += int(reset.sum())
     assert finished > 0                          # random games of Breakthrough end within ~60 plies
+
+
+def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
+    """compute-sanitizer is not available on the GPU pool: carve every device output out of one
+    sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote
+    exactly their own bytes, for ragged sizes that do not fill a tile / warp group / chunk."""
+    import ctypes
+    import torch
+    from wann_b200 import _lib as L
+    lib = L.load()
+    sq, bl = suite
+    for n in (1, 5, 13, 127, 1000):
+        sizes = [("idx", n * 48), ("prior", n * 48 * 4), ("cnt", n), ("kids", n * 48 * 64), ("flg", n * 48),
+                 ("probs", n * 155 * 4), ("logits", n * 155 * 4)]
+        guard = 4096
+        total = guard + sum((s + guard + 255) // 256 * 256 for _, s in sizes)
+        arena = torch.full((total,), 0xA5, dtype=torch.uint8, device="cuda")
+        offs, pos = {}, guard
+        for name, s in sizes:
+            offs[name] = (pos, s)
+            pos += (s + guard + 255) // 256 * 256
+        base = arena.data_ptr()
+        dsq = torch.from_numpy(sq[:n]).cuda()
+        dbl = torch.from_numpy(bl[:n]).cuda()
+        ptr = lambda k: ctypes.c_void_p(base + offs[k][0])   # noqa: E731
+        L.check(lib.wann_eval_expand(ev_bf16._ctx, dsq.data_ptr(), dbl.data_ptr(), n, ptr("idx"), ptr("prior"),
+                                     ptr("cnt"), ptr("kids"), ptr("flg"), L.MEM_DEVICE, ctypes.c_void_p(1)))
+        L.check(lib.wann_eval_probs(ev_bf16._ctx, dsq.data_ptr(), dbl.data_ptr(), n, ptr("probs"), ptr("logits"),
+                                    L.MEM_DEVICE, ctypes.c_void_p(1)))
+        torch.cuda.synchronize()
+        host = arena.cpu().numpy()
+        inside = np.zeros(total, bool)
+        for name, (o, s) in offs.items():
+            inside[o:o + s] = True
+        assert (host[~inside] == 0xA5).all(), "a kernel wrote outside its output buffer (n=%d)" % n
+        # and the in-bounds results are the usual ones
+        o, s = offs["cnt"]
+        assert np.array_equal(host[o:o + s], ev_bf16.eval_topk(sq[:n], bl[:n])[2])
