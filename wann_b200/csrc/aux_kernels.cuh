@@ -104,6 +104,10 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
     if (i < 154) decode_move(i, r, c, d);
     mv_s[i] = static_cast<uint16_t>((r * 8 + c) | (((r + 1) * 8 + c + d) << 6) | ((d == 0) << 12));
   }
+  // PDL: the FC weights above are constants; h5 (and the boards) are only valid once the
+  // conv-stack kernel before us has completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* h = warp_f + w * kTailWarpFloats;            // [4][64]

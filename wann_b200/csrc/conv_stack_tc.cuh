@@ -228,6 +228,11 @@ conv_stack_tc_kernel(const TcParams p) {
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kOffTmemSlot);
+  // Programmatic dependent launch: everything above (and the weight prefetch below) only touches
+  // constants, so it may overlap the previous kernel of the stream; let the next kernel start
+  // its own prologue too.  The epilogue warps -- the only ones that read the positions and write
+  // h5 -- wait for the previous kernels before their first access.
+  ptx::pdl_launch_dependents();
 
   // ---- roles -------------------------------------------------------------------------------
   if (warp == 0) {
@@ -397,6 +402,7 @@ conv_stack_tc_kernel(const TcParams p) {
       return st * kBoardsPerPair + static_cast<int>(rank) * kBoardsPerCta + h * 2 + b;
     };
 
+    ptx::pdl_wait();
     long long st = pair;
     if (st < total_st) {
       for (int h = 0; h < 2; ++h) {

@@ -112,6 +112,7 @@ struct wann_ctx {
   int final_kernel = 3;
   long long chunk = 16384;
   int variant = 0;
+  bool pdl = false;            // programmatic dependent launch conv-stack <-> tail (measured: slower, off)
   int skew = 4;                // conv_stack_tc: stages by which half 1 trails the weight stream (0..6)
   int wimg_copies = 1;         // replicas of the weight image in use (experiment knob; measured: no effect)
   // weights on device
@@ -312,10 +313,20 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       CU(cudaEventCreate(&t1));
       CU(cudaEventRecord(t0, stream));
     }
-    if (ctx->mode == WANN_MODE_FP16)
-      conv_stack_tc_kernel<true><<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
-    else
-      conv_stack_tc_kernel<false><<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * npairs);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = kSmemBytes;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (ctx->mode == WANN_MODE_FP16) CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<true>, p));
+      else CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<false>, p));
+    }
     if (t0 != nullptr) {
       CU(cudaEventRecord(t1, stream));
       std::lock_guard<std::mutex> g(ctx->ev_mu);
@@ -353,7 +364,19 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
     const long long groups = (n + kTailBoards - 1) / kTailBoards;
     const int blocks = static_cast<int>(
         std::min<long long>((groups + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
-    tail_kernel<<<blocks, kTailWarps * 32, kTailSmemBytes, stream>>>(t);
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(blocks);
+      cfg.blockDim = dim3(kTailWarps * 32);
+      cfg.dynamicSmemBytes = kTailSmemBytes;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CU(cudaLaunchKernelEx(&cfg, tail_kernel, t));
+    }
     ++launches;
     if (io.children != nullptr) {
       const int eb = static_cast<int>(std::min<long long>((n + 7) / 8, 16ll * ctx->sm_count));
@@ -960,6 +983,7 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
     ctx->skew = static_cast<int>(value);
     return WANN_OK;
   }
+  if (strcmp(key, "pdl") == 0) { ctx->pdl = value != 0; return WANN_OK; }
   if (strcmp(key, "coalesce") == 0) { ctx->coalesce = value != 0; return WANN_OK; }
   if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
   if (strcmp(key, "chunk") == 0) {
