@@ -10,7 +10,7 @@ ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1))
 sq, bl = synthetic.random_positions(4096, seed=1)
 sq, bl = np.tile(sq, (16, 1)), np.tile(bl, 16)
 sqt, blt = torch.from_numpy(sq).cuda(), torch.from_numpy(bl).cuda()
-for pdl in (0, 1):
+for pdl in (0,):
   ev.set_option("pdl", pdl); print("pdl", pdl)
   for n in (1, 8, 64, 256, 592, 1024, 4096, 65536):
       out = ev.eval_topk(sqt[:n], blt[:n])

@@ -724,6 +724,14 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
                                100 * 192 * 4);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes);
+    // keep the SM's L1/shared split at "max shared" for the small kernels too, so that alternating
+    // conv-stack (227 KB) and tail launches never reconfigure the carve-out
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(expand_children_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) rc = fail(WANN_E_CUDA, "weight upload / kernel attributes: %s", cudaGetErrorString(e));
   }
   if (rc != WANN_OK) {
