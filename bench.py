@@ -147,7 +147,24 @@ def cpu_arm(sample_seconds=15.0):
     t0 = time.perf_counter()
     best_fn(sq[:n], bl[:n])
     dt = time.perf_counter() - t0
-    return n / dt, cores, "port", "%d positions, oracle port (%s, fp32), %.1f s" % (n, best_name, dt)
+    sample = "%d positions, oracle port (%s, fp32), %.1f s" % (n, best_name, dt)
+    # For context: the reference's OWN per-board Python encode + legal-move enumeration
+    # (compiled from its .pyx into oracle/_ref), which sits in front of its TF session.
+    try:
+        from oracle.ref_loader import load_ref
+        ref = load_ref()
+        if ref is not None:
+            boards = [(O.board_from_squares(sq[i], 0 if bl[i] else 1), "Black" if bl[i] else "White")
+                      for i in range(200)]
+            t0 = time.perf_counter()
+            for b, c in boards:
+                ref.utils.convert_board_to_2d_matrix_POEB(b, c)
+                ref.board_utils.enumerate_legal_moves(b, c)
+            sample += "; reference's own Python encode+legal-move code: %.0f us/board (1 thread)" % (
+                (time.perf_counter() - t0) / 200 * 1e6)
+    except Exception:  # noqa: BLE001
+        pass
+    return n / dt, cores, "port", sample
 
 
 def run_reference(args, rank):

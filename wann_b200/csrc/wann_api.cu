@@ -92,6 +92,7 @@ struct Lane {
 };
 
 constexpr int kLanes = 4;
+constexpr long long kDevChunkMul = 4;
 constexpr long long kCombineMaxCall = 256;    // host calls up to this many positions may be merged
 constexpr long long kCombineMaxBatch = 4096;  // positions per merged launch
 
@@ -203,7 +204,9 @@ int alloc_slot(Slot& s, long long cap, int mode) {
   CU(cudaMalloc(&s.d_squares, cap * 64));
   CU(cudaMalloc(&s.d_black, cap));
   CU(cudaMalloc(&s.d_planes, cap * 256 * 4));
-  CU(cudaMalloc(&s.d_h5, cap * 64 * 4));
+  // device-pointer calls need no staging, only h5: they run in chunks 4x as large (fewer launches,
+  // smaller wave-quantisation tail) in the tensor-core modes
+  CU(cudaMalloc(&s.d_h5, cap * 64 * 4 * (mode == WANN_MODE_FP32 ? 1 : kDevChunkMul)));
   CU(cudaMalloc(&s.d_probs, cap * kMoves * 4));
   CU(cudaMalloc(&s.d_logits, cap * kMoves * 4));
   CU(cudaMalloc(&s.d_idx, cap * kMaxLegal));
@@ -419,7 +422,7 @@ struct EvalArgs {
 };
 
 int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void* stream_v) {
-  const long long cap = lane->slot[0].cap;
+  const long long cap = lane->slot[0].cap * (ctx->mode == WANN_MODE_FP32 ? 1 : kDevChunkMul);
   const size_t plane_elt = a.planes_dtype == WANN_PLANES_F32 ? 4 : 1;
   const long long dbg_c = (a.dbg_layer == 5) ? 1 : 192;
   Slot& ws = lane->slot[0];
