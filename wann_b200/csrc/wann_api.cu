@@ -19,6 +19,7 @@
 #include "../../include/wann_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_stack_tc.cuh"
+#include "conv_stack_split.cuh"
 
 namespace {
 
@@ -197,6 +198,42 @@ void build_weight_image(const wann_weights& w, bool f16, std::vector<uint8_t>& i
   }
 }
 
+// WANN_MODE_FP32_TC: every weight as hi = fp16(w), lo = fp16((w - hi) * 4096); per K-block the hi
+// stage is followed by the lo stage (conv_stack_split.cuh).
+void build_weight_image_split(const wann_weights& w, std::vector<uint8_t>& img) {
+  std::vector<uint8_t> hi_img, lo_img;
+  build_weight_image(w, true, hi_img);
+  // residuals: same layout, value (w - float(hi)) * 4096 -- build by transforming the weights
+  std::vector<float> res[5];
+  const size_t k5 = static_cast<size_t>(w.final_kernel) * w.final_kernel;
+  const size_t wsz[5] = {9 * 4 * 192, 9 * 192 * 192, 9 * 192 * 192, 9 * 192 * 192, k5 * 192};
+  wann_weights r = w;
+  for (int l = 0; l < 5; ++l) {
+    res[l].resize(wsz[l]);
+    for (size_t i = 0; i < wsz[l]; ++i) {
+      const uint16_t h = f32_to_f16(w.conv_w[l][i]);
+      __half hh;
+      memcpy(&hh, &h, 2);
+      res[l][i] = (w.conv_w[l][i] - __half2float(hh)) * 4096.f;
+    }
+    r.conv_w[l] = res[l].data();
+  }
+  build_weight_image(r, true, lo_img);
+  img.assign(2 * static_cast<size_t>(kSplitImgBytesPerRank), 0);
+  for (int rank = 0; rank < 2; ++rank) {
+    const uint8_t* h = hi_img.data() + static_cast<size_t>(rank) * kImgBytesPerRank;
+    const uint8_t* l = lo_img.data() + static_cast<size_t>(rank) * kImgBytesPerRank;
+    uint8_t* o = img.data() + static_cast<size_t>(rank) * kSplitImgBytesPerRank;
+    size_t off = 0;
+    for (int kb = 0; kb < kKbPerSupertile; ++kb) {
+      const size_t bytes = (kb >= kKbPerSupertile - kKbL5) ? kStageBytesL5 : kStageBytes;
+      memcpy(o + 2 * off, h + off, bytes);
+      memcpy(o + 2 * off + bytes, l + off, bytes);
+      off += bytes;
+    }
+  }
+}
+
 int alloc_slot(Slot& s, long long cap, int mode) {
   s.cap = cap;
   CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -308,7 +345,8 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
     p.n = n; p.wimg = ctx->d_wimg; p.wimg_copies = ctx->wimg_copies; p.skew = ctx->skew; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
-    const long long total_st = (n + kBoardsPerPair - 1) / kBoardsPerPair;
+    const long long per_pair = (ctx->mode == WANN_MODE_FP32_TC) ? kSplitBoardsPerPair : kBoardsPerPair;
+    const long long total_st = (n + per_pair - 1) / per_pair;
     const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (ctx->time_kernels) {
@@ -327,7 +365,8 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       attr[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      if (ctx->mode == WANN_MODE_FP16) CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<true>, p));
+      if (ctx->mode == WANN_MODE_FP32_TC) CU(cudaLaunchKernelEx(&cfg, conv_stack_split_kernel, p));
+      else if (ctx->mode == WANN_MODE_FP16) CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<true>, p));
       else CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<false>, p));
     }
     if (t0 != nullptr) {
@@ -666,7 +705,7 @@ const char* wann_last_error(void) { return g_err.c_str(); }
 int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx) {
   if (out_ctx == nullptr || w == nullptr) return fail(WANN_E_INVALID, "null argument");
   *out_ctx = nullptr;
-  if (mode != WANN_MODE_BF16 && mode != WANN_MODE_FP32 && mode != WANN_MODE_FP16) return fail(WANN_E_INVALID, "bad mode %d", mode);
+  if (mode != WANN_MODE_BF16 && mode != WANN_MODE_FP32 && mode != WANN_MODE_FP16 && mode != WANN_MODE_FP32_TC) return fail(WANN_E_INVALID, "bad mode %d", mode);
   if (w->final_kernel != 3 && w->final_kernel != 1)
     return fail(WANN_E_INVALID, "final_kernel must be 3 or 1");
   for (int i = 0; i < 5; ++i)
@@ -707,9 +746,11 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
   if (rc == WANN_OK) rc = up(&ctx->d_fc_b, w->fc_b, kMoves);
   if (rc == WANN_OK) {
     std::vector<uint8_t> img;
-    build_weight_image(*w, mode == WANN_MODE_FP16, img);
-    e = cudaMalloc(&ctx->d_wimg, img.size() * kMaxWimgCopies);
-    for (int c = 0; c < kMaxWimgCopies && e == cudaSuccess; ++c)
+    if (mode == WANN_MODE_FP32_TC) build_weight_image_split(*w, img);
+    else build_weight_image(*w, mode == WANN_MODE_FP16, img);
+    const int copies = (mode == WANN_MODE_FP32_TC) ? 1 : kMaxWimgCopies;
+    e = cudaMalloc(&ctx->d_wimg, img.size() * copies);
+    for (int c = 0; c < copies && e == cudaSuccess; ++c)
       e = cudaMemcpy(ctx->d_wimg + c * img.size(), img.data(), img.size(), cudaMemcpyHostToDevice);
     std::vector<float> bias(4 * 192 + 4, 0.f);
     for (int l = 0; l < 4; ++l) memcpy(bias.data() + l * 192, w->conv_b[l], 192 * 4);
@@ -722,6 +763,8 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_stack_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_stack_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_f32_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                100 * 192 * 4);
@@ -886,7 +929,8 @@ int wann_legal_mask(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, 
 int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n,
                        int64_t* stamps /* [4][64] */) {
   if (ctx == nullptr || !squares || !black || !stamps || n <= 0) return fail(WANN_E_INVALID, "bad argument");
-  if (ctx->mode == WANN_MODE_FP32) return fail(WANN_E_INVALID, "profile needs a tensor-core mode");
+  if (ctx->mode == WANN_MODE_FP32 || ctx->mode == WANN_MODE_FP32_TC)
+    return fail(WANN_E_INVALID, "profile needs the bf16/fp16 tensor-core mode");
   CU(cudaSetDevice(ctx->device));
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);

@@ -27,7 +27,7 @@ class PolicyEvaluator(object):
         cw.fc_w = w["output_layer/weights"].ctypes.data
         cw.fc_b = w["output_layer/bias"].ctypes.data
         cw.final_kernel = final_kernel
-        self.mode = {"bf16": L.MODE_BF16, "fp32": L.MODE_FP32, "fp16": L.MODE_FP16}[mode] if isinstance(mode, str) else int(mode)
+        self.mode = {"bf16": L.MODE_BF16, "fp32": L.MODE_FP32, "fp16": L.MODE_FP16, "fp32_tc": L.MODE_FP32_TC}[mode] if isinstance(mode, str) else int(mode)
         self.device = int(device)
         ctx = ctypes.c_void_p()
         L.check(lib.wann_create(ctypes.byref(cw), self.device, self.mode, ctypes.byref(ctx)))
