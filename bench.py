@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32_tc"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

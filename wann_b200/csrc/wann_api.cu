@@ -288,6 +288,8 @@ int acquire_lane(wann_ctx* ctx, Lane** out) {
           for (int k = 0; k < 2; ++k) {
             int rc = alloc_slot(l.slot[k], cap, ctx->mode);
             if (rc != WANN_OK) {
+              free_slot(l.slot[0]);   // leave the lane unallocated so that a later call retries cleanly
+              free_slot(l.slot[1]);
               std::lock_guard<std::mutex> g(ctx->mu);
               l.in_use = false;
               ctx->cv.notify_one();
@@ -792,6 +794,8 @@ int wann_destroy(wann_ctx* ctx) {
   if (ctx == nullptr) return WANN_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  for (auto& pr : ctx->ev_pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  ctx->ev_pairs.clear();
   for (auto& l : ctx->lanes) {
     free_slot(l.slot[0]);
     free_slot(l.slot[1]);
