@@ -156,7 +156,8 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("# oracle", ""), f
+                # no import / path / library reference to oracle/ (prose mentions are fine)
+                assert not re.search(r"(from|import)\s+oracle|oracle[./\\]|liboracle|oracle_", src), f
 
 
 def test_no_cpu_fallback_without_gpu(lib_built):
