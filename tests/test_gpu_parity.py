@@ -507,3 +507,32 @@ def test_fp32_tc_mode_fp32_class_accuracy_on_tensor_cores(weights, suite, ref1k)
     lg_ref, _ = O.forward_fp32(O.encode_planes(sq[:64], bl[:64]), w1)
     with wann_b200.PolicyEvaluator(w1, mode="fp32_tc", final_kernel=1) as ev:
         assert nerr(ev.eval_probs(sq[:64], bl[:64], return_logits=True)[1], lg_ref) < 1e-5
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", ".built")),
+                    reason="compiled reference (oracle/_ref) not shipped")
+def test_reference_multithreaded_mcts_search_runs_on_our_evaluator():
+    """The reference's own MCTS_with_expansions (ThreadPool(10) + main thread, every evaluate call a
+    single node, expansion_MCTS_functions.pyx:77-167) searching on top of NeuralNetsCombined_128:
+    returns a legal move; the coalescer merged concurrent calls."""
+    import io
+    import wann_b200
+    from oracle.ref_loader import load_ref
+    ref = load_ref()
+    mc = ref.module("monte_carlo_tree_search.expansion_MCTS_functions")
+    w1 = wann_b200.weights.synthetic("trained_like", 1, final_kernel=1)
+    names, sizes = set(), []
+    with wann_b200.NeuralNetsCombined_128(w1, mode="bf16") as net:
+        class Spy(object):
+            def evaluate(self, nodes, **kw):
+                names.add(threading.current_thread().name)
+                sizes.append(len(nodes))
+                return net.evaluate(nodes, **kw)
+        board = ref.utils.initial_game_board()
+        best_child, move = mc.MCTS_with_expansions(board, "White", 1, 5, None, None, 0, io.StringIO(), "WaNN",
+                                                   Spy(), 0)
+        st = net.sess.evaluator("white_net").stats()
+    legal = ref.board_utils.enumerate_legal_moves(board, "White")
+    assert move in legal
+    assert len(sizes) > 100 and len(names) >= 2
+    assert st["merged_calls"] >= len(sizes) - 16 and st["merged_launches"] <= st["merged_calls"]
