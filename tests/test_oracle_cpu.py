@@ -326,3 +326,15 @@ def test_forward_against_an_independent_torch_restatement():
         probs = torch.softmax(logits, dim=1).numpy()
         lg, pr = O.forward_fp32(planes, w)
         assert np.abs(lg - logits.numpy()).max() < 2e-4 and np.abs(pr - probs).max() < 1e-5
+
+
+def test_bulk_board_conversion_equals_per_square_conversion(golden):
+    from wann_b200 import boards
+    sq = golden["squares"][:100]
+    dicts = [boards.squares_to_board(s) for s in sq]
+    assert np.array_equal(boards.boards_to_squares(dicts), sq)
+    assert boards.boards_to_squares([]).shape == (0, 64)
+    bad = boards.squares_to_board(sq[0])
+    bad[3]["c"] = "x"
+    with pytest.raises(ValueError):
+        boards.boards_to_squares([bad])

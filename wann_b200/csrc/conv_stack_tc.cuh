@@ -84,7 +84,7 @@ constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemSlot + 16 + 128;   // +128 for base alignment slack
 static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB) exceeded");
 
-constexpr long long kWatchdogCycles = 1ll << 29;
+constexpr long long kWatchdogCycles = 1ll << 31;   // ~1.2 s: no legitimate wait comes close
 constexpr int kProfSteps = 64;
 
 struct TcParams {

@@ -43,6 +43,22 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                    \
   } while (0)
 
+// Switches to the context's device for the duration of an API call and restores the caller's
+// current device afterwards (the host application -- e.g. torch -- keeps its own notion of it).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    status = cudaGetDevice(&prev);
+    if (status == cudaSuccess && prev != dev) {
+      status = cudaSetDevice(dev);
+      switched = status == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 uint16_t f32_to_bf16(float f) {   // round-to-nearest-even, like cvt.rn.bf16.f32
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -679,7 +695,8 @@ int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* strea
   if (a.squares != nullptr && a.black == nullptr) return fail(WANN_E_INVALID, "black_to_move is null");
   if (a.idx != nullptr && (a.squares == nullptr || a.prior == nullptr || a.nlegal == nullptr))
     return fail(WANN_E_INVALID, "top-k needs squares, prior and n_legal");
-  CU(cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
   if (!bypass) ctx->stats[2] += 1;
   if (!bypass && ctx->coalesce && mem == WANN_MEM_HOST && a.squares != nullptr && a.dbg == nullptr &&
       a.children == nullptr && n <= kCombineMaxCall)
@@ -724,7 +741,8 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
   if (prop.major != 10)
     return fail(WANN_E_NO_DEVICE, "device %d is sm_%d%d; this library is sm_100a (B200) only", device,
                 prop.major, prop.minor);
-  CU(cudaSetDevice(device));
+  DeviceGuard dev_guard(device);
+  CU(dev_guard.status);
   wann_ctx* ctx = new wann_ctx();
   for (auto& s : ctx->stats) s = 0;
   ctx->device = device;
@@ -792,7 +810,7 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
 
 int wann_destroy(wann_ctx* ctx) {
   if (ctx == nullptr) return WANN_OK;
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   cudaDeviceSynchronize();
   for (auto& pr : ctx->ev_pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   ctx->ev_pairs.clear();
@@ -875,7 +893,8 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
   if (n < 0) return fail(WANN_E_INVALID, "negative n");
   if (n == 0) return WANN_OK;
   if (!squares || !black || !out) return fail(WANN_E_INVALID, "null buffer");
-  CU(cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);
   if (rc != WANN_OK) return rc;
@@ -935,7 +954,8 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
   if (ctx == nullptr || !squares || !black || !stamps || n <= 0) return fail(WANN_E_INVALID, "bad argument");
   if (ctx->mode == WANN_MODE_FP32 || ctx->mode == WANN_MODE_FP32_TC)
     return fail(WANN_E_INVALID, "profile needs the bf16/fp16 tensor-core mode");
-  CU(cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);
   if (rc != WANN_OK) return rc;
@@ -967,7 +987,8 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
 
 int wann_kernel_times(wann_ctx* ctx, double out[2]) {
   if (ctx == nullptr || out == nullptr) return fail(WANN_E_INVALID, "null argument");
-  CU(cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
   CU(cudaDeviceSynchronize());
   std::lock_guard<std::mutex> g(ctx->ev_mu);
   double ms = 0;

@@ -136,23 +136,20 @@ class NeuralNetsCombined_128(object):
             sq = boards.board_to_squares(game_nodes)[None]
             bl = np.array([boards.color_is_black(player_color)], np.uint8)
         else:                                                   # MCTS.pyx:100-102: list of nodes
-            n = len(game_nodes)
-            sq = np.empty((n, 64), np.int8)
-            bl = np.empty(n, np.uint8)
-            for i, node in enumerate(game_nodes):
-                boards.board_to_squares(node['game_board'], sq[i])
-                bl[i] = boards.color_is_black(node['color'])
+            sq, bl = self._nodes_to_arrays(game_nodes)
         return ev.eval_probs(sq, bl)
+
+    @staticmethod
+    def _nodes_to_arrays(game_nodes):
+        sq = boards.boards_to_squares([node['game_board'] for node in game_nodes])
+        bl = np.fromiter((boards.color_is_black(node['color']) for node in game_nodes), np.uint8,
+                         len(game_nodes))
+        return sq, bl
 
     def evaluate_children(self, game_nodes, is_player=True):
         """Fused variant for callers that only need the ranked legal priors
         (what enumerate_update_and_prune consumes, tree_builder.pyx:428-445)."""
-        n = len(game_nodes)
-        sq = np.empty((n, 64), np.int8)
-        bl = np.empty(n, np.uint8)
-        for i, node in enumerate(game_nodes):
-            boards.board_to_squares(node['game_board'], sq[i])
-            bl[i] = boards.color_is_black(node['color'])
+        sq, bl = self._nodes_to_arrays(game_nodes)
         return self._net(is_player).eval_topk(sq, bl)
 
     def __enter__(self):
