@@ -312,6 +312,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = n_gpus * B * e2e_steps / float(t.item())
 
+    # same, returning the full [N,155] probability rows (what the reference's evaluate() returns)
+    h_probs = torch.empty((B, 155), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        ev.eval_probs(h_args[0], h_args[1], out=h_probs.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ev.eval_probs(h_args[0], h_args[1], out=h_probs.numpy())
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_probs_value = n_gpus * B * e2e_steps / float(t.item())
+
     # ---------------- optional: counters gathered with NCCL, sweep, CPU baseline ----------
     counters = gather_counters([B * args.steps, int(ms * 1e6)], device=dev)
     sweep = {}
@@ -355,6 +369,9 @@ def main():
                        "parallelism": "replicas x%d, leaf batches sharded per GPU, no collective" % n_gpus},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * IN_BYTES,
                     "d2h_bytes_per_step": B * OUT_BYTES, "api": "wann_eval_topk(WANN_MEM_HOST), pinned buffers"},
+            "e2e_probs": {"value": e2e_probs_value, "unit": UNIT, "h2d_bytes_per_step": B * IN_BYTES,
+                          "d2h_bytes_per_step": B * 155 * 4,
+                          "api": "wann_eval_probs(WANN_MEM_HOST): full [N,155] rows, the reference's evaluate() output"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv_stack_tc_kernel", "achieved": achieved,

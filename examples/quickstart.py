@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Quick start: evaluate Breakthrough positions on a B200 three ways.
+
+    python examples/quickstart.py
+
+1. the reference's call surface (drop-in for MCTS.pyx's NeuralNetsCombined_128),
+2. the array API (numpy in / numpy out through the C ABI's host path),
+3. the device-resident API (torch CUDA tensors in / out, children ready for the next leaf batch).
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import wann_b200  # noqa: E402
+from wann_b200 import boards, synthetic  # noqa: E402
+
+sq, black = synthetic.random_positions(4096, seed=0)
+
+# 1. reference surface: list of node dicts -> ndarray [N,155] float32 (MCTS.pyx:85-127)
+nodes = [{"game_board": boards.squares_to_board(s, 0 if b else 1), "color": "Black" if b else "White"}
+         for s, b in zip(sq[:8], black[:8])]
+with wann_b200.NeuralNetsCombined_128() as policy_net:
+    probs = policy_net.evaluate(nodes)
+    best = [boards.move_lookup_by_index(int(i), n["color"]) for i, n in zip(probs.argmax(1), nodes)]
+    print("evaluate():", probs.shape, probs.dtype, "argmax moves", best[:4])
+
+# 2. array API: ranked legal children (indices in the reference's 155-move alphabet, priors)
+with wann_b200.PolicyEvaluator(mode="fp16") as ev:
+    idx, prior, n_legal = ev.eval_topk(sq, black)
+    print("eval_topk(): policy moves", idx[:4, 0], "priors", np.round(prior[:4, 0], 3), "legal", n_legal[:4])
+
+    # 3. device-resident: children boards stay on the GPU
+    import torch
+    out = ev.eval_expand(torch.from_numpy(sq).cuda(), torch.from_numpy(black).cuda())
+    torch.cuda.synchronize()
+    print("eval_expand(): children", tuple(out[3].shape), "on", out[3].device, "| stats", ev.stats())
