@@ -101,6 +101,7 @@ struct TcParams {
   int dbg_layer;
   int variant;               // debug: bit2 = swap the B halves between the CTAs of a pair
   int skew;                  // weight stages by which half 1 trails the stream (0 = free-running)
+  int halves;                // 2 = 8 boards per CTA pair (throughput), 1 = 4 boards (small batches)
   int* err;                  // [8] watchdog record
   long long* prof;           // optional [8][kProfSteps] clock64 stamps of pair 0 (debug):
                              // half h: [4h+0] MMA start, [4h+1] MMA issue end,
@@ -197,7 +198,11 @@ conv_stack_tc_kernel(const TcParams p) {
   const uint32_t rank = ptx::cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
-  const long long total_st = (p.n + kBoardsPerPair - 1) / kBoardsPerPair;
+  // small batches run with ONE half per CTA (4 boards per pair): twice the supertiles to spread
+  // over the SM pairs, and each 5-layer chain has the tensor pipe to itself (lower latency)
+  const int nh = (p.halves == 1) ? 1 : 2;
+  const int boards_per_pair = 4 * nh;
+  const long long total_st = (p.n + boards_per_pair - 1) / boards_per_pair;
   const uint32_t nst = kStages - ((p.variant >> 4) & 7);   // debug: use a shallower weight ring
 
   // ---- one-time setup ---------------------------------------------------------------------
@@ -205,7 +210,7 @@ conv_stack_tc_kernel(const TcParams p) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(bar_full(s), 1);
       ptx::mbar_init(bar_peer_full(s), 1);
-      ptx::mbar_init(bar_empty(s), 2);      // freed when BOTH halves' MMAs on the stage are done
+      ptx::mbar_init(bar_empty(s), nh);     // freed when ALL active halves' MMAs on the stage are done
     }
     for (int h = 0; h < 2; ++h) {
       ptx::mbar_init(bar_acc_full(h), 1);
@@ -278,7 +283,7 @@ conv_stack_tc_kernel(const TcParams p) {
       }
     }
   } else if (warp <= 2) {
-    if (rank == 0) {
+    if (rank == 0 && warp - 1 < nh) {
       // ===== MMA issuer of half h = warp - 1 (leader CTA).  The WHOLE warp runs the loop with
       // uniform control flow (descriptors live in uniform registers); one elected lane issues
       // the tcgen05 ops.  The 64-bit descriptors are {lo = start>>4 | LBO<<16, hi = SBO |
@@ -399,13 +404,13 @@ conv_stack_tc_kernel(const TcParams p) {
       if (signaller) ptx::mbar_arrive_cluster(h ? a_ready_leader1 : a_ready_leader0);
     };
     auto board_of = [&](long long st, int h) {
-      return st * kBoardsPerPair + static_cast<int>(rank) * kBoardsPerCta + h * 2 + b;
+      return st * boards_per_pair + static_cast<int>(rank) * (2 * nh) + h * 2 + b;
     };
 
     ptx::pdl_wait();
     long long st = pair;
     if (st < total_st) {
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < nh; ++h) {
         if (chalf == 0)
           store_input_cell(a_base + h * kATileBytes + cell_in_tile, load_input_cell<kF16>(p, board_of(st, h), y, x));
         signal_a_ready(h);
@@ -416,7 +421,7 @@ conv_stack_tc_kernel(const TcParams p) {
     uint2 next_in[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
     for (; st < total_st && ok; st += npairs) {
       for (int layer = 0; layer < 5 && ok; ++layer, ++lstep) {
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < nh; ++h) {
           const long long board = board_of(st, h);
           const uint32_t cell0 = a_base + h * kATileBytes + cell_in_tile;
           const uint32_t taddr = lane_taddr + h * kC;

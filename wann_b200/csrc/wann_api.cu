@@ -131,6 +131,7 @@ struct wann_ctx {
   long long chunk = 16384;
   int variant = 0;
   bool pdl = false;            // programmatic dependent launch conv-stack <-> tail (measured: slower, off)
+  bool small_batch_halves = true;   // batches <= 4 x (SM pairs) run 4-board supertiles
   int skew = 4;                // conv_stack_tc: stages by which half 1 trails the weight stream (0..6)
   int wimg_copies = 1;         // replicas of the weight image in use (experiment knob; measured: no effect)
   // weights on device
@@ -363,7 +364,11 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
     p.n = n; p.wimg = ctx->d_wimg; p.wimg_copies = ctx->wimg_copies; p.skew = ctx->skew; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
-    const long long per_pair = (ctx->mode == WANN_MODE_FP32_TC) ? kSplitBoardsPerPair : kBoardsPerPair;
+    // small batches: one half per CTA (4 boards per pair) while that still fits one wave of pairs
+    p.halves = (ctx->mode != WANN_MODE_FP32_TC && ctx->small_batch_halves &&
+                n <= 4ll * (ctx->sm_count / 2)) ? 1 : 2;
+    const long long per_pair = (ctx->mode == WANN_MODE_FP32_TC) ? kSplitBoardsPerPair
+                                                               : (p.halves == 1 ? 4 : kBoardsPerPair);
     const long long total_st = (n + per_pair - 1) / per_pair;
     const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -1063,6 +1068,7 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
     ctx->skew = static_cast<int>(value);
     return WANN_OK;
   }
+  if (strcmp(key, "small_batch_halves") == 0) { ctx->small_batch_halves = value != 0; return WANN_OK; }
   if (strcmp(key, "pdl") == 0) { ctx->pdl = value != 0; return WANN_OK; }
   if (strcmp(key, "coalesce") == 0) { ctx->coalesce = value != 0; return WANN_OK; }
   if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
