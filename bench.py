@@ -326,6 +326,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_probs_value = n_gpus * B * e2e_steps / float(t.item())
 
+    # ---------------- BASELINE configs[4]: 8,192 independent game trees over 8 GPUs = 1,024 per GPU,
+    # one leaf per tree per step, device-resident steady state through ONE C-ABI call per step
+    # (wann_tree_step: evaluate -> choose a child -> apply it in place -> restart finished games)
+    from wann_b200.treefarm import TreeFarm
+    trees = {}
+    for n_trees in (1024, 16384):
+        farm = TreeFarm(ev, n_trees, device=dev, seed=17 + rank)
+        for _ in range(40):
+            farm.step_fused()                                   # spread the games over all plies
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tsteps = 200
+        a.record()
+        for _ in range(tsteps):
+            farm.step_fused()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        trees[str(n_trees)] = {"trees_per_gpu": n_trees, "steps": tsteps,
+                               "us_per_step": round(float(t.item()) * 1e3 / tsteps, 2),
+                               "positions_per_s": round(n_gpus * n_trees * tsteps / (float(t.item()) * 1e-3), 1)}
+
     # ---------------- optional: counters gathered with NCCL, sweep, CPU baseline ----------
     counters = gather_counters([B * args.steps, int(ms * 1e6)], device=dev)
     sweep = {}
@@ -382,6 +406,7 @@ def main():
                          "kernel_ms_per_launch": conv_ms / max(conv_launches, 1),
                          "kernel_share_of_step": conv_ms / ms, "traffic": traffic},
             "sweep_positions_per_s_1gpu": sweep,
+            "config5_game_trees": trees,
             "per_rank_counters": counters.tolist(),
         }
         if not args.no_cpu_baseline and n_gpus == 1:

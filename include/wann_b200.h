@@ -134,6 +134,18 @@ int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_
                      int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal,
                      int8_t* child_squares, uint8_t* child_flags, int mem, void* stream);
 
+/* One self-play style step for n independent games, entirely on the device (BASELINE config 5:
+ * independent game trees, each contributing one leaf per step): evaluate the positions, pick ONE
+ * child per game -- greedy != 0: the policy move (get_best_move, board_utils.pyx:262-277);
+ * greedy == 0: sampled in proportion to the ranked legal priors with the counter-based RNG
+ * u = splitmix64(splitmix64(seed ^ step * 0xD1342543DE82EF95) ^ game) >> 40 -- apply it IN PLACE
+ * to `squares` / `black_to_move` (DEVICE pointers), and restart finished games (move index > 131
+ * or no legal move) from the opening position.  chosen_idx uint8 [n] (255 = none) and
+ * finished uint8 [n] are optional outputs.  Asynchronous on `stream` (NULL = synchronise). */
+int wann_tree_step(wann_ctx* ctx, int8_t* squares, uint8_t* black_to_move, int64_t n, int greedy,
+                   uint64_t seed, uint64_t step, uint8_t* chosen_idx, uint8_t* finished,
+                   void* stream);
+
 /* Test/inspection hook: activations after hidden layer `layer` (1..5) as float
  * [n][8][8][C] (C = 192, or 1 for layer 5), host or device per `mem`.  In BF16 mode the
  * values are the bf16-rounded activations the next layer consumes (layer 5: fp32). */

@@ -493,3 +493,59 @@ def expand_children(squares, black_to_move, idx, n_legal):
             out[i, k] = child
             flags[i, k] = f
     return out, flags
+
+
+# ----------------------------------------------------------------------------
+# Self-play style step (BASELINE config 5; wann_tree_step): pick one child per game from the
+# ranked legal priors, apply it, restart finished games.  The selection rule is ours (the
+# reference's tree policy is out of scope); the pieces it is made of are the reference's:
+# policy move = first ranked legal index (board_utils.pyx:262-277), move application
+# (board_utils.pyx:119-120), game over when the move index > 131 (tree_builder.pyx:902-905),
+# restart from initial_game_board (tools/utils.pyx:518-541).
+# ----------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def tree_step(squares, black_to_move, idx, prior, n_legal, greedy=False, seed=0, step=0):
+    """-> (new squares int8 [N,64], new black_to_move uint8 [N], chosen idx uint8 [N] (255 = none),
+    finished uint8 [N]).  Sampling: u = (splitmix64(splitmix64(seed ^ step*K) ^ game) >> 40) / 2^24
+    * sum(priors) in float32, first slot whose running float32 sum exceeds u."""
+    squares = np.asarray(squares, np.int8).reshape(-1, 64)
+    n = squares.shape[0]
+    out_sq = squares.copy()
+    out_bl = np.asarray(black_to_move, np.uint8).copy()
+    chosen = np.full(n, 255, np.uint8)
+    finished = np.ones(n, np.uint8)
+    base = splitmix64((seed ^ ((step * 0xD1342543DE82EF95) & _M64)) & _M64)
+    for g in range(n):
+        cnt = int(n_legal[g])
+        k = 0
+        if not greedy and cnt > 1:
+            pr = np.asarray(prior[g, :cnt], np.float32)
+            total = np.float32(0)
+            for p in pr:
+                total = np.float32(total + p)
+            u = np.float32(np.float32(splitmix64(base ^ g) >> 40) * np.float32(1.0 / 16777216.0)) * total
+            cum, k = np.float32(0), cnt - 1
+            for i, p in enumerate(pr):
+                cum = np.float32(cum + p)
+                if u < cum:
+                    k = i
+                    break
+        if cnt > 0:
+            chosen[g] = idx[g, k]
+            finished[g] = 1 if chosen[g] > 131 else 0
+        if finished[g]:
+            out_sq[g] = initial_squares()
+            out_bl[g] = 0
+        else:
+            out_sq[g] = apply_pov_move(squares[g], int(out_bl[g]), int(chosen[g]))
+            out_bl[g] ^= 1
+    return out_sq, out_bl, chosen, finished

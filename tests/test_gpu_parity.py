@@ -447,6 +447,42 @@ def test_treefarm_steady_state_plays_legal_games(ev_bf16):
     assert finished > 0                          # random games of Breakthrough end within ~60 plies
 
 
+def test_tree_step_fused_matches_oracle(ev_bf16, suite):
+    """wann_tree_step (config 5 as ONE call): the child chosen per game (greedy and sampled, counter-based
+    RNG), the in-place move and the restart equal the oracle's restatement applied to the ranked
+    priors the same context returns for the same boards."""
+    import torch
+    sq, bl = suite
+    dev = torch.device("cuda", ev_bf16.device)
+    for greedy, n, seed, step in ((True, 300, 0, 0), (False, 1024, 11, 5), (False, 1, 3, 9), (False, 1024, 11, 6)):
+        s0, b0 = sq[:n].copy(), bl[:n].copy()
+        idx, pri, cnt = ev_bf16.eval_topk(s0, b0)
+        want = O.tree_step(s0, b0, idx, pri, cnt, greedy=greedy, seed=seed, step=step)
+        ts, tb = torch.from_numpy(s0).to(dev), torch.from_numpy(b0).to(dev)
+        chosen, fin = ev_bf16.tree_step(ts, tb, greedy=greedy, seed=seed, step=step)
+        torch.cuda.synchronize()
+        got = (ts.cpu().numpy(), tb.cpu().numpy(), chosen.cpu().numpy(), fin.cpu().numpy())
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+        if not greedy and n > 1:
+            assert (want[2] != idx[:n, 0]).any()          # sampling really leaves the policy move sometimes
+    # a farm playing whole games through the fused call: always legal, games finish and restart
+    from wann_b200.treefarm import TreeFarm
+    farm = TreeFarm(ev_bf16, 512, seed=5)
+    finished = 0
+    for _ in range(80):
+        before_sq, before_bl = farm.sq.cpu().numpy(), farm.black.cpu().numpy()
+        chosen, fin = farm.step_fused(want_outputs=True)
+        chosen, fin = chosen.cpu().numpy(), fin.cpu().numpy().astype(bool)
+        mask = O.legal_mask(before_sq, before_bl)
+        assert mask[np.arange(512), chosen].all()
+        after = farm.sq.cpu().numpy()
+        assert (after[fin] == O.initial_squares()).all() and not O.game_over(after).any()
+        assert np.array_equal(fin, chosen > 131)
+        finished += int(fin.sum())
+    assert finished > 0
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote

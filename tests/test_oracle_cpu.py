@@ -130,6 +130,35 @@ def test_ranked_children_semantics():
         assert idx[i, 0] == O.top1_legal(probs[i:i + 1], mask[i:i + 1])[0]
 
 
+def test_tree_step_oracle_semantics():
+    """The self-play step restatement: greedy takes ranked slot 0; sampling is a pure function of
+    (seed, step, game); winning moves (index > 131) restart the game; everything else applies the move."""
+    sq, bl = O.random_positions_fast(64, seed=12)
+    mask = O.legal_mask(sq, bl)
+    probs = np.random.RandomState(1).dirichlet(np.ones(155), size=64).astype(np.float32)
+    idx, pri, cnt = O.ranked_children(probs, mask)
+    s1, b1, ch, fin = O.tree_step(sq, bl, idx, pri, cnt, greedy=True)
+    assert (ch == idx[:, 0]).all() and np.array_equal(fin, (ch > 131).astype(np.uint8))
+    kids, flg = O.expand_children(sq, bl, ch[:, None], np.ones(64, np.uint8))
+    live = fin == 0
+    assert np.array_equal(s1[live], kids[live, 0]) and (b1[live] == (bl[live] ^ 1)).all()
+    assert (s1[~live] == O.initial_squares()).all() and (b1[~live] == 0).all()
+    a = O.tree_step(sq, bl, idx, pri, cnt, greedy=False, seed=7, step=3)
+    b = O.tree_step(sq, bl, idx, pri, cnt, greedy=False, seed=7, step=3)
+    c = O.tree_step(sq, bl, idx, pri, cnt, greedy=False, seed=7, step=4)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and not np.array_equal(a[2], c[2])
+    assert mask[np.arange(64), a[2]].all()
+    # empirical frequencies follow the priors: one position, many (seed, step) draws
+    i = int(np.argmax(cnt))
+    rep = lambda x: np.repeat(x[i:i + 1], 1, axis=0)
+    hits = np.zeros(int(cnt[i]))
+    for s in range(2000):
+        hits[list(idx[i]).index(O.tree_step(rep(sq), rep(bl), rep(idx), rep(pri), rep(cnt), seed=1, step=s)[2][0])] += 1
+    p = pri[i, :cnt[i]] / pri[i, :cnt[i]].sum()
+    assert np.abs(hits / 2000 - p).max() < 0.04
+    assert O.splitmix64(0) == 0xE220A8397B1DCDAF      # published SplitMix64 first output for seed 0
+
+
 def test_bf16_round_matches_torch():
     import torch
     x = np.random.RandomState(0).standard_normal(4096).astype(np.float32) * 3

@@ -292,6 +292,66 @@ __global__ void __launch_bounds__(256) expand_children_kernel(const int8_t* __re
   }
 }
 
+// Self-play style step (BASELINE config 5: independent game trees, one leaf per tree per step):
+// pick ONE child per game from its ranked legal priors -- greedy (slot 0 = the policy move,
+// board_utils.pyx:262-277) or sampled in proportion to the priors -- apply the move in place
+// (board_utils.pyx:119-120), flip the side to move, and restart a finished game (move index > 131,
+// tree_builder.pyx:902-905, or no legal move) from the opening position (utils.pyx:518-541).
+// Counter-based RNG: u = splitmix64(seed, step, game) -> 24-bit uniform; reproducible on the host.
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) tree_step_kernel(int8_t* __restrict__ squares, uint8_t* __restrict__ black,
+                                                        const uint8_t* __restrict__ idx,
+                                                        const float* __restrict__ prior,
+                                                        const uint8_t* __restrict__ n_legal, long long n,
+                                                        long long game0, int greedy, uint64_t seed, uint64_t step,
+                                                        uint8_t* __restrict__ chosen, uint8_t* __restrict__ finished) {
+  const long long g = blockIdx.x * 256ll + threadIdx.x;
+  if (g >= n) return;
+  const int cnt = n_legal[g];
+  int k = 0;
+  if (!greedy && cnt > 1) {
+    const float* pr = prior + g * kMaxLegal;
+    float total = 0.f;
+    for (int i = 0; i < cnt; ++i) total += pr[i];
+    const uint64_t r = splitmix64(splitmix64(seed ^ (step * 0xD1342543DE82EF95ull)) ^ static_cast<uint64_t>(game0 + g));
+    const float u = static_cast<float>(r >> 40) * (1.0f / 16777216.0f) * total;
+    float cum = 0.f;
+    k = cnt - 1;
+    for (int i = 0; i < cnt; ++i) {
+      cum += pr[i];
+      if (u < cum) { k = i; break; }
+    }
+  }
+  uint8_t mv = 255, fin = 1;
+  int8_t* b = squares + g * 64;
+  if (cnt > 0) {
+    mv = idx[g * kMaxLegal + k];
+    fin = mv > 131;
+  }
+  if (fin) {   // game over (or stuck): restart from the opening, White to move
+    uint32_t* w = reinterpret_cast<uint32_t*>(b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = i < 4 ? 0x01010101u : (i >= 12 ? 0x02020202u : 0u);
+    black[g] = 0;
+  } else {
+    int r, c, d;
+    decode_move(mv, r, c, d);
+    int frm = r * 8 + c, to = (r + 1) * 8 + c + d;
+    if (black[g]) { frm = 63 - frm; to = 63 - to; }
+    b[to] = b[frm];
+    b[frm] = 0;
+    black[g] ^= 1;
+  }
+  if (chosen != nullptr) chosen[g] = mv;
+  if (finished != nullptr) finished[g] = fin;
+}
+
 // --------------------------------------------------------------------------------------------
 // fp32 accuracy mode (CUDA cores).  One CTA per board, 256 threads: warp = output row y,
 // lane -> output channels lane + 32*j.  Input board staged zero-padded in shared memory.

@@ -881,6 +881,51 @@ int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
   return run_eval(ctx, a, n, mem, stream);
 }
 
+int wann_tree_step(wann_ctx* ctx, int8_t* squares, uint8_t* black, int64_t n, int greedy, uint64_t seed,
+                   uint64_t step, uint8_t* chosen_idx, uint8_t* finished, void* stream_v) {
+  if (ctx == nullptr) return fail(WANN_E_INVALID, "null context");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
+  if (n == 0) return WANN_OK;
+  if (squares == nullptr || black == nullptr) return fail(WANN_E_INVALID, "null buffer");
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
+  ctx->stats[2] += 1;
+  Lane* lane = nullptr;
+  int rc = acquire_lane(ctx, &lane);
+  if (rc != WANN_OK) return rc;
+  Slot& ws = lane->slot[0];
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ws.stream;
+  lane_wait(lane, stream);
+  auto body = [&]() -> int {
+    for (long long off = 0; off < n; off += ws.cap) {
+      const long long m = std::min<long long>(ws.cap, n - off);
+      ChunkIO io;
+      io.squares = squares + off * 64; io.black = black + off;
+      io.idx = ws.d_idx; io.prior = ws.d_prior; io.nlegal = ws.d_nlegal;
+      int r = enqueue_eval(ctx, ws, stream, io, m);
+      if (r != WANN_OK) return r;
+      tree_step_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, stream>>>(
+          squares + off * 64, black + off, ws.d_idx, ws.d_prior, ws.d_nlegal, m, off, greedy, seed, step,
+          chosen_idx ? chosen_idx + off : nullptr, finished ? finished + off : nullptr);
+      CU(cudaGetLastError());
+      ctx->stats[1] += 1;
+    }
+    if (stream_v == nullptr) {
+      CU(cudaStreamSynchronize(stream));
+      lane->last_valid = false;
+    } else {
+      CU(cudaEventRecord(lane->last, stream));
+      lane->last_valid = true;
+      lane->last_stream = stream;
+    }
+    return WANN_OK;
+  };
+  rc = body();
+  if (rc != WANN_OK) cudaStreamSynchronize(stream);
+  release_lane(ctx, lane);
+  return rc;
+}
+
 int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, int layer,
                            float* out, int mem) {
   if (layer < 1 || layer > 5) return fail(WANN_E_INVALID, "layer must be 1..5");

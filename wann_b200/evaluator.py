@@ -182,6 +182,18 @@ class PolicyEvaluator(object):
                                            L.MEM_HOST, None))
         return idx, pri, cnt, kids, flg
 
+    def tree_step(self, squares, black, greedy=False, seed=0, step=0, want_outputs=True):
+        """In-place self-play step on torch CUDA tensors (see wann_tree_step).  Returns
+        (chosen_idx uint8 [n], finished uint8 [n]) device tensors, or None."""
+        import torch
+        n = squares.shape[0]
+        chosen = torch.empty((n,), dtype=torch.uint8, device=squares.device) if want_outputs else None
+        fin = torch.empty((n,), dtype=torch.uint8, device=squares.device) if want_outputs else None
+        L.check(self._lib.wann_tree_step(self._ctx, squares.data_ptr(), black.data_ptr(), n, int(bool(greedy)),
+                                         int(seed), int(step), chosen.data_ptr() if want_outputs else None,
+                                         fin.data_ptr() if want_outputs else None, self._torch_stream(squares)))
+        return (chosen, fin) if want_outputs else None
+
     def debug_activations(self, squares, black, layer):
         sq, bl = self._np_in(squares, black)
         n = sq.shape[0]

@@ -20,6 +20,7 @@ class TreeFarm(object):
         self.greedy = greedy
         self.gen = torch.Generator(device=self.dev)
         self.gen.manual_seed(seed)
+        self.seed, self.step_no = int(seed), 0
         self.opening = torch.from_numpy(synthetic.initial_squares()).to(self.dev)
         self.sq = self.opening[None].repeat(self.n, 1).contiguous()
         self.black = torch.zeros(self.n, dtype=torch.uint8, device=self.dev)
@@ -45,6 +46,16 @@ class TreeFarm(object):
         self.last_reset = reset
         self.plies += self.n
         return idx, pri, cnt, k
+
+    def step_fused(self, want_outputs=False):
+        """Same step as ONE C-ABI call (wann_tree_step): evaluation, child choice (counter-based RNG,
+        reproducible on the host), move application and restart all stay on the device, boards are
+        updated in place.  Returns (chosen idx, finished) device tensors when asked."""
+        out = self.ev.tree_step(self.sq, self.black, greedy=self.greedy, seed=self.seed, step=self.step_no,
+                                want_outputs=want_outputs)
+        self.step_no += 1
+        self.plies += self.n
+        return out
 
     def run(self, steps):
         for _ in range(steps):
