@@ -159,6 +159,35 @@ def test_tree_step_oracle_semantics():
     assert O.splitmix64(0) == 0xE220A8397B1DCDAF      # published SplitMix64 first output for seed 0
 
 
+def test_oracle_matches_the_references_own_serialized_graph():
+    """The reference ships its inference graph twice (cppModels/policyNet.pb and the checkpoint's
+    model.meta, TensorFlow 1.0.0).  Executing THAT node list (ops, edges, strides/padding/data_format,
+    the Reshape constant, variable shapes) with textbook op kernels gives the oracle's logits and
+    probabilities: the oracle's reading of policy_net_utils.pyx is the graph TensorFlow built."""
+    from oracle import graph_interp as G
+    pb, meta = G.load("policyNet_pb"), G.load("model_meta")
+    assert [dict(n, name="") for n in pb[:-1]] == [dict(n, name="") for n in meta[:-1]]
+    assert [n["name"] for n in pb[:-1]] == [n["name"] for n in meta[:-1]]
+    assert (pb[-1]["op"], pb[-1]["inputs"]) == (meta[-1]["op"], meta[-1]["inputs"]) == ("Softmax", ["output_layer/output"])
+    ops = [n["op"] for n in pb]
+    assert ops.count("Conv2D") == 5 and ops.count("Relu") == 5 and ops.count("MatMul") == 1
+    var_shapes = {n["name"]: tuple(n["attr"]["shape"]) for n in pb if n["op"] == "VariableV2"}
+    assert var_shapes == {k: tuple(v) for k, v in O.weight_shapes().items()}
+    sq, bl = O.random_positions_fast(12, seed=21)
+    sq[0], bl[0] = O.initial_squares(), 0
+    planes = O.encode_planes(sq, bl)
+    for preset, seed in (("trained_like", 1), ("ref_init", 2)):
+        w = O.synthetic_weights(preset, seed)
+        vals = G.run(pb, {"Placeholder": planes.astype(np.float32)}, w, return_all=True)
+        lg, pr, acts = O.forward_fp32(planes, w, return_all=True)
+        assert vals["output_layer/Softmax"].shape == (12, 155)
+        assert np.abs(vals["output_layer/output"] - lg).max() <= 2e-5 * np.abs(lg).max()
+        assert np.abs(vals["output_layer/Softmax"] - pr).max() <= 2e-6
+        for i in range(1, 6):
+            a = vals["hidden_layer/%d/Relu" % i]
+            assert np.abs(a - acts[i - 1]).max() <= 2e-5 * max(np.abs(a).max(), 1e-6)
+
+
 def test_bf16_round_matches_torch():
     import torch
     x = np.random.RandomState(0).standard_normal(4096).astype(np.float32) * 3
