@@ -173,14 +173,21 @@ int wann_host_free(void* ptr);
 
 /* Counters since create: [0] positions evaluated, [1] kernel launches, [2] calls,
  * [3] H2D bytes, [4] D2H bytes, [5] merged launches made by the coalescer, [6] calls they
- * served, [7] reserved. */
+ * served, [7] positions re-evaluated by the margin-refinement pass (counted when a call ends with a
+ * host synchronisation). */
 int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]);
 
 /* Tunables (optional).  key: "chunk" (positions per internal chunk, default 16384),
  * "coalesce" (0/1: merge concurrent HOST calls of <= 256 positions into one launch -- flat
  * combining, no added latency for a lone caller; the reference calls evaluate with batch 1 from
  * 11 threads), "wimg_copies" (1..8 replicas of the weight image; experiment knob), "variant" (debug bits),
- * "time_kernels" (0/1, see wann_kernel_times). */
+ * "time_kernels" (0/1, see wann_kernel_times),
+ * "refine_margin_micro" (bf16/fp16 modes; margin in 1e-6 logit units, 0 = off): positions whose two
+ * best LEGAL moves are closer than the margin -- log(prior_1 / prior_2) < margin, the only
+ * positions where 16-bit operand rounding can flip the policy move of get_best_move
+ * (board_utils.pyx:262-277) -- are evaluated a second time in the same call by the fp32-class
+ * split kernel (WANN_MODE_FP32_TC arithmetic) and every output row of theirs is overwritten.
+ * Needs board inputs (squares); plane inputs are not refined. */
 int wann_set_option(wann_ctx* ctx, const char* key, int64_t value);
 
 /* Library/ABI version (major*100+minor). */

@@ -483,6 +483,59 @@ def test_tree_step_fused_matches_oracle(ev_bf16, suite):
     assert finished > 0
 
 
+@pytest.mark.parametrize("mode,margin", [("fp16", 0.02), ("bf16", 0.15)])
+def test_margin_refinement_pass(mode, margin, weights, suite, ref1k):
+    """refine_margin: positions whose two best LEGAL priors are closer than the margin (the only ones
+    where 16-bit operand rounding can flip get_best_move's choice) are re-evaluated in the same call
+    with the fp32-class split kernel.  Flagged rows == the fp32_tc mode's rows, every other row is
+    untouched, the counter matches, and top-1 then agrees with the fp32 oracle (north_star: >= 99.9 %)."""
+    import torch
+    import wann_b200
+    sq, bl = suite
+    n = sq.shape[0]
+    with wann_b200.PolicyEvaluator(weights, mode=mode) as plain, \
+            wann_b200.PolicyEvaluator(weights, mode="fp32_tc") as exact, \
+            wann_b200.PolicyEvaluator(weights, mode=mode, refine_margin=margin) as ev:
+        i0, p0, c0 = plain.eval_topk(sq, bl)
+        pr0, lg0 = plain.eval_probs(sq, bl, return_logits=True)
+        ix, px, cx = exact.eval_topk(sq, bl)
+        prx, lgx = exact.eval_probs(sq, bl, return_logits=True)
+        ratio = np.float32(np.exp(-np.float32(margin)))
+        flagged = (c0 >= 2) & (p0[:, 1] >= p0[:, 0] * ratio)
+        edge = np.abs(p0[:, 1] - p0[:, 0] * ratio) <= 1e-6 * p0[:, 0]      # float-rounding of the threshold itself
+        assert 0 < flagged.sum() < n // 2
+        before = ev.stats()["refined_positions"]
+        i1, p1, c1 = ev.eval_topk(sq, bl)
+        assert ev.stats()["refined_positions"] - before == flagged.sum() or edge.any()
+        pr1, lg1 = ev.eval_probs(sq, bl, return_logits=True)
+        f, u = flagged & ~edge, ~flagged & ~edge
+        for got, fast, slow in ((i1, i0, ix), (p1, p0, px), (c1, c0, cx), (pr1, pr0, prx), (lg1, lg0, lgx)):
+            assert np.array_equal(got[u], fast[u])                        # untouched rows: bit-identical
+            assert np.array_equal(got[f], slow[f])                        # refined rows: the fp32_tc result
+        # the policy move now agrees with the fp32 oracle
+        want = O.top1_legal(ref1k["probs"], ref1k["mask"])
+        assert (i1[:, 0] == want).mean() >= 0.999
+        # device path, several chunks (65,536 positions per device chunk) and a ragged tail
+        big = 70001
+        reps = (big + n - 1) // n
+        bsq, bbl = np.tile(sq, (reps, 1))[:big], np.tile(bl, reps)[:big]
+        dev = torch.device("cuda", ev.device)
+        di, dp, dc = ev.eval_topk(torch.from_numpy(bsq).to(dev), torch.from_numpy(bbl).to(dev))
+        torch.cuda.synchronize()
+        assert np.array_equal(di.cpu().numpy(), np.tile(i1, (reps, 1))[:big])
+        assert np.array_equal(dp.cpu().numpy(), np.tile(p1, (reps, 1))[:big])
+        assert np.array_equal(dc.cpu().numpy(), np.tile(c1, reps)[:big])
+        # children are built from the refined ranking
+        ei, ep, ec, kids, flg = ev.eval_expand(sq[:300], bl[:300])
+        assert np.array_equal(ei, i1[:300]) and np.array_equal(ep, p1[:300])
+        wk, wf = O.expand_children(sq[:300], bl[:300], ei, ec)
+        assert np.array_equal(kids, wk) and np.array_equal(flg, wf)
+        # switching it off restores the plain path
+        ev.set_refine_margin(0)
+        i2, p2, c2 = ev.eval_topk(sq, bl)
+        assert np.array_equal(i2, i0) and np.array_equal(p2, p0)
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote

@@ -24,13 +24,16 @@ lo, po = C.forward(O.encode_planes(sq[:m], bl[:m]), w)
 rep = {"positions": n, "weights": "synthetic trained_like seed 1", "logit_sigma": float(l32.std()),
        "fp32_gpu_vs_cpu_oracle_logits_maxnorm": float(np.abs(l32[:m] - lo).max() / np.abs(lo).max()),
        "fp32_gpu_vs_cpu_oracle_top1": float((i32[:m, 0] == O.top1_legal(po, mask[:m])).mean())}
-for mode in ("bf16", "fp16"):
-    with wann_b200.PolicyEvaluator(w, mode=mode) as ev:
+for mode, refine in (("bf16", 0.0), ("fp16", 0.0), ("bf16", 0.15), ("fp16", 0.02), ("fp16", 0.01)):
+    with wann_b200.PolicyEvaluator(w, mode=mode, refine_margin=refine) as ev:
         p, l = ev.eval_probs(sq, bl, return_logits=True)
+        r0 = ev.stats()["refined_positions"]
         idx, pri, cnt = ev.eval_topk(sq, bl)
+        refined = ev.stats()["refined_positions"] - r0
     agree = idx[:, 0] == i32[:, 0]
     d = np.abs(l - l32)
-    rep[mode] = {
+    rep[mode if not refine else "%s+refine%g" % (mode, refine)] = {
+        "refine_margin_logits": refine, "refined_fraction": refined / n,
         "logits_max_abs": float(d.max()), "logits_maxnorm": float(d.max() / np.abs(l32).max()),
         "logits_mean_abs": float(d.mean()),
         "logits_rel_rms": float(np.sqrt((d ** 2).mean()) / l32.std()),

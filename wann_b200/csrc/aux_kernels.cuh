@@ -78,6 +78,17 @@ struct TailParams {
   uint8_t* idx;             // [n][48] or null
   float* prior;             // [n][48]
   uint8_t* n_legal;         // [n]
+  // margin refinement (wann_set_option "refine_margin_milli"):
+  //   flagging pass: boards whose two best LEGAL priors are closer than the margin
+  //                  (p2 >= p1 * refine_ratio, refine_ratio = exp(-margin)) are appended to
+  //                  refine_list, counted in refine_count[0] (this chunk) and [1] (running total);
+  //   refinement pass: h5 holds COMPACT rows for the boards gather[0 .. *n_dev); board row
+  //                  gather[i] of squares / black / every output is (re)written from h5 row i.
+  int* refine_list = nullptr;
+  int* refine_count = nullptr;
+  float refine_ratio = 0.f;
+  const int* gather = nullptr;
+  const int* n_dev = nullptr;
 };
 
 // One warp handles 4 boards per pass (each FC weight read from shared memory feeds 4 FMAs);
@@ -92,6 +103,10 @@ constexpr int kTailSmemBytes = (64 * kMoves + 160) * 4 + 160 * 2 +
 
 __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams p) {
   extern __shared__ float tsm[];
+  // refinement pass: the board count lives on the device (this launch is never made under PDL, so
+  // the flagging pass has completed); CTAs without work leave before touching the FC weights
+  const long long n_eff = (p.n_dev != nullptr) ? min(p.n, static_cast<long long>(*p.n_dev)) : p.n;
+  if (blockIdx.x * static_cast<long long>(kTailWarps * kTailBoards) >= n_eff) return;
   float* w_s = tsm;                                   // [64][155]
   float* b_s = w_s + 64 * kMoves;                     // [160]
   uint16_t* mv_s = reinterpret_cast<uint16_t*>(b_s + 160);   // [160] from | to<<6 | fwd<<12
@@ -114,11 +129,16 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
   float* cp = h + kTailBoards * 64;                   // [48] compact priors
   int8_t* pov = reinterpret_cast<int8_t*>(warp_b + w * (kTailBoards * 64 + 64));   // [4][64]
   uint8_t* cj = reinterpret_cast<uint8_t*>(pov + kTailBoards * 64);                // [48] compact indices
-  const long long ngroups = (p.n + kTailBoards - 1) / kTailBoards;
+  const bool flagging = p.refine_list != nullptr && p.squares != nullptr;
+  const long long ngroups = (n_eff + kTailBoards - 1) / kTailBoards;
   for (long long g = blockIdx.x * static_cast<long long>(kTailWarps) + w; g < ngroups;
        g += static_cast<long long>(gridDim.x) * kTailWarps) {
     const long long board0 = g * kTailBoards;
-    const int nb = static_cast<int>(min(static_cast<long long>(kTailBoards), p.n - board0));
+    const int nb = static_cast<int>(min(static_cast<long long>(kTailBoards), n_eff - board0));
+    long long dst[kTailBoards];     // row of squares / black / outputs that h5 row board0 + t belongs to
+#pragma unroll
+    for (int t = 0; t < kTailBoards; ++t)
+      dst[t] = (p.gather != nullptr && t < nb) ? static_cast<long long>(p.gather[board0 + t]) : board0 + t;
 #pragma unroll
     for (int t = 0; t < kTailBoards * 2; ++t) {        // 4 boards x 64 floats, coalesced
       const int i = t * 32 + lane;
@@ -128,8 +148,8 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
 #pragma unroll
       for (int t = 0; t < kTailBoards; ++t)
         if (t < nb) {
-          const int blk = p.black[board0 + t];
-          const int8_t* sq = p.squares + (board0 + t) * 64;
+          const int blk = p.black[dst[t]];
+          const int8_t* sq = p.squares + dst[t] * 64;
           pov[t * 64 + lane] = static_cast<int8_t>(pov_square(sq, blk, lane));
           pov[t * 64 + lane + 32] = static_cast<int8_t>(pov_square(sq, blk, lane + 32));
         }
@@ -158,7 +178,7 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
 #pragma unroll
     for (int t = 0; t < kTailBoards; ++t) {
       if (t >= nb) break;
-      const long long board = board0 + t;
+      const long long board = dst[t];
       float e[5];
       float mx = -INFINITY;
 #pragma unroll
@@ -190,7 +210,7 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
           if (p.logits != nullptr) p.logits[board * kMoves + j] = e[k];
         }
       }
-      if (p.idx != nullptr) {
+      if (p.idx != nullptr || flagging) {
         // legal gather: prior_i = softmax155[idx_i] (no renormalisation); compact in ascending
         // index order, then rank: descending by prior, ties by ascending index.
         const int8_t* pv = pov + t * 64;
@@ -227,15 +247,23 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
                 const float other = cp[o];
                 rank += (other > me) || (other == me && o < c);
               }
-              p.idx[board * kMaxLegal + rank] = cj[c];
-              p.prior[board * kMaxLegal + rank] = me;
-            } else {
+              if (p.idx != nullptr) {
+                p.idx[board * kMaxLegal + rank] = cj[c];
+                p.prior[board * kMaxLegal + rank] = me;
+              }
+              if (flagging && rank < 2) cp[kMaxLegal + rank] = me;   // the two best legal priors
+            } else if (p.idx != nullptr) {
               p.idx[board * kMaxLegal + c] = 255;
               p.prior[board * kMaxLegal + c] = 0.f;
             }
           }
         }
-        if (lane == 0) p.n_legal[board] = static_cast<uint8_t>(cnt);
+        if (lane == 0 && p.idx != nullptr) p.n_legal[board] = static_cast<uint8_t>(cnt);
+        __syncwarp();
+        if (flagging && lane == 0 && cnt >= 2 && cp[kMaxLegal + 1] >= cp[kMaxLegal] * p.refine_ratio) {
+          p.refine_list[atomicAdd(p.refine_count, 1)] = static_cast<int>(board);
+          atomicAdd(p.refine_count + 1, 1);
+        }
         __syncwarp();
       }
     }

@@ -55,7 +55,11 @@ conv_stack_split_kernel(const TcParams p) {
   const uint32_t rank = ptx::cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
-  const long long total_st = (p.n + kSplitBoardsPerPair - 1) / kSplitBoardsPerPair;
+  // refinement pass: the number of boards is only known on the device (written by the tail kernel
+  // launched before us on the same stream, never under programmatic dependent launch)
+  const long long n_eff = (p.n_dev != nullptr) ? min(p.n, static_cast<long long>(*p.n_dev)) : p.n;
+  const long long total_st = (n_eff + kSplitBoardsPerPair - 1) / kSplitBoardsPerPair;
+  if (pair >= total_st) return;   // both CTAs of the pair leave together, before any cluster traffic
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -219,11 +223,15 @@ conv_stack_split_kernel(const TcParams p) {
     auto board_of = [&](long long st) {
       return st * kSplitBoardsPerPair + static_cast<int>(rank) * 2 + b;
     };
+    auto load_in = [&](long long board) {
+      if (board >= n_eff) return make_uint2(0u, 0u);
+      return load_input_cell<true>(p, p.gather != nullptr ? static_cast<long long>(p.gather[board]) : board, y, x);
+    };
 
     ptx::pdl_wait();
     long long st = pair;
     if (st < total_st) {
-      if (chalf == 0) store_input_cell(cell_hi, load_input_cell<true>(p, board_of(st), y, x));
+      if (chalf == 0) store_input_cell(cell_hi, load_in(board_of(st)));
       signal_a_ready();
     }
     uint32_t lstep = 0;
@@ -235,7 +243,7 @@ conv_stack_split_kernel(const TcParams p) {
         ptx::tc_fence_after();
         if (layer < 4) {
           const float* bs = bias_s + layer * kC + chalf * 96;
-          float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < p.n)
+          float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < n_eff)
                            ? p.dbg + (board * 64 + y * 8 + x) * kC + chalf * 96 : nullptr;
 #pragma unroll 1
           for (int ch = 0; ch < 3; ++ch) {
@@ -292,9 +300,9 @@ conv_stack_split_kernel(const TcParams p) {
                                       (tap % 4) * 4);
           }
           const float hval = fmaxf(acc + bias_s[4 * kC], 0.f);
-          if (board < p.n) p.h5[board * 64 + y * 8 + x] = hval;
+          if (board < n_eff) p.h5[board * 64 + y * 8 + x] = hval;
           if (st + npairs < total_st)
-            store_input_cell(cell_hi, load_input_cell<true>(p, board_of(st + npairs), y, x));
+            store_input_cell(cell_hi, load_in(board_of(st + npairs)));
         }
         signal_a_ready();
       }

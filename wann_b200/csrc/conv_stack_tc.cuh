@@ -106,6 +106,10 @@ struct TcParams {
   long long* prof;           // optional [8][kProfSteps] clock64 stamps of pair 0 (debug):
                              // half h: [4h+0] MMA start, [4h+1] MMA issue end,
                              //         [4h+2] epilogue start, [4h+3] epilogue end
+  // margin refinement pass (conv_stack_split_kernel only): evaluate the boards gather[0..*n_dev)
+  // of `squares` and write their h5 rows COMPACTLY (row i <- board gather[i]); both null otherwise
+  const int* gather = nullptr;
+  const int* n_dev = nullptr;
 };
 
 // bounded mbarrier wait: returns false (and records who/where) instead of hanging the GPU

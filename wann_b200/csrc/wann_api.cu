@@ -97,6 +97,8 @@ struct Slot {
   int* h_err = nullptr;     // pinned
   float* d_act0 = nullptr;  // fp32 mode ping-pong activations
   float* d_act1 = nullptr;
+  float* d_h5r = nullptr;   // margin refinement: compact h5 rows of the flagged boards (lazy)
+  int* d_rlist = nullptr;   //                    their board indices (lazy)
   long long cap = 0;        // positions
 };
 
@@ -140,6 +142,10 @@ struct wann_ctx {
   float* d_fc_w = nullptr;
   float* d_fc_b = nullptr;
   uint8_t* d_wimg = nullptr;   // tensor-core weight stage images, [2][kImgBytesPerRank]
+  uint8_t* d_wimg_split = nullptr;   // bf16/fp16 modes: the fp16 hi/lo split image of the refinement pass
+  // margin refinement: boards whose two best legal priors are closer than `margin` logits are
+  // re-evaluated by conv_stack_split_kernel (fp32-class); refine_ratio = exp(-margin), 0 = off
+  std::atomic<float> refine_ratio{0.f};
   float* d_bias_tc = nullptr;  // [4*192 + 1]
   Lane lanes[kLanes];
   std::mutex mu;
@@ -287,6 +293,7 @@ void free_slot(Slot& s) {
   cudaFree(s.d_nlegal); cudaFree(s.d_planes_out); cudaFree(s.d_mask); cudaFree(s.d_err);
   if (s.h_err) cudaFreeHost(s.h_err);
   cudaFree(s.d_act0); cudaFree(s.d_act1); cudaFree(s.d_children); cudaFree(s.d_cflags);
+  cudaFree(s.d_h5r); cudaFree(s.d_rlist);
   s = Slot();
 }
 
@@ -426,6 +433,18 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
     t.h5 = ws.d_h5; t.squares = io.squares; t.black = io.black; t.n = n;
     t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
     t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal;
+    const float refine_ratio = ctx->refine_ratio.load();
+    const bool refine = refine_ratio > 0.f && io.squares != nullptr && io.dbg == nullptr && io.prof == nullptr &&
+                        (ctx->mode == WANN_MODE_BF16 || ctx->mode == WANN_MODE_FP16);
+    int* d_rcount = ws.d_err + 4;     // [0] flagged boards of this chunk, [1] running total
+    if (refine) {
+      if (ws.d_h5r == nullptr) {
+        CU(cudaMalloc(&ws.d_h5r, ws.cap * kDevChunkMul * 64 * 4));
+        CU(cudaMalloc(&ws.d_rlist, ws.cap * kDevChunkMul * sizeof(int)));
+      }
+      CU(cudaMemsetAsync(d_rcount, 0, sizeof(int), stream));
+      t.refine_list = ws.d_rlist; t.refine_count = d_rcount; t.refine_ratio = refine_ratio;
+    }
     const long long groups = (n + kTailBoards - 1) / kTailBoards;
     const int blocks = static_cast<int>(
         std::min<long long>((groups + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
@@ -443,6 +462,23 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       CU(cudaLaunchKernelEx(&cfg, tail_kernel, t));
     }
     ++launches;
+    if (refine) {
+      // pass 2: the flagged boards again, fp32-class (fp16 hi/lo split on the tensor cores), their
+      // rows of every output overwritten.  Grids are sized for "all flagged"; CTAs beyond the
+      // device-side count return at once.
+      TcParams p = {};
+      p.squares = io.squares; p.black = io.black; p.n = n; p.wimg = ctx->d_wimg_split; p.wimg_copies = 1;
+      p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5r; p.err = ws.d_err; p.halves = 2;
+      p.gather = ws.d_rlist; p.n_dev = d_rcount;
+      const long long total_st = (n + kSplitBoardsPerPair - 1) / kSplitBoardsPerPair;
+      const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
+      conv_stack_split_kernel<<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
+      TailParams t2 = t;
+      t2.h5 = ws.d_h5r; t2.refine_list = nullptr; t2.refine_count = nullptr;
+      t2.gather = ws.d_rlist; t2.n_dev = d_rcount;
+      tail_kernel<<<blocks, kTailWarps * 32, kTailSmemBytes, stream>>>(t2);
+      launches += 2;
+    }
     if (io.children != nullptr) {
       const int eb = static_cast<int>(std::min<long long>((n + 7) / 8, 16ll * ctx->sm_count));
       expand_children_kernel<<<eb, 256, 0, stream>>>(io.squares, io.black, io.idx, io.nlegal, n, io.children,
@@ -456,7 +492,19 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   return WANN_OK;
 }
 
-int check_device_err(Slot& s) {
+// D2H of the slot's watchdog record and refinement counter (read after the stream has drained)
+cudaError_t copy_device_err(wann_ctx* ctx, Slot& s, cudaStream_t stream) {
+  cudaError_t e = cudaMemcpyAsync(s.h_err, s.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess && ctx->refine_ratio.load() > 0.f)
+    e = cudaMemsetAsync(s.d_err + 5, 0, sizeof(int), stream);   // running total handed to the host
+  return e;
+}
+
+int check_device_err(wann_ctx* ctx, Slot& s) {
+  if (s.h_err[5] != 0) {
+    ctx->stats[7] += static_cast<uint64_t>(s.h_err[5]);   // positions re-evaluated by the refinement pass
+    s.h_err[5] = 0;
+  }
   if (s.h_err[0] != 0) {
     const int code = s.h_err[0], blk = s.h_err[1], par = s.h_err[2];
     memset(s.h_err, 0, 8 * sizeof(int));
@@ -510,10 +558,10 @@ int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void*
     if (rc != WANN_OK) return rc;
   }
   if (stream_v == nullptr) {
-    CU(cudaMemcpyAsync(ws.h_err, ws.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CU(copy_device_err(ctx, ws, stream));
     CU(cudaStreamSynchronize(stream));
     lane->last_valid = false;
-    return check_device_err(ws);
+    return check_device_err(ctx, ws);
   }
   // caller's stream: later users of this lane on OTHER streams wait for this event
   CU(cudaEventRecord(lane->last, stream));
@@ -539,7 +587,7 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
     if (s.busy) {
       s.busy = false;
       CU(cudaEventSynchronize(s.done));
-      int rc = check_device_err(s);
+      int rc = check_device_err(ctx, s);
       if (rc != WANN_OK) return rc;
     }
     ChunkIO io;
@@ -589,7 +637,7 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
       }
       if (a.dbg) D2H(a.dbg + off * 64 * dbg_c, d_dbg, m * 64 * dbg_c * 4);
       if (e == cudaSuccess)
-        e = cudaMemcpyAsync(s.h_err, s.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+        e = copy_device_err(ctx, s, s.stream);
       if (e == cudaSuccess) e = cudaEventRecord(s.done, s.stream);
       if (e == cudaSuccess) s.busy = true;
       else rc = fail(WANN_E_CUDA, "D2H enqueue: %s", cudaGetErrorString(e));
@@ -604,7 +652,7 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
       s.busy = false;
       cudaError_t e = cudaEventSynchronize(s.done);
       if (e != cudaSuccess && rc == WANN_OK) rc = fail(WANN_E_CUDA, "event sync: %s", cudaGetErrorString(e));
-      if (rc == WANN_OK) rc = check_device_err(s);
+      if (rc == WANN_OK) rc = check_device_err(ctx, s);
     }
   }
   ctx->stats[3] += h2d;
@@ -777,6 +825,12 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
     e = cudaMalloc(&ctx->d_wimg, img.size() * copies);
     for (int c = 0; c < copies && e == cudaSuccess; ++c)
       e = cudaMemcpy(ctx->d_wimg + c * img.size(), img.data(), img.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && mode != WANN_MODE_FP32_TC) {
+      std::vector<uint8_t> simg;
+      build_weight_image_split(*w, simg);
+      e = cudaMalloc(&ctx->d_wimg_split, simg.size());
+      if (e == cudaSuccess) e = cudaMemcpy(ctx->d_wimg_split, simg.data(), simg.size(), cudaMemcpyHostToDevice);
+    }
     std::vector<float> bias(4 * 192 + 4, 0.f);
     for (int l = 0; l < 4; ++l) memcpy(bias.data() + l * 192, w->conv_b[l], 192 * 4);
     bias[4 * 192] = w->conv_b[4][0];
@@ -829,7 +883,7 @@ int wann_destroy(wann_ctx* ctx) {
     cudaFreeHost(ctx->c_idx); cudaFreeHost(ctx->c_prior); cudaFreeHost(ctx->c_nlegal);
   }
   for (int i = 0; i < 5; ++i) { cudaFree(ctx->d_conv_w[i]); cudaFree(ctx->d_conv_b[i]); }
-  cudaFree(ctx->d_fc_w); cudaFree(ctx->d_fc_b); cudaFree(ctx->d_wimg); cudaFree(ctx->d_bias_tc);
+  cudaFree(ctx->d_fc_w); cudaFree(ctx->d_fc_b); cudaFree(ctx->d_wimg); cudaFree(ctx->d_wimg_split); cudaFree(ctx->d_bias_tc);
   delete ctx;
   return WANN_OK;
 }
@@ -1116,6 +1170,14 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "small_batch_halves") == 0) { ctx->small_batch_halves = value != 0; return WANN_OK; }
   if (strcmp(key, "pdl") == 0) { ctx->pdl = value != 0; return WANN_OK; }
   if (strcmp(key, "coalesce") == 0) { ctx->coalesce = value != 0; return WANN_OK; }
+  if (strcmp(key, "refine_margin_micro") == 0) {
+    // margin in 1e-6 logit units; 0 switches the refinement pass off
+    if (value < 0 || value > 20000000) return fail(WANN_E_INVALID, "refine margin out of range");
+    if (value > 0 && ctx->mode != WANN_MODE_BF16 && ctx->mode != WANN_MODE_FP16)
+      return fail(WANN_E_INVALID, "margin refinement applies to the bf16/fp16 tensor-core modes");
+    ctx->refine_ratio = value == 0 ? 0.f : expf(-static_cast<float>(value) * 1e-6f);
+    return WANN_OK;
+  }
   if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
   if (strcmp(key, "chunk") == 0) {
     if (value < 8 || value > (1 << 20)) return fail(WANN_E_INVALID, "chunk out of range");

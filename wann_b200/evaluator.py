@@ -16,7 +16,8 @@ def _is_torch(x):
 
 
 class PolicyEvaluator(object):
-    def __init__(self, weights=None, device=0, mode="bf16", final_kernel=3, chunk=None, coalesce=False):
+    def __init__(self, weights=None, device=0, mode="bf16", final_kernel=3, chunk=None, coalesce=False,
+                 refine_margin=0.0):
         lib = L.load()
         w = W.validate(weights if weights is not None else W.default_weights(final_kernel=final_kernel), final_kernel)
         self._keep = w
@@ -37,6 +38,8 @@ class PolicyEvaluator(object):
             self.set_option("chunk", chunk)
         if coalesce:
             self.set_option("coalesce", 1)
+        if refine_margin:
+            self.set_refine_margin(refine_margin)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -55,12 +58,17 @@ class PolicyEvaluator(object):
     def set_option(self, key, value):
         L.check(self._lib.wann_set_option(self._ctx, key.encode(), int(value)))
 
+    def set_refine_margin(self, margin_logits):
+        """bf16/fp16 modes: re-evaluate, inside the same call, every position whose two best legal
+        moves are closer than `margin_logits` with fp32-class arithmetic (0 switches it off)."""
+        self.set_option("refine_margin_micro", int(round(float(margin_logits) * 1e6)))
+
     def stats(self):
         arr = (ctypes.c_uint64 * 8)()
         L.check(self._lib.wann_get_stats(self._ctx, ctypes.byref(arr)))
         keys = ["positions", "kernel_launches", "calls", "h2d_bytes", "d2h_bytes", "merged_launches",
-                "merged_calls"]
-        return dict(zip(keys, list(arr)[:7]))
+                "merged_calls", "refined_positions"]
+        return dict(zip(keys, list(arr)))
 
     @staticmethod
     def _np_in(squares, black):
