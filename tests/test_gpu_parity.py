@@ -265,6 +265,16 @@ def test_session_shim_is_a_drop_in(weights, suite, ref1k):
         assert np.array_equal(net.evaluate([nodes[5]])[0], out[5])     # tree_builder.pyx:830
         idx, pri, cnt = net.evaluate_children(nodes)
         assert np.array_equal(idx[:, 0], O.top1_legal(out, ref1k["mask"][:40]))
+    # the shim's DEFAULT arithmetic (fp16 operands + margin refinement): every policy move equals
+    # the fp32 graph's (get_best_move, board_utils.pyx:262-277), probabilities in the 1e-3 class
+    all_nodes = [{"game_board": boards.squares_to_board(sq[i], 0 if bl[i] else 1),
+                  "color": "Black" if bl[i] else "White"} for i in range(len(sq))]
+    _, pr_ref = O.forward_fp32(ref1k["planes"], w1)
+    with wann_b200.NeuralNetsCombined_128(w1) as net:
+        out = net.evaluate(all_nodes)
+        assert nerr(out, pr_ref) < 5e-3          # probabilities: d p = p * d logit, logits are in the 1.5e-3 class
+        assert np.array_equal(O.top1_legal(out, ref1k["mask"]), O.top1_legal(pr_ref, ref1k["mask"]))
+        assert net.sess.evaluator("white_net").stats()["refined_positions"] > 0
     sess, y_pred, X = wann_b200.instantiate_session(weights, mode="fp32")    # policy_net_utils.pyx:64
     got = sess.run(y_pred, feed_dict={X: [p for p in ref1k["planes"][:16]]})
     assert nerr(got, ref1k["probs"][:16]) < 1e-5
@@ -534,6 +544,28 @@ def test_margin_refinement_pass(mode, margin, weights, suite, ref1k):
         ev.set_refine_margin(0)
         i2, p2, c2 = ev.eval_topk(sq, bl)
         assert np.array_equal(i2, i0) and np.array_equal(p2, p0)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_zero_copy_small_host_calls_equal_the_dma_path(mode, weights, suite, ref1k):
+    """Host calls of <= 512 positions read their inputs from / write their outputs to pinned mapped
+    host memory directly (no cudaMemcpy): bit-identical to the staged DMA path, for every input form."""
+    import wann_b200
+    sq, bl = suite
+    with wann_b200.PolicyEvaluator(weights, mode=mode) as ev:
+        for n in (1, 7, 300, 512):
+            res = {}
+            for zc in (0, 1):
+                ev.set_option("zero_copy", zc)
+                pr, lg = ev.eval_probs(sq[:n], bl[:n], return_logits=True)
+                res[zc] = (pr, lg) + tuple(ev.eval_topk(sq[:n], bl[:n])) + \
+                    (ev.eval_planes(ref1k["planes"][:n]), ev.eval_planes(ref1k["planes"][:n].astype(np.float32)))
+            for a, b in zip(res[0], res[1]):
+                assert np.array_equal(a, b)
+        ev.set_option("zero_copy", 1)
+        h0 = ev.stats()["h2d_bytes"]
+        ev.eval_topk(sq[:5], bl[:5])
+        assert ev.stats()["h2d_bytes"] - h0 == 5 * 65
 
 
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):

@@ -89,6 +89,10 @@ struct TailParams {
   float refine_ratio = 0.f;
   const int* gather = nullptr;
   const int* n_dev = nullptr;
+  // zero-copy small calls: the slot's device-side watchdog / refinement record is mirrored into
+  // host-mapped memory by the last kernel of the call (saves a D2H copy on the latency path)
+  const int* err_src = nullptr;
+  int* err_dst = nullptr;
 };
 
 // One warp handles 4 boards per pass (each FC weight read from shared memory feeds 4 FMAs);
@@ -106,6 +110,10 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
   // refinement pass: the board count lives on the device (this launch is never made under PDL, so
   // the flagging pass has completed); CTAs without work leave before touching the FC weights
   const long long n_eff = (p.n_dev != nullptr) ? min(p.n, static_cast<long long>(*p.n_dev)) : p.n;
+  if (p.err_dst != nullptr && blockIdx.x == 0 && threadIdx.x < 8) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    p.err_dst[threadIdx.x] = p.err_src[threadIdx.x];
+  }
   if (blockIdx.x * static_cast<long long>(kTailWarps * kTailBoards) >= n_eff) return;
   float* w_s = tsm;                                   // [64][155]
   float* b_s = w_s + 64 * kMoves;                     // [160]

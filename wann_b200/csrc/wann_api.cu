@@ -99,6 +99,9 @@ struct Slot {
   float* d_act1 = nullptr;
   float* d_h5r = nullptr;   // margin refinement: compact h5 rows of the flagged boards (lazy)
   int* d_rlist = nullptr;   //                    their board indices (lazy)
+  uint32_t refine_seen = 0; // value of the monotonic device counter d_err[5] already added to the stats
+  uint8_t* z_in = nullptr;  // zero-copy small host calls: pinned, device-mapped staging (lazy)
+  uint8_t* z_out = nullptr;
   long long cap = 0;        // positions
 };
 
@@ -114,6 +117,7 @@ constexpr int kLanes = 4;
 constexpr long long kDevChunkMul = 4;
 constexpr long long kCombineMaxCall = 256;    // host calls up to this many positions may be merged
 constexpr long long kCombineMaxBatch = 4096;  // positions per merged launch
+constexpr long long kZeroCopyMax = 512;       // host calls up to this many positions skip the DMA copies
 
 // One small host call waiting to be merged with its concurrent siblings (flat combining).
 struct CombineReq {
@@ -134,6 +138,7 @@ struct wann_ctx {
   int variant = 0;
   bool pdl = false;            // programmatic dependent launch conv-stack <-> tail (measured: slower, off)
   bool small_batch_halves = true;   // batches <= 4 x (SM pairs) run 4-board supertiles
+  bool zero_copy = true;            // host calls <= kZeroCopyMax positions: kernels read/write mapped host memory
   int skew = 4;                // conv_stack_tc: stages by which half 1 trails the weight stream (0..6)
   int wimg_copies = 1;         // replicas of the weight image in use (experiment knob; measured: no effect)
   // weights on device
@@ -294,6 +299,8 @@ void free_slot(Slot& s) {
   if (s.h_err) cudaFreeHost(s.h_err);
   cudaFree(s.d_act0); cudaFree(s.d_act1); cudaFree(s.d_children); cudaFree(s.d_cflags);
   cudaFree(s.d_h5r); cudaFree(s.d_rlist);
+  if (s.z_in) cudaFreeHost(s.z_in);
+  if (s.z_out) cudaFreeHost(s.z_out);
   s = Slot();
 }
 
@@ -360,6 +367,7 @@ struct ChunkIO {   // device pointers for one chunk
   long long* prof = nullptr;
   int8_t* children = nullptr;
   uint8_t* cflags = nullptr;
+  int* err_mirror = nullptr;    // host-mapped copy of the slot's d_err, written by the last kernel
 };
 
 // Enqueue encode -> conv stack -> tail for `n` positions on `stream`, using `ws` workspaces.
@@ -445,6 +453,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       CU(cudaMemsetAsync(d_rcount, 0, sizeof(int), stream));
       t.refine_list = ws.d_rlist; t.refine_count = d_rcount; t.refine_ratio = refine_ratio;
     }
+    if (io.err_mirror != nullptr && !refine) { t.err_src = ws.d_err; t.err_dst = io.err_mirror; }
     const long long groups = (n + kTailBoards - 1) / kTailBoards;
     const int blocks = static_cast<int>(
         std::min<long long>((groups + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
@@ -476,6 +485,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       TailParams t2 = t;
       t2.h5 = ws.d_h5r; t2.refine_list = nullptr; t2.refine_count = nullptr;
       t2.gather = ws.d_rlist; t2.n_dev = d_rcount;
+      if (io.err_mirror != nullptr) { t2.err_src = ws.d_err; t2.err_dst = io.err_mirror; }
       tail_kernel<<<blocks, kTailWarps * 32, kTailSmemBytes, stream>>>(t2);
       launches += 2;
     }
@@ -493,20 +503,18 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
 }
 
 // D2H of the slot's watchdog record and refinement counter (read after the stream has drained)
-cudaError_t copy_device_err(wann_ctx* ctx, Slot& s, cudaStream_t stream) {
-  cudaError_t e = cudaMemcpyAsync(s.h_err, s.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess && ctx->refine_ratio.load() > 0.f)
-    e = cudaMemsetAsync(s.d_err + 5, 0, sizeof(int), stream);   // running total handed to the host
-  return e;
+cudaError_t copy_device_err(wann_ctx*, Slot& s, cudaStream_t stream) {
+  return cudaMemcpyAsync(s.h_err, s.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream);
 }
 
 int check_device_err(wann_ctx* ctx, Slot& s) {
-  if (s.h_err[5] != 0) {
-    ctx->stats[7] += static_cast<uint64_t>(s.h_err[5]);   // positions re-evaluated by the refinement pass
-    s.h_err[5] = 0;
-  }
+  // d_err[5]: monotonic count of positions re-evaluated by the refinement pass on this slot
+  const uint32_t refined = static_cast<uint32_t>(s.h_err[5]);
+  ctx->stats[7] += static_cast<uint64_t>(refined - s.refine_seen);
+  s.refine_seen = refined;
   if (s.h_err[0] != 0) {
     const int code = s.h_err[0], blk = s.h_err[1], par = s.h_err[2];
+    s.refine_seen = 0;
     memset(s.h_err, 0, 8 * sizeof(int));
     cudaMemset(s.d_err, 0, 8 * sizeof(int));
     return fail(WANN_E_KERNEL, "conv_stack_tc watchdog: wait site %d timed out (block %d, parity %d)",
@@ -570,9 +578,72 @@ int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void*
   return WANN_OK;
 }
 
+// Small HOST calls (<= kZeroCopyMax positions -- what the reference's tree produces): no DMA copies
+// at all.  Inputs are staged into pinned, device-mapped memory that the kernels read directly over
+// PCIe (65 B per position), the tail kernel writes probabilities / ranked priors and the watchdog
+// record straight into mapped host memory, and the call ends with one stream synchronisation.
+// Replaces 2 H2D + up to 6 D2H cudaMemcpyAsync per call.
+int eval_host_small(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
+  Slot& s = lane->slot[0];
+  const size_t plane_elt = a.planes_dtype == WANN_PLANES_F32 ? 4 : 1;
+  constexpr size_t kIn = static_cast<size_t>(kZeroCopyMax) * 256 * 4;
+  constexpr size_t kOutProbs = static_cast<size_t>(kZeroCopyMax) * kMoves * 4;
+  constexpr size_t kOutIdx = static_cast<size_t>(kZeroCopyMax) * kMaxLegal;
+  if (s.z_in == nullptr) {
+    CU(cudaHostAlloc(&s.z_in, kIn, cudaHostAllocMapped));
+    CU(cudaHostAlloc(&s.z_out, 2 * kOutProbs + 5 * kOutIdx + kZeroCopyMax + 64, cudaHostAllocMapped));
+  }
+  lane_wait(lane, s.stream);
+  lane->last_valid = false;
+  uint8_t* z_probs = s.z_out;
+  uint8_t* z_logits = z_probs + kOutProbs;
+  uint8_t* z_prior = z_logits + kOutProbs;
+  uint8_t* z_idx = z_prior + 4 * kOutIdx;
+  uint8_t* z_nlegal = z_idx + kOutIdx;
+  int* z_err = reinterpret_cast<int*>(z_nlegal + kZeroCopyMax);   // 32 B, 4-byte aligned
+  ChunkIO io;
+  uint64_t h2d = 0, d2h = 0;
+  if (a.squares) {
+    int8_t* zs = reinterpret_cast<int8_t*>(s.z_in);
+    uint8_t* zb = s.z_in + n * 64;
+    memcpy(zs, a.squares, n * 64);
+    memcpy(zb, a.black, n);
+    io.squares = zs; io.black = zb;
+    h2d = n * 65;
+  } else {
+    memcpy(s.z_in, a.planes, n * 256 * plane_elt);
+    io.planes = s.z_in; io.planes_f32 = a.planes_dtype == WANN_PLANES_F32;
+    h2d = n * 256 * plane_elt;
+  }
+  io.probs = a.probs ? reinterpret_cast<float*>(z_probs) : nullptr;
+  io.logits = a.logits ? reinterpret_cast<float*>(z_logits) : nullptr;
+  if (a.idx) { io.idx = z_idx; io.prior = reinterpret_cast<float*>(z_prior); io.nlegal = z_nlegal; }
+  io.err_mirror = z_err;
+  int rc = enqueue_eval(ctx, s, s.stream, io, n);
+  if (rc != WANN_OK) return rc;
+  CU(cudaStreamSynchronize(s.stream));
+  memcpy(s.h_err, z_err, 8 * sizeof(int));
+  rc = check_device_err(ctx, s);
+  if (rc != WANN_OK) return rc;
+  if (a.probs) { memcpy(a.probs, z_probs, n * kMoves * 4); d2h += n * kMoves * 4; }
+  if (a.logits) { memcpy(a.logits, z_logits, n * kMoves * 4); d2h += n * kMoves * 4; }
+  if (a.idx) {
+    memcpy(a.idx, z_idx, n * kMaxLegal);
+    memcpy(a.prior, z_prior, n * kMaxLegal * 4);
+    memcpy(a.nlegal, z_nlegal, n);
+    d2h += n * (kMaxLegal * 5 + 1);
+  }
+  ctx->stats[3] += h2d;
+  ctx->stats[4] += d2h;
+  return WANN_OK;
+}
+
 // HOST memory: chunked, double-buffered over the lane's two slots so that the H2D copy of
 // chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
 int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
+  if (ctx->zero_copy && n <= kZeroCopyMax && a.dbg == nullptr && a.children == nullptr &&
+      (a.probs != nullptr || a.logits != nullptr || a.idx != nullptr))
+    return eval_host_small(ctx, lane, a, n);
   const long long cap = lane->slot[0].cap;
   const size_t plane_elt = a.planes_dtype == WANN_PLANES_F32 ? 4 : 1;
   const long long dbg_c = (a.dbg_layer == 5) ? 1 : 192;
@@ -1169,6 +1240,7 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
   }
   if (strcmp(key, "small_batch_halves") == 0) { ctx->small_batch_halves = value != 0; return WANN_OK; }
   if (strcmp(key, "pdl") == 0) { ctx->pdl = value != 0; return WANN_OK; }
+  if (strcmp(key, "zero_copy") == 0) { ctx->zero_copy = value != 0; return WANN_OK; }
   if (strcmp(key, "coalesce") == 0) { ctx->coalesce = value != 0; return WANN_OK; }
   if (strcmp(key, "refine_margin_micro") == 0) {
     // margin in 1e-6 logit units; 0 switches the refinement pass off

@@ -9,6 +9,8 @@ so that MCTS.pyx, expansion_MCTS_functions.pyx / tree_builder.pyx (policy_net.ev
 and policy_net_utils.pyx (sess.run(y_pred, feed_dict={X: batch})) work unchanged on top of the
 B200 kernels.  Documented divergence: inputs longer than 16,384 return the correct [N,155]
 array (the reference's multi-chunk concatenation, MCTS.pyx:124, is broken)."""
+import os
+
 import numpy as np
 
 from . import boards
@@ -69,38 +71,52 @@ class Session(object):
         self.close()
 
 
-def _make(weights, device, mode, final_kernel):
+# Default arithmetic of the shim: fp16 operands on the tensor cores (logits within 1.5e-3 of the
+# fp32 graph at the bf16 mode's speed) plus the margin-refinement pass, which re-evaluates the
+# ~2 % of positions whose two best legal moves are within 0.02 logits with fp32-class arithmetic:
+# the policy move (get_best_move, board_utils.pyx:262-277) then equals the fp32 graph's on every
+# one of 100,000 test positions (profiles/r01_accuracy_100k_with_refinement.json).
+# Override per call (mode=..., refine_margin=...) or with WANN_B200_MODE / WANN_B200_REFINE_MARGIN.
+DEFAULT_MODE = os.environ.get("WANN_B200_MODE", "fp16")
+DEFAULT_REFINE_MARGIN = float(os.environ.get("WANN_B200_REFINE_MARGIN", "0.02"))
+
+
+def _make(weights, device, mode, final_kernel, refine_margin=None):
+    mode = DEFAULT_MODE if mode is None else mode
+    if refine_margin is None:
+        refine_margin = DEFAULT_REFINE_MARGIN if mode in ("fp16", "bf16") else 0.0
     # coalesce=True: the reference calls evaluate concurrently from its ThreadPool(10) + main
     # thread, each with a single node (expansion_MCTS_functions.pyx:105-119); concurrent small
     # calls are merged into one launch inside the C++ runtime.
     return PolicyEvaluator(weights if weights is not None else W.default_weights(final_kernel=final_kernel), device=device,
-                           mode=mode, final_kernel=final_kernel, coalesce=True)
+                           mode=mode, final_kernel=final_kernel, coalesce=True, refine_margin=refine_margin)
 
 
-def instantiate_session(weights=None, device=0, mode="bf16"):
+def instantiate_session(weights=None, device=0, mode=None, refine_margin=None):
     """policy_net_utils.pyx:64-76 / PolicyNet.py:25-36 -> (sess, y_pred, X)."""
-    sess = Session({"policy": _make(weights, device, mode, 3)})
+    sess = Session({"policy": _make(weights, device, mode, 3, refine_margin)})
     return sess, _Endpoint("policy", "y_pred"), _Endpoint("policy", "X")
 
 
-def _both(weights_white, weights_black, device, mode, final_kernel):
-    white = _make(weights_white, device, mode, final_kernel)
+def _both(weights_white, weights_black, device, mode, final_kernel, refine_margin=None):
+    white = _make(weights_white, device, mode, final_kernel, refine_margin)
     black = white if weights_black is None and weights_white is None else \
-        _make(weights_black if weights_black is not None else weights_white, device, mode, final_kernel)
+        _make(weights_black if weights_black is not None else weights_white, device, mode, final_kernel,
+              refine_margin)
     sess = Session({"white_net": white, "black_net": black})
     return (sess, _Endpoint("white_net", "y_pred"), _Endpoint("white_net", "X"),
             _Endpoint("black_net", "y_pred"), _Endpoint("black_net", "X"))
 
 
-def instantiate_session_both(weights_white=None, weights_black=None, device=0, mode="bf16"):
+def instantiate_session_both(weights_white=None, weights_black=None, device=0, mode=None, refine_margin=None):
     """policy_net_utils.pyx:19-39 -> (sess, y_pred_white, X_white, y_pred_black, X_black)."""
-    return _both(weights_white, weights_black, device, mode, 3)
+    return _both(weights_white, weights_black, device, mode, 3, refine_margin)
 
 
-def instantiate_session_both_128(weights_white=None, weights_black=None, device=0, mode="bf16",
-                                 final_kernel=1):
+def instantiate_session_both_128(weights_white=None, weights_black=None, device=0, mode=None,
+                                 final_kernel=1, refine_margin=None):
     """policy_net_utils.pyx:40-60: the `_128` nets (last conv 1x1, :135)."""
-    return _both(weights_white, weights_black, device, mode, final_kernel)
+    return _both(weights_white, weights_black, device, mode, final_kernel, refine_margin)
 
 
 def call_policy_net(board_representation, weights=None):
@@ -119,10 +135,11 @@ class NeuralNetsCombined_128(object):
 
     BATCH_SIZE = 16384   # MCTS.pyx:96 (kept as the internal chunk size)
 
-    def __init__(self, weights_white=None, weights_black=None, device=0, mode="bf16", final_kernel=1):
+    def __init__(self, weights_white=None, weights_black=None, device=0, mode=None, final_kernel=1,
+                 refine_margin=None):
         (self.sess, self.output_white, self.input_white,
          self.output_black, self.input_black) = instantiate_session_both_128(
-            weights_white, weights_black, device, mode, final_kernel)
+            weights_white, weights_black, device, mode, final_kernel, refine_margin)
 
     def _net(self, is_player):
         # MCTS.pyx:111-116: is_player -> the 'white' (winner) net, else the 'black' net
