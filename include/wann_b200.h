@@ -117,7 +117,8 @@ int wann_eval_planes(wann_ctx* ctx, const void* planes, int planes_dtype, int64_
  * For each position: idx uint8 [n][48] legal move indices, prior float [n][48] their
  * softmax-155 probabilities, sorted by prior descending (ties: ascending index), padded
  * with 255 / 0; n_legal uint8 [n].  idx[.][0] is the policy move of get_best_move
- * (board_utils.pyx:262-277). */
+ * (board_utils.pyx:262-277).  DEVICE idx / prior buffers must be 16-byte aligned (rows are
+ * written as 16-byte vectors). */
 int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
                    int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal, int mem,
                    void* stream);

