@@ -132,8 +132,13 @@ def cpu_arm(sample_seconds=15.0):
         _, pr = C.forward(pl, w)
         return C.rank(pr, C.legal_mask(s, b))
 
+    def run_torch(s, b):
+        from oracle import torch_oracle as T
+        _, pr = T.forward(C.encode(s, b), w, threads=cores)
+        return C.rank(pr, C.legal_mask(s, b))
+
     best, best_name = None, None
-    for name, fn in (("numpy+OpenBLAS", run_numpy), ("C+OpenMP", run_c)):
+    for name, fn in (("numpy+OpenBLAS", run_numpy), ("C+OpenMP", run_c), ("torch CPU/oneDNN", run_torch)):
         try:
             fn(sq[:64], bl[:64])
             t0 = time.perf_counter()

@@ -368,22 +368,14 @@ def test_child_construction_oracle_vs_reference_golden(golden):
 def test_forward_against_an_independent_torch_restatement():
     """Third, independent restatement of the graph with torch CPU ops (conv2d on NCHW with
     OIHW kernels = w.permute(3,2,0,1), padding 1) -- the oracle must agree with it."""
-    import torch
-    import torch.nn.functional as F
+    from oracle import torch_oracle as T
     sq, bl = O.random_positions_fast(32, seed=21)
     for fk in (3, 1):
         w = O.synthetic_weights("trained_like", 7, final_kernel=fk)
         planes = O.encode_planes(sq, bl)
-        x = torch.from_numpy(planes.astype(np.float32)).permute(0, 3, 1, 2)       # NHWC -> NCHW
-        for i in range(1, 6):
-            k = torch.from_numpy(w["hidden_layer/%d/weights" % i]).permute(3, 2, 0, 1).contiguous()
-            x = F.relu(F.conv2d(x, k, torch.from_numpy(w["hidden_layer/%d/bias" % i]),
-                                padding=(k.shape[-1] - 1) // 2))
-        h = x.permute(0, 2, 3, 1).reshape(-1, 64)                                 # row-major r*8+c
-        logits = h @ torch.from_numpy(w["output_layer/weights"]) + torch.from_numpy(w["output_layer/bias"])
-        probs = torch.softmax(logits, dim=1).numpy()
+        logits, probs = T.forward(planes, w)
         lg, pr = O.forward_fp32(planes, w)
-        assert np.abs(lg - logits.numpy()).max() < 2e-4 and np.abs(pr - probs).max() < 1e-5
+        assert np.abs(lg - logits).max() < 2e-4 and np.abs(pr - probs).max() < 1e-5
 
 
 def test_bulk_board_conversion_equals_per_square_conversion(golden):
