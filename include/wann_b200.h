@@ -135,6 +135,30 @@ int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_
                      int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal,
                      int8_t* child_squares, uint8_t* child_flags, int mem, void* stream);
 
+/* wann_eval_expand + CHILD SEEDING: everything the reference derives from the priors right after
+ * the evaluation, for every ranked legal child -- get_child / check_for_winning_move /
+ * set_game_over_values (tree_builder.pyx:530-536,902-914), update_child (capture close to home and
+ * the prior -> visits/wins seeds, tree_search_utils.pyx:963-1014), assign_children's "maybe gameover
+ * next move" branch (game-saving captures, set_game_over_values_1_step_lookahead,
+ * tree_builder.pyx:563-576,916-921) or else eval_children / evaluation_function
+ * (tree_search_utils.pyx:812-858,1056-1071), one level of update_tree_wins/_losses (:43-66) and
+ * update_win_status_from_children (:86-132).
+ *   child_stats    int32 [n][48][4]  visits, wins, gameover_visits, gameover_wins (zeros for pads)
+ *   child_flags    uint8 [n][48]     bit0 win, bit1 capture, bit2 capture close to home, bit3 game-
+ *                                    saving move, bit4 doomed (loses to the 1-step lookahead; the
+ *                                    child's win_status is True), bit5 evaluation_function(child) == 1
+ *                                    (win_status of a child: bit0 -> False, bit4 -> True, else None;
+ *                                    UCT_multiplier = 1 + prior)
+ *   parent_summary int32 [n][8]      visits, wins, gameover_visits, gameover_wins the parent gains,
+ *                                    its win_status (-1 None / 0 False / 1 True), threat (opponent one
+ *                                    step from the far rank), winning children, doomed children.
+ * The propagation ABOVE the parent is the tree's business.  child_squares may be NULL (seeds only).
+ * DEVICE child_stats / parent_summary must be 16-byte aligned. */
+int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
+                            int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal,
+                            int8_t* child_squares, uint8_t* child_flags, int32_t* child_stats,
+                            int32_t* parent_summary, int mem, void* stream);
+
 /* One self-play style step for n independent games, entirely on the device (BASELINE config 5:
  * independent game trees, each contributing one leaf per step): evaluate the positions, pick ONE
  * child per game -- greedy != 0: the policy move (get_best_move, board_utils.pyx:262-277);

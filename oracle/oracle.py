@@ -549,3 +549,121 @@ def tree_step(squares, black_to_move, idx, prior, n_legal, greedy=False, seed=0,
             out_sq[g] = apply_pov_move(squares[g], int(out_bl[g]), int(chosen[g]))
             out_bl[g] ^= 1
     return out_sq, out_bl, chosen, finished
+
+
+# ----------------------------------------------------------------------------
+# Child seeding: what the reference does with the priors right after the evaluation
+# (SURVEY 8(a) a10 + 8(f)-1).  Restates, per parent position,
+#   get_child                      tree_builder.pyx:530-536  (TreeNode zeros, TreeNode.pyx:7-20)
+#   check_for_winning_move         tree_builder.pyx:902-905 -> set_game_over_values :907-914
+#   update_child                   tree_search_utils.pyx:907-1017 (capture close to home :963-980,
+#                                  prior -> visits/wins seeds :982-1014)
+#   assign_children                tree_builder.pyx:538-620 ("maybe gameover next move" :563-581:
+#                                  game-saving captures, set_game_over_values_1_step_lookahead :916-921;
+#                                  otherwise eval_children, tree_search_utils.pyx:1056-1071 with
+#                                  evaluation_function :812-858)
+#   update_tree_wins / _losses     tree_search_utils.pyx:43-66 (one level: child -> parent)
+#   update_win_status_from_children  tree_search_utils.pyx:86-132
+# for a parent WITHOUT a parent of its own (the propagation above the parent is tree business).
+# Pinned by tests/golden/ref_seed_golden.npz (made by the compiled reference).
+# ----------------------------------------------------------------------------
+SEED_WIN, SEED_CAPTURE, SEED_CLOSE_TO_HOME, SEED_GAME_SAVING, SEED_DOOMED, SEED_EVAL_ONE = 1, 2, 4, 8, 16, 32
+
+# evaluation_function's weighted_board (tree_search_utils.pyx:814-823), rank 1..8 x file a..h,
+# used in ABSOLUTE coordinates for both colours
+EVAL_TABLE = np.array([
+    [5, 28, 28, 12, 12, 28, 28, 5],
+    [2, 3, 3, 3, 3, 3, 3, 2],
+    [3, 5, 10, 10, 10, 10, 5, 3],
+    [6, 9, 16, 16, 16, 16, 9, 6],
+    [9, 15, 21, 21, 21, 21, 15, 9],
+    [14, 22, 22, 22, 22, 22, 22, 14],
+    [21, 23, 23, 23, 23, 23, 23, 21],
+    [24, 24, 24, 24, 24, 24, 24, 24]], np.int32).reshape(64)
+
+
+def seed_children(squares, black_to_move, idx, prior, n_legal):
+    """idx uint8 [N,48] / prior float32 [N,48] / n_legal [N]: the children in ANY order (e.g. the
+    ranked order of ranked_children).  Returns
+      stats  int32 [N,48,4]  visits, wins, gameover_visits, gameover_wins of every child,
+      flags  uint8 [N,48]    SEED_* bits,
+      parent int32 [N,6]     visits, wins, gameover_visits, gameover_wins the parent has gained,
+                             its win_status (-1 None / 0 False / 1 True), threat (the opponent can
+                             reach the far rank next move)."""
+    squares = np.asarray(squares, np.int8).reshape(-1, 64)
+    n = squares.shape[0]
+    stats = np.zeros((n, MAX_LEGAL, 4), np.int32)
+    flags = np.zeros((n, MAX_LEGAL), np.uint8)
+    parent = np.zeros((n, 6), np.int32)
+    threshold = float(np.float32(1.001))                      # `float threshold = 1.001`, tree_search_utils.pyx:95
+    for i in range(n):
+        blk = int(black_to_move[i])
+        pov = pov_squares(squares[i:i + 1], np.array([blk], np.uint8))[0]
+        threat = bool((pov[8:16] == 2).any())                 # tree_builder.pyx:556-563 in the mover's frame
+        pv = pw = pgv = pgw = 0
+        statuses, considering = [], []
+        ev_l = ev_w = 0
+        for k in range(int(n_legal[i])):
+            j = int(idx[i, k])
+            p32 = np.float32(prior[i, k])
+            r, rem = divmod(j, 22)
+            c = (rem + 1) // 3
+            d = rem - 3 * c
+            to = (r + 1) * 8 + c + d
+            capture = pov[to] == 2
+            win = j > 131                                     # tree_builder.pyx:904 (154 is never a child)
+            v = w = gv = gw = 0
+            ws = None
+            f = (SEED_WIN if win else 0) | (SEED_CAPTURE if capture else 0)
+            uct = 1.0 + float(p32)                            # `1 + child_val` with `double child_val`, :984
+            if win:                                           # set_game_over_values + update_tree_losses(child)
+                w, gv, v, ws = 0, 65536 + 1, 65536 + 1, False
+                pw += 1; pv += 1; pgw += 1; pgv += 1          # -> update_tree_wins(parent, 1, gameover=True)
+            if 23 <= j <= 42 and capture:                     # tree_search_utils.pyx:963-980
+                gv, gw, v, w = 100, 0, 100, 0
+                uct = float(np.float32(1) + p32)              # `1+NN_output[child_index]`: a float32 scalar
+                f |= SEED_CLOSE_TO_HOME
+            elif not win:                                     # :982-1014
+                nv = int(p32 * np.float32(100))               # float32 product (numpy scalar * int)
+                v = 100
+                ww = v - nv
+                w = min(ww, 75)
+                if ww < 70:
+                    gv, gw = v, ww
+            if threat:                                        # tree_builder.pyx:563-576
+                if capture:
+                    gv, gw, v, w = 1000, 0, 65536, 0
+                    f |= SEED_GAME_SAVING
+                elif not win:                                 # set_game_over_values_1_step_lookahead + update_tree_wins(child)
+                    v = w = gw = gv = 65536 + 1
+                    ws = True
+                    f |= SEED_DOOMED
+                    pv += 1; pgv += 1                         # -> update_tree_losses(parent, 1, gameover=True)
+            else:                                             # eval_children, tree_search_utils.pyx:1056-1071
+                child = apply_pov_move(squares[i], blk, j)
+                result = int(EVAL_TABLE[child == WHITE].sum()) - int(EVAL_TABLE[child == BLACK].sum())
+                child_is_white = bool(blk)                    # the child is to be moved by the other colour
+                outcome = 1 if (result > 0) == child_is_white else 0
+                if outcome == 1:
+                    ev_l += 1
+                    f |= SEED_EVAL_ONE
+                else:
+                    ev_w += 1
+            stats[i, k] = (v, w, gv, gw)
+            flags[i, k] = f
+            statuses.append(ws)
+            if uct > threshold:
+                considering.append(ws)
+        pv += ev_l + ev_w                                     # update_tree_losses(parent, L); update_tree_wins(parent, W)
+        pw += ev_w
+        if False not in statuses and considering:             # tree_search_utils.pyx:113-114
+            statuses = considering
+        pws = -1
+        if int(n_legal[i]) > 0:
+            if False in statuses:                             # :122-123
+                pws = 1
+            elif True in statuses and None not in statuses:   # :124-125 -> update_tree_losses(parent, 1, gameover=True)
+                pws = 0
+                pv += 1; pgv += 1
+        parent[i] = (pv, pw, pgv, pgw, pws, int(threat))
+    return stats, flags, parent

@@ -19,6 +19,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def seed_golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_seed_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def lib_built():
     from wann_b200 import build
     return build.build()

@@ -569,6 +569,44 @@ def test_zero_copy_small_host_calls_equal_the_dma_path(mode, weights, suite, ref
         assert ev.stats()["h2d_bytes"] - h0 == 5 * 65
 
 
+def test_child_seeding_bit_exact(ev_fp32, ev_bf16, seed_golden, suite):
+    """wann_eval_expand_seeded: child statistics, flags and parent summaries are integer work -> bit-exact
+    against the oracle applied to the ranked priors the same call returns (host and device paths), and
+    against the compiled reference's own expansion (golden) when the kernel is fed the golden NN output
+    through an identity-like check of the oracle on the same children."""
+    import torch
+    g = seed_golden
+    for ev, (sq, bl) in ((ev_bf16, (g["squares"], g["black"])), (ev_fp32, (g["squares"][:200], g["black"][:200])),
+                         (ev_bf16, suite)):
+        idx, pri, cnt, kids, flg, st, ps = ev.eval_expand_seeded(sq, bl)
+        i0, p0, c0, k0, f0 = ev.eval_expand(sq, bl)
+        assert np.array_equal(idx, i0) and np.array_equal(pri, p0) and np.array_equal(kids, k0)
+        assert np.array_equal(flg & 3, f0)
+        want_st, want_fl, want_ps = O.seed_children(sq, bl, idx, pri, cnt)
+        assert np.array_equal(st, want_st) and np.array_equal(flg, want_fl)
+        assert np.array_equal(ps[:, :6], want_ps)
+        assert np.array_equal(ps[:, 6], ((flg & 1) != 0).sum(1)) and np.array_equal(ps[:, 7], ((flg & 16) != 0).sum(1))
+        # seeds only (no child boards), device path
+        dev = torch.device("cuda", ev.device)
+        out = ev.eval_expand_seeded(torch.from_numpy(sq).to(dev), torch.from_numpy(bl).to(dev), with_children=False)
+        torch.cuda.synchronize()
+        assert out[3] is None
+        for got, want in zip((out[0], out[1], out[2], out[4], out[5], out[6]), (idx, pri, cnt, flg, st, ps)):
+            assert np.array_equal(got.cpu().numpy(), want)
+    # the integer part that does not depend on the net at all must equal the reference-made golden:
+    # which children win, which are doomed / game saving, and the threat flag
+    sq, bl = g["squares"], g["black"]
+    idx, pri, cnt, _, flg, st, ps = ev_bf16.eval_expand_seeded(sq, bl, with_children=False)
+    for i in range(len(sq)):
+        k = int(cnt[i])
+        order = np.argsort(idx[i, :k])
+        assert np.array_equal(idx[i, :k][order], g["c_idx"][i, :k])
+        big = g["c_stats"][i, :k, 0] >= 65536                       # win / doomed / game-saving seeds
+        assert np.array_equal(st[i, :k][order][big], g["c_stats"][i, :k][big].astype(np.int32))
+        ws = np.where(flg[i, :k] & 1, 0, np.where(flg[i, :k] & 16, 1, -1))[order]
+        assert np.array_equal(ws, g["c_win"][i, :k])
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote

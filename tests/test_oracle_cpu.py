@@ -188,6 +188,56 @@ def test_oracle_matches_the_references_own_serialized_graph():
             assert np.abs(a - acts[i - 1]).max() <= 2e-5 * max(np.abs(a).max(), 1e-6)
 
 
+def _golden_children(g):
+    """children of the seed golden in ascending index order with the NN output gathered as priors"""
+    idx, cnt, nn = g["c_idx"], g["n_children"], g["nn"]
+    pri = np.zeros(idx.shape, np.float32)
+    for i in range(len(idx)):
+        pri[i, :cnt[i]] = nn[i, idx[i, :cnt[i]]]
+    return idx, pri, cnt
+
+
+def test_child_seeding_oracle_vs_reference_golden(seed_golden):
+    """641 positions expanded ONCE by the compiled reference tree code (expand_descendants_to_depth_wrt_NN
+    -> get_child / update_child / assign_children / eval_children / update_win_status_from_children) with
+    a synthetic NN output: the oracle's seed_children reproduces every child's visits / wins /
+    gameover_visits / gameover_wins / gameover / win_status and the root's resulting statistics."""
+    g = seed_golden
+    sq, bl = g["squares"], g["black"]
+    idx, pri, cnt = _golden_children(g)
+    assert np.array_equal(cnt, O.legal_mask(sq, bl).sum(1))
+    stats, flags, parent = O.seed_children(sq, bl, idx, pri, cnt)
+    live = idx != 255
+    assert np.array_equal(stats[live], g["c_stats"][live].astype(np.int32))
+    assert np.array_equal((flags & O.SEED_WIN)[live] != 0, g["c_gameover"][live] != 0)
+    ws = np.where(flags & O.SEED_WIN, 0, np.where(flags & O.SEED_DOOMED, 1, -1))
+    assert np.array_equal(ws[live], g["c_win"][live])
+    assert np.array_equal(parent[:, :4], g["root_stats"].astype(np.int32))
+    assert np.array_equal(parent[:, 4], g["root_win"])
+    assert np.allclose(1.0 + pri[live].astype(np.float64), g["c_uct"][live], rtol=0, atol=1.2e-7)
+    # every branch is exercised by the fixture
+    for bit in (O.SEED_WIN, O.SEED_CAPTURE, O.SEED_CLOSE_TO_HOME, O.SEED_GAME_SAVING, O.SEED_DOOMED, O.SEED_EVAL_ONE):
+        assert ((flags & bit) != 0).sum() > 10
+    assert set(np.unique(parent[:, 4])) == {-1, 0, 1} and 0 < parent[:, 5].sum() < len(sq)
+    # the reference's child order (sort by UCT_multiplier descending, tree_builder.pyx:557) is the
+    # ranked order of ranked_children: identical where 1 + prior separates neighbours; a capture close
+    # to home carries a float32-rounded multiplier (tree_search_utils.pyx:978), so it may swap with a
+    # neighbour whose prior is within one float32 ulp of 1.0 (1.2e-7) -- documented tie-class divergence
+    ridx, rpri, rcnt = O.ranked_children(g["nn"], O.legal_mask(sq, bl))
+    same = 0
+    for i in range(len(sq)):
+        k = int(cnt[i])
+        uct_of = dict(zip(g["c_idx"][i, :k].tolist(), g["c_uct"][i, :k].tolist()))
+        ref_u = np.array([uct_of[j] for j in g["order"][i, :k].tolist()])
+        our_u = np.array([uct_of[j] for j in ridx[i, :k].tolist()])
+        assert (np.diff(ref_u) <= 1.2e-7).all()      # mixed float32 / double keys compare in float32 (numpy scalars)
+        assert (np.diff(our_u) <= 2.4e-7).all()
+        assert sorted(ridx[i, :k].tolist()) == sorted(g["order"][i, :k].tolist())
+        assert ridx[i, 0] == g["order"][i, 0] or abs(ref_u[0] - our_u[0]) <= 2.4e-7      # best_child
+        same += np.array_equal(ridx[i, :k], g["order"][i, :k])
+    assert same >= 0.9 * len(sq)
+
+
 def test_bf16_round_matches_torch():
     import torch
     x = np.random.RandomState(0).standard_normal(4096).astype(np.float32) * 3

@@ -336,6 +336,126 @@ __global__ void __launch_bounds__(256) expand_children_kernel(const int8_t* __re
   }
 }
 
+// Child seeding (SURVEY 8(a) a10 + 8(f)-1): what the reference does with the priors right after the
+// evaluation, for every ranked legal child of every position --
+//   check_for_winning_move / set_game_over_values           tree_builder.pyx:902-914
+//   update_child (capture close to home, prior -> seeds)     tree_search_utils.pyx:963-1014
+//   assign_children: "maybe gameover next move" branch       tree_builder.pyx:563-576 (game-saving
+//     captures, set_game_over_values_1_step_lookahead :916-921), else eval_children with
+//     evaluation_function                                     tree_search_utils.pyx:812-858,1056-1071
+//   one level of update_tree_wins / _losses                  tree_search_utils.pyx:43-66
+//   update_win_status_from_children                          tree_search_utils.pyx:86-132
+// One warp per board; lane c seeds children c and c + 32; the parent summary is built from warp
+// ballots.  stats: int32 [n][48][4] = visits, wins, gameover_visits, gameover_wins (one 16-byte
+// store per child); flags: uint8 [n][48] (bit0 win, bit1 capture, bit2 capture close to home,
+// bit3 game-saving move, bit4 doomed = loses to a 1-step lookahead, bit5 evaluation_function == 1);
+// parent: int32 [n][8] = visits, wins, gameover_visits, gameover_wins gained by the parent, its
+// win_status (-1 None / 0 False / 1 True), threat, number of winning children, of doomed children.
+__constant__ int8_t kEvalTable[64] = {5, 28, 28, 12, 12, 28, 28, 5,   2, 3, 3, 3, 3, 3, 3, 2,
+                                      3, 5, 10, 10, 10, 10, 5, 3,     6, 9, 16, 16, 16, 16, 9, 6,
+                                      9, 15, 21, 21, 21, 21, 15, 9,   14, 22, 22, 22, 22, 22, 22, 14,
+                                      21, 23, 23, 23, 23, 23, 23, 21, 24, 24, 24, 24, 24, 24, 24, 24};
+
+__global__ void __launch_bounds__(256) seed_children_kernel(const int8_t* __restrict__ squares,
+                                                            const uint8_t* __restrict__ black,
+                                                            const uint8_t* __restrict__ idx,
+                                                            const float* __restrict__ prior,
+                                                            const uint8_t* __restrict__ n_legal, long long n,
+                                                            int32_t* __restrict__ stats, uint8_t* __restrict__ flags,
+                                                            int32_t* __restrict__ parent) {
+  __shared__ int8_t brd[8][64];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long board = blockIdx.x * 8ll + w; board < n; board += gridDim.x * 8ll) {
+    const int blk = black[board];
+    const int cnt = min(static_cast<int>(n_legal[board]), kMaxLegal);
+    const int s0 = squares[board * 64 + lane], s1 = squares[board * 64 + lane + 32];
+    brd[w][lane] = static_cast<int8_t>(s0);
+    brd[w][lane + 32] = static_cast<int8_t>(s1);
+    // evaluation_function of the PARENT board: sum over white - sum over black, absolute squares
+    int res = (s0 == 1 ? kEvalTable[lane] : (s0 == 2 ? -kEvalTable[lane] : 0)) +
+              (s1 == 1 ? kEvalTable[lane + 32] : (s1 == 2 ? -kEvalTable[lane + 32] : 0));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+    // threat: an opponent piece one step from the mover's home rank (rank 2 for White, rank 7 for Black)
+    const int opp = blk ? 1 : 2;
+    const bool on_row = blk ? (lane + 32 >= 48 && lane + 32 < 56 && s1 == opp) : (lane >= 8 && lane < 16 && s0 == opp);
+    const bool threat = __any_sync(0xffffffffu, on_row);
+    __syncwarp();
+    int n_win = 0, n_doomed = 0, n_l = 0, n_w = 0;
+    bool any_false = false, any_true = false, any_none = false;        // all children
+    bool c_any = false, c_true = false, c_none = false;                // children over the 1.001 threshold
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int k = lane + 32 * half;
+      const bool live = k < cnt;
+      int v = 0, wn = 0, gv = 0, gw = 0, f = 0, ws = -1;
+      bool cons = false;
+      if (live) {
+        const int j = idx[board * kMaxLegal + k];
+        const float p = prior[board * kMaxLegal + k];
+        int r, c, d;
+        decode_move(j, r, c, d);
+        int frm = r * 8 + c, to = (r + 1) * 8 + c + d;
+        if (blk) { frm = 63 - frm; to = 63 - to; }
+        const bool capture = brd[w][to] == opp;
+        const bool win = j > 131;
+        f = (win ? 1 : 0) | (capture ? 2 : 0);
+        double uct = 1.0 + static_cast<double>(p);
+        if (win) { wn = 0; gv = 65537; v = 65537; ws = 0; }
+        if (j >= 23 && j <= 42 && capture) {
+          gv = 100; gw = 0; v = 100; wn = 0;
+          uct = static_cast<double>(__fadd_rn(1.0f, p));
+          f |= 4;
+        } else if (!win) {
+          const int nv = static_cast<int>(__fmul_rn(p, 100.0f));
+          v = 100;
+          const int ww = v - nv;
+          wn = min(ww, 75);
+          if (ww < 70) { gv = v; gw = ww; }
+        }
+        if (threat) {
+          if (capture) { gv = 1000; gw = 0; v = 65536; wn = 0; f |= 8; }
+          else if (!win) { v = wn = gw = gv = 65537; ws = 1; f |= 16; }
+        } else {
+          const int t_to = kEvalTable[to], t_frm = kEvalTable[frm];
+          int rc = blk ? res - (t_to - t_frm) : res + (t_to - t_frm);
+          if (capture) rc += blk ? -t_to : t_to;
+          const bool child_is_white = blk != 0;
+          if ((rc > 0) == child_is_white) f |= 32;
+        }
+        cons = uct > static_cast<double>(1.001f);
+        reinterpret_cast<int4*>(stats)[board * kMaxLegal + k] = make_int4(v, wn, gv, gw);
+      } else if (k < kMaxLegal) {
+        reinterpret_cast<int4*>(stats)[board * kMaxLegal + k] = make_int4(0, 0, 0, 0);
+      }
+      if (k < kMaxLegal) flags[board * kMaxLegal + k] = static_cast<uint8_t>(f);
+      n_win += __popc(__ballot_sync(0xffffffffu, live && (f & 1)));
+      n_doomed += __popc(__ballot_sync(0xffffffffu, live && (f & 16)));
+      n_l += __popc(__ballot_sync(0xffffffffu, live && !threat && (f & 32)));
+      n_w += __popc(__ballot_sync(0xffffffffu, live && !threat && !(f & 32)));
+      any_false |= __any_sync(0xffffffffu, live && ws == 0);
+      any_true |= __any_sync(0xffffffffu, live && ws == 1);
+      any_none |= __any_sync(0xffffffffu, live && ws == -1);
+      c_any |= __any_sync(0xffffffffu, live && cons);
+      c_true |= __any_sync(0xffffffffu, live && cons && ws == 1);
+      c_none |= __any_sync(0xffffffffu, live && cons && ws == -1);
+    }
+    if (lane == 0) {
+      int pv = n_win + n_doomed + n_l + n_w, pw = n_win + n_w, pgv = n_win + n_doomed, pgw = n_win, pws = -1;
+      if (cnt > 0) {
+        const bool use_c = !any_false && c_any;          // tree_search_utils.pyx:113-114
+        const bool has_true = use_c ? c_true : any_true, has_none = use_c ? c_none : any_none;
+        if (any_false) pws = 1;
+        else if (has_true && !has_none) { pws = 0; pv += 1; pgv += 1; }
+      }
+      int4* out = reinterpret_cast<int4*>(parent + board * 8);
+      out[0] = make_int4(pv, pw, pgv, pgw);
+      out[1] = make_int4(pws, threat ? 1 : 0, n_win, n_doomed);
+    }
+    __syncwarp();
+  }
+}
+
 // Self-play style step (BASELINE config 5: independent game trees, one leaf per tree per step):
 // pick ONE child per game from its ranked legal priors -- greedy (slot 0 = the policy move,
 // board_utils.pyx:262-277) or sampled in proportion to the priors -- apply the move in place

@@ -93,6 +93,8 @@ struct Slot {
   uint8_t* d_mask = nullptr;
   int8_t* d_children = nullptr;   // [cap][48][64], allocated on first use
   uint8_t* d_cflags = nullptr;    // [cap][48]
+  int32_t* d_cstats = nullptr;    // [cap][48][4] child seeds (lazy)
+  int32_t* d_psum = nullptr;      // [cap][8] parent summaries (lazy)
   int* d_err = nullptr;
   int* h_err = nullptr;     // pinned
   float* d_act0 = nullptr;  // fp32 mode ping-pong activations
@@ -298,7 +300,7 @@ void free_slot(Slot& s) {
   cudaFree(s.d_nlegal); cudaFree(s.d_planes_out); cudaFree(s.d_mask); cudaFree(s.d_err);
   if (s.h_err) cudaFreeHost(s.h_err);
   cudaFree(s.d_act0); cudaFree(s.d_act1); cudaFree(s.d_children); cudaFree(s.d_cflags);
-  cudaFree(s.d_h5r); cudaFree(s.d_rlist);
+  cudaFree(s.d_h5r); cudaFree(s.d_rlist); cudaFree(s.d_cstats); cudaFree(s.d_psum);
   if (s.z_in) cudaFreeHost(s.z_in);
   if (s.z_out) cudaFreeHost(s.z_out);
   s = Slot();
@@ -367,6 +369,8 @@ struct ChunkIO {   // device pointers for one chunk
   long long* prof = nullptr;
   int8_t* children = nullptr;
   uint8_t* cflags = nullptr;
+  int32_t* cstats = nullptr;    // child seeds [n][48][4] (with cflags and psum)
+  int32_t* psum = nullptr;      // parent summaries [n][8]
   int* err_mirror = nullptr;    // host-mapped copy of the slot's d_err, written by the last kernel
 };
 
@@ -495,6 +499,12 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
                                                      io.cflags);
       ++launches;
     }
+    if (io.cstats != nullptr) {
+      const int eb = static_cast<int>(std::min<long long>((n + 7) / 8, 16ll * ctx->sm_count));
+      seed_children_kernel<<<eb, 256, 0, stream>>>(io.squares, io.black, io.idx, io.prior, io.nlegal, n, io.cstats,
+                                                   io.cflags, io.psum);
+      ++launches;
+    }
   }
   CU(cudaGetLastError());
   ctx->stats[0] += static_cast<uint64_t>(n);
@@ -526,6 +536,8 @@ int check_device_err(wann_ctx* ctx, Slot& s) {
 struct EvalArgs {
   int8_t* children = nullptr;     // [n][48][64] optional (needs idx)
   uint8_t* cflags = nullptr;      // [n][48]
+  int32_t* cstats = nullptr;      // [n][48][4] optional child seeds (needs idx, cflags, psum)
+  int32_t* psum = nullptr;        // [n][8]
   const int8_t* squares = nullptr;
   const uint8_t* black = nullptr;
   const void* planes = nullptr;
@@ -562,6 +574,8 @@ int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void*
     io.dbg_layer = a.dbg_layer;
     io.children = a.children ? a.children + off * kMaxLegal * 64 : nullptr;
     io.cflags = a.cflags ? a.cflags + off * kMaxLegal : nullptr;
+    io.cstats = a.cstats ? a.cstats + off * kMaxLegal * 4 : nullptr;
+    io.psum = a.psum ? a.psum + off * 8 : nullptr;
     int rc = enqueue_eval(ctx, ws, stream, io, m);
     if (rc != WANN_OK) return rc;
   }
@@ -641,7 +655,7 @@ int eval_host_small(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
 // HOST memory: chunked, double-buffered over the lane's two slots so that the H2D copy of
 // chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
 int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
-  if (ctx->zero_copy && n <= kZeroCopyMax && a.dbg == nullptr && a.children == nullptr &&
+  if (ctx->zero_copy && n <= kZeroCopyMax && a.dbg == nullptr && a.children == nullptr && a.cstats == nullptr &&
       (a.probs != nullptr || a.logits != nullptr || a.idx != nullptr))
     return eval_host_small(ctx, lane, a, n);
   const long long cap = lane->slot[0].cap;
@@ -677,11 +691,17 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
     io.logits = a.logits ? s.d_logits : nullptr;
     if (a.idx) { io.idx = s.d_idx; io.prior = s.d_prior; io.nlegal = s.d_nlegal; }
     if (a.children) {
-      if (s.d_children == nullptr) {
-        CU(cudaMalloc(&s.d_children, s.cap * kMaxLegal * 64));
-        CU(cudaMalloc(&s.d_cflags, s.cap * kMaxLegal));
-      }
+      if (s.d_children == nullptr) CU(cudaMalloc(&s.d_children, s.cap * kMaxLegal * 64));
+      if (s.d_cflags == nullptr) CU(cudaMalloc(&s.d_cflags, s.cap * kMaxLegal));
       io.children = s.d_children; io.cflags = s.d_cflags;
+    }
+    if (a.cstats) {
+      if (s.d_cflags == nullptr) CU(cudaMalloc(&s.d_cflags, s.cap * kMaxLegal));
+      if (s.d_cstats == nullptr) {
+        CU(cudaMalloc(&s.d_cstats, s.cap * kMaxLegal * 4 * sizeof(int32_t)));
+        CU(cudaMalloc(&s.d_psum, s.cap * 8 * sizeof(int32_t)));
+      }
+      io.cflags = s.d_cflags; io.cstats = s.d_cstats; io.psum = s.d_psum;
     }
     float* d_dbg = nullptr;
     if (a.dbg) {
@@ -702,9 +722,11 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
         D2H(a.prior + off * kMaxLegal, s.d_prior, m * kMaxLegal * 4);
         D2H(a.nlegal + off, s.d_nlegal, m);
       }
-      if (a.children) {
-        D2H(a.children + off * kMaxLegal * 64, s.d_children, m * kMaxLegal * 64);
-        D2H(a.cflags + off * kMaxLegal, s.d_cflags, m * kMaxLegal);
+      if (a.children) D2H(a.children + off * kMaxLegal * 64, s.d_children, m * kMaxLegal * 64);
+      if (a.cflags) D2H(a.cflags + off * kMaxLegal, s.d_cflags, m * kMaxLegal);
+      if (a.cstats) {
+        D2H(a.cstats + off * kMaxLegal * 4, s.d_cstats, m * kMaxLegal * 4 * sizeof(int32_t));
+        D2H(a.psum + off * 8, s.d_psum, m * 8 * sizeof(int32_t));
       }
       if (a.dbg) D2H(a.dbg + off * 64 * dbg_c, d_dbg, m * 64 * dbg_c * 4);
       if (e == cudaSuccess)
@@ -826,7 +848,7 @@ int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* strea
   CU(dev_guard.status);
   if (!bypass) ctx->stats[2] += 1;
   if (!bypass && ctx->coalesce && mem == WANN_MEM_HOST && a.squares != nullptr && a.dbg == nullptr &&
-      a.children == nullptr && n <= kCombineMaxCall)
+      a.children == nullptr && a.cstats == nullptr && n <= kCombineMaxCall)
     return run_combined(ctx, a, n);
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);
@@ -1006,6 +1028,23 @@ int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
   EvalArgs a;
   a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
   a.children = child_squares; a.cflags = child_flags;
+  return run_eval(ctx, a, n, mem, stream);
+}
+
+int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, uint8_t* idx,
+                            float* prior, uint8_t* n_legal, int8_t* child_squares, uint8_t* child_flags,
+                            int32_t* child_stats, int32_t* parent_summary, int mem, void* stream) {
+  if ((idx == nullptr || prior == nullptr || n_legal == nullptr || child_flags == nullptr ||
+       child_stats == nullptr || parent_summary == nullptr) && n > 0)
+    return fail(WANN_E_INVALID, "null output buffer");
+  if (squares == nullptr && n > 0) return fail(WANN_E_INVALID, "squares is null");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
+  if (mem == WANN_MEM_DEVICE &&
+      ((reinterpret_cast<uintptr_t>(child_stats) | reinterpret_cast<uintptr_t>(parent_summary)) & 15u))
+    return fail(WANN_E_INVALID, "device child_stats / parent_summary buffers must be 16-byte aligned");
+  EvalArgs a;
+  a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
+  a.children = child_squares; a.cflags = child_flags; a.cstats = child_stats; a.psum = parent_summary;
   return run_eval(ctx, a, n, mem, stream);
 }
 

@@ -190,6 +190,33 @@ class PolicyEvaluator(object):
                                            L.MEM_HOST, None))
         return idx, pri, cnt, kids, flg
 
+    def eval_expand_seeded(self, squares, black, with_children=True):
+        """eval_expand + child seeding (wann_eval_expand_seeded).  -> idx, prior, n_legal,
+        child_squares (or None), child_flags uint8 [n,48] (6 bits), child_stats int32 [n,48,4]
+        (visits, wins, gameover_visits, gameover_wins), parent_summary int32 [n,8]."""
+        if _is_torch(squares):
+            import torch
+            n, dev = squares.shape[0], squares.device
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)   # noqa: E731
+            idx, pri, cnt = mk((n, L.MAX_LEGAL), torch.uint8), mk((n, L.MAX_LEGAL), torch.float32), mk((n,), torch.uint8)
+            kids = mk((n, L.MAX_LEGAL, 64), torch.int8) if with_children else None
+            flg, st, ps = mk((n, L.MAX_LEGAL), torch.uint8), mk((n, L.MAX_LEGAL, 4), torch.int32), mk((n, 8), torch.int32)
+            L.check(self._lib.wann_eval_expand_seeded(
+                self._ctx, squares.data_ptr(), black.data_ptr(), n, idx.data_ptr(), pri.data_ptr(), cnt.data_ptr(),
+                kids.data_ptr() if with_children else None, flg.data_ptr(), st.data_ptr(), ps.data_ptr(),
+                L.MEM_DEVICE, self._torch_stream(squares)))
+            return idx, pri, cnt, kids, flg, st, ps
+        sq, bl = self._np_in(squares, black)
+        n = sq.shape[0]
+        idx, pri, cnt = np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL), np.float32), np.empty(n, np.uint8)
+        kids = np.empty((n, L.MAX_LEGAL, 64), np.int8) if with_children else None
+        flg, st, ps = np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL, 4), np.int32), np.empty((n, 8), np.int32)
+        L.check(self._lib.wann_eval_expand_seeded(
+            self._ctx, sq.ctypes.data, bl.ctypes.data, n, idx.ctypes.data, pri.ctypes.data, cnt.ctypes.data,
+            kids.ctypes.data if with_children else None, flg.ctypes.data, st.ctypes.data, ps.ctypes.data,
+            L.MEM_HOST, None))
+        return idx, pri, cnt, kids, flg, st, ps
+
     def tree_step(self, squares, black, greedy=False, seed=0, step=0, want_outputs=True):
         """In-place self-play step on torch CUDA tensors (see wann_tree_step).  Returns
         (chosen_idx uint8 [n], finished uint8 [n]) device tensors, or None."""
