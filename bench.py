@@ -111,9 +111,13 @@ def make_positions(n, seed):
     return np.tile(base_sq, (reps, 1))[perm], np.tile(base_bl, reps)[perm]
 
 
-def cpu_arm(sample_seconds=15.0):
-    """The oracle port timed on the host cores: encode -> fp32 forward -> legal mask -> rank.
-    Returns (positions/s, cores, kind, sample description)."""
+_CPU_ARM = {}
+
+
+def _cpu_arm_setup():
+    """Pick, once, the fastest of the three CPU implementations of the path on this host."""
+    if _CPU_ARM:
+        return _CPU_ARM
     from oracle import c_oracle as C
     from oracle import oracle as O
     cores = os.cpu_count() or 1
@@ -137,7 +141,7 @@ def cpu_arm(sample_seconds=15.0):
         _, pr = T.forward(C.encode(s, b), w, threads=cores)
         return C.rank(pr, C.legal_mask(s, b))
 
-    best, best_name = None, None
+    best = None
     for name, fn in (("numpy+OpenBLAS", run_numpy), ("C+OpenMP", run_c), ("torch CPU/oneDNN", run_torch)):
         try:
             fn(sq[:64], bl[:64])
@@ -146,15 +150,11 @@ def cpu_arm(sample_seconds=15.0):
             rate = 256 / (time.perf_counter() - t0)
         except Exception:  # noqa: BLE001
             continue
-        if best is None or rate > best:
-            best, best_name, best_fn = rate, name, fn
-    n = int(min(len(sq), max(256, best * sample_seconds)))
-    t0 = time.perf_counter()
-    best_fn(sq[:n], bl[:n])
-    dt = time.perf_counter() - t0
-    sample = "%d positions, oracle port (%s, fp32), %.1f s" % (n, best_name, dt)
+        if best is None or rate > best[0]:
+            best = (rate, name, fn)
     # For context: the reference's OWN per-board Python encode + legal-move enumeration
     # (compiled from its .pyx into oracle/_ref), which sits in front of its TF session.
+    extra = ""
     try:
         from oracle.ref_loader import load_ref
         ref = load_ref()
@@ -165,11 +165,24 @@ def cpu_arm(sample_seconds=15.0):
             for b, c in boards:
                 ref.utils.convert_board_to_2d_matrix_POEB(b, c)
                 ref.board_utils.enumerate_legal_moves(b, c)
-            sample += "; reference's own Python encode+legal-move code: %.0f us/board (1 thread)" % (
+            extra = "; reference's own Python encode+legal-move code: %.0f us/board (1 thread)" % (
                 (time.perf_counter() - t0) / 200 * 1e6)
     except Exception:  # noqa: BLE001
         pass
-    return n / dt, cores, "port", sample
+    _CPU_ARM.update(cores=cores, sq=sq, bl=bl, rate=best[0], name=best[1], fn=best[2], extra=extra)
+    return _CPU_ARM
+
+
+def cpu_arm(sample_seconds=15.0):
+    """The oracle port timed on the host cores: encode -> fp32 forward -> legal mask -> rank, on a
+    bounded sample of the bench workload.  Returns (positions/s, cores, kind, sample description)."""
+    a = _cpu_arm_setup()
+    n = int(min(len(a["sq"]), max(256, a["rate"] * sample_seconds)))
+    t0 = time.perf_counter()
+    a["fn"](a["sq"][:n], a["bl"][:n])
+    dt = time.perf_counter() - t0
+    sample = "%d positions, oracle port (%s, fp32), %.1f s" % (n, a["name"], dt) + a["extra"]
+    return n / dt, a["cores"], "port", sample
 
 
 def run_reference(args, rank):
@@ -177,8 +190,10 @@ def run_reference(args, rank):
         return
     vals = []
     sample = ""
+    # the whole run stays within ~2.5 minutes whatever K and W are
+    per_step = max(0.25, min(15.0, 150.0 / (args.warmup + args.steps)))
     for i in range(args.warmup + args.steps):
-        v, cores, kind, sample = cpu_arm(sample_seconds=max(2.0, min(15.0, 120.0 / (args.warmup + args.steps))))
+        v, cores, kind, sample = cpu_arm(sample_seconds=per_step)
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
