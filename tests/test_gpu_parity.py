@@ -607,6 +607,36 @@ def test_child_seeding_bit_exact(ev_fp32, ev_bf16, seed_golden, suite):
         assert np.array_equal(ws, g["c_win"][i, :k])
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_fused_tail_equals_the_standalone_tail_kernel(mode, weights, suite, ref1k):
+    """bf16/fp16 modes run the tail (FC-155 -> softmax -> legal gather -> rank) on two extra warps INSIDE
+    the conv-stack kernel; the stand-alone tail_kernel (option fuse_tail = 0) must give bit-identical
+    probabilities, logits and ranked priors for every batch shape, input form and call path."""
+    import torch
+    import wann_b200
+    sq, bl = suite
+    big_sq, big_bl = np.tile(sq, (5, 1))[:4999], np.tile(bl, 5)[:4999]
+    with wann_b200.PolicyEvaluator(weights, mode=mode) as ev:
+        dev = torch.device("cuda", ev.device)
+        for n in (1, 3, 4, 5, 8, 9, 295, 296, 297, 600, 1024, 4999):
+            s_, b_ = big_sq[:n], big_bl[:n]
+            res = {}
+            for fuse in (0, 1):
+                ev.set_option("fuse_tail", fuse)
+                k0 = ev.stats()["kernel_launches"]
+                pr, lg = ev.eval_probs(s_, b_, return_logits=True)
+                launches = ev.stats()["kernel_launches"] - k0
+                assert launches == (1 if fuse else 2)
+                tk = ev.eval_topk(s_, b_)
+                dv = ev.eval_topk(torch.from_numpy(s_).to(dev), torch.from_numpy(b_).to(dev))
+                torch.cuda.synchronize()
+                res[fuse] = (pr, lg) + tuple(tk) + tuple(x.cpu().numpy() for x in dv)
+                if n <= 1024:
+                    res[fuse] += (ev.eval_planes(ref1k["planes"][:n]),)
+            for a, b in zip(res[0], res[1]):
+                assert np.array_equal(a, b)
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote

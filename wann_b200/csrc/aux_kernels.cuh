@@ -106,6 +106,149 @@ constexpr int kTailWarpBytes = kTailBoards * 64 + 64 + kMaxLegal;    // pov[4][6
 constexpr int kTailSmemBytes = (64 * kMoves + 160) * 4 + 160 * 2 +
                                kTailWarps * (kTailWarpFloats * 4 + kTailWarpBytes);
 
+// The per-group body shared by tail_kernel (FC weights in shared memory, 4 boards per warp) and the
+// fused tail warps of conv_stack_tc_kernel (FC weights read through L1/L2, 2 boards per warp):
+// logits -> softmax -> outputs -> legal gather -> rank -> (margin flag).  h / pov hold the group's
+// 5th feature maps and side-to-move boards; dst[t] is the output row of board t.
+struct TailScratch {
+  const float* h;      // [NB][64]
+  float* cp;           // [64]  compact priors (+ the two best at [48], [49])
+  float* rp;           // [48]  ranked priors, 16-byte aligned
+  const int8_t* pov;   // [NB][64]
+  uint8_t* cj;         // [64]  compact indices
+  uint8_t* ri;         // [48]  ranked indices, 16-byte aligned
+};
+
+template <int NB, bool kGlobalW>
+__device__ __forceinline__ void tail_group(const TailParams& p, const float* __restrict__ w,
+                                           const float* __restrict__ b_s, const uint16_t* __restrict__ mv_s,
+                                           const TailScratch& sc, int nb, const long long (&dst)[NB], int lane,
+                                           bool flagging) {
+  const float* h = sc.h;
+  float* cp = sc.cp;
+  float* rp = sc.rp;
+  const int8_t* pov = sc.pov;
+  uint8_t* cj = sc.cj;
+  uint8_t* ri = sc.ri;
+  // logits[t][j] = sum_q h[t][q] * W[q][j] + b[j]   (reshape [-1,64] row-major, matmul, bias_add)
+  float lg[NB][5];
+#pragma unroll
+  for (int t = 0; t < NB; ++t)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lg[t][k] = 0.f;
+#pragma unroll 8
+  for (int q = 0; q < 64; ++q) {
+    const float* wr = w + q * kMoves + lane;
+    float wv[5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wv[k] = kGlobalW ? __ldg(wr + 32 * k) : wr[32 * k];
+    wv[4] = (lane < kMoves - 128) ? (kGlobalW ? __ldg(wr + 128) : wr[128]) : 0.f;
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+      const float hq = h[t * 64 + q];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) lg[t][k] = fmaf(hq, wv[k], lg[t][k]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NB; ++t) {
+    if (t >= nb) break;
+    const long long board = dst[t];
+    float e[5];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int j = lane + 32 * k;
+      if (j < kMoves) {
+        e[k] = lg[t][k] + b_s[j];
+        mx = fmaxf(mx, e[k]);
+      } else {
+        e[k] = -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f, pr[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      pr[k] = (lane + 32 * k < kMoves) ? expf(e[k] - mx) : 0.f;
+      sum += pr[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int j = lane + 32 * k;
+      pr[k] = pr[k] / sum;
+      if (j < kMoves) {
+        if (p.probs != nullptr) p.probs[board * kMoves + j] = pr[k];
+        if (p.logits != nullptr) p.logits[board * kMoves + j] = e[k];
+      }
+    }
+    if (p.idx != nullptr || flagging) {
+      // legal gather: prior_i = softmax155[idx_i] (no renormalisation); compact in ascending
+      // index order, then rank: descending by prior, ties by ascending index.
+      const int8_t* pv = pov + t * 64;
+      int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int j = lane + 32 * k;
+        bool legal = false;
+        if (j < 154) {
+          const uint32_t m = mv_s[j];
+          const int tgt = pv[(m >> 6) & 63];
+          legal = pv[m & 63] == 1 && ((m >> 12) ? tgt == 0 : tgt != 1);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, legal);
+        if (legal) {
+          const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+          if (pos < kMaxLegal) {   // a real position has <= 48 legal moves (16 pieces x 3);
+            cp[pos] = pr[k];       // malformed boards are truncated to the 48 lowest indices
+            cj[pos] = static_cast<uint8_t>(j);
+          }
+        }
+        cnt += __popc(mask);
+      }
+      cnt = min(cnt, kMaxLegal);
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c = lane + 32 * half;
+        if (c < kMaxLegal) {
+          if (c < cnt) {
+            const float me = cp[c];
+            int rank = 0;
+            for (int o = 0; o < cnt; ++o) {
+              const float other = cp[o];
+              rank += (other > me) || (other == me && o < c);
+            }
+            ri[rank] = cj[c];
+            rp[rank] = me;
+            if (flagging && rank < 2) cp[kMaxLegal + rank] = me;   // the two best legal priors
+          } else {
+            ri[c] = 255;
+            rp[c] = 0.f;
+          }
+        }
+      }
+      __syncwarp();
+      if (p.idx != nullptr) {   // one ranked row = 12 + 3 sixteen-byte stores (+ the count)
+        if (lane < 12)
+          reinterpret_cast<float4*>(p.prior + board * kMaxLegal)[lane] = reinterpret_cast<const float4*>(rp)[lane];
+        else if (lane < 15)
+          reinterpret_cast<uint4*>(p.idx + board * kMaxLegal)[lane - 12] = reinterpret_cast<const uint4*>(ri)[lane - 12];
+        else if (lane == 15)
+          p.n_legal[board] = static_cast<uint8_t>(cnt);
+      }
+      if (flagging && lane == 0 && cnt >= 2 && cp[kMaxLegal + 1] >= cp[kMaxLegal] * p.refine_ratio) {
+        p.refine_list[atomicAdd(p.refine_count, 1)] = static_cast<int>(board);
+        atomicAdd(p.refine_count + 1, 1);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams p) {
   extern __shared__ float tsm[];
   // refinement pass: the board count lives on the device (this launch is never made under PDL, so
@@ -166,123 +309,8 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
         }
     }
     __syncwarp();
-    // logits[t][j] = sum_q h[t][q] * W[q][j] + b[j]   (reshape [-1,64] row-major, matmul, bias_add)
-    float lg[kTailBoards][5];
-#pragma unroll
-    for (int t = 0; t < kTailBoards; ++t)
-#pragma unroll
-      for (int k = 0; k < 5; ++k) lg[t][k] = 0.f;
-#pragma unroll 4
-    for (int q = 0; q < 64; ++q) {
-      const float* wr = w_s + q * kMoves + lane;
-      float wv[5];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) wv[k] = wr[32 * k];
-      wv[4] = (lane < kMoves - 128) ? wr[128] : 0.f;
-#pragma unroll
-      for (int t = 0; t < kTailBoards; ++t) {
-        const float hq = h[t * 64 + q];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) lg[t][k] = fmaf(hq, wv[k], lg[t][k]);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < kTailBoards; ++t) {
-      if (t >= nb) break;
-      const long long board = dst[t];
-      float e[5];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int j = lane + 32 * k;
-        if (j < kMoves) {
-          e[k] = lg[t][k] + b_s[j];
-          mx = fmaxf(mx, e[k]);
-        } else {
-          e[k] = -INFINITY;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float sum = 0.f, pr[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        pr[k] = (lane + 32 * k < kMoves) ? expf(e[k] - mx) : 0.f;
-        sum += pr[k];
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int j = lane + 32 * k;
-        pr[k] = pr[k] / sum;
-        if (j < kMoves) {
-          if (p.probs != nullptr) p.probs[board * kMoves + j] = pr[k];
-          if (p.logits != nullptr) p.logits[board * kMoves + j] = e[k];
-        }
-      }
-      if (p.idx != nullptr || flagging) {
-        // legal gather: prior_i = softmax155[idx_i] (no renormalisation); compact in ascending
-        // index order, then rank: descending by prior, ties by ascending index.
-        const int8_t* pv = pov + t * 64;
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const int j = lane + 32 * k;
-          bool legal = false;
-          if (j < 154) {
-            const uint32_t m = mv_s[j];
-            const int tgt = pv[(m >> 6) & 63];
-            legal = pv[m & 63] == 1 && ((m >> 12) ? tgt == 0 : tgt != 1);
-          }
-          const uint32_t mask = __ballot_sync(0xffffffffu, legal);
-          if (legal) {
-            const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-            if (pos < kMaxLegal) {   // a real position has <= 48 legal moves (16 pieces x 3);
-              cp[pos] = pr[k];       // malformed boards are truncated to the 48 lowest indices
-              cj[pos] = static_cast<uint8_t>(j);
-            }
-          }
-          cnt += __popc(mask);
-        }
-        cnt = min(cnt, kMaxLegal);
-        __syncwarp();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int c = lane + 32 * half;
-          if (c < kMaxLegal) {
-            if (c < cnt) {
-              const float me = cp[c];
-              int rank = 0;
-              for (int o = 0; o < cnt; ++o) {
-                const float other = cp[o];
-                rank += (other > me) || (other == me && o < c);
-              }
-              ri[rank] = cj[c];
-              rp[rank] = me;
-              if (flagging && rank < 2) cp[kMaxLegal + rank] = me;   // the two best legal priors
-            } else {
-              ri[c] = 255;
-              rp[c] = 0.f;
-            }
-          }
-        }
-        __syncwarp();
-        if (p.idx != nullptr) {   // one ranked row = 12 + 3 sixteen-byte stores (+ the count)
-          if (lane < 12)
-            reinterpret_cast<float4*>(p.prior + board * kMaxLegal)[lane] = reinterpret_cast<const float4*>(rp)[lane];
-          else if (lane < 15)
-            reinterpret_cast<uint4*>(p.idx + board * kMaxLegal)[lane - 12] = reinterpret_cast<const uint4*>(ri)[lane - 12];
-          else if (lane == 15)
-            p.n_legal[board] = static_cast<uint8_t>(cnt);
-        }
-        if (flagging && lane == 0 && cnt >= 2 && cp[kMaxLegal + 1] >= cp[kMaxLegal] * p.refine_ratio) {
-          p.refine_list[atomicAdd(p.refine_count, 1)] = static_cast<int>(board);
-          atomicAdd(p.refine_count + 1, 1);
-        }
-        __syncwarp();
-      }
-    }
+    TailScratch sc = {h, cp, rp, pov, cj, ri};
+    tail_group<kTailBoards, false>(p, w_s, b_s, mv_s, sc, nb, dst, lane, flagging);
     __syncwarp();
   }
 }

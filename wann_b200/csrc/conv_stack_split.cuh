@@ -201,7 +201,7 @@ conv_stack_split_kernel(const TcParams p) {
       } while (false);
     }
 #undef WANN_SPLIT_KBLOCK
-  } else if (warp >= kFirstEpiWarp) {
+  } else if (warp >= kFirstEpiWarp && warp < kFirstTailWarp) {
     // ===== epilogue warps =======================================================================
     const int ew = warp - kFirstEpiWarp;
     const int quad = warp & 3;

@@ -32,15 +32,20 @@
 //   * conv1 (4->192) runs as 9 taps x K=16 (4 real channels), conv2-4 as 9 taps x 3 x K=64,
 //     conv5 (192->1, 3x3) as a 1x1 GEMM with N=16 whose columns are the 9 TAPS
 //     (P[pixel][tap] = <act4[pixel], w5[tap]>) followed by a 9-point stencil sum in the epilogue.
-//   * Warp roles per CTA (352 threads): warp 0 = weight producer, warps 1/2 = MMA issuers of
+//   * Warp roles per CTA (416 threads): warp 0 = weight producer, warps 1/2 = MMA issuers of
 //     half 0/1 (leader CTA; in the peer CTA warp 1 relays "my half of the stage has landed"),
-//     warps 3..10 = epilogue.
+//     warps 3..10 = epilogue, warps 11/12 = FUSED TAIL of half 0/1: the conv5 epilogue hands the
+//     5th feature map of the half's two boards over in shared memory and the tail warp runs
+//     FC-155 + bias -> softmax -> legal gather -> rank (aux_kernels.cuh tail_group) while the tensor
+//     pipe is already on the next supertile: the whole evaluation is ONE kernel and h5 never
+//     exists in global memory.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "aux_kernels.cuh"
 #include "ptx.cuh"
 
 namespace wann {
@@ -71,7 +76,9 @@ constexpr int kImgBytesPerRank = (kKbL1 + 3 * kKbMid) * kStageBytes + kKbL5 * kS
 
 constexpr int kNumEpiWarps = 8;
 constexpr int kFirstEpiWarp = 3;
-constexpr int kThreads = 32 * (kFirstEpiWarp + kNumEpiWarps);   // 352
+constexpr int kNumTailWarps = 2;
+constexpr int kFirstTailWarp = kFirstEpiWarp + kNumEpiWarps;                    // 11
+constexpr int kThreads = 32 * (kFirstEpiWarp + kNumEpiWarps + kNumTailWarps);   // 416
 constexpr int kBiasFloats = 4 * kC + 4;
 
 // shared memory carve-up (bytes from the 128-aligned base)
@@ -79,9 +86,20 @@ constexpr int kOffA = 0;
 constexpr int kOffB = (kOffA + kABytes + 127) / 128 * 128;
 constexpr int kOffBias = kOffB + kStages * kStageBytes;
 constexpr int kOffBar = kOffBias + kBiasFloats * 4;
-constexpr int kNumBars = 3 * kStages + 4;
+constexpr int kNumBars = 3 * kStages + 8;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmemSlot + 16 + 128;   // +128 for base alignment slack
+// fused tail: h5 hand-over [2 halves][2 boards][64] f32, FC bias [160] f32, move table [160] u16,
+// then per tail warp 240 floats (h copy [2][64], compact priors [64], ranked priors [48]) and
+// 240 bytes (pov [2][64], compact indices [64], ranked indices [48])
+constexpr int kOffTail = kOffTmemSlot + 16;
+constexpr int kTailH5Bytes = 2 * 2 * 64 * 4;
+constexpr int kTailWarpF = 240, kTailWarpB = 240;
+constexpr int kOffTailBias = kOffTail + kTailH5Bytes;
+constexpr int kOffTailMoves = kOffTailBias + 160 * 4;
+constexpr int kOffTailWarpF = kOffTailMoves + 160 * 2;
+constexpr int kOffTailWarpB = kOffTailWarpF + kNumTailWarps * kTailWarpF * 4;
+constexpr int kSmemBytes = kOffTailWarpB + kNumTailWarps * kTailWarpB + 128;   // +128 for base alignment slack
+static_assert(kOffTail % 16 == 0 && kOffTailWarpF % 16 == 0 && kOffTailWarpB % 16 == 0, "tail scratch alignment");
 static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB) exceeded");
 
 constexpr long long kWatchdogCycles = 1ll << 31;   // ~1.2 s: no legitimate wait comes close
@@ -110,6 +128,11 @@ struct TcParams {
   // of `squares` and write their h5 rows COMPACTLY (row i <- board gather[i]); both null otherwise
   const int* gather = nullptr;
   const int* n_dev = nullptr;
+  // fused tail (conv_stack_tc_kernel only): when fuse_tail != 0 the tail warps produce tail.probs /
+  // logits / idx / prior / n_legal (and the refinement flags) themselves and h5 may be null
+  int fuse_tail = 0;
+  TailParams tail;
+  int* err_mirror = nullptr;   // host-mapped copy of err[0..5], written by the last CTA to finish
 };
 
 // bounded mbarrier wait: returns false (and records who/where) instead of hanging the GPU
@@ -195,6 +218,9 @@ conv_stack_tc_kernel(const TcParams p) {
   auto bar_empty = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto bar_acc_full = [&](int h) { return bar_base + 8u * (3 * kStages + h); };
   auto bar_a_ready = [&](int h) { return bar_base + 8u * (3 * kStages + 2 + h); };
+  auto bar_h5_full = [&](int h) { return bar_base + 8u * (3 * kStages + 4 + h); };
+  auto bar_h5_empty = [&](int h) { return bar_base + 8u * (3 * kStages + 6 + h); };
+  float* h5s = reinterpret_cast<float*>(smem_gen + kOffTail);      // [half][board][64]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -219,6 +245,8 @@ conv_stack_tc_kernel(const TcParams p) {
     for (int h = 0; h < 2; ++h) {
       ptx::mbar_init(bar_acc_full(h), 1);
       ptx::mbar_init(bar_a_ready(h), 2);    // one arrival per CTA of the pair
+      ptx::mbar_init(bar_h5_full(h), 128);  // the 128 conv5 epilogue threads of the half
+      ptx::mbar_init(bar_h5_empty(h), 1);   // the half's tail warp
     }
     ptx::fence_mbar_init();
   }
@@ -387,7 +415,7 @@ conv_stack_tc_kernel(const TcParams p) {
       }
 #undef WANN_KBLOCK
     }
-  } else {
+  } else if (warp < kFirstTailWarp) {
     // ===== epilogue warps: all 8 serve half 0, then half 1, alternately =======================
     const int ew = warp - kFirstEpiWarp;       // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -485,11 +513,66 @@ conv_stack_tc_kernel(const TcParams p) {
                                         dx * kCell + (tap % 4) * 4);
             }
             const float hval = fmaxf(acc + bias_s[4 * kC], 0.f);
-            if (board < p.n) p.h5[board * 64 + y * 8 + x] = hval;
+            if (p.fuse_tail) {
+              // hand the half's 5th feature map to its tail warp (which took the previous
+              // supertile's values long ago: a supertile is ~70 k cycles)
+              const uint32_t tcount = lstep / 5u;
+              if (!wait_bar(bar_h5_empty(h), (tcount & 1u) ^ 1u, false, p.err, 820 + h)) { ok = false; break; }
+              h5s[(h * 2 + b) * 64 + y * 8 + x] = hval;
+              ptx::mbar_arrive(bar_h5_full(h));
+            }
+            if (p.h5 != nullptr && board < p.n) p.h5[board * 64 + y * 8 + x] = hval;
             if (st + npairs < total_st) store_input_cell(cell0, next_in[h]);
           }
           signal_a_ready(h);
           if (profiler && lstep < kProfSteps) p.prof[(4 * h + 3) * kProfSteps + lstep] = clock64();
+        }
+      }
+    }
+  }
+
+  else {
+    // ===== fused tail warp of half h: FC-155 + bias -> softmax -> legal gather -> rank ==========
+    const int h = warp - kFirstTailWarp;
+    if (p.fuse_tail) {
+      float* tb_s = reinterpret_cast<float*>(smem_gen + kOffTailBias);
+      uint16_t* tmv_s = reinterpret_cast<uint16_t*>(smem_gen + kOffTailMoves);
+      for (int i = tid - kFirstTailWarp * 32; i < 160; i += kNumTailWarps * 32) {
+        tb_s[i] = i < kMoves ? p.tail.fc_b[i] : 0.f;
+        int r = 0, c = 0, d = 0;
+        if (i < 154) decode_move(i, r, c, d);
+        tmv_s[i] = static_cast<uint16_t>((r * 8 + c) | (((r + 1) * 8 + c + d) << 6) | ((d == 0) << 12));
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(kNumTailWarps * 32) : "memory");
+      if (h < nh) {
+        float* wf = reinterpret_cast<float*>(smem_gen + kOffTailWarpF) + h * kTailWarpF;
+        uint8_t* wb = smem_gen + kOffTailWarpB + h * kTailWarpB;
+        float* hc = wf;                                   // [2][64]
+        int8_t* pov = reinterpret_cast<int8_t*>(wb);      // [2][64]
+        TailScratch sc = {hc, wf + 128, wf + 192, pov, wb + 128, wb + 192};
+        const bool flagging = p.tail.refine_list != nullptr && p.tail.squares != nullptr;
+        ptx::pdl_wait();
+        uint32_t tcount = 0;
+        for (long long st = pair; st < total_st; st += npairs, ++tcount) {
+          const long long board0 = st * boards_per_pair + static_cast<int>(rank) * (2 * nh) + h * 2;
+          const int nb = static_cast<int>(max(0ll, min(2ll, p.n - board0)));
+          const long long dst[2] = {board0, board0 + 1};
+          if (p.tail.squares != nullptr) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+              if (t < nb) {
+                const int blk = p.tail.black[dst[t]];
+                const int8_t* sq = p.tail.squares + dst[t] * 64;
+                pov[t * 64 + lane] = static_cast<int8_t>(pov_square(sq, blk, lane));
+                pov[t * 64 + lane + 32] = static_cast<int8_t>(pov_square(sq, blk, lane + 32));
+              }
+          }
+          if (!wait_bar(bar_h5_full(h), tcount & 1u, false, p.err, 800 + h)) break;
+          reinterpret_cast<float4*>(hc)[lane] = reinterpret_cast<const float4*>(h5s + h * 128)[lane];
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_h5_empty(h));
+          if (nb > 0) tail_group<2, true>(p.tail, p.tail.fc_w, tb_s, tmv_s, sc, nb, dst, lane, flagging);
+          __syncwarp();
         }
       }
     }
@@ -500,6 +583,15 @@ conv_stack_tc_kernel(const TcParams p) {
   __syncthreads();
   ptx::cluster_sync_all();
   if (warp == 0) ptx::tmem_dealloc<2>(tmem_base, 512);
+  if (p.err_mirror != nullptr && tid == 0) {
+    // zero-copy calls: the LAST CTA to finish mirrors the watchdog record into mapped host memory
+    __threadfence();
+    if (atomicAdd(p.err + 6, 1) == static_cast<int>(gridDim.x) - 1) {
+      __threadfence();
+      for (int i = 0; i < 6; ++i) p.err_mirror[i] = reinterpret_cast<volatile int*>(p.err)[i];
+      p.err[6] = 0;
+    }
+  }
 }
 
 }  // namespace wann

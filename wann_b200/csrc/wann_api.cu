@@ -140,6 +140,7 @@ struct wann_ctx {
   int variant = 0;
   bool pdl = false;            // programmatic dependent launch conv-stack <-> tail (measured: slower, off)
   bool small_batch_halves = true;   // batches <= 4 x (SM pairs) run 4-board supertiles
+  bool fuse_tail = true;            // bf16/fp16 modes: tail warps inside the conv-stack kernel (one kernel per evaluation)
   bool zero_copy = true;            // host calls <= kZeroCopyMax positions: kernels read/write mapped host memory
   int skew = 4;                // conv_stack_tc: stages by which half 1 trails the weight stream (0..6)
   int wimg_copies = 1;         // replicas of the weight image in use (experiment knob; measured: no effect)
@@ -378,11 +379,39 @@ struct ChunkIO {   // device pointers for one chunk
 int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io, long long n) {
   if (n <= 0) return WANN_OK;
   uint64_t launches = 0;
+  // ---- the tail (FC-155 -> softmax -> legal gather -> rank) and the refinement set-up ---------
+  const bool want_tail = io.probs != nullptr || io.logits != nullptr || io.idx != nullptr;
+  const bool tc16 = ctx->mode == WANN_MODE_BF16 || ctx->mode == WANN_MODE_FP16;
+  TailParams t;
+  t.h5 = ws.d_h5; t.squares = io.squares; t.black = io.black; t.n = n;
+  t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
+  t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal;
+  const float refine_ratio = ctx->refine_ratio.load();
+  const bool refine = want_tail && refine_ratio > 0.f && io.squares != nullptr && io.dbg == nullptr &&
+                      io.prof == nullptr && tc16;
+  int* d_rcount = ws.d_err + 4;     // [0] flagged boards of this chunk, [1] running total
+  if (refine) {
+    if (ws.d_h5r == nullptr) {
+      CU(cudaMalloc(&ws.d_h5r, ws.cap * kDevChunkMul * 64 * 4));
+      CU(cudaMalloc(&ws.d_rlist, ws.cap * kDevChunkMul * sizeof(int)));
+    }
+    CU(cudaMemsetAsync(d_rcount, 0, sizeof(int), stream));
+    t.refine_list = ws.d_rlist; t.refine_count = d_rcount; t.refine_ratio = refine_ratio;
+  }
+  // bf16/fp16 modes: the tail runs INSIDE the conv-stack kernel (two tail warps per CTA); the
+  // stand-alone tail_kernel serves the other modes, the refinement pass and the debug hooks
+  const bool fused = want_tail && tc16 && ctx->fuse_tail && io.dbg == nullptr;
   if (ctx->mode != WANN_MODE_FP32) {
     TcParams p;
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
     p.n = n; p.wimg = ctx->d_wimg; p.wimg_copies = ctx->wimg_copies; p.skew = ctx->skew; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
+    if (fused) {
+      p.fuse_tail = 1;
+      p.tail = t;
+      p.h5 = nullptr;                       // the 5th feature map never leaves the SM
+      if (io.err_mirror != nullptr && !refine) p.err_mirror = io.err_mirror;
+    }
     // small batches: one half per CTA (4 boards per pair) while that still fits one wave of pairs
     p.halves = (ctx->mode != WANN_MODE_FP32_TC && ctx->small_batch_halves &&
                 n <= 4ll * (ctx->sm_count / 2)) ? 1 : 2;
@@ -440,28 +469,12 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   }
   if (io.dbg != nullptr && io.dbg_layer == 5)
     CU(cudaMemcpyAsync(io.dbg, ws.d_h5, n * 64 * 4, cudaMemcpyDeviceToDevice, stream));
-  if (io.probs != nullptr || io.logits != nullptr || io.idx != nullptr) {
-    TailParams t;
-    t.h5 = ws.d_h5; t.squares = io.squares; t.black = io.black; t.n = n;
-    t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
-    t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal;
-    const float refine_ratio = ctx->refine_ratio.load();
-    const bool refine = refine_ratio > 0.f && io.squares != nullptr && io.dbg == nullptr && io.prof == nullptr &&
-                        (ctx->mode == WANN_MODE_BF16 || ctx->mode == WANN_MODE_FP16);
-    int* d_rcount = ws.d_err + 4;     // [0] flagged boards of this chunk, [1] running total
-    if (refine) {
-      if (ws.d_h5r == nullptr) {
-        CU(cudaMalloc(&ws.d_h5r, ws.cap * kDevChunkMul * 64 * 4));
-        CU(cudaMalloc(&ws.d_rlist, ws.cap * kDevChunkMul * sizeof(int)));
-      }
-      CU(cudaMemsetAsync(d_rcount, 0, sizeof(int), stream));
-      t.refine_list = ws.d_rlist; t.refine_count = d_rcount; t.refine_ratio = refine_ratio;
-    }
-    if (io.err_mirror != nullptr && !refine) { t.err_src = ws.d_err; t.err_dst = io.err_mirror; }
+  if (want_tail) {
+    if (io.err_mirror != nullptr && !refine && !fused) { t.err_src = ws.d_err; t.err_dst = io.err_mirror; }
     const long long groups = (n + kTailBoards - 1) / kTailBoards;
     const int blocks = static_cast<int>(
         std::min<long long>((groups + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
-    {
+    if (!fused) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(blocks);
       cfg.blockDim = dim3(kTailWarps * 32);
@@ -473,8 +486,8 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       CU(cudaLaunchKernelEx(&cfg, tail_kernel, t));
+      ++launches;
     }
-    ++launches;
     if (refine) {
       // pass 2: the flagged boards again, fp32-class (fp16 hi/lo split on the tensor cores), their
       // rows of every output overwritten.  Grids are sized for "all flagged"; CTAs beyond the
@@ -1283,6 +1296,7 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "small_batch_halves") == 0) { ctx->small_batch_halves = value != 0; return WANN_OK; }
   if (strcmp(key, "pdl") == 0) { ctx->pdl = value != 0; return WANN_OK; }
   if (strcmp(key, "zero_copy") == 0) { ctx->zero_copy = value != 0; return WANN_OK; }
+  if (strcmp(key, "fuse_tail") == 0) { ctx->fuse_tail = value != 0; return WANN_OK; }
   if (strcmp(key, "coalesce") == 0) { ctx->coalesce = value != 0; return WANN_OK; }
   if (strcmp(key, "refine_margin_micro") == 0) {
     // margin in 1e-6 logit units; 0 switches the refinement pass off
