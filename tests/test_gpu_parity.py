@@ -637,6 +637,39 @@ def test_fused_tail_equals_the_standalone_tail_kernel(mode, weights, suite, ref1
                 assert np.array_equal(a, b)
 
 
+def test_full_size_seeded_expansion_properties(weights):
+    """BASELINE's top batch (65,536 positions, plus a ragged tail crossing the device chunk) through the
+    widest call -- fused evaluation + margin refinement + child seeding, device resident: size-independent
+    invariants on every row and the oracle on a sample."""
+    import torch
+    import wann_b200
+    from wann_b200 import synthetic
+    n = 65536 + 17
+    base_sq, base_bl = synthetic.random_positions(4096, seed=77)
+    reps = (n + 4095) // 4096
+    sq, bl = np.tile(base_sq, (reps, 1))[:n], np.tile(base_bl, reps)[:n]
+    with wann_b200.PolicyEvaluator(weights, mode="fp16", refine_margin=0.02) as ev:
+        dev = torch.device("cuda", ev.device)
+        out = ev.eval_expand_seeded(torch.from_numpy(sq).to(dev), torch.from_numpy(bl).to(dev), with_children=False)
+        torch.cuda.synchronize()
+        idx, pri, cnt, _, flg, st, ps = [x.cpu().numpy() if x is not None else None for x in out]
+    mask = O.legal_mask(sq[:4096], bl[:4096])
+    assert np.array_equal(cnt[:4096], mask.sum(1))
+    live = np.arange(48)[None] < cnt[:, None]
+    assert (np.diff(pri, axis=1)[live[:, 1:]] <= 0).all()                       # ranked, no renormalisation
+    assert (idx[~live] == 255).all() and (pri[~live] == 0).all() and (st[~live] == 0).all() and (flg[~live] == 0).all()
+    assert ((pri * live).sum(1) <= 1.0 + 1e-5).all()
+    # identical positions (the pool is tiled) give identical rows, wherever they sit in a chunk or tile
+    for a in (idx, pri, cnt, flg, st, ps):
+        assert np.array_equal(a[:4096], a[4096:8192]) and np.array_equal(a[:17], a[65536:])
+    assert np.array_equal(ps[:, 6], ((flg & 1) != 0).sum(1)) and np.array_equal(ps[:, 7], ((flg & 16) != 0).sum(1))
+    assert ((ps[:, 5] == 1) == (((flg & 24) != 0).any(1) | ((ps[:, 5] == 1) & ((flg & 32) == 0).all(1)))).all()
+    assert (ps[:, 2] <= ps[:, 0]).all() and (ps[:, 3] <= ps[:, 1]).all()        # gameover stats are a subset
+    pick = np.random.RandomState(3).choice(n, 300, replace=False)
+    want_st, want_fl, want_ps = O.seed_children(sq[pick], bl[pick], idx[pick], pri[pick], cnt[pick])
+    assert np.array_equal(st[pick], want_st) and np.array_equal(flg[pick], want_fl) and np.array_equal(ps[pick, :6], want_ps)
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote
