@@ -10,7 +10,8 @@ sort -> ranked child priors) over one batch of synthetic leaf positions per GPU.
 Workload = BASELINE.json configs[3] (the batch sweep the metric is quoted on) at its top batch,
 65,536 positions per GPU per step, leaf batches sharded one slice per GPU (weak scaling, no
 collective on the data path).  The smaller configs (1 / 256 / 1024 positions) are parity-test
-cases; their throughput is listed under "sweep" for information.
+cases; their throughput (and the rest of the sweep, per-GPU batch sizes, whole-job
+positions/s) is listed under "sweep_positions_per_s" for information.
 
 `value`  : whole-job positions/s, inputs resident in HBM, device pointers through the C ABI.
 `e2e`    : same metric through the public host-buffer API (wann_eval_topk with pinned host
@@ -401,13 +402,16 @@ def main():
 
     # ---------------- optional: counters gathered with NCCL, sweep, CPU baseline ----------
     counters = gather_counters([B * args.steps, int(ms * 1e6)], device=dev)
+    # configs[3]: the batch sweep 64 ... 65,536 positions PER GPU (plus 1 = configs[0], 256 = configs[2],
+    # 1,024 = configs[1]), every rank on its own slice, device pointers, asynchronous back-to-back calls;
+    # whole-job positions/s from the max-over-ranks CUDA-event time
     sweep = {}
-    if rank == 0 and not args.no_sweep:
-        for nb in (1, 256, 1024, 8192, 65536):
+    if not args.no_sweep:
+        for nb in (1, 64, 256, 1024, 4096, 8192, 16384, 65536):
             o = tuple(x[:nb] for x in outs[0])
             for _ in range(3):
                 ev.eval_topk(sq_pool[:nb], bl_pool[:nb], out=o)
-            torch.cuda.synchronize()
+            barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 20
             a.record()
@@ -416,7 +420,10 @@ def main():
                 ev.eval_topk(sq_pool[off:off + nb], bl_pool[off:off + nb], out=o)
             b.record()
             torch.cuda.synchronize()
-            sweep[str(nb)] = round(nb * reps / (a.elapsed_time(b) * 1e-3), 1)
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sweep[str(nb)] = round(n_gpus * nb * reps / (float(t.item()) * 1e-3), 1)
     if world > 1:
         dist.barrier()
 
@@ -454,7 +461,7 @@ def main():
                          "flop_per_position": FLOP_PER_POS_CONV, "positions_per_launch": per_launch_pos,
                          "kernel_ms_per_launch": conv_ms / max(conv_launches, 1),
                          "kernel_share_of_step": conv_ms / ms, "traffic": traffic},
-            "sweep_positions_per_s_1gpu": sweep,
+            "sweep_positions_per_s": sweep,
             "config5_game_trees": trees,
             "fp16_margin_refined": refined,
             "per_rank_counters": counters.tolist(),

@@ -670,6 +670,39 @@ def test_full_size_seeded_expansion_properties(weights):
     assert np.array_equal(st[pick], want_st) and np.array_equal(flg[pick], want_fl) and np.array_equal(ps[pick, :6], want_ps)
 
 
+def test_multi_gpu_evaluator_single_process(weights, suite, ev_bf16):
+    """One process, every visible GPU (sharded by position, one host thread per GPU): bit-identical to
+    one GPU evaluating the whole batch; also the session shim with device=[...]."""
+    import torch
+    import wann_b200
+    sq, bl = suite
+    big_sq, big_bl = np.tile(sq, (4, 1))[:3001], np.tile(bl, 4)[:3001]
+    devices = list(range(torch.cuda.device_count()))
+    want_pr, want_lg = ev_bf16.eval_probs(big_sq, big_bl, return_logits=True)
+    want_tk = ev_bf16.eval_topk(big_sq, big_bl)
+    with wann_b200.MultiGpuEvaluator(weights, devices=devices, mode="bf16", min_per_gpu=256) as m:
+        pr, lg = m.eval_probs(big_sq, big_bl, return_logits=True)
+        assert np.array_equal(pr, want_pr) and np.array_equal(lg, want_lg)
+        for got, want in zip(m.eval_topk(big_sq, big_bl), want_tk):
+            assert np.array_equal(got, want)
+        out = m.eval_expand_seeded(big_sq[:700], big_bl[:700], with_children=False)
+        ref = ev_bf16.eval_expand_seeded(big_sq[:700], big_bl[:700], with_children=False)
+        for got, want in zip(out, ref):
+            assert (got is None and want is None) or np.array_equal(got, want)
+        assert np.array_equal(m.eval_probs(sq[:3], bl[:3]), want_pr[:3])
+        assert m.stats()["positions"] >= 2 * 3001 + 700 + 3
+        if len(devices) > 1:
+            per = [ev.stats()["positions"] for ev in m.evs]
+            assert min(per) > 0                                   # every GPU took a slice
+    w1 = wann_b200.weights.synthetic("trained_like", 1, final_kernel=1)
+    with wann_b200.NeuralNetsCombined_128(w1, device=devices, mode="fp32") as multi, \
+            wann_b200.NeuralNetsCombined_128(w1, device=0, mode="fp32") as single:
+        from wann_b200 import boards
+        nodes = [{"game_board": boards.squares_to_board(sq[i], 0 if bl[i] else 1),
+                  "color": "Black" if bl[i] else "White"} for i in range(64)]
+        assert np.array_equal(multi.evaluate(nodes), single.evaluate(nodes))
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote

@@ -337,6 +337,59 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_multi_gpu_evaluator_shards_by_position_with_fake_devices():
+    """MultiGpuEvaluator (one process, several GPUs): contiguous slices per device, outputs assembled in
+    input order, small calls go to ONE device round-robin, a device's error surfaces in the caller.
+    The evaluators here are stand-ins (evaluator_factory seam): this is host logic, no kernels."""
+    from wann_b200.multi import MultiGpuEvaluator, plan_shards
+    assert plan_shards(0, 8) == [] and plan_shards(100, 8) == [(0, 0, 100)]
+    assert plan_shards(1024, 8, 512) == [(0, 0, 512), (1, 512, 1024)]
+    sh = plan_shards(65536 + 5, 8)
+    assert [s[0] for s in sh] == list(range(8)) and sh[0][1] == 0 and sh[-1][2] == 65541
+    assert all(a[2] == b[1] for a, b in zip(sh, sh[1:])) and max(h - l for _, l, h in sh) - min(h - l for _, l, h in sh) <= 1
+
+    class Fake(object):
+        def __init__(self, dev):
+            self.dev, self.calls, self.closed = dev, [], False
+
+        def eval_probs(self, sq, bl, return_logits=False, out=None):
+            self.calls.append(len(sq))
+            if self.dev == 3 and len(sq) == 700:
+                raise RuntimeError("device 3 failed")
+            out[:] = sq[:, :1].astype(np.float32) + 1000 * self.dev          # row id + which device served it
+            return (out, out * 2) if return_logits else out
+
+        def eval_topk(self, sq, bl, out=None):
+            out[0][:] = self.dev
+            out[1][:] = sq[:, :1]
+            out[2][:] = 7
+            return out
+
+        def stats(self):
+            return {"positions": sum(self.calls)}
+
+        def close(self):
+            self.closed = True
+
+    m = MultiGpuEvaluator(devices=[0, 1, 2, 3], min_per_gpu=100, evaluator_factory=Fake)
+    n = 1003
+    sq = np.zeros((n, 64), np.int8)
+    sq[:, 0] = np.arange(n) % 100
+    bl = np.zeros(n, np.uint8)
+    pr, lg = m.eval_probs(sq, bl, return_logits=True)
+    assert pr.shape == (n, 155) and np.array_equal(pr[:, 0] % 1000, np.arange(n) % 100)
+    assert np.array_equal(pr[:, 0] // 1000, np.repeat([0, 1, 2, 3], [251, 251, 251, 250])) and np.array_equal(lg, pr * 2)
+    idx, pri, cnt = m.eval_topk(sq, bl)
+    assert np.array_equal(idx[:, 0], np.repeat([0, 1, 2, 3], [251, 251, 251, 250])) and (cnt == 7).all()
+    served = [int(m.eval_probs(sq[:5], bl[:5])[0, 0] // 1000) for _ in range(8)]
+    assert sorted(set(served)) == [0, 1, 2, 3]                                # small calls rotate over the devices
+    assert m.stats()["positions"] == n + 8 * 5
+    with pytest.raises(RuntimeError, match="device 3 failed"):
+        m.eval_probs(np.zeros((2800, 64), np.int8), np.zeros(2800, np.uint8))
+    m.close()
+    assert all(ev.closed for ev in m.evs)
+
+
 def test_two_rank_gloo_sharding_and_counter_gather():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")

@@ -88,8 +88,13 @@ def _make(weights, device, mode, final_kernel, refine_margin=None):
     # coalesce=True: the reference calls evaluate concurrently from its ThreadPool(10) + main
     # thread, each with a single node (expansion_MCTS_functions.pyx:105-119); concurrent small
     # calls are merged into one launch inside the C++ runtime.
-    return PolicyEvaluator(weights if weights is not None else W.default_weights(final_kernel=final_kernel), device=device,
-                           mode=mode, final_kernel=final_kernel, coalesce=True, refine_margin=refine_margin)
+    w = weights if weights is not None else W.default_weights(final_kernel=final_kernel)
+    if isinstance(device, (list, tuple)):          # one process, several GPUs: host batches are sharded by position
+        from .multi import MultiGpuEvaluator
+        return MultiGpuEvaluator(w, devices=list(device), mode=mode, final_kernel=final_kernel, coalesce=True,
+                                 refine_margin=refine_margin)
+    return PolicyEvaluator(w, device=device, mode=mode, final_kernel=final_kernel, coalesce=True,
+                           refine_margin=refine_margin)
 
 
 def instantiate_session(weights=None, device=0, mode=None, refine_margin=None):
