@@ -137,13 +137,16 @@ struct wann_ctx {
   int sm_count = 0;
   int final_kernel = 3;
   long long chunk = 16384;
-  int variant = 0;
-  bool pdl = false;            // programmatic dependent launch conv-stack <-> tail (measured: slower, off)
-  bool small_batch_halves = true;   // batches <= 4 x (SM pairs) run 4-board supertiles
-  bool fuse_tail = true;            // bf16/fp16 modes: tail warps inside the conv-stack kernel (one kernel per evaluation)
-  bool zero_copy = true;            // host calls <= kZeroCopyMax positions: kernels read/write mapped host memory
-  int skew = 4;                // conv_stack_tc: stages by which half 1 trails the weight stream (0..6)
-  int wimg_copies = 1;         // replicas of the weight image in use (experiment knob; measured: no effect)
+  // options may be changed by wann_set_option while other threads evaluate: atomics, read once per call
+  std::atomic<int> variant{0};
+  std::atomic<int> pdl{-1};                // programmatic dependent launch between consecutive evaluations of a stream:
+                                           // -1 auto (on for <= 2 waves of supertiles: N=1 35 -> 31 us, 1,024 95 -> 92 us back to
+                                           // back; off beyond: 4,096 positions measured 7 % slower with it), 0 off, 1 on
+  std::atomic<bool> small_batch_halves{true};   // batches <= 4 x (SM pairs) run 4-board supertiles
+  std::atomic<bool> fuse_tail{true};            // bf16/fp16 modes: tail warps inside the conv-stack kernel (one kernel per evaluation)
+  std::atomic<bool> zero_copy{true};            // host calls <= kZeroCopyMax positions: kernels read/write mapped host memory
+  std::atomic<int> skew{4};                // conv_stack_tc: stages by which half 1 trails the weight stream (0..6)
+  std::atomic<int> wimg_copies{1};         // replicas of the weight image in use (experiment knob; measured: no effect)
   // weights on device
   float* d_conv_w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* d_conv_b[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -162,7 +165,7 @@ struct wann_ctx {
   // flat-combining coalescer for concurrent small HOST calls (the reference calls evaluate with
   // batch 1 from 11 threads, tree_builder.pyx:186-189): whoever finds the combiner idle becomes
   // the leader, merges every queued request into ONE launch and hands the results back.
-  bool coalesce = false;
+  std::atomic<bool> coalesce{false};
   std::mutex cmu;
   std::condition_variable ccv;
   std::deque<CombineReq*> cq;
@@ -170,7 +173,7 @@ struct wann_ctx {
   int8_t* c_sq = nullptr; uint8_t* c_bl = nullptr; float* c_probs = nullptr; float* c_logits = nullptr;
   uint8_t* c_idx = nullptr; float* c_prior = nullptr; uint8_t* c_nlegal = nullptr;   // pinned staging
   // optional CUDA-event timing of the conv-stack kernel (bench.py roofline)
-  bool time_kernels = false;
+  std::atomic<bool> time_kernels{false};
   std::mutex ev_mu;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
 };
@@ -433,7 +436,9 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       cfg.stream = stream;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
+      const int pdl = ctx->pdl.load();
+      attr[0].val.programmaticStreamSerializationAllowed =
+          (pdl > 0 || (pdl < 0 && total_st <= 2ll * (ctx->sm_count / 2))) ? 1 : 0;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       if (ctx->mode == WANN_MODE_FP32_TC) CU(cudaLaunchKernelEx(&cfg, conv_stack_split_kernel, p));
@@ -482,7 +487,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       cfg.stream = stream;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
+      attr[0].val.programmaticStreamSerializationAllowed = ctx->pdl.load() > 0 ? 1 : 0;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       CU(cudaLaunchKernelEx(&cfg, tail_kernel, t));
@@ -1294,7 +1299,7 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
     return WANN_OK;
   }
   if (strcmp(key, "small_batch_halves") == 0) { ctx->small_batch_halves = value != 0; return WANN_OK; }
-  if (strcmp(key, "pdl") == 0) { ctx->pdl = value != 0; return WANN_OK; }
+  if (strcmp(key, "pdl") == 0) { ctx->pdl = value < 0 ? -1 : (value != 0); return WANN_OK; }
   if (strcmp(key, "zero_copy") == 0) { ctx->zero_copy = value != 0; return WANN_OK; }
   if (strcmp(key, "fuse_tail") == 0) { ctx->fuse_tail = value != 0; return WANN_OK; }
   if (strcmp(key, "coalesce") == 0) { ctx->coalesce = value != 0; return WANN_OK; }
