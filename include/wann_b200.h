@@ -81,6 +81,12 @@ typedef struct wann_ctx wann_ctx;
  * weights to `device`, builds the tensor-core weight images, allocates lanes/workspaces. */
 int wann_create(const wann_weights* weights, int device, int mode, wann_ctx** out_ctx);
 
+/* Replace the weights of a live context (a newer checkpoint of the same architecture: the
+ * reference's training scripts overwrite policy_net_model/model and a self-play loop reloads it,
+ * policy_net_utils.pyx:68-73 Saver.restore).  Blocks until the evaluations in flight have finished;
+ * evaluations issued afterwards use the new weights.  final_kernel must equal the context's. */
+int wann_set_weights(wann_ctx* ctx, const wann_weights* weights);
+
 /* Replaces sess.close() (MCTS.pyx:132-133). */
 int wann_destroy(wann_ctx* ctx);
 

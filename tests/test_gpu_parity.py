@@ -703,6 +703,46 @@ def test_multi_gpu_evaluator_single_process(weights, suite, ev_bf16):
         assert np.array_equal(multi.evaluate(nodes), single.evaluate(nodes))
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp32", "fp32_tc"])
+def test_set_weights_swaps_a_live_context(mode, suite):
+    """wann_set_weights: a newer checkpoint of the same architecture replaces the weights of a live
+    context (every device-side form: fp32 tensors, tensor-core images, split image, bias) -- the results
+    afterwards are those of a context created with the new weights, also while other threads evaluate."""
+    import wann_b200
+    sq, bl = suite
+    w_a = wann_b200.weights.synthetic("trained_like", 1)
+    w_b = wann_b200.weights.synthetic("trained_like", 2)
+    with wann_b200.PolicyEvaluator(w_a, mode=mode, refine_margin=0.05 if mode == "bf16" else 0.0) as ev, \
+            wann_b200.PolicyEvaluator(w_b, mode=mode, refine_margin=0.05 if mode == "bf16" else 0.0) as fresh:
+        n = 600 if mode != "fp32" else 200
+        before = ev.eval_topk(sq[:n], bl[:n])
+        want = fresh.eval_topk(sq[:n], bl[:n]) + (fresh.eval_probs(sq[:n], bl[:n]),)
+        assert not np.array_equal(before[1], want[1])
+        stop, errs = [False], []
+
+        def hammer():
+            try:
+                while not stop[0]:
+                    ev.eval_probs(sq[:64], bl[:64])
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=hammer) for _ in range(3)]
+        [t.start() for t in th]
+        ev.set_weights(w_b)
+        stop[0] = True
+        [t.join() for t in th]
+        assert not errs
+        got = ev.eval_topk(sq[:n], bl[:n]) + (ev.eval_probs(sq[:n], bl[:n]),)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+        with pytest.raises(ValueError):                                   # another architecture: refused by the shim ...
+            ev.set_weights(wann_b200.weights.synthetic("trained_like", 2, final_kernel=1))
+        _, cw = ev._c_weights(w_b, 3)
+        cw.final_kernel = 1                                               # ... and by the C ABI itself
+        import ctypes
+        assert ev._lib.wann_set_weights(ev._ctx, ctypes.byref(cw)) != 0
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote

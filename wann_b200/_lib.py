@@ -14,7 +14,7 @@ PLANES_I8, PLANES_F32 = 0, 1
 N_MOVES, MAX_LEGAL = 155, 48
 
 EXPORTS = [
-    "wann_create", "wann_destroy", "wann_last_error", "wann_encode", "wann_legal_mask",
+    "wann_create", "wann_set_weights", "wann_destroy", "wann_last_error", "wann_encode", "wann_legal_mask",
     "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_eval_expand", "wann_eval_expand_seeded", "wann_tree_step", "wann_debug_activations",
     "wann_debug_profile", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
@@ -54,6 +54,7 @@ def load():
     lib.wann_eval_topk.argtypes = [vp, vp, vp, i64, vp, vp, vp, ci, vp]
     lib.wann_eval_expand.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, ci, vp]
     lib.wann_eval_expand_seeded.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+    lib.wann_set_weights.argtypes = [vp, ctypes.POINTER(WannWeights)]
     lib.wann_tree_step.argtypes = [vp, vp, vp, i64, ci, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp]
     lib.wann_debug_activations.argtypes = [vp, vp, vp, i64, ci, vp, ci]
     lib.wann_debug_profile.argtypes = [vp, vp, vp, i64, vp]

@@ -115,6 +115,43 @@ struct Lane {
   cudaStream_t last_stream = nullptr;   // stream `last` was recorded on
 };
 
+// Readers-writer gate with WRITER preference (glibc's rwlock lets a steady stream of readers starve
+// the writer): evaluations enter as readers, wann_set_weights as the writer.
+struct WeightsGate {
+  std::mutex m;
+  std::condition_variable cv;
+  int readers = 0, writers_waiting = 0;
+  bool writer = false;
+  void reader_enter() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return !writer && writers_waiting == 0; });
+    ++readers;
+  }
+  void reader_exit() {
+    std::lock_guard<std::mutex> lk(m);
+    if (--readers == 0) cv.notify_all();
+  }
+  void writer_enter() {
+    std::unique_lock<std::mutex> lk(m);
+    ++writers_waiting;
+    cv.wait(lk, [&] { return !writer && readers == 0; });
+    --writers_waiting;
+    writer = true;
+  }
+  void writer_exit() {
+    std::lock_guard<std::mutex> lk(m);
+    writer = false;
+    cv.notify_all();
+  }
+};
+struct ReaderScope {
+  WeightsGate* g;
+  explicit ReaderScope(WeightsGate* gate) : g(gate) { if (g) g->reader_enter(); }
+  ~ReaderScope() { if (g) g->reader_exit(); }
+  ReaderScope(const ReaderScope&) = delete;
+  ReaderScope& operator=(const ReaderScope&) = delete;
+};
+
 constexpr int kLanes = 4;
 constexpr long long kDevChunkMul = 4;
 constexpr long long kCombineMaxCall = 256;    // host calls up to this many positions may be merged
@@ -158,6 +195,7 @@ struct wann_ctx {
   // re-evaluated by conv_stack_split_kernel (fp32-class); refine_ratio = exp(-margin), 0 = off
   std::atomic<float> refine_ratio{0.f};
   float* d_bias_tc = nullptr;  // [4*192 + 1]
+  WeightsGate weights_gate;       // evaluations are readers, wann_set_weights the writer
   Lane lanes[kLanes];
   std::mutex mu;
   std::condition_variable cv;
@@ -356,6 +394,47 @@ void release_lane(wann_ctx* ctx, Lane* l) {
     l->in_use = false;
   }
   ctx->cv.notify_one();
+}
+
+// (Re)build every device-side form of the weights: the fp32 TF-layout tensors (fp32 mode, FC of the
+// tail), the tensor-core stage images and the bias vector.  Buffers are allocated on first use and
+// overwritten afterwards (wann_set_weights); the caller guarantees that no evaluation is in flight.
+int upload_weights(wann_ctx* ctx, const wann_weights& w) {
+  const size_t k5 = static_cast<size_t>(w.final_kernel) * w.final_kernel;
+  const size_t wsz[5] = {9 * 4 * 192, 9 * 192 * 192, 9 * 192 * 192, 9 * 192 * 192, k5 * 192};
+  const size_t bsz[5] = {192, 192, 192, 192, 1};
+  auto up = [&](float** d, const float* h, size_t nfl) -> int {
+    if (*d == nullptr) CU(cudaMalloc(d, nfl * 4));
+    CU(cudaMemcpy(*d, h, nfl * 4, cudaMemcpyHostToDevice));
+    return WANN_OK;
+  };
+  for (int i = 0; i < 5; ++i) {
+    int rc = up(&ctx->d_conv_w[i], w.conv_w[i], wsz[i]);
+    if (rc == WANN_OK) rc = up(&ctx->d_conv_b[i], w.conv_b[i], bsz[i]);
+    if (rc != WANN_OK) return rc;
+  }
+  int rc = up(&ctx->d_fc_w, w.fc_w, 64 * kMoves);
+  if (rc == WANN_OK) rc = up(&ctx->d_fc_b, w.fc_b, kMoves);
+  if (rc != WANN_OK) return rc;
+  std::vector<uint8_t> img;
+  if (ctx->mode == WANN_MODE_FP32_TC) build_weight_image_split(w, img);
+  else build_weight_image(w, ctx->mode == WANN_MODE_FP16, img);
+  const int copies = (ctx->mode == WANN_MODE_FP32_TC) ? 1 : kMaxWimgCopies;
+  if (ctx->d_wimg == nullptr) CU(cudaMalloc(&ctx->d_wimg, img.size() * copies));
+  for (int c = 0; c < copies; ++c)
+    CU(cudaMemcpy(ctx->d_wimg + c * img.size(), img.data(), img.size(), cudaMemcpyHostToDevice));
+  if (ctx->mode != WANN_MODE_FP32_TC) {   // the refinement pass's fp16 hi/lo split image
+    std::vector<uint8_t> simg;
+    build_weight_image_split(w, simg);
+    if (ctx->d_wimg_split == nullptr) CU(cudaMalloc(&ctx->d_wimg_split, simg.size()));
+    CU(cudaMemcpy(ctx->d_wimg_split, simg.data(), simg.size(), cudaMemcpyHostToDevice));
+  }
+  std::vector<float> bias(4 * 192 + 4, 0.f);
+  for (int l = 0; l < 4; ++l) memcpy(bias.data() + l * 192, w.conv_b[l], 192 * 4);
+  bias[4 * 192] = w.conv_b[4][0];
+  if (ctx->d_bias_tc == nullptr) CU(cudaMalloc(&ctx->d_bias_tc, bias.size() * 4));
+  CU(cudaMemcpy(ctx->d_bias_tc, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  return WANN_OK;
 }
 
 struct ChunkIO {   // device pointers for one chunk
@@ -864,6 +943,7 @@ int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* strea
     return fail(WANN_E_INVALID, "device idx / prior buffers must be 16-byte aligned");
   DeviceGuard dev_guard(ctx->device);
   CU(dev_guard.status);
+  ReaderScope weights_scope(bypass ? nullptr : &ctx->weights_gate);   // (a combined call runs under its leader's)
   if (!bypass) ctx->stats[2] += 1;
   if (!bypass && ctx->coalesce && mem == WANN_MEM_HOST && a.squares != nullptr && a.dbg == nullptr &&
       a.children == nullptr && a.cstats == nullptr && n <= kCombineMaxCall)
@@ -916,40 +996,8 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
   ctx->mode = mode;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->final_kernel = w->final_kernel;
-  const size_t k5 = static_cast<size_t>(w->final_kernel) * w->final_kernel;
-  const size_t wsz[5] = {9 * 4 * 192, 9 * 192 * 192, 9 * 192 * 192, 9 * 192 * 192, k5 * 192};
-  const size_t bsz[5] = {192, 192, 192, 192, 1};
-  auto up = [&](float** d, const float* h, size_t nfl) -> int {
-    CU(cudaMalloc(d, nfl * 4));
-    CU(cudaMemcpy(*d, h, nfl * 4, cudaMemcpyHostToDevice));
-    return WANN_OK;
-  };
-  int rc = WANN_OK;
-  for (int i = 0; i < 5 && rc == WANN_OK; ++i) {
-    rc = up(&ctx->d_conv_w[i], w->conv_w[i], wsz[i]);
-    if (rc == WANN_OK) rc = up(&ctx->d_conv_b[i], w->conv_b[i], bsz[i]);
-  }
-  if (rc == WANN_OK) rc = up(&ctx->d_fc_w, w->fc_w, 64 * kMoves);
-  if (rc == WANN_OK) rc = up(&ctx->d_fc_b, w->fc_b, kMoves);
+  int rc = upload_weights(ctx, *w);
   if (rc == WANN_OK) {
-    std::vector<uint8_t> img;
-    if (mode == WANN_MODE_FP32_TC) build_weight_image_split(*w, img);
-    else build_weight_image(*w, mode == WANN_MODE_FP16, img);
-    const int copies = (mode == WANN_MODE_FP32_TC) ? 1 : kMaxWimgCopies;
-    e = cudaMalloc(&ctx->d_wimg, img.size() * copies);
-    for (int c = 0; c < copies && e == cudaSuccess; ++c)
-      e = cudaMemcpy(ctx->d_wimg + c * img.size(), img.data(), img.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && mode != WANN_MODE_FP32_TC) {
-      std::vector<uint8_t> simg;
-      build_weight_image_split(*w, simg);
-      e = cudaMalloc(&ctx->d_wimg_split, simg.size());
-      if (e == cudaSuccess) e = cudaMemcpy(ctx->d_wimg_split, simg.data(), simg.size(), cudaMemcpyHostToDevice);
-    }
-    std::vector<float> bias(4 * 192 + 4, 0.f);
-    for (int l = 0; l < 4; ++l) memcpy(bias.data() + l * 192, w->conv_b[l], 192 * 4);
-    bias[4 * 192] = w->conv_b[4][0];
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_bias_tc, bias.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_bias_tc, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_stack_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                kSmemBytes);
@@ -979,6 +1027,25 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
   }
   *out_ctx = ctx;
   return WANN_OK;
+}
+
+int wann_set_weights(wann_ctx* ctx, const wann_weights* w) {
+  if (ctx == nullptr || w == nullptr) return fail(WANN_E_INVALID, "null argument");
+  if (w->final_kernel != ctx->final_kernel)
+    return fail(WANN_E_INVALID, "final_kernel %d differs from the context's %d", w->final_kernel, ctx->final_kernel);
+  for (int i = 0; i < 5; ++i)
+    if (!w->conv_w[i] || !w->conv_b[i]) return fail(WANN_E_INVALID, "null conv weight %d", i + 1);
+  if (!w->fc_w || !w->fc_b) return fail(WANN_E_INVALID, "null output_layer weights");
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
+  // new evaluations wait; asynchronous ones already enqueued finish with the old weights
+  ctx->weights_gate.writer_enter();
+  int rc = WANN_OK;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) rc = fail(WANN_E_CUDA, "device synchronise: %s", cudaGetErrorString(e));
+  else rc = upload_weights(ctx, *w);
+  ctx->weights_gate.writer_exit();
+  return rc;
 }
 
 int wann_destroy(wann_ctx* ctx) {
@@ -1074,6 +1141,7 @@ int wann_tree_step(wann_ctx* ctx, int8_t* squares, uint8_t* black, int64_t n, in
   if (squares == nullptr || black == nullptr) return fail(WANN_E_INVALID, "null buffer");
   DeviceGuard dev_guard(ctx->device);
   CU(dev_guard.status);
+  ReaderScope weights_scope(&ctx->weights_gate);
   ctx->stats[2] += 1;
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);

@@ -19,15 +19,9 @@ class PolicyEvaluator(object):
     def __init__(self, weights=None, device=0, mode="bf16", final_kernel=3, chunk=None, coalesce=False,
                  refine_margin=0.0):
         lib = L.load()
-        w = W.validate(weights if weights is not None else W.default_weights(final_kernel=final_kernel), final_kernel)
+        self.final_kernel = final_kernel
+        w, cw = self._c_weights(weights, final_kernel)
         self._keep = w
-        cw = L.WannWeights()
-        for i in range(5):
-            cw.conv_w[i] = w["hidden_layer/%d/weights" % (i + 1)].ctypes.data
-            cw.conv_b[i] = w["hidden_layer/%d/bias" % (i + 1)].ctypes.data
-        cw.fc_w = w["output_layer/weights"].ctypes.data
-        cw.fc_b = w["output_layer/bias"].ctypes.data
-        cw.final_kernel = final_kernel
         self.mode = {"bf16": L.MODE_BF16, "fp32": L.MODE_FP32, "fp16": L.MODE_FP16, "fp32_tc": L.MODE_FP32_TC}[mode] if isinstance(mode, str) else int(mode)
         self.device = int(device)
         ctx = ctypes.c_void_p()
@@ -40,6 +34,25 @@ class PolicyEvaluator(object):
             self.set_option("coalesce", 1)
         if refine_margin:
             self.set_refine_margin(refine_margin)
+
+    @staticmethod
+    def _c_weights(weights, final_kernel):
+        w = W.validate(weights if weights is not None else W.default_weights(final_kernel=final_kernel), final_kernel)
+        cw = L.WannWeights()
+        for i in range(5):
+            cw.conv_w[i] = w["hidden_layer/%d/weights" % (i + 1)].ctypes.data
+            cw.conv_b[i] = w["hidden_layer/%d/bias" % (i + 1)].ctypes.data
+        cw.fc_w = w["output_layer/weights"].ctypes.data
+        cw.fc_b = w["output_layer/bias"].ctypes.data
+        cw.final_kernel = final_kernel
+        return w, cw
+
+    def set_weights(self, weights):
+        """Swap in a newer checkpoint of the same architecture (wann_set_weights): waits for the
+        evaluations in flight, later ones use the new weights."""
+        w, cw = self._c_weights(weights, self.final_kernel)
+        L.check(self._lib.wann_set_weights(self._ctx, ctypes.byref(cw)))
+        self._keep = w
 
     # ------------------------------------------------------------------ plumbing
     def close(self):

@@ -60,6 +60,14 @@ class MultiGpuEvaluator(object):
     def __exit__(self, *exc):
         self.close()
 
+    def set_weights(self, weights):
+        for ev in self.evs:
+            ev.set_weights(weights)
+
+    def set_refine_margin(self, margin_logits):
+        for ev in self.evs:
+            ev.set_refine_margin(margin_logits)
+
     def stats(self):
         per = [ev.stats() for ev in self.evs]
         return {k: sum(p[k] for p in per) for k in per[0]}
