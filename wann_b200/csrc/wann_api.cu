@@ -455,7 +455,43 @@ struct ChunkIO {   // device pointers for one chunk
   int32_t* cstats = nullptr;    // child seeds [n][48][4] (with cflags and psum)
   int32_t* psum = nullptr;      // parent summaries [n][8]
   int* err_mirror = nullptr;    // host-mapped copy of the slot's d_err, written by the last kernel
+  bool defer_refine = false;    // flag only; the caller reads the count and runs enqueue_refine_pass itself
 };
+
+bool refine_active(const wann_ctx* ctx, const ChunkIO& io) {
+  return (io.probs != nullptr || io.logits != nullptr || io.idx != nullptr) && ctx->refine_ratio.load() > 0.f &&
+         io.squares != nullptr && io.dbg == nullptr && io.prof == nullptr &&
+         (ctx->mode == WANN_MODE_BF16 || ctx->mode == WANN_MODE_FP16);
+}
+
+// Refinement pass 2: the flagged boards (ws.d_rlist[0 .. d_err[4])) again, fp32-class (fp16 hi/lo
+// split on the tensor cores), their rows of every output overwritten.  `count` < 0: the number of
+// flagged boards is only known on the device -- grids are sized for "all flagged" and CTAs beyond
+// the device-side count return at once; otherwise grids are sized for `count`.
+int enqueue_refine_pass(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io, long long n,
+                        long long count) {
+  const long long m = count < 0 ? n : count;
+  int* d_rcount = ws.d_err + 4;
+  TcParams p = {};
+  p.squares = io.squares; p.black = io.black; p.n = n; p.wimg = ctx->d_wimg_split; p.wimg_copies = 1;
+  p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5r; p.err = ws.d_err; p.halves = 2;
+  p.gather = ws.d_rlist; p.n_dev = d_rcount;
+  const long long total_st = (m + kSplitBoardsPerPair - 1) / kSplitBoardsPerPair;
+  const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
+  conv_stack_split_kernel<<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
+  TailParams t2;
+  t2.h5 = ws.d_h5r; t2.squares = io.squares; t2.black = io.black; t2.n = n;
+  t2.fc_w = ctx->d_fc_w; t2.fc_b = ctx->d_fc_b; t2.probs = io.probs; t2.logits = io.logits;
+  t2.idx = io.idx; t2.prior = io.prior; t2.n_legal = io.nlegal;
+  t2.gather = ws.d_rlist; t2.n_dev = d_rcount;
+  if (io.err_mirror != nullptr) { t2.err_src = ws.d_err; t2.err_dst = io.err_mirror; }
+  const long long groups = (m + kTailBoards - 1) / kTailBoards;
+  const int blocks = static_cast<int>(std::min<long long>((groups + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
+  tail_kernel<<<blocks, kTailWarps * 32, kTailSmemBytes, stream>>>(t2);
+  CU(cudaGetLastError());
+  ctx->stats[1] += 2;
+  return WANN_OK;
+}
 
 // Enqueue encode -> conv stack -> tail for `n` positions on `stream`, using `ws` workspaces.
 int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io, long long n) {
@@ -469,8 +505,8 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
   t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal;
   const float refine_ratio = ctx->refine_ratio.load();
-  const bool refine = want_tail && refine_ratio > 0.f && io.squares != nullptr && io.dbg == nullptr &&
-                      io.prof == nullptr && tc16;
+  const bool refine = io.defer_refine || refine_active(ctx, io);   // (a deferring caller has already decided)
+  const bool mirror_here = io.err_mirror != nullptr && (!refine || io.defer_refine);   // else pass 2 mirrors
   int* d_rcount = ws.d_err + 4;     // [0] flagged boards of this chunk, [1] running total
   if (refine) {
     if (ws.d_h5r == nullptr) {
@@ -492,7 +528,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       p.fuse_tail = 1;
       p.tail = t;
       p.h5 = nullptr;                       // the 5th feature map never leaves the SM
-      if (io.err_mirror != nullptr && !refine) p.err_mirror = io.err_mirror;
+      if (mirror_here) p.err_mirror = io.err_mirror;
     }
     // small batches: one half per CTA (4 boards per pair) while that still fits one wave of pairs
     p.halves = (ctx->mode != WANN_MODE_FP32_TC && ctx->small_batch_halves &&
@@ -554,7 +590,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   if (io.dbg != nullptr && io.dbg_layer == 5)
     CU(cudaMemcpyAsync(io.dbg, ws.d_h5, n * 64 * 4, cudaMemcpyDeviceToDevice, stream));
   if (want_tail) {
-    if (io.err_mirror != nullptr && !refine && !fused) { t.err_src = ws.d_err; t.err_dst = io.err_mirror; }
+    if (mirror_here && !fused) { t.err_src = ws.d_err; t.err_dst = io.err_mirror; }
     const long long groups = (n + kTailBoards - 1) / kTailBoards;
     const int blocks = static_cast<int>(
         std::min<long long>((groups + kTailWarps - 1) / kTailWarps, 2ll * ctx->sm_count));
@@ -572,23 +608,9 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       CU(cudaLaunchKernelEx(&cfg, tail_kernel, t));
       ++launches;
     }
-    if (refine) {
-      // pass 2: the flagged boards again, fp32-class (fp16 hi/lo split on the tensor cores), their
-      // rows of every output overwritten.  Grids are sized for "all flagged"; CTAs beyond the
-      // device-side count return at once.
-      TcParams p = {};
-      p.squares = io.squares; p.black = io.black; p.n = n; p.wimg = ctx->d_wimg_split; p.wimg_copies = 1;
-      p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5r; p.err = ws.d_err; p.halves = 2;
-      p.gather = ws.d_rlist; p.n_dev = d_rcount;
-      const long long total_st = (n + kSplitBoardsPerPair - 1) / kSplitBoardsPerPair;
-      const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
-      conv_stack_split_kernel<<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
-      TailParams t2 = t;
-      t2.h5 = ws.d_h5r; t2.refine_list = nullptr; t2.refine_count = nullptr;
-      t2.gather = ws.d_rlist; t2.n_dev = d_rcount;
-      if (io.err_mirror != nullptr) { t2.err_src = ws.d_err; t2.err_dst = io.err_mirror; }
-      tail_kernel<<<blocks, kTailWarps * 32, kTailSmemBytes, stream>>>(t2);
-      launches += 2;
+    if (refine && !io.defer_refine) {
+      int rc = enqueue_refine_pass(ctx, ws, stream, io, n, -1);
+      if (rc != WANN_OK) return rc;
     }
     if (io.children != nullptr) {
       const int eb = static_cast<int>(std::min<long long>((n + 7) / 8, 16ll * ctx->sm_count));
@@ -730,9 +752,17 @@ int eval_host_small(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
   io.logits = a.logits ? reinterpret_cast<float*>(z_logits) : nullptr;
   if (a.idx) { io.idx = z_idx; io.prior = reinterpret_cast<float*>(z_prior); io.nlegal = z_nlegal; }
   io.err_mirror = z_err;
+  // margin refinement: the host is about to synchronise anyway, so it reads the number of flagged
+  // boards itself and launches pass 2 only when there are any (98 % of batch-1 calls: none)
+  io.defer_refine = refine_active(ctx, io);
   int rc = enqueue_eval(ctx, s, s.stream, io, n);
   if (rc != WANN_OK) return rc;
   CU(cudaStreamSynchronize(s.stream));
+  if (io.defer_refine && z_err[0] == 0 && z_err[4] > 0) {
+    rc = enqueue_refine_pass(ctx, s, s.stream, io, n, z_err[4]);
+    if (rc != WANN_OK) return rc;
+    CU(cudaStreamSynchronize(s.stream));
+  }
   memcpy(s.h_err, z_err, 8 * sizeof(int));
   rc = check_device_err(ctx, s);
   if (rc != WANN_OK) return rc;
