@@ -197,6 +197,57 @@ def _golden_children(g):
     return idx, pri, cnt
 
 
+def test_frozen_graphdef_writer_matches_the_references_graph(tmp_path):
+    """tf_graphdef.save_frozen_graph: the GraphDef it writes parses with the TensorFlow protobuf schema
+    (tensorboard's copy), is node for node the reference's own inference graph (tests/golden/ref_graph.json)
+    with every VariableV2 frozen into a Const, executes in the graph interpreter to the oracle's
+    probabilities, and reads back to the same weights."""
+    from wann_b200 import tf_graphdef as GD
+    from oracle import graph_interp as G
+    w = O.synthetic_weights("trained_like", 5)
+    path = str(tmp_path / "policyNet_frozen.pb")
+    GD.save_frozen_graph(path, w)
+    back = GD.load_frozen_weights(path)
+    assert set(back) == set(w) and all(np.array_equal(back[k], w[k]) for k in w)
+    ours = GD.parse_graph(open(path, "rb").read())
+    ref = G.load("policyNet_pb")
+    assert [n["name"] for n in ours] == [n["name"] for n in ref]
+    for a, b in zip(ours, ref):
+        assert a["inputs"] == b["inputs"]
+        if b["op"] == "VariableV2":
+            assert a["op"] == "Const" and list(a["attr"]["value"].shape) == b["attr"]["shape"]
+        elif b["op"] == "Const":
+            assert a["op"] == "Const" and a["attr"]["value"].tolist() == b["attr"]["value"]["values"]
+        else:
+            assert a["op"] == b["op"]
+            for k, v in b["attr"].items():
+                if b["op"] == "Placeholder" and k == "shape":
+                    continue                                     # the reference's placeholder leaves it unknown
+                assert a["attr"][k] == v, (a["name"], k)
+    # the real TensorFlow schema reads it too
+    gp = pytest.importorskip("tensorboard.compat.proto.graph_pb2")
+    g = gp.GraphDef()
+    g.ParseFromString(open(path, "rb").read())
+    assert len(g.node) == len(ref) and g.versions.producer == 21
+    conv = [n for n in g.node if n.op == "Conv2D"][0]
+    assert conv.attr["padding"].s == b"SAME" and list(conv.attr["strides"].list.i) == [1, 1, 1, 1]
+    k1 = [n for n in g.node if n.name == "hidden_layer/1/weights"][0].attr["value"].tensor
+    assert np.array_equal(np.frombuffer(k1.tensor_content, np.float32).reshape(3, 3, 4, 192), w["hidden_layer/1/weights"])
+    # and it EXECUTES: frozen graph -> interpreter -> the oracle's probabilities
+    nodes = [{"name": n["name"], "op": n["op"], "inputs": n["inputs"],
+              "attr": ({"value": {"dtype": str(n["attr"]["value"].dtype), "shape": list(n["attr"]["value"].shape),
+                                  "values": n["attr"]["value"].reshape(-1).tolist()}} if n["op"] == "Const"
+                       else dict(n["attr"], dtype=n["attr"].get("dtype", "float32")))} for n in ours]
+    sq, bl = O.random_positions_fast(6, seed=2)
+    planes = O.encode_planes(sq, bl)
+    pr = G.run(nodes, {"Placeholder": planes.astype(np.float32)}, {})
+    assert np.abs(pr - O.forward_fp32(planes, w)[1]).max() <= 2e-6
+    with pytest.raises(KeyError):
+        open(path, "wb").write(open("/root/reference/cppModels/policyNet.pb", "rb").read()
+                               if os.path.exists("/root/reference/cppModels/policyNet.pb") else b"")
+        GD.load_frozen_weights(path)                             # the reference's own .pb is NOT frozen
+
+
 def test_child_seeding_oracle_vs_reference_golden(seed_golden):
     """641 positions expanded ONCE by the compiled reference tree code (expand_descendants_to_depth_wrt_NN
     -> get_child / update_child / assign_children / eval_children / update_win_status_from_children) with

@@ -68,10 +68,15 @@ def validate(w, final_kernel=3):
 def default_weights(scope="", final_kernel=3):
     """Weights used when the reference-shaped constructors are called with no arguments
     (the reference hard-codes its checkpoint path, policy_net_utils.pyx:69).  Order:
-    $WANN_B200_CHECKPOINT (TF-V2 bundle prefix, CRC-verified) else the synthetic
+    $WANN_B200_CHECKPOINT (TF-V2 bundle prefix, CRC-verified), else $WANN_B200_FROZEN_GRAPH
+    (frozen GraphDef .pb, tf_graphdef.py), else the synthetic
     'trained_like' preset (seed from $WANN_B200_SEED, default 1)."""
     prefix = os.environ.get("WANN_B200_CHECKPOINT")
     if prefix:
         from . import tf_bundle
         return tf_bundle.load_policy_weights(prefix, scope=scope, final_kernel=final_kernel)
+    frozen = os.environ.get("WANN_B200_FROZEN_GRAPH")
+    if frozen:                                    # a frozen GraphDef (.pb) of the same architecture
+        from . import tf_graphdef
+        return tf_graphdef.load_frozen_weights(frozen, final_kernel=final_kernel)
     return synthetic("trained_like", int(os.environ.get("WANN_B200_SEED", "1")), final_kernel)
