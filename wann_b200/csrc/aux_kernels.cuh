@@ -22,15 +22,28 @@ __device__ __forceinline__ int pov_square(const int8_t* sq64, int blk, int i) {
   return s;
 }
 
-// One thread per square; writes 4 plane bytes (char4) -> fully coalesced 4 B stores.
-__global__ void encode_kernel(const int8_t* __restrict__ squares, const uint8_t* __restrict__ black,
-                              long long n, int8_t* __restrict__ planes) {
-  const long long total = n * 64;
+// One thread per FOUR squares: one 4-byte load (for Black the mirrored word, bytes reversed: the
+// 180-degree rotation of tools/utils.pyx:563-600) and one 16-byte store of the four P/O/E/1 cells.
+// HBM-bound: 65 B in, 256 B out per position.
+__global__ void __launch_bounds__(256) encode_kernel(const int8_t* __restrict__ squares,
+                                                     const uint8_t* __restrict__ black, long long n,
+                                                     int8_t* __restrict__ planes) {
+  const long long total = n * 16;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long board = i >> 6;
-    const int s = pov_square(squares + board * 64, black[board], static_cast<int>(i & 63));
-    reinterpret_cast<char4*>(planes)[i] = make_char4(s == 1, s == 2, s == 0, 1);
+    const long long board = i >> 4;
+    const int q = static_cast<int>(i & 15);
+    const int blk = black[board];
+    uint32_t w = reinterpret_cast<const uint32_t*>(squares + board * 64)[blk ? 15 - q : q];
+    if (blk) w = __byte_perm(w, 0u, 0x0123);          // reverse the four squares
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int sq = (w >> (8 * k)) & 0xFF;
+      if (blk && sq) sq = 3 - sq;                       // Black sees its own pieces as "player"
+      out[k] = (sq == 1 ? 1u : 0u) | (sq == 2 ? 0x100u : 0u) | (sq == 0 ? 0x10000u : 0u) | 0x1000000u;
+    }
+    reinterpret_cast<uint4*>(planes)[i] = make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
 
@@ -51,17 +64,56 @@ __device__ __forceinline__ bool move_is_legal(const int8_t* pov, int idx) {
   return d == 0 ? (t == 0) : (t != 1);
 }
 
-__global__ void legal_mask_kernel(const int8_t* __restrict__ squares,
-                                  const uint8_t* __restrict__ black, long long n,
-                                  uint8_t* __restrict__ mask) {
+// One warp per board, warps fully independent (no CTA barrier in the loop, so the 64 resident warps
+// of an SM hide each other's load latency): both candidate squares of a lane (own and mirrored) and
+// the colour are loaded at once, legality comes from a per-CTA move table, the 155 mask bytes are
+// staged in the warp's shared-memory row and written as 4-byte words where the output row is aligned
+// (a row starts at board * 155, i.e. at any byte offset), single bytes at its ends.
+// 65 B in, 155 B out per position; measured 0.74 TB/s (instruction/latency-bound, not HBM-bound: a
+// register-only bitboard variant with 64-bit shifts was slower, 124 vs 78 us per 262,144 boards).
+__global__ void __launch_bounds__(256) legal_mask_kernel(const int8_t* __restrict__ squares,
+                                                         const uint8_t* __restrict__ black, long long n,
+                                                         uint8_t* __restrict__ mask) {
   __shared__ int8_t pov[8][64];
+  __shared__ uint8_t out_s[8][160];
+  __shared__ uint16_t mv_s[160];                 // from | to << 6 | forward << 12 per move index
+  for (int i = threadIdx.x; i < 160; i += blockDim.x) {
+    int r = 0, c = 0, d = 0;
+    if (i < 154) decode_move(i, r, c, d);
+    mv_s[i] = static_cast<uint16_t>((r * 8 + c) | (((r + 1) * 8 + c + d) << 6) | ((d == 0) << 12));
+  }
+  __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long long board = blockIdx.x * 8ll + w; board < n; board += gridDim.x * 8ll) {
+    const int8_t* b64 = squares + board * 64;
+    const int a0 = b64[lane], a1 = b64[lane + 32], m0 = b64[63 - lane], m1 = b64[31 - lane];   // no dependent load
     const int blk = black[board];
-    pov[w][lane] = static_cast<int8_t>(pov_square(squares + board * 64, blk, lane));
-    pov[w][lane + 32] = static_cast<int8_t>(pov_square(squares + board * 64, blk, lane + 32));
+    int s0 = blk ? m0 : a0, s1 = blk ? m1 : a1;
+    if (blk && s0) s0 = 3 - s0;
+    if (blk && s1) s1 = 3 - s1;
+    pov[w][lane] = static_cast<int8_t>(s0);
+    pov[w][lane + 32] = static_cast<int8_t>(s1);
     __syncwarp();
-    for (int j = lane; j < kMoves; j += 32) mask[board * kMoves + j] = move_is_legal(pov[w], j);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int j = lane + 32 * k;
+      if (j < kMoves) {
+        const uint32_t m = mv_s[j];
+        const int tgt = pov[w][(m >> 6) & 63];
+        out_s[w][j] = (j < 154) && pov[w][m & 63] == 1 && ((m >> 12) ? tgt == 0 : tgt != 1);
+      }
+    }
+    __syncwarp();
+    uint8_t* dst = mask + board * kMoves;
+    const int head = static_cast<int>((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+    const int words = (kMoves - head) >> 2;
+    if (lane < head) dst[lane] = out_s[w][lane];
+    for (int i = lane; i < words; i += 32) {
+      const uint8_t* src = &out_s[w][head + 4 * i];
+      reinterpret_cast<uint32_t*>(dst + head)[i] = src[0] | (src[1] << 8) | (src[2] << 16) | (src[3] << 24);
+    }
+    const int done = head + 4 * words;
+    if (lane < kMoves - done) dst[done + lane] = out_s[w][done + lane];
     __syncwarp();
   }
 }
@@ -392,6 +444,9 @@ __global__ void __launch_bounds__(256) seed_children_kernel(const int8_t* __rest
                                                             int32_t* __restrict__ stats, uint8_t* __restrict__ flags,
                                                             int32_t* __restrict__ parent) {
   __shared__ int8_t brd[8][64];
+  __shared__ int8_t tab[64];        // lanes index the table divergently: shared memory, not the constant cache
+  if (threadIdx.x < 64) tab[threadIdx.x] = kEvalTable[threadIdx.x];
+  __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long long board = blockIdx.x * 8ll + w; board < n; board += gridDim.x * 8ll) {
     const int blk = black[board];
@@ -400,8 +455,8 @@ __global__ void __launch_bounds__(256) seed_children_kernel(const int8_t* __rest
     brd[w][lane] = static_cast<int8_t>(s0);
     brd[w][lane + 32] = static_cast<int8_t>(s1);
     // evaluation_function of the PARENT board: sum over white - sum over black, absolute squares
-    int res = (s0 == 1 ? kEvalTable[lane] : (s0 == 2 ? -kEvalTable[lane] : 0)) +
-              (s1 == 1 ? kEvalTable[lane + 32] : (s1 == 2 ? -kEvalTable[lane + 32] : 0));
+    int res = (s0 == 1 ? tab[lane] : (s0 == 2 ? -tab[lane] : 0)) +
+              (s1 == 1 ? tab[lane + 32] : (s1 == 2 ? -tab[lane + 32] : 0));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
     // threat: an opponent piece one step from the mover's home rank (rank 2 for White, rank 7 for Black)
@@ -445,7 +500,7 @@ __global__ void __launch_bounds__(256) seed_children_kernel(const int8_t* __rest
           if (capture) { gv = 1000; gw = 0; v = 65536; wn = 0; f |= 8; }
           else if (!win) { v = wn = gw = gv = 65537; ws = 1; f |= 16; }
         } else {
-          const int t_to = kEvalTable[to], t_frm = kEvalTable[frm];
+          const int t_to = tab[to], t_frm = tab[frm];
           int rc = blk ? res - (t_to - t_frm) : res + (t_to - t_frm);
           if (capture) rc += blk ? -t_to : t_to;
           const bool child_is_white = blk != 0;

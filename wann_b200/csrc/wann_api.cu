@@ -1226,6 +1226,9 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
   if (n < 0) return fail(WANN_E_INVALID, "negative n");
   if (n == 0) return WANN_OK;
   if (!squares || !black || !out) return fail(WANN_E_INVALID, "null buffer");
+  if (mem == WANN_MEM_DEVICE && !is_mask &&
+      ((reinterpret_cast<uintptr_t>(squares) & 3u) || (reinterpret_cast<uintptr_t>(out) & 15u)))
+    return fail(WANN_E_INVALID, "device squares must be 4-byte and planes 16-byte aligned");
   DeviceGuard dev_guard(ctx->device);
   CU(dev_guard.status);
   Lane* lane = nullptr;
@@ -1235,8 +1238,11 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
   cudaStream_t stream = (mem == WANN_MEM_DEVICE && stream_v) ? static_cast<cudaStream_t>(stream_v) : s.stream;
   lane_wait(lane, stream);
   auto body = [&]() -> int {
-    for (long long off = 0; off < n; off += s.cap) {
-      const long long m = std::min<long long>(s.cap, n - off);
+    // HOST buffers are staged through the slot (chunks of its capacity); DEVICE buffers need no
+    // staging: one launch over all n positions (the kernels are grid-stride loops)
+    const long long step = (mem == WANN_MEM_HOST) ? s.cap : n;
+    for (long long off = 0; off < n; off += step) {
+      const long long m = std::min<long long>(step, n - off);
       const int8_t* dsq = squares + off * 64;
       const uint8_t* dbl = black + off;
       uint8_t* dout = static_cast<uint8_t*>(out) + off * out_per_pos;
@@ -1250,7 +1256,7 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
         const int blocks = static_cast<int>(std::min<long long>((m + 7) / 8, 8ll * ctx->sm_count));
         legal_mask_kernel<<<blocks, 256, 0, stream>>>(dsq, dbl, m, dout);
       } else {
-        const int blocks = static_cast<int>(std::min<long long>((m * 64 + 255) / 256, 16ll * ctx->sm_count));
+        const int blocks = static_cast<int>(std::min<long long>((m * 16 + 255) / 256, 16ll * ctx->sm_count));
         encode_kernel<<<blocks, 256, 0, stream>>>(dsq, dbl, m, reinterpret_cast<int8_t*>(dout));
       }
       CU(cudaGetLastError());
