@@ -64,56 +64,82 @@ __device__ __forceinline__ bool move_is_legal(const int8_t* pov, int idx) {
   return d == 0 ? (t == 0) : (t != 1);
 }
 
-// One warp per board, warps fully independent (no CTA barrier in the loop, so the 64 resident warps
-// of an SM hide each other's load latency): both candidate squares of a lane (own and mirrored) and
-// the colour are loaded at once, legality comes from a per-CTA move table, the 155 mask bytes are
-// staged in the warp's shared-memory row and written as 4-byte words where the output row is aligned
-// (a row starts at board * 155, i.e. at any byte offset), single bytes at its ends.
-// 65 B in, 155 B out per position; measured 0.74 TB/s (instruction/latency-bound, not HBM-bound: a
-// register-only bitboard variant with 64-bit shifts was slower, 124 vs 78 us per 262,144 boards).
-__global__ void __launch_bounds__(256) legal_mask_kernel(const int8_t* __restrict__ squares,
-                                                         const uint8_t* __restrict__ black, long long n,
-                                                         uint8_t* __restrict__ mask) {
-  __shared__ int8_t pov[8][64];
-  __shared__ uint8_t out_s[8][160];
-  __shared__ uint16_t mv_s[160];                 // from | to << 6 | forward << 12 per move index
-  for (int i = threadIdx.x; i < 160; i += blockDim.x) {
-    int r = 0, c = 0, d = 0;
-    if (i < 154) decode_move(i, r, c, d);
-    mv_s[i] = static_cast<uint16_t>((r * 8 + c) | (((r + 1) * 8 + c + d) << 6) | ((d == 0) << 12));
-  }
-  __syncthreads();
+// One THREAD per board, bitboards in registers:
+//   * the 64 squares are read as eight 8-byte words; SWAR byte-equality tests (exact for any byte
+//     value) and a multiply-compress turn them into 64-bit "white / black / empty" boards; Black's
+//     point of view is the bit-reversed board with the colours swapped (the 180-degree rotation of
+//     tools/utils.pyx:563-600; a stray value 3 reads as empty for Black, as in pov_square);
+//   * legality for all 154 moves is three shifts: forward = player & (empty >> 8), the diagonals
+//     = player & ~(player >> 7 | 9) off the edge files (board_utils.pyx:331-400);
+//   * the move alphabet order (22 indices per rank: F0 R0 | L1 F1 R1 | ... | L7 F7,
+//     tools/utils.pyx:605-641) is walked once per thread, the 155 mask bytes go to the warp's
+//     shared-memory block, and the warp writes its 32 x 155 contiguous bytes as 16-byte vectors.
+// ~22 warp instructions per board instead of ~200: HBM-bound.  65 B in, 155 B out per position.
+constexpr int kMaskWarps = 4;
+__device__ __forceinline__ uint64_t swar_eq_flags(uint64_t w, uint64_t pattern) {   // 0x80 in every byte == pattern's
+  const uint64_t x = w ^ pattern;
+  const uint64_t t = (x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full;
+  return ~(t | x | 0x7F7F7F7F7F7F7F7Full);
+}
+__device__ __forceinline__ uint64_t swar_compress(uint64_t flags) {   // byte c's 0x80 flag -> bit c
+  return ((flags >> 7) * 0x0102040810204080ull) >> 56;
+}
+
+__global__ void __launch_bounds__(kMaskWarps * 32) legal_mask_kernel(const int8_t* __restrict__ squares,
+                                                                    const uint8_t* __restrict__ black,
+                                                                    long long n, uint8_t* __restrict__ mask) {
+  __shared__ __align__(16) uint8_t out_s[kMaskWarps][32 * kMoves];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (long long board = blockIdx.x * 8ll + w; board < n; board += gridDim.x * 8ll) {
-    const int8_t* b64 = squares + board * 64;
-    const int a0 = b64[lane], a1 = b64[lane + 32], m0 = b64[63 - lane], m1 = b64[31 - lane];   // no dependent load
-    const int blk = black[board];
-    int s0 = blk ? m0 : a0, s1 = blk ? m1 : a1;
-    if (blk && s0) s0 = 3 - s0;
-    if (blk && s1) s1 = 3 - s1;
-    pov[w][lane] = static_cast<int8_t>(s0);
-    pov[w][lane + 32] = static_cast<int8_t>(s1);
-    __syncwarp();
+  for (long long base = (blockIdx.x * static_cast<long long>(kMaskWarps) + w) * 32; base < n;
+       base += static_cast<long long>(gridDim.x) * kMaskWarps * 32) {
+    const long long board = base + lane;
+    if (board < n) {
+      const uint2* src = reinterpret_cast<const uint2*>(squares + board * 64);
+      uint64_t white = 0, blackbb = 0, e0 = 0, t3 = 0;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int j = lane + 32 * k;
-      if (j < kMoves) {
-        const uint32_t m = mv_s[j];
-        const int tgt = pov[w][(m >> 6) & 63];
-        out_s[w][j] = (j < 154) && pov[w][m & 63] == 1 && ((m >> 12) ? tgt == 0 : tgt != 1);
+      for (int r = 0; r < 8; ++r) {
+        const uint2 v = src[r];
+        const uint64_t wd = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
+        white |= swar_compress(swar_eq_flags(wd, 0x0101010101010101ull)) << (8 * r);
+        blackbb |= swar_compress(swar_eq_flags(wd, 0x0202020202020202ull)) << (8 * r);
+        e0 |= swar_compress(swar_eq_flags(wd, 0ull)) << (8 * r);
+        t3 |= swar_compress(swar_eq_flags(wd, 0x0303030303030303ull)) << (8 * r);
       }
+      const bool blk = black[board] != 0;
+      const uint64_t player = blk ? __brevll(blackbb) : white;
+      const uint64_t empty = blk ? __brevll(e0 | t3) : e0;
+      constexpr uint64_t kRows06 = 0x00FFFFFFFFFFFFFFull, kFileA = 0x0101010101010101ull;
+      const uint64_t fwd = player & (empty >> 8) & kRows06;
+      const uint64_t lft = player & ~(player >> 7) & ~kFileA & kRows06;          // d = -1: to = from + 7
+      const uint64_t rgt = player & ~(player >> 9) & ~(kFileA << 7) & kRows06;   // d = +1: to = from + 9
+      uint8_t* row = &out_s[w][lane * kMoves];
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+        const uint32_t f = static_cast<uint32_t>(fwd >> (8 * r)) & 0xFFu;
+        const uint32_t l = static_cast<uint32_t>(lft >> (8 * r)) & 0xFFu;
+        const uint32_t g = static_cast<uint32_t>(rgt >> (8 * r)) & 0xFFu;
+        uint8_t* o = row + 22 * r;
+        o[0] = f & 1u;
+        o[1] = g & 1u;
+#pragma unroll
+        for (int c = 1; c < 7; ++c) {
+          o[3 * c - 1] = (l >> c) & 1u;
+          o[3 * c] = (f >> c) & 1u;
+          o[3 * c + 1] = (g >> c) & 1u;
+        }
+        o[20] = (l >> 7) & 1u;
+        o[21] = (f >> 7) & 1u;
+      }
+      row[154] = 0;                                   // 'no-move' is never a legal child
     }
     __syncwarp();
-    uint8_t* dst = mask + board * kMoves;
-    const int head = static_cast<int>((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
-    const int words = (kMoves - head) >> 2;
-    if (lane < head) dst[lane] = out_s[w][lane];
-    for (int i = lane; i < words; i += 32) {
-      const uint8_t* src = &out_s[w][head + 4 * i];
-      reinterpret_cast<uint32_t*>(dst + head)[i] = src[0] | (src[1] << 8) | (src[2] << 16) | (src[3] << 24);
-    }
-    const int done = head + 4 * words;
-    if (lane < kMoves - done) dst[done + lane] = out_s[w][done + lane];
+    const int nvalid = static_cast<int>(min(32ll, n - base));
+    const int bytes = nvalid * kMoves;
+    uint8_t* dst = mask + base * kMoves;              // base is a multiple of 32 -> 32-byte aligned if mask is
+    const uint8_t* srcb = out_s[w];
+    for (int i = lane; i < bytes / 16; i += 32)
+      reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(srcb)[i];
+    for (int i = (bytes & ~15) + lane; i < bytes; i += 32) dst[i] = srcb[i];
     __syncwarp();
   }
 }

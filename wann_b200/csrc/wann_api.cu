@@ -1229,6 +1229,9 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
   if (mem == WANN_MEM_DEVICE && !is_mask &&
       ((reinterpret_cast<uintptr_t>(squares) & 3u) || (reinterpret_cast<uintptr_t>(out) & 15u)))
     return fail(WANN_E_INVALID, "device squares must be 4-byte and planes 16-byte aligned");
+  if (mem == WANN_MEM_DEVICE && is_mask &&
+      ((reinterpret_cast<uintptr_t>(squares) & 7u) || (reinterpret_cast<uintptr_t>(out) & 15u)))
+    return fail(WANN_E_INVALID, "device squares must be 8-byte and the mask buffer 16-byte aligned");
   DeviceGuard dev_guard(ctx->device);
   CU(dev_guard.status);
   Lane* lane = nullptr;
@@ -1253,8 +1256,9 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
         dout = is_mask ? s.d_mask : reinterpret_cast<uint8_t*>(s.d_planes_out);
       }
       if (is_mask) {
-        const int blocks = static_cast<int>(std::min<long long>((m + 7) / 8, 8ll * ctx->sm_count));
-        legal_mask_kernel<<<blocks, 256, 0, stream>>>(dsq, dbl, m, dout);
+        const long long per_block = kMaskWarps * 32;
+        const int blocks = static_cast<int>(std::min<long long>((m + per_block - 1) / per_block, 11ll * ctx->sm_count));
+        legal_mask_kernel<<<blocks, kMaskWarps * 32, 0, stream>>>(dsq, dbl, m, dout);
       } else {
         const int blocks = static_cast<int>(std::min<long long>((m * 16 + 255) / 256, 16ll * ctx->sm_count));
         encode_kernel<<<blocks, 256, 0, stream>>>(dsq, dbl, m, reinterpret_cast<int8_t*>(dout));
