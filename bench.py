@@ -400,6 +400,40 @@ def main():
                    "value": n_gpus * B * rsteps / (float(t.item()) * 1e-3), "unit": UNIT, "steps": rsteps}
         ev2.close()
 
+    # ---------------- the HBM-bound byte kernels beside the path (north_star: "achieved HBM GB/s for
+    # encode and epilogue"): encode 65 B -> 256 B, legal mask 65 B -> 155 B per position, device resident
+    hbm_kernels = None
+    if rank == 0 and not args.no_sweep:
+        import ctypes
+        from wann_b200 import _lib as L
+        nbk = min(pool_n, 1 << 20)
+        d_planes = torch.empty((nbk, 8, 8, 4), dtype=torch.int8, device=dev)
+        d_mask = torch.empty((nbk, 155), dtype=torch.uint8, device=dev)
+        hbm_peak = 6533.5
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            hbm_peak = json.load(open(pk)).get("hbm_gbs", hbm_peak)
+        hbm_kernels = {"positions": nbk, "peak_gbs": hbm_peak}
+        s1 = ctypes.c_void_p(1)
+        for name, fn, out_t, bpp in (("encode_kernel", ev._lib.wann_encode, d_planes, 65 + 256),
+                                     ("legal_mask_kernel", ev._lib.wann_legal_mask, d_mask, 65 + 155)):
+            call = lambda: L.check(fn(ev._ctx, sq_pool.data_ptr(), bl_pool.data_ptr(), nbk, out_t.data_ptr(),  # noqa: E731
+                                      L.MEM_DEVICE, s1))
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                call()
+            b.record()
+            torch.cuda.synchronize()
+            sec = a.elapsed_time(b) / 10 * 1e-3
+            hbm_kernels[name] = {"bytes_per_position": bpp, "us": round(sec * 1e6, 2),
+                                 "achieved_gbs": round(nbk * bpp / sec / 1e9, 1),
+                                 "frac": round(nbk * bpp / sec / 1e9 / hbm_peak, 4)}
+        del d_planes, d_mask
+
     # ---------------- optional: counters gathered with NCCL, sweep, CPU baseline ----------
     counters = gather_counters([B * args.steps, int(ms * 1e6)], device=dev)
     # configs[3]: the batch sweep 64 ... 65,536 positions PER GPU (plus 1 = configs[0], 256 = configs[2],
@@ -464,6 +498,7 @@ def main():
             "sweep_positions_per_s": sweep,
             "config5_game_trees": trees,
             "fp16_margin_refined": refined,
+            "hbm_kernels": hbm_kernels,
             "per_rank_counters": counters.tolist(),
         }
         if not args.no_cpu_baseline and n_gpus == 1:

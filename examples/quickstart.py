@@ -36,3 +36,9 @@ with wann_b200.PolicyEvaluator(mode="fp16") as ev:
     out = ev.eval_expand(torch.from_numpy(sq).cuda(), torch.from_numpy(black).cuda())
     torch.cuda.synchronize()
     print("eval_expand(): children", tuple(out[3].shape), "on", out[3].device, "| stats", ev.stats())
+
+    # 4. everything the reference derives from the priors when it expands a node (child seeds, flags,
+    #    the parent's gained statistics and win status) -- tree_search_utils.update_child & co.
+    idx, prior, n_legal, _, flags, stats, parent = ev.eval_expand_seeded(sq[:4], black[:4], with_children=False)
+    print("eval_expand_seeded(): first child visits/wins/gameover_visits/gameover_wins", stats[0, 0].tolist(),
+          "| parent gained", parent[0, :4].tolist(), "win_status", int(parent[0, 4]))

@@ -213,6 +213,12 @@ int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]);
  * combining, no added latency for a lone caller; the reference calls evaluate with batch 1 from
  * 11 threads), "wimg_copies" (1..8 replicas of the weight image; experiment knob), "variant" (debug bits),
  * "time_kernels" (0/1, see wann_kernel_times),
+ * "fuse_tail" (bf16/fp16 modes, default 1: FC-155 -> softmax -> legal gather -> rank run on two extra
+ * warps inside the conv-stack kernel, one kernel per evaluation; 0 = the stand-alone tail kernel,
+ * bit-identical), "zero_copy" (default 1: HOST calls of <= 512 positions read their inputs from and
+ * write their outputs to pinned mapped host memory, no DMA copies), "pdl" (-1 auto / 0 / 1:
+ * programmatic dependent launch between consecutive evaluations on a stream),
+ * "small_batch_halves" (default 1: <= 296 positions run 4-board supertiles), "skew" (0..6),
  * "refine_margin_micro" (bf16/fp16 modes; margin in 1e-6 logit units, 0 = off): positions whose two
  * best LEGAL moves are closer than the margin -- log(prior_1 / prior_2) < margin, the only
  * positions where 16-bit operand rounding can flip the policy move of get_best_move
