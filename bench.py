@@ -266,6 +266,9 @@ def main():
 
     B = args.batch
     ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode=args.mode)
+    for opt in os.environ.get("WANN_BENCH_OPTIONS", "").split(","):      # experiments: "skew=5,fuse_tail=0"
+        if "=" in opt:
+            ev.set_option(opt.split("=")[0].strip(), int(opt.split("=")[1]))
     # whole-job pool of leaf positions, this rank's contiguous slice (weak scaling: B per GPU)
     pool_n = POOL_SETS * B
     lo, hi = shard_range(pool_n * n_gpus, rank, n_gpus)
