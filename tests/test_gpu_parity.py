@@ -743,6 +743,25 @@ def test_set_weights_swaps_a_live_context(mode, suite):
         assert ev._lib.wann_set_weights(ev._ctx, ctypes.byref(cw)) != 0
 
 
+def test_cython_binding_evaluates_like_the_shim(tmp_path, suite):
+    """The Cython class of examples/cython_binding (cimport wann_b200, nogil call into the C ABI) returns
+    what the Python shim returns for the same nodes."""
+    pytest.importorskip("Cython")
+    import wann_b200
+    from wann_b200 import boards
+    from test_oracle_cpu import _build_cython_binding
+    mod = _build_cython_binding(tmp_path)
+    sq, bl = suite
+    w1 = wann_b200.weights.synthetic("trained_like", 1, final_kernel=1)
+    nodes = [{"game_board": boards.squares_to_board(sq[i], 0 if bl[i] else 1),
+              "color": "Black" if bl[i] else "White"} for i in range(300)]
+    with mod.PolicyNet(w1) as net, wann_b200.NeuralNetsCombined_128(w1) as shim:
+        got = net.evaluate(nodes)
+        assert got.shape == (300, 155) and got.dtype == np.float32
+        assert np.array_equal(got, shim.evaluate(nodes))
+        assert np.array_equal(net.evaluate(nodes[:1]), got[:1])
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote

@@ -248,6 +248,40 @@ def test_frozen_graphdef_writer_matches_the_references_graph(tmp_path):
         GD.load_frozen_weights(path)                             # the reference's own .pb is NOT frozen
 
 
+def _build_cython_binding(tmp_path):
+    import subprocess
+    import sys
+    ex = os.path.join(ROOT, "examples", "cython_binding")
+    env = dict(os.environ, WANN_CYTHON_BUILD_DIR=str(tmp_path / "gen"))
+    subprocess.check_call([sys.executable, os.path.join(ex, "setup.py"), "-q", "build_ext", "--build-lib", str(tmp_path),
+                           "--build-temp", str(tmp_path / "tmp")], cwd=str(tmp_path), env=env,
+                          stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    sys.path.insert(0, str(tmp_path))
+    try:
+        import importlib
+        return importlib.import_module("wann_eval")
+    finally:
+        sys.path.pop(0)
+
+
+def test_cython_binding_compiles_against_the_header(lib_built, tmp_path):
+    """include/wann_b200.pxd (the reference is Cython) declares the same ABI as wann_b200.h: the example
+    binding a maintainer would add next to MCTS.pyx compiles against both and links to libwann_b200.so;
+    without a GPU the class fails loudly (no CPU fallback)."""
+    pytest.importorskip("Cython")
+    mod = _build_cython_binding(tmp_path)
+    assert mod.abi_version() == 100
+    import re
+    hdr = open(os.path.join(ROOT, "include", "wann_b200.h")).read()
+    pxd = open(os.path.join(ROOT, "include", "wann_b200.pxd")).read()
+    declared = set(re.findall(r"\b(wann_[a-z0-9_]+)\s*\(", hdr))
+    assert declared and declared <= set(re.findall(r"\b(wann_[a-z0-9_]+)\s*\(", pxd))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CUDA device|CPU fallback"):
+            mod.PolicyNet(O.synthetic_weights("trained_like", 1, final_kernel=1))
+
+
 def test_child_seeding_oracle_vs_reference_golden(seed_golden):
     """641 positions expanded ONCE by the compiled reference tree code (expand_descendants_to_depth_wrt_NN
     -> get_child / update_child / assign_children / eval_children / update_win_status_from_children) with
