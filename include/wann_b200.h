@@ -214,7 +214,7 @@ int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]);
 /* Tunables (optional).  key: "chunk" (positions per internal chunk, default 16384),
  * "coalesce" (0/1: merge concurrent HOST calls of <= 256 positions into one launch -- flat
  * combining, no added latency for a lone caller; the reference calls evaluate with batch 1 from
- * 11 threads), "wimg_copies" (1..8 replicas of the weight image; experiment knob), "variant" (debug bits),
+ * 11 threads), "variant" (debug bits),
  * "time_kernels" (0/1, see wann_kernel_times),
  * "fuse_tail" (bf16/fp16 modes, default 1: FC-155 -> softmax -> legal gather -> rank run on two extra
  * warps inside the conv-stack kernel, one kernel per evaluation; 0 = the stand-alone tail kernel,

@@ -111,13 +111,12 @@ struct TcParams {
   const void* planes;        // [n][8][8][4] int8/f32 or null
   int planes_f32;
   long long n;
-  const uint8_t* wimg;       // [wimg_copies][2][kImgBytesPerRank]; pair p reads copy p % wimg_copies
-  int wimg_copies;
+  const uint8_t* wimg;       // [2][kImgBytesPerRank]: the stage images of CTA rank 0 / 1
   const float* bias;         // [4][192] conv1..4 bias, then b5
   float* h5;                 // [n][64]
   float* dbg;                // optional activation dump [n][64][192] (layer 1..4)
   int dbg_layer;
-  int variant;               // debug: bit2 = swap the B halves between the CTAs of a pair
+  int variant;               // debug: bit2 = swap the B halves between the CTAs of a pair, bit3 = skip the MMAs
   int skew;                  // weight stages by which half 1 trails the stream (0 = free-running)
   int halves;                // 2 = 8 boards per CTA pair (throughput), 1 = 4 boards (small batches)
   int* err;                  // [8] watchdog record
@@ -233,7 +232,7 @@ conv_stack_tc_kernel(const TcParams p) {
   const int nh = (p.halves == 1) ? 1 : 2;
   const int boards_per_pair = 4 * nh;
   const long long total_st = (p.n + boards_per_pair - 1) / boards_per_pair;
-  const uint32_t nst = kStages - ((p.variant >> 4) & 7);   // debug: use a shallower weight ring
+  constexpr uint32_t nst = kStages;
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
@@ -276,7 +275,7 @@ conv_stack_tc_kernel(const TcParams p) {
     // ===== weight producer: stream this CTA's half of every weight stage ====================
     if (lane == 0) {
       const uint32_t img_rank = (p.variant & 4) ? (rank ^ 1u) : rank;
-      const uint8_t* img = p.wimg + (static_cast<size_t>(pair % p.wimg_copies) * 2 + img_rank) * kImgBytesPerRank;
+      const uint8_t* img = p.wimg + static_cast<size_t>(img_rank) * kImgBytesPerRank;
       uint32_t s = 0, ph = 0;
       bool ok = true;
       for (long long st = pair; st < total_st && ok; st += npairs) {
@@ -284,18 +283,8 @@ conv_stack_tc_kernel(const TcParams p) {
         for (int kb = 0; kb < kKbPerSupertile; ++kb) {
           const uint32_t bytes = (kb >= kKbPerSupertile - kKbL5) ? kStageBytesL5 : kStageBytes;
           if (!wait_bar(bar_empty(s), ph ^ 1u, false, p.err, 100 + s)) { ok = false; break; }
-          if (p.variant & 256) {            // timing experiment: half the bytes per stage
-            ptx::mbar_arrive_expect_tx(bar_full(s), bytes / 2);
-            ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes / 2, bar_full(s));
-          } else if (p.variant & 512) {     // experiment: 4 concurrent copies per stage
-            ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
-            for (uint32_t q = 0; q < 4; ++q)
-              ptx::bulk_g2s(b_base + s * kStageBytes + q * (bytes / 4), img + off + q * (bytes / 4), bytes / 4,
-                            bar_full(s));
-          } else {
-            ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
-            ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes, bar_full(s));
-          }
+          ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
+          ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes, bar_full(s));
           off += bytes;
           if (++s == nst) { s = 0; ph ^= 1u; }
         }

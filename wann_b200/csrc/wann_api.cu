@@ -164,7 +164,6 @@ struct CombineReq {
   float* probs; float* logits; uint8_t* idx; float* prior; uint8_t* nlegal;
   int rc = 0; std::string err; bool done = false;
 };
-constexpr int kMaxWimgCopies = 8;
 
 }  // namespace
 
@@ -183,7 +182,6 @@ struct wann_ctx {
   std::atomic<bool> fuse_tail{true};            // bf16/fp16 modes: tail warps inside the conv-stack kernel (one kernel per evaluation)
   std::atomic<bool> zero_copy{true};            // host calls <= kZeroCopyMax positions: kernels read/write mapped host memory
   std::atomic<int> skew{4};                // conv_stack_tc: stages by which half 1 trails the weight stream (0..6)
-  std::atomic<int> wimg_copies{1};         // replicas of the weight image in use (experiment knob; measured: no effect)
   // weights on device
   float* d_conv_w[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* d_conv_b[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -419,10 +417,8 @@ int upload_weights(wann_ctx* ctx, const wann_weights& w) {
   std::vector<uint8_t> img;
   if (ctx->mode == WANN_MODE_FP32_TC) build_weight_image_split(w, img);
   else build_weight_image(w, ctx->mode == WANN_MODE_FP16, img);
-  const int copies = (ctx->mode == WANN_MODE_FP32_TC) ? 1 : kMaxWimgCopies;
-  if (ctx->d_wimg == nullptr) CU(cudaMalloc(&ctx->d_wimg, img.size() * copies));
-  for (int c = 0; c < copies; ++c)
-    CU(cudaMemcpy(ctx->d_wimg + c * img.size(), img.data(), img.size(), cudaMemcpyHostToDevice));
+  if (ctx->d_wimg == nullptr) CU(cudaMalloc(&ctx->d_wimg, img.size()));
+  CU(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
   if (ctx->mode != WANN_MODE_FP32_TC) {   // the refinement pass's fp16 hi/lo split image
     std::vector<uint8_t> simg;
     build_weight_image_split(w, simg);
@@ -473,7 +469,7 @@ int enqueue_refine_pass(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const Chun
   const long long m = count < 0 ? n : count;
   int* d_rcount = ws.d_err + 4;
   TcParams p = {};
-  p.squares = io.squares; p.black = io.black; p.n = n; p.wimg = ctx->d_wimg_split; p.wimg_copies = 1;
+  p.squares = io.squares; p.black = io.black; p.n = n; p.wimg = ctx->d_wimg_split;
   p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5r; p.err = ws.d_err; p.halves = 2;
   p.gather = ws.d_rlist; p.n_dev = d_rcount;
   const long long total_st = (m + kSplitBoardsPerPair - 1) / kSplitBoardsPerPair;
@@ -522,7 +518,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   if (ctx->mode != WANN_MODE_FP32) {
     TcParams p;
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
-    p.n = n; p.wimg = ctx->d_wimg; p.wimg_copies = ctx->wimg_copies; p.skew = ctx->skew; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
+    p.n = n; p.wimg = ctx->d_wimg; p.skew = ctx->skew; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
     if (fused) {
       p.fuse_tail = 1;
@@ -1396,11 +1392,6 @@ int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]) {
 int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
   if (ctx == nullptr || key == nullptr) return fail(WANN_E_INVALID, "null argument");
   if (strcmp(key, "variant") == 0) { ctx->variant = static_cast<int>(value); return WANN_OK; }
-  if (strcmp(key, "wimg_copies") == 0) {
-    if (value < 1 || value > kMaxWimgCopies) return fail(WANN_E_INVALID, "wimg_copies out of range");
-    ctx->wimg_copies = static_cast<int>(value);
-    return WANN_OK;
-  }
   if (strcmp(key, "skew") == 0) {
     if (value < 0 || value > 6) return fail(WANN_E_INVALID, "skew out of range");
     ctx->skew = static_cast<int>(value);
