@@ -541,6 +541,15 @@ def test_margin_refinement_pass(mode, margin, weights, suite, ref1k):
         assert np.array_equal(ei, i1[:300]) and np.array_equal(ep, p1[:300])
         wk, wf = O.expand_children(sq[:300], bl[:300], ei, ec)
         assert np.array_equal(kids, wk) and np.array_equal(flg, wf)
+        # small host calls (the host reads the flagged count and launches pass 2 itself) with the fused and
+        # with the stand-alone tail (regression: the latter mirrored the count before the flagging ran)
+        for fuse in (1, 0):
+            ev.set_option("fuse_tail", fuse)
+            for lo, m in ((0, 64), (100, 1), (7, 300)):
+                si, sp, sc = ev.eval_topk(sq[lo:lo + m], bl[lo:lo + m])
+                assert np.array_equal(si, i1[lo:lo + m]) and np.array_equal(sp, p1[lo:lo + m]) and np.array_equal(sc, c1[lo:lo + m])
+                assert np.array_equal(ev.eval_probs(sq[lo:lo + m], bl[lo:lo + m]), pr1[lo:lo + m])
+        ev.set_option("fuse_tail", 1)
         # switching it off restores the plain path
         ev.set_refine_margin(0)
         i2, p2, c2 = ev.eval_topk(sq, bl)
@@ -760,6 +769,18 @@ def test_cython_binding_evaluates_like_the_shim(tmp_path, suite):
         assert got.shape == (300, 155) and got.dtype == np.float32
         assert np.array_equal(got, shim.evaluate(nodes))
         assert np.array_equal(net.evaluate(nodes[:1]), got[:1])
+
+
+def test_soak_random_batches_paths_and_options():
+    """tools/gpu_stress.py for a few seconds: random batch sizes, asynchronous device bursts (PDL on / off /
+    auto), 4 concurrent host threads, options toggled between bursts, bf16 and fp16 + refinement -- every
+    result equals the reference evaluation of the same rows."""
+    import subprocess
+    import sys
+    env = dict(os.environ, SECONDS="10")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_stress.py")], env=env, capture_output=True,
+                         text=True, timeout=200)
+    assert out.returncode == 0 and "stress ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):

@@ -451,11 +451,12 @@ struct ChunkIO {   // device pointers for one chunk
   int32_t* cstats = nullptr;    // child seeds [n][48][4] (with cflags and psum)
   int32_t* psum = nullptr;      // parent summaries [n][8]
   int* err_mirror = nullptr;    // host-mapped copy of the slot's d_err, written by the last kernel
-  bool defer_refine = false;    // flag only; the caller reads the count and runs enqueue_refine_pass itself
+  bool allow_defer = false;     // the caller synchronises anyway: it may read the flagged count itself and run
+                                // enqueue_refine_pass only when needed (decided by enqueue_eval -> *deferred)
 };
 
-bool refine_active(const wann_ctx* ctx, const ChunkIO& io) {
-  return (io.probs != nullptr || io.logits != nullptr || io.idx != nullptr) && ctx->refine_ratio.load() > 0.f &&
+bool refine_active(const wann_ctx* ctx, const ChunkIO& io, float refine_ratio) {
+  return (io.probs != nullptr || io.logits != nullptr || io.idx != nullptr) && refine_ratio > 0.f &&
          io.squares != nullptr && io.dbg == nullptr && io.prof == nullptr &&
          (ctx->mode == WANN_MODE_BF16 || ctx->mode == WANN_MODE_FP16);
 }
@@ -490,7 +491,9 @@ int enqueue_refine_pass(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const Chun
 }
 
 // Enqueue encode -> conv stack -> tail for `n` positions on `stream`, using `ws` workspaces.
-int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io, long long n) {
+int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io, long long n,
+                 bool* deferred = nullptr) {
+  if (deferred != nullptr) *deferred = false;
   if (n <= 0) return WANN_OK;
   uint64_t launches = 0;
   // ---- the tail (FC-155 -> softmax -> legal gather -> rank) and the refinement set-up ---------
@@ -501,8 +504,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
   t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal;
   const float refine_ratio = ctx->refine_ratio.load();
-  const bool refine = io.defer_refine || refine_active(ctx, io);   // (a deferring caller has already decided)
-  const bool mirror_here = io.err_mirror != nullptr && (!refine || io.defer_refine);   // else pass 2 mirrors
+  const bool refine = refine_active(ctx, io, refine_ratio);
   int* d_rcount = ws.d_err + 4;     // [0] flagged boards of this chunk, [1] running total
   if (refine) {
     if (ws.d_h5r == nullptr) {
@@ -515,6 +517,11 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   // bf16/fp16 modes: the tail runs INSIDE the conv-stack kernel (two tail warps per CTA); the
   // stand-alone tail_kernel serves the other modes, the refinement pass and the debug hooks
   const bool fused = want_tail && tc16 && ctx->fuse_tail && io.dbg == nullptr;
+  // deferral needs the flagged count mirrored AFTER the flagging: only the fused kernel's last CTA
+  // does that (the stand-alone tail kernel mirrors the record when it starts)
+  const bool defer = refine && fused && io.allow_defer && io.err_mirror != nullptr;
+  if (deferred != nullptr) *deferred = defer;
+  const bool mirror_here = io.err_mirror != nullptr && (!refine || defer);   // else pass 2 mirrors
   if (ctx->mode != WANN_MODE_FP32) {
     TcParams p;
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
@@ -604,7 +611,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       CU(cudaLaunchKernelEx(&cfg, tail_kernel, t));
       ++launches;
     }
-    if (refine && !io.defer_refine) {
+    if (refine && !defer) {
       int rc = enqueue_refine_pass(ctx, ws, stream, io, n, -1);
       if (rc != WANN_OK) return rc;
     }
@@ -750,11 +757,12 @@ int eval_host_small(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
   io.err_mirror = z_err;
   // margin refinement: the host is about to synchronise anyway, so it reads the number of flagged
   // boards itself and launches pass 2 only when there are any (98 % of batch-1 calls: none)
-  io.defer_refine = refine_active(ctx, io);
-  int rc = enqueue_eval(ctx, s, s.stream, io, n);
+  io.allow_defer = true;
+  bool deferred = false;
+  int rc = enqueue_eval(ctx, s, s.stream, io, n, &deferred);
   if (rc != WANN_OK) return rc;
   CU(cudaStreamSynchronize(s.stream));
-  if (io.defer_refine && z_err[0] == 0 && z_err[4] > 0) {
+  if (deferred && z_err[0] == 0 && z_err[4] > 0) {
     rc = enqueue_refine_pass(ctx, s, s.stream, io, n, z_err[4]);
     if (rc != WANN_OK) return rc;
     CU(cudaStreamSynchronize(s.stream));
