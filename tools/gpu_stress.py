@@ -18,10 +18,11 @@ sq, bl = synthetic.random_positions(P, seed=11)
 dev = torch.device("cuda", 0)
 sq_t, bl_t = torch.from_numpy(sq).to(dev), torch.from_numpy(bl).to(dev)
 report = {}
-for mode, margin in (("bf16", 0.0), ("fp16", 0.02)):
+for mode, margin in (("bf16", 0.0), ("fp16", 0.02), ("fp32_tc", 0.0)):
     with wann_b200.PolicyEvaluator(w, mode=mode, refine_margin=margin) as ev:
         ref_idx, ref_pri, ref_cnt = ev.eval_topk(sq, bl)
         ref_pr = ev.eval_probs(sq, bl)
+        ref_seed = ev.eval_expand_seeded(sq, bl)           # idx, prior, n_legal, children, flags, stats, parent
         n_checks, errs = [0], []
 
         def check(lo, n, idx, pri, cnt, pr):
@@ -38,8 +39,13 @@ for mode, margin in (("bf16", 0.0), ("fp16", 0.02)):
                 lo = int(r.randint(0, P - n))
                 i, p, c = ev.eval_topk(sq[lo:lo + n], bl[lo:lo + n])
                 check(lo, n, i, p, c, ev.eval_probs(sq[lo:lo + n], bl[lo:lo + n]) if r.rand() < 0.3 else None)
+                if r.rand() < 0.2:                             # the widest call, host path
+                    got = ev.eval_expand_seeded(sq[lo:lo + n], bl[lo:lo + n], with_children=bool(r.randint(2)))
+                    n_checks[0] += 1
+                    if not all(g is None or np.array_equal(g, rf[lo:lo + n]) for g, rf in zip(got, ref_seed)):
+                        errs.append(("seeded-host", lo, n))
 
-        t_end = time.time() + secs / 2
+        t_end = time.time() + secs / 3
         threads = [threading.Thread(target=host_thread, args=(s,)) for s in range(4)]
         [t.start() for t in threads]
         while time.time() < t_end and not errs:
@@ -52,7 +58,13 @@ for mode, margin in (("bf16", 0.0), ("fp16", 0.02)):
                 lo = int(rng.randint(0, P - n))
                 out = ev.eval_topk(sq_t[lo:lo + n], bl_t[lo:lo + n])
                 pend.append((lo, n, out))
+            n = int(rng.choice([1, 7, 600, 5000]))
+            lo = int(rng.randint(0, P - n))
+            seeded = ev.eval_expand_seeded(sq_t[lo:lo + n], bl_t[lo:lo + n], with_children=bool(rng.randint(2)))
             torch.cuda.synchronize()
+            n_checks[0] += 1
+            if not all(g is None or np.array_equal(g.cpu().numpy(), rf[lo:lo + n]) for g, rf in zip(seeded, ref_seed)):
+                errs.append(("seeded-device", lo, n))
             for lo, n, out in pend:
                 check(lo, n, out[0].cpu().numpy(), out[1].cpu().numpy(), out[2].cpu().numpy(), None)
         [t.join() for t in threads]
