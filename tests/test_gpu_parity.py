@@ -465,8 +465,10 @@ def test_tree_step_fused_matches_oracle(ev_bf16, suite):
     import torch
     sq, bl = suite
     dev = torch.device("cuda", ev_bf16.device)
-    for greedy, n, seed, step in ((True, 300, 0, 0), (False, 1024, 11, 5), (False, 1, 3, 9), (False, 1024, 11, 6)):
-        s0, b0 = sq[:n].copy(), bl[:n].copy()
+    big_sq, big_bl = np.tile(sq, (20, 1)), np.tile(bl, 20)
+    for greedy, n, seed, step in ((True, 300, 0, 0), (False, 1024, 11, 5), (False, 1, 3, 9), (False, 1024, 11, 6),
+                                  (False, 20000, 4, 2)):            # 20,000 games: two internal chunks
+        s0, b0 = big_sq[:n].copy(), big_bl[:n].copy()
         idx, pri, cnt = ev_bf16.eval_topk(s0, b0)
         want = O.tree_step(s0, b0, idx, pri, cnt, greedy=greedy, seed=seed, step=step)
         ts, tb = torch.from_numpy(s0).to(dev), torch.from_numpy(b0).to(dev)
