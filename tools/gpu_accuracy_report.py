@@ -12,7 +12,8 @@ from oracle import oracle as O, c_oracle as C
 
 n = int(os.environ.get("N", "100000"))
 sq, bl = synthetic.random_positions(n, seed=20260601)
-w = W.synthetic("trained_like", 1)
+seed = int(os.environ.get("WSEED", "1"))
+w = W.synthetic("trained_like", seed)
 with wann_b200.PolicyEvaluator(w, mode="fp32") as ev:
     p32, l32 = ev.eval_probs(sq, bl, return_logits=True)
     i32, _, c32 = ev.eval_topk(sq, bl)
@@ -21,7 +22,7 @@ lg = np.where(mask, l32, -np.inf); srt = np.sort(lg, axis=1); margin = srt[:, -1
 m = 4096
 C.set_threads(os.cpu_count())
 lo, po = C.forward(O.encode_planes(sq[:m], bl[:m]), w)
-rep = {"positions": n, "weights": "synthetic trained_like seed 1", "logit_sigma": float(l32.std()),
+rep = {"positions": n, "weights": "synthetic trained_like seed %d" % seed, "logit_sigma": float(l32.std()),
        "fp32_gpu_vs_cpu_oracle_logits_maxnorm": float(np.abs(l32[:m] - lo).max() / np.abs(lo).max()),
        "fp32_gpu_vs_cpu_oracle_top1": float((i32[:m, 0] == O.top1_legal(po, mask[:m])).mean())}
 for mode, refine in (("bf16", 0.0), ("fp16", 0.0), ("bf16", 0.15), ("fp16", 0.02), ("fp16", 0.01)):
@@ -45,4 +46,4 @@ for mode, refine in (("bf16", 0.0), ("fp16", 0.0), ("bf16", 0.15), ("fp16", 0.02
         "legal_count_equal": bool((cnt == c32).all()),
     }
 print(json.dumps(rep, indent=1))
-open(os.path.join(ROOT, "gpurun_out", "accuracy_report.json"), "w").write(json.dumps(rep, indent=1))
+open(os.path.join(ROOT, "gpurun_out", "accuracy_report%s.json" % ("" if seed == 1 else "_seed%d" % seed)), "w").write(json.dumps(rep, indent=1))
