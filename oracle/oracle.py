@@ -667,3 +667,22 @@ def seed_children(squares, black_to_move, idx, prior, n_legal):
                 pv += 1; pgv += 1
         parent[i] = (pv, pw, pgv, pgw, pws, int(threat))
     return stats, flags, parent
+
+
+# ----------------------------------------------------------------------------
+# A deterministic stand-in policy for TREE tests (tests/golden/make_tree_golden.py): a seeded function
+# of the position, so that the reference's search and ours can be fed the same "network".
+# ----------------------------------------------------------------------------
+def synthetic_policy(squares, black_to_move):
+    """-> float32 [155], sums to ~1.  Every value is a multiple of 2^-23 (so 1 + p is exact in float32,
+    which keeps the reference's mixed float32 / double UCT_multiplier sort keys out of the picture) and
+    carries its move index in its low 8 bits (so no two moves tie: the reference breaks ties by its
+    history-dependent piece-list order, which a board alone does not determine)."""
+    import zlib
+    sq = np.asarray(squares, np.int8).reshape(64)
+    seed = zlib.crc32(sq.tobytes() + (b"B" if black_to_move else b"W"))
+    lg = np.random.RandomState(seed).standard_normal(N_MOVES) * 2.5
+    e = np.exp(lg - lg.max())
+    p = e / e.sum()
+    q = np.round(p * (1 << 15)).astype(np.int64) * 256 + np.arange(N_MOVES)
+    return (q.astype(np.float64) / (1 << 23)).astype(np.float32)

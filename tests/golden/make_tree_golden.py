@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Golden TREES, grown by the compiled reference search (oracle/_ref), single-threaded and therefore
+deterministic: for a few start positions, K calls of
+  expansion_MCTS_functions.run_MCTS_with_expansions_simulation            (:300-316)
+    -> select_UCT_child / choose_UCT_or_best_child / find_best_UCT_child   (:339-350, tree_search_utils.pyx:251-403)
+    -> expand_leaf_node -> tree_builder.expand_descendants_to_depth_wrt_NN (:333-337, tree_builder.pyx:122-215)
+with a deterministic synthetic policy net (oracle.synthetic_policy: a seeded function of the position,
+probabilities quantised to 2^-20 so that 1 + p is exact in float32).  The whole tree is dumped after
+every checkpoint: per node parent, move index, colour, visits, wins, gameover_visits, gameover_wins,
+win_status, gameover, subtree_checked, subtree_being_checked, threads_checking_node and the children
+in the reference's order.
+
+Run in the build container only:  python tests/golden/make_tree_golden.py
+Output: tests/golden/ref_tree_golden.npz (committed)."""
+import io
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.ref_loader import load_ref  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+FILES = "abcdefgh"
+V = {"e": 0, "w": 1, "b": 2}
+WS = {None: -1, False: 0, True: 1}
+
+
+def to_squares(board):
+    return np.array([V[board[r][c]] for r in range(1, 9) for c in FILES], np.int8)
+
+
+class Net(object):
+    def __init__(self):
+        self.calls = 0
+
+    def evaluate(self, nodes, **kw):
+        self.calls += len(nodes)
+        return np.stack([O.synthetic_policy(to_squares(n["game_board"]), n["color"] == "Black") for n in nodes])
+
+
+def dump(root):
+    """BFS over the reference's dict tree -> arrays (children of a node are contiguous, in its order)."""
+    rows, queue, parent_of = [], [(root, -1)], []
+    i = 0
+    while i < len(queue):
+        node, par = queue[i]
+        kids = node["children"]
+        rows.append((par, node["index"], node["color"] == "Black", node["visits"], int(node["wins"]),
+                     node["gameover_visits"], int(node["gameover_wins"]), WS[node["win_status"]],
+                     bool(node["gameover"]), bool(node["subtree_checked"]), bool(node["subtree_being_checked"]),
+                     node["threads_checking_node"], -1 if kids is None else len(kids), node["height"]))
+        if kids is not None:
+            for k in kids:
+                queue.append((k, i))
+        i += 1
+    return np.array(rows, np.int64)
+
+
+def main():
+    ref = load_ref()
+    assert ref is not None
+    U, B = ref.utils, ref.board_utils
+    mc = ref.module("monte_carlo_tree_search.expansion_MCTS_functions")
+    tsu = ref.module("monte_carlo_tree_search.tree_search_utils")
+    TreeNode = ref.module("monte_carlo_tree_search.TreeNode").TreeNode
+    rng = np.random.RandomState(77)
+    # start positions: the opening and two positions from a seeded random play-out (plies 14 and 31)
+    starts = [(U.initial_game_board(), "White", 0)]
+    board, color = U.initial_game_board(), "White"
+    for ply in range(32):
+        legal = B.enumerate_legal_moves(board, color)
+        if ply in (14, 31):
+            starts.append((B.copy_game_board(board), color, ply))
+        mv = legal[rng.randint(len(legal))]
+        f, t = mv.split("-")
+        nb = B.copy_game_board(board)
+        nb[int(t[1])][t[0]] = board[int(f[1])][f[0]]
+        nb[int(f[1])][f[0]] = "e"
+        board, color = nb, ("Black" if color == "White" else "White")
+    out = {}
+    checkpoints = (1, 2, 5, 12, 25, 40)
+    for s, (board, color, ply) in enumerate(starts):
+        wp = [c + str(r) for r in range(1, 9) for c in FILES if board[r][c] == "w"]
+        bp = [c + str(r) for r in range(1, 9) for c in FILES if board[r][c] == "b"]
+        root = TreeNode(B.copy_game_board(board), wp, bp, color, 0, None, ply)
+        sim_info = tsu.SimulationInfo(io.StringIO())
+        sim_info.update(time_to_think=10 ** 6, start_time=time.time(), root=root, main_pid="not-this-thread")
+        net, lock = Net(), threading.Lock()
+        out["start%d_squares" % s] = to_squares(board)
+        out["start%d_black" % s] = np.uint8(color == "Black")
+        done_sims = 0
+        for cp in checkpoints:
+            while done_sims < cp:
+                mc.run_MCTS_with_expansions_simulation(root, 5, sim_info, net, sim_info["start_time"], 10 ** 6, lock)
+                done_sims += 1
+            out["start%d_after%d" % (s, cp)] = dump(root)
+            out["start%d_evals%d" % (s, cp)] = np.int64(net.calls)
+        print("start", s, color, "ply", ply, "sims", done_sims, "evaluations", net.calls, "nodes",
+              len(out["start%d_after%d" % (s, checkpoints[-1])]), "root win_status", root["win_status"])
+    out["checkpoints"] = np.array(checkpoints)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_tree_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -282,6 +282,29 @@ def test_cython_binding_compiles_against_the_header(lib_built, tmp_path):
             mod.PolicyNet(O.synthetic_weights("trained_like", 1, final_kernel=1))
 
 
+def test_array_tree_restatement_reproduces_the_references_trees():
+    """tests/golden/ref_tree_golden.npz holds whole search trees grown by the compiled reference
+    (run_MCTS_with_expansions_simulation, single-threaded, a deterministic synthetic policy) from three
+    start positions, checkpointed after 1..40 simulations (up to 29,955 nodes).  oracle/tree_oracle.py --
+    the reference's selection / expansion / statistics / solver restated over flat arrays -- grows the
+    SAME trees, node for node, field for field (visits, wins, gameover statistics, win status, the
+    checked / being-checked flags, thread counters, child order)."""
+    from oracle.tree_oracle import ArrayTree
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_tree_golden.npz"))
+    for s, height in enumerate((0, 14, 31)):
+        t = ArrayTree(g["start%d_squares" % s], int(g["start%d_black" % s]), O.synthetic_policy, height=height)
+        sims = 0
+        for cp in g["checkpoints"]:
+            while sims < cp:
+                t.run_simulation()
+                sims += 1
+            assert t.evaluations == int(g["start%d_evals%d" % (s, cp)])
+            assert np.array_equal(t.dump(), g["start%d_after%d" % (s, cp)]), (s, cp)
+    p = O.synthetic_policy(O.initial_squares(), 0)
+    assert p.dtype == np.float32 and len(set(p.tolist())) == 155 and abs(float(p.sum()) - 1) < 1e-2
+    assert np.array_equal((np.float32(1) + p).astype(np.float64), 1.0 + p.astype(np.float64))   # 1 + p exact in float32
+
+
 def test_child_seeding_oracle_vs_reference_golden(seed_golden):
     """641 positions expanded ONCE by the compiled reference tree code (expand_descendants_to_depth_wrt_NN
     -> get_child / update_child / assign_children / eval_children / update_win_status_from_children) with
