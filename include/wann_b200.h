@@ -180,6 +180,40 @@ int wann_tree_step(wann_ctx* ctx, int8_t* squares, uint8_t* black_to_move, int64
                    uint64_t seed, uint64_t step, uint8_t* chosen_idx, uint8_t* finished,
                    void* stream);
 
+/* ---- Forest of array-based search trees (host side; no context, no GPU work of its own) --------
+ * The reference's search tree -- TreeNode dicts, select_UCT_child / find_best_UCT_child / get_UCT,
+ * expand_descendants_to_depth_wrt_NN, update_tree_wins/_losses, the win-status solver, the
+ * checked / being-checked bookkeeping (expansion_MCTS_functions.pyx:300-350, tree_search_utils.pyx:43-467,
+ * tree_builder.pyx:122-215,294-355,530-620) -- over flat arrays, many independent trees advancing in
+ * lock step (BASELINE config 5).  Each tree does exactly what ONE thread of the reference's search
+ * does, suspended where the reference calls policy_net.evaluate (tree_builder.pyx:189):
+ *   wann_forest_next   runs every tree until it needs a position evaluated (or has done
+ *                      max_simulations calls of run_MCTS_with_expansions_simulation, or is solved) and
+ *                      writes the m <= n requested positions, compacted, to squares_out / black_out
+ *                      (tree_ids[i] = the tree row i belongs to, optional);
+ *   (caller)           ONE wann_eval_expand_seeded call over those m rows (child_squares may be NULL);
+ *   wann_forest_apply  attaches the children with the reference's seeds, propagates statistics and
+ *                      win statuses, and leaves every tree ready for the next wann_forest_next.
+ * Trees grown this way are node-for-node the trees the compiled reference grows single-threaded
+ * (tests/golden/ref_tree_golden.npz).  Tie-break: children arrive ranked by prior, equal priors by
+ * ascending move index (the reference's order for exact ties depends on its piece-list history). */
+typedef struct wann_forest wann_forest;
+int wann_forest_create(int64_t n_trees, const int8_t* squares, const uint8_t* black_to_move,
+                       const int32_t* heights /* ply of each root, may be NULL */, wann_forest** out);
+int wann_forest_destroy(wann_forest* forest);
+int wann_forest_next(wann_forest* forest, int64_t max_simulations, int8_t* squares_out,
+                     uint8_t* black_out, int64_t* tree_ids, int64_t* m_out);
+int wann_forest_apply(wann_forest* forest, const uint8_t* idx, const float* prior, const uint8_t* n_legal,
+                      const uint8_t* child_flags, const int32_t* child_stats, const int32_t* parent_summary);
+/* out[8] = nodes, simulations, evaluations, root visits, root wins, root win_status (-1/0/1),
+ * finished (root subtree checked), move index of the root's best child (children[0]) or -1. */
+int wann_forest_info(wann_forest* forest, int64_t tree, int64_t out[8]);
+/* Breadth-first dump of one tree, 14 int64 per node: parent row, move index, black to move, visits,
+ * wins, gameover_visits, gameover_wins, win_status, gameover, subtree_checked, subtree_being_checked,
+ * threads_checking_node, number of children (-1 = not expanded), height.  Returns the number of
+ * nodes (call with rows = NULL to size the buffer), -1 on a bad argument. */
+int64_t wann_forest_dump(wann_forest* forest, int64_t tree, int64_t* rows, int64_t capacity);
+
 /* Test/inspection hook: activations after hidden layer `layer` (1..5) as float
  * [n][8][8][C] (C = 192, or 1 for layer 5), host or device per `mem`.  In BF16 mode the
  * values are the bf16-rounded activations the next layer consumes (layer 5: fp32). */

@@ -305,6 +305,46 @@ def test_array_tree_restatement_reproduces_the_references_trees():
     assert np.array_equal((np.float32(1) + p).astype(np.float64), 1.0 + p.astype(np.float64))   # 1 + p exact in float32
 
 
+class _CpuSeeds(object):
+    """Stands in for PolicyEvaluator.eval_expand_seeded in CPU tests: the same rows, computed by the
+    oracle from the deterministic synthetic policy."""
+
+    def eval_expand_seeded(self, sq, bl, with_children=False):
+        probs = np.stack([O.synthetic_policy(s, b) for s, b in zip(sq, bl)])
+        idx, pri, cnt = O.ranked_children(probs, O.legal_mask(sq, bl))
+        st, fl, ps = O.seed_children(sq, bl, idx, pri, cnt)
+        ps8 = np.zeros((len(sq), 8), np.int32)
+        ps8[:, :6] = ps
+        return idx, pri, cnt, None, fl, st, ps8
+
+
+def test_native_search_forest_reproduces_the_references_trees(lib_built):
+    """The PRODUCT tree (wann_forest_*, array_tree.hpp: C++ struct-of-arrays, resumable at the evaluation,
+    three trees advancing in lock step in one forest) grows node for node the trees of the compiled
+    reference search (tests/golden/ref_tree_golden.npz), checkpoint by checkpoint."""
+    import wann_b200
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_tree_golden.npz"))
+    sq = np.stack([g["start%d_squares" % s] for s in range(3)])
+    bl = np.array([int(g["start%d_black" % s]) for s in range(3)], np.uint8)
+    with wann_b200.SearchForest(sq, bl, heights=[0, 14, 31]) as forest:
+        for cp in g["checkpoints"]:
+            steps, evals = forest.run(_CpuSeeds(), int(cp))
+            assert steps > 0 and evals >= steps
+            for s in range(3):
+                info = forest.info(s)
+                assert info["simulations"] == cp and info["evaluations"] == int(g["start%d_evals%d" % (s, cp)])
+                want = g["start%d_after%d" % (s, cp)]
+                assert np.array_equal(forest.dump(s), want), (s, cp)
+                assert info["nodes"] == len(want) and info["root_visits"] == want[0, 3] and info["root_wins"] == want[0, 4]
+                assert info["best_child_index"] == want[1, 1]
+        sq2, bl2, ids = forest.next(40)
+        assert len(sq2) == 0 and len(ids) == 0                     # budget reached: nothing to evaluate
+    with pytest.raises(wann_b200.WannError):
+        f = wann_b200.SearchForest(sq, bl)
+        f.next(1)
+        f.next(1)                                                  # apply must follow next
+
+
 def test_child_seeding_oracle_vs_reference_golden(seed_golden):
     """641 positions expanded ONCE by the compiled reference tree code (expand_descendants_to_depth_wrt_NN
     -> get_child / update_child / assign_children / eval_children / update_win_status_from_children) with

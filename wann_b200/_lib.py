@@ -18,6 +18,8 @@ EXPORTS = [
     "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_eval_expand", "wann_eval_expand_seeded", "wann_tree_step", "wann_debug_activations",
     "wann_debug_profile", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
+    "wann_forest_create", "wann_forest_destroy", "wann_forest_next", "wann_forest_apply", "wann_forest_info",
+    "wann_forest_dump",
 ]
 
 
@@ -54,6 +56,13 @@ def load():
     lib.wann_eval_topk.argtypes = [vp, vp, vp, i64, vp, vp, vp, ci, vp]
     lib.wann_eval_expand.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, ci, vp]
     lib.wann_eval_expand_seeded.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+    lib.wann_forest_create.argtypes = [i64, vp, vp, vp, ctypes.POINTER(vp)]
+    lib.wann_forest_destroy.argtypes = [vp]
+    lib.wann_forest_next.argtypes = [vp, i64, vp, vp, vp, ctypes.POINTER(i64)]
+    lib.wann_forest_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.wann_forest_info.argtypes = [vp, i64, vp]
+    lib.wann_forest_dump.argtypes = [vp, i64, vp, i64]
+    lib.wann_forest_dump.restype = i64
     lib.wann_set_weights.argtypes = [vp, ctypes.POINTER(WannWeights)]
     lib.wann_tree_step.argtypes = [vp, vp, vp, i64, ci, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp]
     lib.wann_debug_activations.argtypes = [vp, vp, vp, i64, ci, vp, ci]

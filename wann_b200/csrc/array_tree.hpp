@@ -1,0 +1,377 @@
+// array_tree.hpp -- the reference's search tree over flat arrays, many independent trees per forest.
+//
+// Host-side C++ (no CUDA): what ONE thread of the reference's search does per tree, restated over
+// struct-of-arrays nodes instead of Python dicts, and made RESUMABLE at the one point
+// where the reference blocks -- policy_net.evaluate (tree_builder.pyx:189) -- so that a forest of
+// trees advances in lock step: every tree hands out the position it needs evaluated, ONE batched
+// wann_eval_expand_seeded call serves them all, every tree applies its row and runs on to its next
+// evaluation.  BASELINE config 5 with the reference's own search semantics per tree.
+//
+//   run_simulation           expansion_MCTS_functions.pyx:300-350
+//   choose / find_best_UCT   tree_search_utils.pyx:251-403, get_UCT :405-467
+//   expand_descendants       tree_builder.pyx:122-215, do_updates_in_the_same_process :294-340,
+//                            update_parent :344-355, get_child :530-536, assign_children :538-620
+//   statistics / solver      update_tree_wins/_losses :43-66, update_win_statuses & co :70-132,
+//                            backpropagate_num_checked_children :134-158, thread counters :161-242
+// The child seeds (update_child, check_for_winning_move, the "maybe gameover next move" branch,
+// evaluation_function) arrive from seed_children_kernel as flags + statistics per ranked child.
+// Semantics are pinned by tests/golden/ref_tree_golden.npz (whole trees grown by the compiled
+// reference) through oracle/tree_oracle.py and directly.
+#pragma once
+#include <stdint.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace wann_tree {
+
+constexpr int kMaxLegal = 48;
+enum : uint8_t { kSeedWin = 1, kSeedCapture = 2, kSeedCloseToHome = 4, kSeedGameSaving = 8, kSeedDoomed = 16, kSeedEvalOne = 32 };
+
+struct Tree {
+  // ---- nodes (TreeNode.pyx:7-50), struct of arrays ---------------------------------------------
+  std::vector<int32_t> parent, first, count, height, threads;
+  std::vector<int64_t> visits, wins, gv, gw;
+  std::vector<int8_t> ws;                       // -1 None / 0 False / 1 True
+  std::vector<uint8_t> index, black, gameover, checked, being_checked, uct_f32;
+  std::vector<double> uct;                      // UCT_multiplier (a float32-rounded number when uct_f32)
+  std::vector<int8_t> boards;                   // 64 bytes per node
+  int32_t root = 0;
+  // ---- resumable state ---------------------------------------------------------------------------
+  enum Phase : uint8_t { kIdle, kWaitEval, kFinished };
+  Phase phase = kIdle;
+  int32_t ex_leaf = -1, ex_depth = 0, ex_limit = 0, pending = -1;
+  bool ex_final = false;                        // the expansion run_simulation makes for a solved, childless root
+  std::vector<int32_t> frontier;
+  int64_t simulations = 0, evaluations = 0;
+
+  int32_t new_node(int32_t par, int idx, bool blk, const int8_t* board, int32_t h, double u, bool u_f32) {
+    parent.push_back(par); first.push_back(-1); count.push_back(-1); height.push_back(h); threads.push_back(0);
+    visits.push_back(0); wins.push_back(0); gv.push_back(0); gw.push_back(0); ws.push_back(-1);
+    index.push_back(static_cast<uint8_t>(idx)); black.push_back(blk); gameover.push_back(0); checked.push_back(0);
+    being_checked.push_back(0); uct_f32.push_back(u_f32); uct.push_back(u);
+    boards.insert(boards.end(), board, board + 64);
+    return static_cast<int32_t>(parent.size()) - 1;
+  }
+  void init(const int8_t* squares, bool blk, int32_t h) { root = new_node(-1, 0, blk, squares, h, 1.0, false); }
+
+  // ---- statistics (tree_search_utils.pyx:43-66) -------------------------------------------------
+  void update_tree_wins(int32_t n, int64_t amount, bool go) {
+    bool win = true;                            // node win => parent loss => grandparent win ...
+    while (n >= 0) {
+      if (win) wins[n] += amount;
+      visits[n] += amount;
+      if (go) { if (win) gw[n] += amount; gv[n] += amount; }
+      n = parent[n];
+      win = !win;
+    }
+  }
+  void update_tree_losses(int32_t n, int64_t amount, bool go) {
+    visits[n] += amount;
+    if (go) gv[n] += amount;
+    if (parent[n] >= 0) update_tree_wins(parent[n], amount, go);
+  }
+
+  // mixed float32 / double comparison of the reference (numpy scalar vs Python float: in float32)
+  bool uct_gt(int32_t c, float thr) const {
+    return uct_f32[c] ? static_cast<float>(uct[c]) > thr : uct[c] > static_cast<double>(thr);
+  }
+
+  // ---- solver (tree_search_utils.pyx:70-132) ----------------------------------------------------
+  void update_win_statuses(int32_t n, int8_t status) {
+    if (status == 0) update_tree_losses(n, 1, true);
+    ws[n] = status;
+    if (parent[n] >= 0) update_win_status_from_children(parent[n]);
+  }
+  void update_win_status_from_children(int32_t n) {
+    if (count[n] < 0) return;
+    bool any_f = false, any_t = false, any_n = false, c_any = false, c_t = false, c_n = false;
+    for (int32_t c = first[n]; c < first[n] + count[n]; ++c) {
+      const int8_t s = ws[c];
+      any_f |= s == 0; any_t |= s == 1; any_n |= s == -1;
+      if (uct_gt(c, 1.001f)) { c_any = true; c_t |= s == 1; c_n |= s == -1; }
+    }
+    const bool use_c = !any_f && c_any;
+    const bool has_t = use_c ? c_t : any_t, has_n = use_c ? c_n : any_n;
+    if (any_f) update_win_statuses(n, 1);
+    else if (has_t && !has_n) update_win_statuses(n, 0);
+  }
+  void backpropagate_num_checked_children(int32_t n) {      // :134-158
+    while (n >= 0) {
+      int k = 0;
+      for (int32_t c = first[n]; c < first[n] + count[n]; ++c) k += checked[c];
+      if (k == count[n]) { checked[n] = 1; n = parent[n]; }
+      else { checked[n] = 0; n = -1; }
+    }
+  }
+
+  // ---- thread counters (:161-242) ----------------------------------------------------------------
+  void crement_threads(int32_t n, int amount) {
+    if (amount == 0) threads[n] = 0; else threads[n] += amount;
+    if (parent[n] >= 0) update_num_children_being_checked(parent[n]);
+  }
+  void update_num_children_being_checked(int32_t n) {
+    while (n >= 0 && count[n] >= 0) {
+      int k = 0;
+      for (int32_t c = first[n]; c < first[n] + count[n]; ++c)
+        k += (threads[c] > 0 && count[c] < 0) || being_checked[c] || ws[c] != -1;
+      const uint8_t previous = being_checked[n];
+      being_checked[n] = k == count[n];
+      if (previous != being_checked[n] && parent[n] >= 0) n = parent[n]; else break;
+    }
+  }
+
+  // ---- selection (:251-467) -----------------------------------------------------------------------
+  double get_uct(int32_t c, int64_t parent_visits) const {
+    const int64_t nw = wins[c], nv = visits[c], tw = gw[c], tg = gv[c];
+    // max(0.10, UCT_multiplier - 1): a float32 multiplier is subtracted and compared in float32
+    double nn_prob;
+    if (uct_f32[c]) {
+      const float d = static_cast<float>(uct[c]) - 1.0f;
+      nn_prob = d > 0.10f ? static_cast<double>(d) : 0.10;
+    } else {
+      const double d = uct[c] - 1.0;
+      nn_prob = d > 0.10 ? d : 0.10;
+    }
+    double rate;
+    if (tg > 10 && black[c] != black[root]) rate = static_cast<double>(tg - tw) / static_cast<double>(tg) + 1.0;
+    else rate = static_cast<double>(nv - nw) / static_cast<double>(nv);
+    const int64_t sib = parent_visits - nv > 1 ? parent_visits - nv : 1;
+    return rate + 1.0 * nn_prob * (std::sqrt(static_cast<double>(sib)) / static_cast<double>(1 + nv));
+  }
+  int32_t find_best_uct_child(int32_t n) const {
+    const int32_t lo = first[n], hi = first[n] + count[n];
+    auto ok_threads = [&](int32_t c) { return threads[c] <= 0 || count[c] >= 0; };
+    auto open_ = [&](int32_t c) { return ws[c] == -1 && !being_checked[c]; };
+    // the cascading filters, as predicates tried in order until one admits a child
+    float first_thr = 0.f, second_thr = 0.f;
+    const bool solved = ws[n] != -1;
+    if (!solved) {
+      if (black[n] == black[root]) {
+        int band;                                  // best_prob < .1 / < .2 / < .3 / else
+        if (height[n] >= 60) band = 0;             // best_prob = .01
+        else if (uct_f32[lo]) {                    // float32 multiplier: float32 difference, float32 comparisons
+          const float bp = static_cast<float>(uct[lo]) - 1.0f;
+          band = bp < .1f ? 0 : bp < .2f ? 1 : bp < .3f ? 2 : 3;
+        } else {
+          const double bp = uct[lo] - 1.0;
+          band = bp < .1 ? 0 : bp < .2 ? 1 : bp < .3 ? 2 : 3;
+        }
+        if (band == 0) { first_thr = second_thr = 1.04f; }
+        else if (band == 1) { first_thr = 1.10f; second_thr = 1.05f; }
+        else if (band == 2) { first_thr = 1.15f; second_thr = 1.10f; }
+        else { first_thr = 1.20f; second_thr = 1.15f; }
+      } else { first_thr = 1.1f; second_thr = 1.01f; }
+    }
+    auto admit = [&](int stage, int32_t c) -> bool {
+      switch (stage) {
+        case 0: return open_(c) && ok_threads(c);                                            // solved node
+        case 1: return !(checked[c] || being_checked[c]) && ok_threads(c);
+        case 2: return !checked[c] && ok_threads(c);
+        case 10: return open_(c) && uct_gt(c, first_thr) && ok_threads(c);                   // open node
+        case 11: return open_(c) && uct_gt(c, second_thr) && (gw[c] <= 1000 || gw[c] * 2 < gv[c]) && ok_threads(c);
+        case 12: return open_(c) && uct_gt(c, second_thr) && ok_threads(c);
+        default: return open_(c) && ok_threads(c);                                           // 13
+      }
+    };
+    int stages[4];
+    int ns = 0;
+    if (solved) { stages[0] = 0; stages[1] = 1; stages[2] = 2; ns = 3; }
+    else if (n == root) { stages[0] = 10; stages[1] = 11; stages[2] = 12; stages[3] = 13; ns = 4; }
+    else { stages[0] = 10; stages[1] = 13; ns = 2; }
+    for (int s = 0; s < ns; ++s) {
+      int32_t best = -1;
+      double best_v = 0;
+      const int64_t pv = visits[n];
+      for (int32_t c = lo; c < hi; ++c) {
+        if (!admit(stages[s], c)) continue;
+        const double v = get_uct(c, pv);
+        if (best < 0 || v > best_v) { best = c; best_v = v; }      // the FIRST maximum wins
+      }
+      if (best >= 0) return best;
+    }
+    return -1;
+  }
+  int32_t choose_uct_or_best_child(int32_t n) const { return count[n] == 1 ? first[n] : find_best_uct_child(n); }
+
+  // ---- expansion ----------------------------------------------------------------------------------
+  static void apply_move(const int8_t* board, bool blk, int idx, int8_t* out) {
+    memcpy(out, board, 64);
+    const int r = idx / 22, rem = idx - 22 * r, c = (rem + 1) / 3, d = rem - 3 * c;
+    int frm = r * 8 + c, to = (r + 1) * 8 + c + d;
+    if (blk) { frm = 63 - frm; to = 63 - to; }
+    out[to] = out[frm];
+    out[frm] = 0;
+  }
+  // update_parent -> get_child x k -> assign_children with the seeds of one evaluated position.
+  // `next` receives what the reference's assign_children returns (next-frontier candidates).
+  void expand_one(int32_t n, const uint8_t* idx, const float* prior, int k, const uint8_t* flags,
+                  const int32_t* stats, bool threat, std::vector<int32_t>& next) {
+    next.clear();
+    ++evaluations;
+    const bool blk = black[n];
+    const int32_t base = static_cast<int32_t>(parent.size());
+    int8_t child[64];
+    for (int j = 0; j < k; ++j) {                  // get_child: created (a winner's loss propagated) before the sort
+      const uint8_t f = flags[j];
+      const float p = prior[j];
+      const bool f32 = f & kSeedCloseToHome;
+      const double u = f32 ? static_cast<double>(1.0f + p) : 1.0 + static_cast<double>(p);
+      apply_move(&boards[static_cast<size_t>(n) * 64], blk, idx[j], child);
+      const int32_t c = new_node(n, idx[j], !blk, child, height[n] + 1, u, f32);
+      if (f & kSeedWin) {                          // set_game_over_values + update_tree_losses(child)
+        gameover[c] = checked[c] = 1;
+        ws[c] = 0;
+        gv[c] = visits[c] = 65536;
+        update_tree_losses(c, 1, true);
+      }
+    }
+    crement_threads(n, -1);                        // assign_children
+    if (k > 0 && count[n] < 0) {
+      int64_t ev_l = 0, ev_w = 0;
+      for (int j = 0; j < k; ++j) {
+        const int32_t c = base + j;
+        const uint8_t f = flags[j];
+        const int32_t* st = stats + 4 * j;
+        if (threat) {
+          if (f & kSeedGameSaving) { visits[c] = st[0]; wins[c] = st[1]; gv[c] = st[2]; gw[c] = st[3]; next.push_back(c); }
+          else if (f & kSeedDoomed) {              // set_game_over_values_1_step_lookahead + update_tree_wins(child)
+            visits[c] = wins[c] = gw[c] = gv[c] = 65536;
+            ws[c] = 1;
+            update_tree_wins(c, 1, true);
+          }
+        } else {
+          if (!(f & kSeedWin)) { visits[c] = st[0]; wins[c] = st[1]; gv[c] = st[2]; gw[c] = st[3]; }
+          if (f & kSeedEvalOne) ++ev_l; else ++ev_w;
+        }
+      }
+      first[n] = base;
+      count[n] = k;
+      if (!threat) {
+        for (int j = 0; j < k; ++j) next.push_back(base + j);
+        update_tree_losses(n, ev_l, false);        // eval_children
+        update_tree_wins(n, ev_w, false);
+      }
+      update_win_status_from_children(n);
+      backpropagate_num_checked_children(n);
+      update_num_children_being_checked(n);
+    }
+  }
+
+  // expand_descendants_to_depth_wrt_NN, resumable: runs until an evaluation is needed (returns the
+  // node) or the expansion is over (returns -1).
+  int32_t expand_run() {
+    while (ex_depth < ex_limit) {
+      if (ws[root] == -1) { if (count[ex_leaf] < 0 && ws[ex_leaf] == -1) frontier.push_back(ex_leaf); }
+      else if (count[ex_leaf] < 0 && !gameover[ex_leaf]) frontier.push_back(ex_leaf);
+      if (!frontier.empty()) {                     // (the reference's 0 < len < 256; a frontier has one node)
+        ex_limit = 800;
+        const int32_t p = frontier[0];
+        if (threads[p] <= 1 && count[p] < 0) {     // do_updates_in_the_same_process
+          if (threads[p] <= 0) crement_threads(p, 1);
+          pending = p;
+          return p;                                // -> policy_net.evaluate
+        }
+        crement_threads(p, -1);
+        frontier.clear();
+        ++ex_depth;
+      } else {
+        ex_depth = ex_limit;
+        crement_threads(ex_leaf, 0);
+      }
+    }
+    return -1;
+  }
+  void expand_begin(int32_t leaf, int depth, int limit) {
+    ex_leaf = leaf; ex_depth = depth; ex_limit = limit;
+    frontier.clear();
+  }
+  // continuation after the evaluation of `pending`
+  void expand_resume(const uint8_t* idx, const float* prior, int k, const uint8_t* flags, const int32_t* stats,
+                     bool threat) {
+    std::vector<int32_t> kids;
+    expand_one(pending, idx, prior, k, flags, stats, threat, kids);
+    frontier.clear();
+    if (ex_depth + 1 < ex_limit && !kids.empty()) {
+      const int32_t c0 = kids[0];
+      if (ws[c0] == -1 && threads[c0] <= 0 && !being_checked[c0]) frontier.push_back(c0);
+    }
+    ++ex_depth;
+    if (ex_depth < ex_limit)
+      for (int32_t c : frontier) crement_threads(c, 1);
+    pending = -1;
+  }
+
+  // ---- the per-tree driver: advance until an evaluation is needed or `max_sims` are done ---------
+  // Returns the node to evaluate, or -1 (finished / budget reached).
+  int32_t advance(int64_t max_sims) {
+    while (true) {
+      if (phase == kFinished) return -1;
+      if (phase == kWaitEval) {                    // continue the expansion that was interrupted
+        const int32_t need = expand_run();
+        if (need >= 0) return need;
+        if (!ex_final) {                           // tail of run_MCTS_with_expansions_simulation
+          const bool done = checked[root] || ws[root] != -1;
+          if (done && count[root] < 0) {
+            ex_final = true;
+            expand_begin(root, 0, 1);
+            continue;
+          }
+        }
+        ex_final = false;
+        phase = kIdle;
+        ++simulations;
+        continue;
+      }
+      // kIdle: start a simulation
+      if (simulations >= max_sims) return -1;
+      if (checked[root]) { phase = kFinished; return -1; }
+      int32_t n = root;
+      bool expanding = false;
+      while (true) {                               // play_MCTS_game_with_expansions / select_UCT_child
+        if (gameover[n]) break;
+        if (count[n] < 0) {
+          if (threads[n] <= 0) {
+            crement_threads(n, 1);
+            expand_begin(n, 0, 5);
+            expanding = true;
+          }
+          break;
+        }
+        while (n >= 0 && count[n] >= 0) {
+          threads[n] = 0;
+          n = choose_uct_or_best_child(n);
+        }
+        if (n < 0) break;
+      }
+      phase = kWaitEval;                           // (an empty expansion falls straight through above)
+      if (!expanding) { ex_depth = ex_limit = 0; frontier.clear(); }
+    }
+  }
+
+  // BFS dump in the layout of tests/golden/make_tree_golden.py; returns the number of rows (nodes)
+  int64_t dump(int64_t* rows, int64_t capacity) const {
+    std::vector<std::pair<int32_t, int64_t>> order;
+    order.emplace_back(root, -1);
+    for (size_t i = 0; i < order.size(); ++i) {
+      const int32_t n = order[i].first;
+      if (static_cast<int64_t>(i) < capacity) {
+        int64_t* r = rows + i * 14;
+        r[0] = order[i].second; r[1] = index[n]; r[2] = black[n]; r[3] = visits[n]; r[4] = wins[n]; r[5] = gv[n];
+        r[6] = gw[n]; r[7] = ws[n]; r[8] = gameover[n]; r[9] = checked[n]; r[10] = being_checked[n];
+        r[11] = threads[n]; r[12] = count[n]; r[13] = height[n];
+      }
+      if (count[n] >= 0)
+        for (int32_t c = first[n]; c < first[n] + count[n]; ++c) order.emplace_back(c, static_cast<int64_t>(i));
+    }
+    return static_cast<int64_t>(order.size());
+  }
+};
+
+struct Forest {
+  std::vector<Tree> trees;
+  std::vector<int32_t> need;                       // node each tree is waiting on (-1 = none)
+};
+
+}  // namespace wann_tree

@@ -20,6 +20,7 @@
 #include "aux_kernels.cuh"
 #include "conv_stack_tc.cuh"
 #include "conv_stack_split.cuh"
+#include "array_tree.hpp"
 
 namespace {
 
@@ -1429,6 +1430,88 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
     return WANN_OK;
   }
   return fail(WANN_E_INVALID, "unknown option %s", key);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forest of array-based search trees (array_tree.hpp): host-side, no context needed.
+struct wann_forest {
+  wann_tree::Forest f;
+  std::vector<int64_t> waiting;      // trees whose rows were handed out by the last wann_forest_next
+};
+
+int wann_forest_create(int64_t n, const int8_t* squares, const uint8_t* black, const int32_t* heights,
+                       wann_forest** out) {
+  if (out == nullptr || n < 0 || (n > 0 && (squares == nullptr || black == nullptr)))
+    return fail(WANN_E_INVALID, "bad argument");
+  wann_forest* fo = new wann_forest();
+  fo->f.trees.resize(static_cast<size_t>(n));
+  for (int64_t t = 0; t < n; ++t) fo->f.trees[t].init(squares + t * 64, black[t] != 0, heights ? heights[t] : 0);
+  *out = fo;
+  return WANN_OK;
+}
+
+int wann_forest_destroy(wann_forest* fo) {
+  delete fo;
+  return WANN_OK;
+}
+
+int wann_forest_next(wann_forest* fo, int64_t max_simulations, int8_t* squares_out, uint8_t* black_out,
+                     int64_t* tree_ids, int64_t* m_out) {
+  if (fo == nullptr || squares_out == nullptr || black_out == nullptr || m_out == nullptr)
+    return fail(WANN_E_INVALID, "null argument");
+  if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
+  const int64_t n = static_cast<int64_t>(fo->f.trees.size());
+  std::vector<int32_t> node(static_cast<size_t>(n), -1);
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int64_t t = 0; t < n; ++t) node[t] = fo->f.trees[t].advance(max_simulations);
+  int64_t m = 0;
+  for (int64_t t = 0; t < n; ++t) {
+    if (node[t] < 0) continue;
+    const wann_tree::Tree& tr = fo->f.trees[t];
+    memcpy(squares_out + m * 64, &tr.boards[static_cast<size_t>(node[t]) * 64], 64);
+    black_out[m] = tr.black[node[t]];
+    if (tree_ids != nullptr) tree_ids[m] = t;
+    fo->waiting.push_back(t);
+    ++m;
+  }
+  *m_out = m;
+  return WANN_OK;
+}
+
+int wann_forest_apply(wann_forest* fo, const uint8_t* idx, const float* prior, const uint8_t* n_legal,
+                      const uint8_t* child_flags, const int32_t* child_stats, const int32_t* parent_summary) {
+  if (fo == nullptr) return fail(WANN_E_INVALID, "null forest");
+  const int64_t m = static_cast<int64_t>(fo->waiting.size());
+  if (m > 0 && (!idx || !prior || !n_legal || !child_flags || !child_stats || !parent_summary))
+    return fail(WANN_E_INVALID, "null argument");
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int64_t i = 0; i < m; ++i) {
+    wann_tree::Tree& tr = fo->f.trees[fo->waiting[i]];
+    tr.expand_resume(idx + i * kMaxLegal, prior + i * kMaxLegal, std::min<int>(n_legal[i], kMaxLegal),
+                     child_flags + i * kMaxLegal, child_stats + i * kMaxLegal * 4, parent_summary[i * 8 + 5] != 0);
+  }
+  fo->waiting.clear();
+  return WANN_OK;
+}
+
+int wann_forest_info(wann_forest* fo, int64_t tree, int64_t out[8]) {
+  if (fo == nullptr || out == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size()))
+    return fail(WANN_E_INVALID, "bad argument");
+  const wann_tree::Tree& tr = fo->f.trees[tree];
+  out[0] = static_cast<int64_t>(tr.parent.size());
+  out[1] = tr.simulations;
+  out[2] = tr.evaluations;
+  out[3] = tr.visits[tr.root];
+  out[4] = tr.wins[tr.root];
+  out[5] = tr.ws[tr.root];
+  out[6] = tr.phase == wann_tree::Tree::kFinished;
+  out[7] = tr.count[tr.root] > 0 ? tr.index[tr.first[tr.root]] : -1;     // best_child = children[0] (tree_builder.pyx:561)
+  return WANN_OK;
+}
+
+int64_t wann_forest_dump(wann_forest* fo, int64_t tree, int64_t* rows, int64_t capacity) {
+  if (fo == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size())) return -1;
+  return fo->f.trees[tree].dump(rows, rows ? capacity : 0);
 }
 
 }  // extern "C"

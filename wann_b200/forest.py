@@ -1,0 +1,90 @@
+"""SearchForest: many independent search trees with the reference's own search semantics, advancing
+in lock step on one evaluator (BASELINE config 5).  Python handle on a wann_forest (include/wann_b200.h):
+the trees live in the C++ runtime as flat arrays; each step
+
+    positions = forest.next(max_simulations)        # every tree runs to its next policy_net.evaluate
+    rows = evaluator.eval_expand_seeded(positions)   # ONE batched GPU call for all of them
+    forest.apply(rows)                               # children + seeds attached, statistics propagated
+
+What a tree does between two evaluations is exactly what one thread of the reference's search does
+(expansion_MCTS_functions.pyx:300-350, tree_search_utils.pyx, tree_builder.pyx), see array_tree.hpp."""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+
+DUMP_FIELDS = ("parent", "index", "black", "visits", "wins", "gameover_visits", "gameover_wins", "win_status",
+               "gameover", "subtree_checked", "subtree_being_checked", "threads_checking_node", "n_children", "height")
+
+
+class SearchForest(object):
+    def __init__(self, squares, black_to_move, heights=None):
+        self._lib = L.load()
+        sq = np.ascontiguousarray(squares, np.int8).reshape(-1, 64)
+        bl = np.ascontiguousarray(black_to_move, np.uint8).reshape(-1)
+        self.n = sq.shape[0]
+        h = None if heights is None else np.ascontiguousarray(heights, np.int32).reshape(-1)
+        ptr = ctypes.c_void_p()
+        L.check(self._lib.wann_forest_create(self.n, sq.ctypes.data, bl.ctypes.data,
+                                             None if h is None else h.ctypes.data, ctypes.byref(ptr)))
+        self._f = ptr
+        self._sq = np.empty((self.n, 64), np.int8)
+        self._bl = np.empty(self.n, np.uint8)
+        self._ids = np.empty(self.n, np.int64)
+
+    def close(self):
+        if getattr(self, "_f", None):
+            self._lib.wann_forest_destroy(self._f)
+            self._f = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def next(self, max_simulations):
+        """-> (squares int8 [m,64], black uint8 [m], tree_ids int64 [m]) of the trees that need an
+        evaluation; m == 0 when every tree has done max_simulations simulations (or is solved)."""
+        m = ctypes.c_int64()
+        L.check(self._lib.wann_forest_next(self._f, int(max_simulations), self._sq.ctypes.data, self._bl.ctypes.data,
+                                           self._ids.ctypes.data, ctypes.byref(m)))
+        m = m.value
+        return self._sq[:m], self._bl[:m], self._ids[:m]
+
+    def apply(self, idx, prior, n_legal, child_flags, child_stats, parent_summary):
+        a = [np.ascontiguousarray(idx, np.uint8), np.ascontiguousarray(prior, np.float32),
+             np.ascontiguousarray(n_legal, np.uint8), np.ascontiguousarray(child_flags, np.uint8),
+             np.ascontiguousarray(child_stats, np.int32), np.ascontiguousarray(parent_summary, np.int32)]
+        L.check(self._lib.wann_forest_apply(self._f, *[x.ctypes.data for x in a]))
+
+    def run(self, evaluator, simulations):
+        """Grow every tree by `simulations` simulations on `evaluator` (anything with
+        eval_expand_seeded(squares, black, with_children=False)).  Returns (steps, evaluations)."""
+        steps = evals = 0
+        while True:
+            sq, bl, _ = self.next(simulations)
+            if len(sq) == 0:
+                return steps, evals
+            idx, pri, cnt, _, flg, st, ps = evaluator.eval_expand_seeded(sq, bl, with_children=False)
+            self.apply(idx, pri, cnt, flg, st, ps)
+            steps += 1
+            evals += len(sq)
+
+    def info(self, tree):
+        out = (ctypes.c_int64 * 8)()
+        L.check(self._lib.wann_forest_info(self._f, int(tree), out))
+        keys = ("nodes", "simulations", "evaluations", "root_visits", "root_wins", "root_win_status", "finished",
+                "best_child_index")
+        return dict(zip(keys, list(out)))
+
+    def dump(self, tree):
+        n = self._lib.wann_forest_dump(self._f, int(tree), None, 0)
+        if n < 0:
+            raise L.WannError("bad tree index")
+        rows = np.empty((n, 14), np.int64)
+        self._lib.wann_forest_dump(self._f, int(tree), rows.ctypes.data, n)
+        return rows
