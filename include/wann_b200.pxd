@@ -65,3 +65,16 @@ cdef extern from "wann_b200.h" nogil:
     int wann_get_stats(wann_ctx* ctx, uint64_t* stats)
     int wann_set_option(wann_ctx* ctx, const char* key, int64_t value)
     int wann_version()
+
+    ctypedef struct wann_forest:
+        pass
+
+    int wann_forest_create(int64_t n_trees, const int8_t* squares, const uint8_t* black_to_move,
+                           const int32_t* heights, wann_forest** out)
+    int wann_forest_destroy(wann_forest* forest)
+    int wann_forest_next(wann_forest* forest, int64_t max_simulations, int8_t* squares_out, uint8_t* black_out,
+                         int64_t* tree_ids, int64_t* m_out)
+    int wann_forest_apply(wann_forest* forest, const uint8_t* idx, const float* prior, const uint8_t* n_legal,
+                          const uint8_t* child_flags, const int32_t* child_stats, const int32_t* parent_summary)
+    int wann_forest_info(wann_forest* forest, int64_t tree, int64_t* out)
+    int64_t wann_forest_dump(wann_forest* forest, int64_t tree, int64_t* rows, int64_t capacity)
