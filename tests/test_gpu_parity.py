@@ -785,6 +785,39 @@ def test_soak_random_batches_paths_and_options():
     assert out.returncode == 0 and "stress ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_search_forest_on_the_gpu_evaluator(weights, suite):
+    """BASELINE config 5 with the reference's own search per tree: a forest of native array trees
+    (wann_forest_*) advancing in lock step on ONE wann_eval_expand_seeded call per step.  Every tree equals
+    the array-tree restatement (oracle/tree_oracle.py -- itself node-for-node the compiled reference's
+    tree, tests/golden/ref_tree_golden.npz) grown on the same network one evaluation at a time."""
+    import wann_b200
+    from oracle.tree_oracle import ArrayTree
+    sq, bl = suite
+    pick = [0, 5, 17, 33, 101, 250, 400, 777, 901, 1000]
+    starts_sq = np.concatenate([O.initial_squares()[None], sq[pick]])
+    starts_bl = np.concatenate([[0], bl[pick]]).astype(np.uint8)
+    heights = np.arange(len(starts_sq), dtype=np.int32) * 3
+    with wann_b200.PolicyEvaluator(weights, mode="fp16", refine_margin=0.02) as ev:
+        with wann_b200.SearchForest(starts_sq, starts_bl, heights) as forest:
+            steps, evals = forest.run(ev, 6)
+            assert steps > 10 and evals > steps            # several trees per step
+            policy = lambda s, b: ev.eval_probs(np.asarray(s, np.int8)[None], np.array([b], np.uint8))[0]   # noqa: E731
+            for t in range(len(starts_sq)):
+                ref = ArrayTree(starts_sq[t], int(starts_bl[t]), policy, height=int(heights[t]))
+                for _ in range(6):
+                    ref.run_simulation()
+                got, want = forest.dump(t), ref.dump()
+                assert got.shape == want.shape and np.array_equal(got, want), t
+                info = forest.info(t)
+                assert info["evaluations"] == ref.evaluations and info["simulations"] == 6
+        # a larger forest just runs: 512 trees, every evaluation a legal expansion
+        big = wann_b200.SearchForest(np.tile(sq[:512], (1, 1)), bl[:512])
+        steps, evals = big.run(ev, 3)
+        nodes = sum(big.info(t)["nodes"] for t in range(512))
+        assert evals > 512 * 3 and nodes > evals * 10
+        big.close()
+
+
 def test_no_out_of_bounds_writes_canary(ev_bf16, suite):
     """compute-sanitizer is not available on the GPU pool: carve every device output out of one
     sentinel-filled arena (guard bands before/after each buffer) and check that the kernels wrote
