@@ -30,13 +30,17 @@ constexpr int kMaxLegal = 48;
 enum : uint8_t { kSeedWin = 1, kSeedCapture = 2, kSeedCloseToHome = 4, kSeedGameSaving = 8, kSeedDoomed = 16, kSeedEvalOne = 32 };
 
 struct Tree {
-  // ---- nodes (TreeNode.pyx:7-50), struct of arrays ---------------------------------------------
-  std::vector<int32_t> parent, first, count, height, threads;
-  std::vector<int64_t> visits, wins, gv, gw;
-  std::vector<int8_t> ws;                       // -1 None / 0 False / 1 True
-  std::vector<uint8_t> index, black, gameover, checked, being_checked, uct_f32;
-  std::vector<double> uct;                      // UCT_multiplier (a float32-rounded number when uct_f32)
-  std::vector<int8_t> boards;                   // 64 bytes per node
+  // ---- nodes (TreeNode.pyx:7-50): one 136-byte record per node (children of a node are contiguous,
+  // so selection walks one cache-friendly run instead of seventeen arrays) ---------------------------
+  struct Node {
+    int64_t visits, wins, gv, gw;
+    double uct;                                 // UCT_multiplier (a float32-rounded number when uct_f32)
+    int32_t parent, first, count, height, threads;
+    int8_t ws;                                  // -1 None / 0 False / 1 True
+    uint8_t index, black, gameover, checked, being_checked, uct_f32;
+    int8_t board[64];
+  };
+  std::vector<Node> nodes;
   int32_t root = 0;
   // ---- resumable state ---------------------------------------------------------------------------
   enum Phase : uint8_t { kIdle, kWaitEval, kFinished };
@@ -47,12 +51,16 @@ struct Tree {
   int64_t simulations = 0, evaluations = 0;
 
   int32_t new_node(int32_t par, int idx, bool blk, const int8_t* board, int32_t h, double u, bool u_f32) {
-    parent.push_back(par); first.push_back(-1); count.push_back(-1); height.push_back(h); threads.push_back(0);
-    visits.push_back(0); wins.push_back(0); gv.push_back(0); gw.push_back(0); ws.push_back(-1);
-    index.push_back(static_cast<uint8_t>(idx)); black.push_back(blk); gameover.push_back(0); checked.push_back(0);
-    being_checked.push_back(0); uct_f32.push_back(u_f32); uct.push_back(u);
-    boards.insert(boards.end(), board, board + 64);
-    return static_cast<int32_t>(parent.size()) - 1;
+    Node nd;
+    nd.visits = nd.wins = nd.gv = nd.gw = 0;
+    nd.uct = u;
+    nd.parent = par; nd.first = -1; nd.count = -1; nd.height = h; nd.threads = 0;
+    nd.ws = -1;
+    nd.index = static_cast<uint8_t>(idx); nd.black = blk; nd.gameover = 0; nd.checked = 0; nd.being_checked = 0;
+    nd.uct_f32 = u_f32;
+    memcpy(nd.board, board, 64);
+    nodes.push_back(nd);
+    return static_cast<int32_t>(nodes.size()) - 1;
   }
   void init(const int8_t* squares, bool blk, int32_t h) { root = new_node(-1, 0, blk, squares, h, 1.0, false); }
 
@@ -60,35 +68,35 @@ struct Tree {
   void update_tree_wins(int32_t n, int64_t amount, bool go) {
     bool win = true;                            // node win => parent loss => grandparent win ...
     while (n >= 0) {
-      if (win) wins[n] += amount;
-      visits[n] += amount;
-      if (go) { if (win) gw[n] += amount; gv[n] += amount; }
-      n = parent[n];
+      if (win) nodes[n].wins += amount;
+      nodes[n].visits += amount;
+      if (go) { if (win) nodes[n].gw += amount; nodes[n].gv += amount; }
+      n = nodes[n].parent;
       win = !win;
     }
   }
   void update_tree_losses(int32_t n, int64_t amount, bool go) {
-    visits[n] += amount;
-    if (go) gv[n] += amount;
-    if (parent[n] >= 0) update_tree_wins(parent[n], amount, go);
+    nodes[n].visits += amount;
+    if (go) nodes[n].gv += amount;
+    if (nodes[n].parent >= 0) update_tree_wins(nodes[n].parent, amount, go);
   }
 
   // mixed float32 / double comparison of the reference (numpy scalar vs Python float: in float32)
   bool uct_gt(int32_t c, float thr) const {
-    return uct_f32[c] ? static_cast<float>(uct[c]) > thr : uct[c] > static_cast<double>(thr);
+    return nodes[c].uct_f32 ? static_cast<float>(nodes[c].uct) > thr : nodes[c].uct > static_cast<double>(thr);
   }
 
   // ---- solver (tree_search_utils.pyx:70-132) ----------------------------------------------------
   void update_win_statuses(int32_t n, int8_t status) {
     if (status == 0) update_tree_losses(n, 1, true);
-    ws[n] = status;
-    if (parent[n] >= 0) update_win_status_from_children(parent[n]);
+    nodes[n].ws = status;
+    if (nodes[n].parent >= 0) update_win_status_from_children(nodes[n].parent);
   }
   void update_win_status_from_children(int32_t n) {
-    if (count[n] < 0) return;
+    if (nodes[n].count < 0) return;
     bool any_f = false, any_t = false, any_n = false, c_any = false, c_t = false, c_n = false;
-    for (int32_t c = first[n]; c < first[n] + count[n]; ++c) {
-      const int8_t s = ws[c];
+    for (int32_t c = nodes[n].first; c < nodes[n].first + nodes[n].count; ++c) {
+      const int8_t s = nodes[c].ws;
       any_f |= s == 0; any_t |= s == 1; any_n |= s == -1;
       if (uct_gt(c, 1.001f)) { c_any = true; c_t |= s == 1; c_n |= s == -1; }
     }
@@ -100,62 +108,62 @@ struct Tree {
   void backpropagate_num_checked_children(int32_t n) {      // :134-158
     while (n >= 0) {
       int k = 0;
-      for (int32_t c = first[n]; c < first[n] + count[n]; ++c) k += checked[c];
-      if (k == count[n]) { checked[n] = 1; n = parent[n]; }
-      else { checked[n] = 0; n = -1; }
+      for (int32_t c = nodes[n].first; c < nodes[n].first + nodes[n].count; ++c) k += nodes[c].checked;
+      if (k == nodes[n].count) { nodes[n].checked = 1; n = nodes[n].parent; }
+      else { nodes[n].checked = 0; n = -1; }
     }
   }
 
   // ---- thread counters (:161-242) ----------------------------------------------------------------
   void crement_threads(int32_t n, int amount) {
-    if (amount == 0) threads[n] = 0; else threads[n] += amount;
-    if (parent[n] >= 0) update_num_children_being_checked(parent[n]);
+    if (amount == 0) nodes[n].threads = 0; else nodes[n].threads += amount;
+    if (nodes[n].parent >= 0) update_num_children_being_checked(nodes[n].parent);
   }
   void update_num_children_being_checked(int32_t n) {
-    while (n >= 0 && count[n] >= 0) {
+    while (n >= 0 && nodes[n].count >= 0) {
       int k = 0;
-      for (int32_t c = first[n]; c < first[n] + count[n]; ++c)
-        k += (threads[c] > 0 && count[c] < 0) || being_checked[c] || ws[c] != -1;
-      const uint8_t previous = being_checked[n];
-      being_checked[n] = k == count[n];
-      if (previous != being_checked[n] && parent[n] >= 0) n = parent[n]; else break;
+      for (int32_t c = nodes[n].first; c < nodes[n].first + nodes[n].count; ++c)
+        k += (nodes[c].threads > 0 && nodes[c].count < 0) || nodes[c].being_checked || nodes[c].ws != -1;
+      const uint8_t previous = nodes[n].being_checked;
+      nodes[n].being_checked = k == nodes[n].count;
+      if (previous != nodes[n].being_checked && nodes[n].parent >= 0) n = nodes[n].parent; else break;
     }
   }
 
   // ---- selection (:251-467) -----------------------------------------------------------------------
   double get_uct(int32_t c, int64_t parent_visits) const {
-    const int64_t nw = wins[c], nv = visits[c], tw = gw[c], tg = gv[c];
+    const int64_t nw = nodes[c].wins, nv = nodes[c].visits, tw = nodes[c].gw, tg = nodes[c].gv;
     // max(0.10, UCT_multiplier - 1): a float32 multiplier is subtracted and compared in float32
     double nn_prob;
-    if (uct_f32[c]) {
-      const float d = static_cast<float>(uct[c]) - 1.0f;
+    if (nodes[c].uct_f32) {
+      const float d = static_cast<float>(nodes[c].uct) - 1.0f;
       nn_prob = d > 0.10f ? static_cast<double>(d) : 0.10;
     } else {
-      const double d = uct[c] - 1.0;
+      const double d = nodes[c].uct - 1.0;
       nn_prob = d > 0.10 ? d : 0.10;
     }
     double rate;
-    if (tg > 10 && black[c] != black[root]) rate = static_cast<double>(tg - tw) / static_cast<double>(tg) + 1.0;
+    if (tg > 10 && nodes[c].black != nodes[root].black) rate = static_cast<double>(tg - tw) / static_cast<double>(tg) + 1.0;
     else rate = static_cast<double>(nv - nw) / static_cast<double>(nv);
     const int64_t sib = parent_visits - nv > 1 ? parent_visits - nv : 1;
     return rate + 1.0 * nn_prob * (std::sqrt(static_cast<double>(sib)) / static_cast<double>(1 + nv));
   }
   int32_t find_best_uct_child(int32_t n) const {
-    const int32_t lo = first[n], hi = first[n] + count[n];
-    auto ok_threads = [&](int32_t c) { return threads[c] <= 0 || count[c] >= 0; };
-    auto open_ = [&](int32_t c) { return ws[c] == -1 && !being_checked[c]; };
+    const int32_t lo = nodes[n].first, hi = nodes[n].first + nodes[n].count;
+    auto ok_threads = [&](int32_t c) { return nodes[c].threads <= 0 || nodes[c].count >= 0; };
+    auto open_ = [&](int32_t c) { return nodes[c].ws == -1 && !nodes[c].being_checked; };
     // the cascading filters, as predicates tried in order until one admits a child
     float first_thr = 0.f, second_thr = 0.f;
-    const bool solved = ws[n] != -1;
+    const bool solved = nodes[n].ws != -1;
     if (!solved) {
-      if (black[n] == black[root]) {
+      if (nodes[n].black == nodes[root].black) {
         int band;                                  // best_prob < .1 / < .2 / < .3 / else
-        if (height[n] >= 60) band = 0;             // best_prob = .01
-        else if (uct_f32[lo]) {                    // float32 multiplier: float32 difference, float32 comparisons
-          const float bp = static_cast<float>(uct[lo]) - 1.0f;
+        if (nodes[n].height >= 60) band = 0;             // best_prob = .01
+        else if (nodes[lo].uct_f32) {                    // float32 multiplier: float32 difference, float32 comparisons
+          const float bp = static_cast<float>(nodes[lo].uct) - 1.0f;
           band = bp < .1f ? 0 : bp < .2f ? 1 : bp < .3f ? 2 : 3;
         } else {
-          const double bp = uct[lo] - 1.0;
+          const double bp = nodes[lo].uct - 1.0;
           band = bp < .1 ? 0 : bp < .2 ? 1 : bp < .3 ? 2 : 3;
         }
         if (band == 0) { first_thr = second_thr = 1.04f; }
@@ -167,10 +175,10 @@ struct Tree {
     auto admit = [&](int stage, int32_t c) -> bool {
       switch (stage) {
         case 0: return open_(c) && ok_threads(c);                                            // solved node
-        case 1: return !(checked[c] || being_checked[c]) && ok_threads(c);
-        case 2: return !checked[c] && ok_threads(c);
+        case 1: return !(nodes[c].checked || nodes[c].being_checked) && ok_threads(c);
+        case 2: return !nodes[c].checked && ok_threads(c);
         case 10: return open_(c) && uct_gt(c, first_thr) && ok_threads(c);                   // open node
-        case 11: return open_(c) && uct_gt(c, second_thr) && (gw[c] <= 1000 || gw[c] * 2 < gv[c]) && ok_threads(c);
+        case 11: return open_(c) && uct_gt(c, second_thr) && (nodes[c].gw <= 1000 || nodes[c].gw * 2 < nodes[c].gv) && ok_threads(c);
         case 12: return open_(c) && uct_gt(c, second_thr) && ok_threads(c);
         default: return open_(c) && ok_threads(c);                                           // 13
       }
@@ -183,7 +191,7 @@ struct Tree {
     for (int s = 0; s < ns; ++s) {
       int32_t best = -1;
       double best_v = 0;
-      const int64_t pv = visits[n];
+      const int64_t pv = nodes[n].visits;
       for (int32_t c = lo; c < hi; ++c) {
         if (!admit(stages[s], c)) continue;
         const double v = get_uct(c, pv);
@@ -193,7 +201,7 @@ struct Tree {
     }
     return -1;
   }
-  int32_t choose_uct_or_best_child(int32_t n) const { return count[n] == 1 ? first[n] : find_best_uct_child(n); }
+  int32_t choose_uct_or_best_child(int32_t n) const { return nodes[n].count == 1 ? nodes[n].first : find_best_uct_child(n); }
 
   // ---- expansion ----------------------------------------------------------------------------------
   static void apply_move(const int8_t* board, bool blk, int idx, int8_t* out) {
@@ -210,44 +218,44 @@ struct Tree {
                   const int32_t* stats, bool threat, std::vector<int32_t>& next) {
     next.clear();
     ++evaluations;
-    const bool blk = black[n];
-    const int32_t base = static_cast<int32_t>(parent.size());
+    const bool blk = nodes[n].black;
+    const int32_t base = static_cast<int32_t>(nodes.size());
     int8_t child[64];
     for (int j = 0; j < k; ++j) {                  // get_child: created (a winner's loss propagated) before the sort
       const uint8_t f = flags[j];
       const float p = prior[j];
       const bool f32 = f & kSeedCloseToHome;
       const double u = f32 ? static_cast<double>(1.0f + p) : 1.0 + static_cast<double>(p);
-      apply_move(&boards[static_cast<size_t>(n) * 64], blk, idx[j], child);
-      const int32_t c = new_node(n, idx[j], !blk, child, height[n] + 1, u, f32);
+      apply_move(nodes[n].board, blk, idx[j], child);
+      const int32_t c = new_node(n, idx[j], !blk, child, nodes[n].height + 1, u, f32);
       if (f & kSeedWin) {                          // set_game_over_values + update_tree_losses(child)
-        gameover[c] = checked[c] = 1;
-        ws[c] = 0;
-        gv[c] = visits[c] = 65536;
+        nodes[c].gameover = nodes[c].checked = 1;
+        nodes[c].ws = 0;
+        nodes[c].gv = nodes[c].visits = 65536;
         update_tree_losses(c, 1, true);
       }
     }
     crement_threads(n, -1);                        // assign_children
-    if (k > 0 && count[n] < 0) {
+    if (k > 0 && nodes[n].count < 0) {
       int64_t ev_l = 0, ev_w = 0;
       for (int j = 0; j < k; ++j) {
         const int32_t c = base + j;
         const uint8_t f = flags[j];
         const int32_t* st = stats + 4 * j;
         if (threat) {
-          if (f & kSeedGameSaving) { visits[c] = st[0]; wins[c] = st[1]; gv[c] = st[2]; gw[c] = st[3]; next.push_back(c); }
+          if (f & kSeedGameSaving) { nodes[c].visits = st[0]; nodes[c].wins = st[1]; nodes[c].gv = st[2]; nodes[c].gw = st[3]; next.push_back(c); }
           else if (f & kSeedDoomed) {              // set_game_over_values_1_step_lookahead + update_tree_wins(child)
-            visits[c] = wins[c] = gw[c] = gv[c] = 65536;
-            ws[c] = 1;
+            nodes[c].visits = nodes[c].wins = nodes[c].gw = nodes[c].gv = 65536;
+            nodes[c].ws = 1;
             update_tree_wins(c, 1, true);
           }
         } else {
-          if (!(f & kSeedWin)) { visits[c] = st[0]; wins[c] = st[1]; gv[c] = st[2]; gw[c] = st[3]; }
+          if (!(f & kSeedWin)) { nodes[c].visits = st[0]; nodes[c].wins = st[1]; nodes[c].gv = st[2]; nodes[c].gw = st[3]; }
           if (f & kSeedEvalOne) ++ev_l; else ++ev_w;
         }
       }
-      first[n] = base;
-      count[n] = k;
+      nodes[n].first = base;
+      nodes[n].count = k;
       if (!threat) {
         for (int j = 0; j < k; ++j) next.push_back(base + j);
         update_tree_losses(n, ev_l, false);        // eval_children
@@ -263,13 +271,13 @@ struct Tree {
   // node) or the expansion is over (returns -1).
   int32_t expand_run() {
     while (ex_depth < ex_limit) {
-      if (ws[root] == -1) { if (count[ex_leaf] < 0 && ws[ex_leaf] == -1) frontier.push_back(ex_leaf); }
-      else if (count[ex_leaf] < 0 && !gameover[ex_leaf]) frontier.push_back(ex_leaf);
+      if (nodes[root].ws == -1) { if (nodes[ex_leaf].count < 0 && nodes[ex_leaf].ws == -1) frontier.push_back(ex_leaf); }
+      else if (nodes[ex_leaf].count < 0 && !nodes[ex_leaf].gameover) frontier.push_back(ex_leaf);
       if (!frontier.empty()) {                     // (the reference's 0 < len < 256; a frontier has one node)
         ex_limit = 800;
         const int32_t p = frontier[0];
-        if (threads[p] <= 1 && count[p] < 0) {     // do_updates_in_the_same_process
-          if (threads[p] <= 0) crement_threads(p, 1);
+        if (nodes[p].threads <= 1 && nodes[p].count < 0) {     // do_updates_in_the_same_process
+          if (nodes[p].threads <= 0) crement_threads(p, 1);
           pending = p;
           return p;                                // -> policy_net.evaluate
         }
@@ -295,7 +303,7 @@ struct Tree {
     frontier.clear();
     if (ex_depth + 1 < ex_limit && !kids.empty()) {
       const int32_t c0 = kids[0];
-      if (ws[c0] == -1 && threads[c0] <= 0 && !being_checked[c0]) frontier.push_back(c0);
+      if (nodes[c0].ws == -1 && nodes[c0].threads <= 0 && !nodes[c0].being_checked) frontier.push_back(c0);
     }
     ++ex_depth;
     if (ex_depth < ex_limit)
@@ -312,8 +320,8 @@ struct Tree {
         const int32_t need = expand_run();
         if (need >= 0) return need;
         if (!ex_final) {                           // tail of run_MCTS_with_expansions_simulation
-          const bool done = checked[root] || ws[root] != -1;
-          if (done && count[root] < 0) {
+          const bool done = nodes[root].checked || nodes[root].ws != -1;
+          if (done && nodes[root].count < 0) {
             ex_final = true;
             expand_begin(root, 0, 1);
             continue;
@@ -326,21 +334,21 @@ struct Tree {
       }
       // kIdle: start a simulation
       if (simulations >= max_sims) return -1;
-      if (checked[root]) { phase = kFinished; return -1; }
+      if (nodes[root].checked) { phase = kFinished; return -1; }
       int32_t n = root;
       bool expanding = false;
       while (true) {                               // play_MCTS_game_with_expansions / select_UCT_child
-        if (gameover[n]) break;
-        if (count[n] < 0) {
-          if (threads[n] <= 0) {
+        if (nodes[n].gameover) break;
+        if (nodes[n].count < 0) {
+          if (nodes[n].threads <= 0) {
             crement_threads(n, 1);
             expand_begin(n, 0, 5);
             expanding = true;
           }
           break;
         }
-        while (n >= 0 && count[n] >= 0) {
-          threads[n] = 0;
+        while (n >= 0 && nodes[n].count >= 0) {
+          nodes[n].threads = 0;
           n = choose_uct_or_best_child(n);
         }
         if (n < 0) break;
@@ -358,12 +366,12 @@ struct Tree {
       const int32_t n = order[i].first;
       if (static_cast<int64_t>(i) < capacity) {
         int64_t* r = rows + i * 14;
-        r[0] = order[i].second; r[1] = index[n]; r[2] = black[n]; r[3] = visits[n]; r[4] = wins[n]; r[5] = gv[n];
-        r[6] = gw[n]; r[7] = ws[n]; r[8] = gameover[n]; r[9] = checked[n]; r[10] = being_checked[n];
-        r[11] = threads[n]; r[12] = count[n]; r[13] = height[n];
+        r[0] = order[i].second; r[1] = nodes[n].index; r[2] = nodes[n].black; r[3] = nodes[n].visits; r[4] = nodes[n].wins; r[5] = nodes[n].gv;
+        r[6] = nodes[n].gw; r[7] = nodes[n].ws; r[8] = nodes[n].gameover; r[9] = nodes[n].checked; r[10] = nodes[n].being_checked;
+        r[11] = nodes[n].threads; r[12] = nodes[n].count; r[13] = nodes[n].height;
       }
-      if (count[n] >= 0)
-        for (int32_t c = first[n]; c < first[n] + count[n]; ++c) order.emplace_back(c, static_cast<int64_t>(i));
+      if (nodes[n].count >= 0)
+        for (int32_t c = nodes[n].first; c < nodes[n].first + nodes[n].count; ++c) order.emplace_back(c, static_cast<int64_t>(i));
     }
     return static_cast<int64_t>(order.size());
   }

@@ -1468,8 +1468,8 @@ int wann_forest_next(wann_forest* fo, int64_t max_simulations, int8_t* squares_o
   for (int64_t t = 0; t < n; ++t) {
     if (node[t] < 0) continue;
     const wann_tree::Tree& tr = fo->f.trees[t];
-    memcpy(squares_out + m * 64, &tr.boards[static_cast<size_t>(node[t]) * 64], 64);
-    black_out[m] = tr.black[node[t]];
+    memcpy(squares_out + m * 64, tr.nodes[node[t]].board, 64);
+    black_out[m] = tr.nodes[node[t]].black;
     if (tree_ids != nullptr) tree_ids[m] = t;
     fo->waiting.push_back(t);
     ++m;
@@ -1498,14 +1498,14 @@ int wann_forest_info(wann_forest* fo, int64_t tree, int64_t out[8]) {
   if (fo == nullptr || out == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size()))
     return fail(WANN_E_INVALID, "bad argument");
   const wann_tree::Tree& tr = fo->f.trees[tree];
-  out[0] = static_cast<int64_t>(tr.parent.size());
+  out[0] = static_cast<int64_t>(tr.nodes.size());
   out[1] = tr.simulations;
   out[2] = tr.evaluations;
-  out[3] = tr.visits[tr.root];
-  out[4] = tr.wins[tr.root];
-  out[5] = tr.ws[tr.root];
+  out[3] = tr.nodes[tr.root].visits;
+  out[4] = tr.nodes[tr.root].wins;
+  out[5] = tr.nodes[tr.root].ws;
   out[6] = tr.phase == wann_tree::Tree::kFinished;
-  out[7] = tr.count[tr.root] > 0 ? tr.index[tr.first[tr.root]] : -1;     // best_child = children[0] (tree_builder.pyx:561)
+  out[7] = tr.nodes[tr.root].count > 0 ? tr.nodes[tr.nodes[tr.root].first].index : -1;     // best_child = children[0] (tree_builder.pyx:561)
   return WANN_OK;
 }
 
