@@ -375,6 +375,34 @@ def main():
                                "us_per_step": round(float(t.item()) * 1e3 / tsteps, 2),
                                "positions_per_s": round(n_gpus * n_trees * tsteps / (float(t.item()) * 1e-3), 1)}
 
+    # ---------------- configs[4] with the REFERENCE'S OWN SEARCH per tree: a forest of native array trees
+    # (wann_forest_*, node-for-node the compiled reference's trees) advancing in lock step, one
+    # wann_eval_expand_seeded call per step (host buffers), 1,024 trees per GPU
+    forest_line = None
+    if not args.no_sweep:
+        from wann_b200 import SearchForest
+        ev3 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode="fp16",
+                                        refine_margin=args.refine_margin)
+        n_trees, sims = 1024, 10
+        forest = SearchForest(sq_np[:n_trees], bl_np[:n_trees])
+        forest.run(ev3, 1)                                          # warm-up: first expansions, lane allocation
+        barrier()
+        t0 = time.perf_counter()
+        fsteps, fevals = forest.run(ev3, sims)
+        dt = time.perf_counter() - t0
+        nodes = sum(forest.info(t)["nodes"] for t in range(n_trees))
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        cnts = torch.tensor([fevals, nodes], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
+        forest_line = {"trees_per_gpu": n_trees, "simulations_per_tree": sims - 1, "lock_steps": fsteps,
+                       "evaluations": int(cnts[0].item()), "tree_nodes": int(cnts[1].item()),
+                       "evaluations_per_s": round(float(cnts[0].item()) / float(t.item()), 1),
+                       "host_cores": os.cpu_count()}
+        forest.close()
+        ev3.close()
+
     # ---------------- fp16 operands + margin refinement: the configuration that meets north_star's
     # top-1 >= 99.9 % gate (profiles/*accuracy*.json) -- same workload, device resident
     refined = None
@@ -501,6 +529,7 @@ def main():
             "sweep_positions_per_s": sweep,
             "config5_game_trees": trees,
             "fp16_margin_refined": refined,
+            "config5_search_forest": forest_line,
             "hbm_kernels": hbm_kernels,
             "per_rank_counters": counters.tolist(),
         }

@@ -48,4 +48,25 @@ with wann_b200.PolicyEvaluator(w, mode="fp16", refine_margin=0.02) as ev:
                                       "tree_apply": round(t_apply / wall, 3)}}
         forest.close()
         print(T, rep[str(T)], flush=True)
+    # two half-forests on two host threads: one's tree code overlaps the other's evaluation (the C ABI
+    # releases the GIL and is re-entrant)
+    import threading
+    for T in (1024, 8192):
+        rs, rb = synthetic.random_positions(T, seed=3)
+        halves = [wann_b200.SearchForest(rs[h::2], rb[h::2]) for h in range(2)]
+        res = [None, None]
+
+        def work(h):
+            res[h] = halves[h].run(ev, sims)
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(h,)) for h in range(2)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        wall = time.perf_counter() - t0
+        evals = res[0][1] + res[1][1]
+        nodes = sum(f.info(t)["nodes"] for f in halves for t in range(f.n))
+        rep["%d_two_half_forests" % T] = {"trees": T, "evaluations": evals, "nodes": nodes, "wall_s": round(wall, 3),
+                                          "evaluations_per_s": round(evals / wall, 1), "nodes_per_s": round(nodes / wall, 1)}
+        print(T, "two half forests", rep["%d_two_half_forests" % T], flush=True)
+        [f.close() for f in halves]
 open(os.path.join(ROOT, "gpurun_out", "forest.json"), "w").write(json.dumps(rep, indent=1))
