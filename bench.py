@@ -381,6 +381,8 @@ def main():
     forest_line = None
     if not args.no_sweep:
         from wann_b200 import SearchForest
+        from wann_b200.forest import host_threads
+        host_threads(max(1, (os.cpu_count() or 1) // max(1, world)))      # torchrun exports OMP_NUM_THREADS=1
         ev3 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode="fp16",
                                         refine_margin=args.refine_margin)
         n_trees, sims = 1024, 10
@@ -399,7 +401,7 @@ def main():
         forest_line = {"trees_per_gpu": n_trees, "simulations_per_tree": sims - 1, "lock_steps": fsteps,
                        "evaluations": int(cnts[0].item()), "tree_nodes": int(cnts[1].item()),
                        "evaluations_per_s": round(float(cnts[0].item()) / float(t.item()), 1),
-                       "host_cores": os.cpu_count()}
+                       "host_threads_per_rank": host_threads()}
         forest.close()
         ev3.close()
 

@@ -197,6 +197,10 @@ int wann_tree_step(wann_ctx* ctx, int8_t* squares, uint8_t* black_to_move, int64
  * Trees grown this way are node-for-node the trees the compiled reference grows single-threaded
  * (tests/golden/ref_tree_golden.npz).  Tie-break: children arrive ranked by prior, equal priors by
  * ascending move index (the reference's order for exact ties depends on its piece-list history). */
+/* Host threads used by wann_forest_next / wann_forest_apply (OpenMP over the trees): n > 0 sets the
+ * number (launchers such as torchrun export OMP_NUM_THREADS=1), any n returns the current maximum. */
+int wann_host_threads(int n);
+
 typedef struct wann_forest wann_forest;
 int wann_forest_create(int64_t n_trees, const int8_t* squares, const uint8_t* black_to_move,
                        const int32_t* heights /* ply of each root, may be NULL */, wann_forest** out);

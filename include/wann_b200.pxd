@@ -66,6 +66,8 @@ cdef extern from "wann_b200.h" nogil:
     int wann_set_option(wann_ctx* ctx, const char* key, int64_t value)
     int wann_version()
 
+    int wann_host_threads(int n)
+
     ctypedef struct wann_forest:
         pass
 

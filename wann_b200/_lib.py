@@ -19,7 +19,7 @@ EXPORTS = [
     "wann_debug_profile", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
     "wann_forest_create", "wann_forest_destroy", "wann_forest_next", "wann_forest_apply", "wann_forest_info",
-    "wann_forest_dump",
+    "wann_forest_dump", "wann_host_threads",
 ]
 
 
@@ -56,6 +56,7 @@ def load():
     lib.wann_eval_topk.argtypes = [vp, vp, vp, i64, vp, vp, vp, ci, vp]
     lib.wann_eval_expand.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, ci, vp]
     lib.wann_eval_expand_seeded.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+    lib.wann_host_threads.argtypes = [ci]
     lib.wann_forest_create.argtypes = [i64, vp, vp, vp, ctypes.POINTER(vp)]
     lib.wann_forest_destroy.argtypes = [vp]
     lib.wann_forest_next.argtypes = [vp, i64, vp, vp, vp, ctypes.POINTER(i64)]

@@ -5,6 +5,7 @@
 // There is NO CPU fallback: every entry point either runs the CUDA kernels or fails.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <omp.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -1438,6 +1439,11 @@ struct wann_forest {
   wann_tree::Forest f;
   std::vector<int64_t> waiting;      // trees whose rows were handed out by the last wann_forest_next
 };
+
+int wann_host_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
 
 int wann_forest_create(int64_t n, const int8_t* squares, const uint8_t* black, const int32_t* heights,
                        wann_forest** out) {

@@ -18,6 +18,12 @@ DUMP_FIELDS = ("parent", "index", "black", "visits", "wins", "gameover_visits", 
                "gameover", "subtree_checked", "subtree_being_checked", "threads_checking_node", "n_children", "height")
 
 
+def host_threads(n=0):
+    """Host threads the forest's tree code uses (OpenMP over trees); n > 0 sets it.  Launchers such as
+    torchrun export OMP_NUM_THREADS=1: call host_threads(os.cpu_count() // world_size) there."""
+    return int(L.load().wann_host_threads(int(n)))
+
+
 class SearchForest(object):
     def __init__(self, squares, black_to_move, heights=None):
         self._lib = L.load()
