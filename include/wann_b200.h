@@ -210,7 +210,10 @@ int wann_forest_next(wann_forest* forest, int64_t max_simulations, int8_t* squar
 int wann_forest_apply(wann_forest* forest, const uint8_t* idx, const float* prior, const uint8_t* n_legal,
                       const uint8_t* child_flags, const int32_t* child_stats, const int32_t* parent_summary);
 /* out[8] = nodes, simulations, evaluations, root visits, root wins, root win_status (-1/0/1),
- * finished (root subtree checked), move index of the root's best child (children[0]) or -1. */
+ * finished (root subtree checked), and the move the search would play now: the move index of the
+ * child chosen by randomly_choose_a_winning_move (tree_search_utils.pyx:469-486 with
+ * check_for_forced_win :559-582 and choose_best_true_loser :493-557; expansion_MCTS_functions.pyx:129),
+ * -1 while the root is unexpanded. */
 int wann_forest_info(wann_forest* forest, int64_t tree, int64_t out[8]);
 /* Breadth-first dump of one tree, 14 int64 per node: parent row, move index, black to move, visits,
  * wins, gameover_visits, gameover_wins, win_status, gameover, subtree_checked, subtree_being_checked,

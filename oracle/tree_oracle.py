@@ -308,6 +308,57 @@ class ArrayTree(object):
             if n < 0:
                 return
 
+    # ------------------------------------------------------------------ the move the search plays
+    def best_move(self):
+        """randomly_choose_a_winning_move (tree_search_utils.pyx:469-486; deterministic despite its name:
+        it returns best_nodes[0]) with check_for_forced_win :559-582 and choose_best_true_loser :493-557.
+        -> node of the chosen child (its move index is self.index[node]).  The expressions are kept as the
+        reference writes them: a capture close to home carries a numpy float32 UCT_multiplier, and numpy's
+        scalar promotion then decides in which precision each sum and comparison happens."""
+        kids = list(self.children(self.root))
+        over = [c for c in kids if self.gameover[c]]
+        if over:
+            return over[0]
+        lost = [c for c in kids if self.ws[c] == 0]
+        if lost:
+            return lost[0]
+        return self._choose_best_true_loser(kids)
+
+    def _choose_best_true_loser(self, kids):
+        prob_scaling = 3
+        best_child = kids[0]
+        action_value_threshold = self.gw[best_child] / 2
+        top = self.uct[best_child]
+        if top < 1.1:
+            first = second = 1.04
+        elif top < 1.2:
+            first, second = 1.10, 1.05
+        elif top < 1.3:
+            first, second = 1.15, 1.10
+        else:
+            first, second = 1.20, 1.15
+        losses = lambda c: self.gv[c] - self.gw[c]          # noqa: E731
+        filtered = [c for c in kids if (self.uct[c] > first or losses(c) > action_value_threshold) and self.ws[c] != 1]
+        if not filtered:
+            filtered = [c for c in kids if (self.uct[c] > second or losses(c) > action_value_threshold) and self.ws[c] != 1]
+        if not filtered:
+            filtered = [c for c in kids if self.ws[c] != 1]
+        if not filtered:
+            return kids[0]
+        best, best_losses = None, None
+        for c in filtered:                                   # max(): the first maximum
+            if best is None or losses(c) > best_losses:
+                best, best_losses = c, losses(c)
+        highest = best_losses
+        best_rate = best_losses / max(1, self.gv[best]) + (self.uct[best] - 1) / prob_scaling
+        for c in filtered:
+            true_losses = losses(c)
+            loss_rate = (true_losses / max(1, self.gv[c])) + (self.uct[c] - 1) / prob_scaling
+            if loss_rate > best_rate and loss_rate - best_rate > 0.05 and highest != 0 and true_losses / highest > .30 \
+                    and self.ws[c] != 1:
+                best, best_rate = c, loss_rate
+        return best
+
     # ------------------------------------------------------------------ comparison with the golden dump
     def dump(self):
         """Same BFS layout as tests/golden/make_tree_golden.py: children contiguous, in tree order."""

@@ -72,9 +72,11 @@ def main():
     # start positions: the opening and two positions from a seeded random play-out (plies 14 and 31)
     starts = [(U.initial_game_board(), "White", 0)]
     board, color = U.initial_game_board(), "White"
-    for ply in range(32):
+    for ply in range(59):
+        if B.game_over(board)[0]:
+            break
         legal = B.enumerate_legal_moves(board, color)
-        if ply in (14, 31):
+        if ply in (14, 31, 44, 52, 58):
             starts.append((B.copy_game_board(board), color, ply))
         mv = legal[rng.randint(len(legal))]
         f, t = mv.split("-")
@@ -100,6 +102,9 @@ def main():
                 done_sims += 1
             out["start%d_after%d" % (s, cp)] = dump(root)
             out["start%d_evals%d" % (s, cp)] = np.int64(net.calls)
+            # the move the search would play now (expansion_MCTS_functions.pyx:129: randomly_choose_a_winning_move,
+            # deterministic despite its name) as the move index of the chosen child
+            out["start%d_move%d" % (s, cp)] = np.int64(tsu.randomly_choose_a_winning_move(root)["index"])
         print("start", s, color, "ply", ply, "sims", done_sims, "evaluations", net.calls, "nodes",
               len(out["start%d_after%d" % (s, checkpoints[-1])]), "root win_status", root["win_status"])
     out["checkpoints"] = np.array(checkpoints)

@@ -284,14 +284,15 @@ def test_cython_binding_compiles_against_the_header(lib_built, tmp_path):
 
 def test_array_tree_restatement_reproduces_the_references_trees():
     """tests/golden/ref_tree_golden.npz holds whole search trees grown by the compiled reference
-    (run_MCTS_with_expansions_simulation, single-threaded, a deterministic synthetic policy) from three
-    start positions, checkpointed after 1..40 simulations (up to 29,955 nodes).  oracle/tree_oracle.py --
+    (run_MCTS_with_expansions_simulation, single-threaded, a deterministic synthetic policy) from six
+    start positions (plies 0..58; three end up solved), checkpointed after 1..40 simulations (up to 29,955
+    nodes), with the move randomly_choose_a_winning_move would play at each checkpoint.  oracle/tree_oracle.py --
     the reference's selection / expansion / statistics / solver restated over flat arrays -- grows the
     SAME trees, node for node, field for field (visits, wins, gameover statistics, win status, the
     checked / being-checked flags, thread counters, child order)."""
     from oracle.tree_oracle import ArrayTree
     g = np.load(os.path.join(ROOT, "tests", "golden", "ref_tree_golden.npz"))
-    for s, height in enumerate((0, 14, 31)):
+    for s, height in enumerate((0, 14, 31, 44, 52, 58)):
         t = ArrayTree(g["start%d_squares" % s], int(g["start%d_black" % s]), O.synthetic_policy, height=height)
         sims = 0
         for cp in g["checkpoints"]:
@@ -300,6 +301,7 @@ def test_array_tree_restatement_reproduces_the_references_trees():
                 sims += 1
             assert t.evaluations == int(g["start%d_evals%d" % (s, cp)])
             assert np.array_equal(t.dump(), g["start%d_after%d" % (s, cp)]), (s, cp)
+            assert t.index[t.best_move()] == int(g["start%d_move%d" % (s, cp)])      # the move the search plays
     p = O.synthetic_policy(O.initial_squares(), 0)
     assert p.dtype == np.float32 and len(set(p.tolist())) == 155 and abs(float(p.sum()) - 1) < 1e-2
     assert np.array_equal((np.float32(1) + p).astype(np.float64), 1.0 + p.astype(np.float64))   # 1 + p exact in float32
@@ -320,23 +322,24 @@ class _CpuSeeds(object):
 
 def test_native_search_forest_reproduces_the_references_trees(lib_built):
     """The PRODUCT tree (wann_forest_*, array_tree.hpp: C++ struct-of-arrays, resumable at the evaluation,
-    three trees advancing in lock step in one forest) grows node for node the trees of the compiled
-    reference search (tests/golden/ref_tree_golden.npz), checkpoint by checkpoint."""
+    six trees advancing in lock step in one forest) grows node for node the trees of the compiled
+    reference search (tests/golden/ref_tree_golden.npz) -- three open positions, three that the solver
+    decides -- checkpoint by checkpoint, and plays the move the reference's search would play."""
     import wann_b200
     g = np.load(os.path.join(ROOT, "tests", "golden", "ref_tree_golden.npz"))
-    sq = np.stack([g["start%d_squares" % s] for s in range(3)])
-    bl = np.array([int(g["start%d_black" % s]) for s in range(3)], np.uint8)
-    with wann_b200.SearchForest(sq, bl, heights=[0, 14, 31]) as forest:
+    sq = np.stack([g["start%d_squares" % s] for s in range(6)])
+    bl = np.array([int(g["start%d_black" % s]) for s in range(6)], np.uint8)
+    with wann_b200.SearchForest(sq, bl, heights=[0, 14, 31, 44, 52, 58]) as forest:
         for cp in g["checkpoints"]:
             steps, evals = forest.run(_CpuSeeds(), int(cp))
             assert steps > 0 and evals >= steps
-            for s in range(3):
+            for s in range(6):
                 info = forest.info(s)
                 assert info["simulations"] == cp and info["evaluations"] == int(g["start%d_evals%d" % (s, cp)])
                 want = g["start%d_after%d" % (s, cp)]
                 assert np.array_equal(forest.dump(s), want), (s, cp)
                 assert info["nodes"] == len(want) and info["root_visits"] == want[0, 3] and info["root_wins"] == want[0, 4]
-                assert info["best_child_index"] == want[1, 1]
+                assert info["move_index"] == int(g["start%d_move%d" % (s, cp)])
         sq2, bl2, ids = forest.next(40)
         assert len(sq2) == 0 and len(ids) == 0                     # budget reached: nothing to evaluate
     with pytest.raises(wann_b200.WannError):

@@ -358,6 +358,66 @@ struct Tree {
     }
   }
 
+  // ---- the move the search plays: randomly_choose_a_winning_move (tree_search_utils.pyx:469-486;
+  // deterministic despite its name), check_for_forced_win :559-582, choose_best_true_loser :493-557.
+  // Num mirrors the reference's scalars: a Python float (weak) or a numpy float32 (the UCT_multiplier
+  // of a capture close to home); numpy's promotion rules decide the precision of each operation.
+  struct Num { double v; bool f32; };
+  static Num num_op(Num a, Num b, char op) {
+    if (a.f32 || b.f32) {
+      const float x = static_cast<float>(a.v), y = static_cast<float>(b.v);
+      const float r = op == '+' ? x + y : op == '-' ? x - y : x / y;
+      return {static_cast<double>(r), true};
+    }
+    return {op == '+' ? a.v + b.v : op == '-' ? a.v - b.v : a.v / b.v, false};
+  }
+  static bool num_gt(Num a, Num b) {
+    return (a.f32 || b.f32) ? static_cast<float>(a.v) > static_cast<float>(b.v) : a.v > b.v;
+  }
+  Num num_uct(int32_t c) const { return {nodes[c].uct, nodes[c].uct_f32 != 0}; }
+  Num loss_rate_of(int32_t c) const {   // true_losses / max(1, gameover_visits) + (UCT_multiplier - 1) / 3
+    const int64_t losses = nodes[c].gv - nodes[c].gw, total = nodes[c].gv > 1 ? nodes[c].gv : 1;
+    const Num rate = {static_cast<double>(losses) / static_cast<double>(total), false};
+    return num_op(rate, num_op(num_op(num_uct(c), Num{1.0, false}, '-'), Num{3.0, false}, '/'), '+');
+  }
+  int32_t best_move() const {
+    const int32_t lo = nodes[root].first, k = nodes[root].count;
+    if (k <= 0) return -1;
+    for (int32_t c = lo; c < lo + k; ++c) if (nodes[c].gameover) return c;      // check_for_forced_win
+    for (int32_t c = lo; c < lo + k; ++c) if (nodes[c].ws == 0) return c;
+    // choose_best_true_loser
+    const double action_value_threshold = static_cast<double>(nodes[lo].gw) / 2.0;
+    const Num top = num_uct(lo);
+    double first_thr, second_thr;
+    if (num_gt(Num{1.1, false}, top)) first_thr = second_thr = 1.04;
+    else if (num_gt(Num{1.2, false}, top)) { first_thr = 1.10; second_thr = 1.05; }
+    else if (num_gt(Num{1.3, false}, top)) { first_thr = 1.15; second_thr = 1.10; }
+    else { first_thr = 1.20; second_thr = 1.15; }
+    auto losses = [&](int32_t c) { return nodes[c].gv - nodes[c].gw; };
+    std::vector<int32_t> filtered;
+    for (int pass = 0; pass < 3 && filtered.empty(); ++pass)
+      for (int32_t c = lo; c < lo + k; ++c) {
+        if (nodes[c].ws == 1) continue;
+        const bool keep = pass == 2 || num_gt(num_uct(c), Num{pass == 0 ? first_thr : second_thr, false}) ||
+                          static_cast<double>(losses(c)) > action_value_threshold;
+        if (keep) filtered.push_back(c);
+      }
+    if (filtered.empty()) return lo;
+    int32_t best = filtered[0];
+    for (int32_t c : filtered) if (losses(c) > losses(best)) best = c;            // max(): the first maximum
+    const int64_t highest = losses(best);
+    Num best_rate = loss_rate_of(best);
+    for (int32_t c : filtered) {
+      const Num rate = loss_rate_of(c);
+      if (num_gt(rate, best_rate) && num_gt(num_op(rate, best_rate, '-'), Num{0.05, false}) && highest != 0 &&
+          static_cast<double>(losses(c)) / static_cast<double>(highest) > .30 && nodes[c].ws != 1) {
+        best = c;
+        best_rate = rate;
+      }
+    }
+    return best;
+  }
+
   // BFS dump in the layout of tests/golden/make_tree_golden.py; returns the number of rows (nodes)
   int64_t dump(int64_t* rows, int64_t capacity) const {
     std::vector<std::pair<int32_t, int64_t>> order;

@@ -1511,7 +1511,8 @@ int wann_forest_info(wann_forest* fo, int64_t tree, int64_t out[8]) {
   out[4] = tr.nodes[tr.root].wins;
   out[5] = tr.nodes[tr.root].ws;
   out[6] = tr.phase == wann_tree::Tree::kFinished;
-  out[7] = tr.nodes[tr.root].count > 0 ? tr.nodes[tr.nodes[tr.root].first].index : -1;     // best_child = children[0] (tree_builder.pyx:561)
+  const int32_t mv = tr.best_move();       // randomly_choose_a_winning_move (tree_search_utils.pyx:469-486)
+  out[7] = mv >= 0 ? tr.nodes[mv].index : -1;
   return WANN_OK;
 }
 

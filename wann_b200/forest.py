@@ -84,7 +84,7 @@ class SearchForest(object):
         out = (ctypes.c_int64 * 8)()
         L.check(self._lib.wann_forest_info(self._f, int(tree), out))
         keys = ("nodes", "simulations", "evaluations", "root_visits", "root_wins", "root_win_status", "finished",
-                "best_child_index")
+                "move_index")
         return dict(zip(keys, list(out)))
 
     def dump(self, tree):
