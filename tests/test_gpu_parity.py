@@ -810,6 +810,7 @@ def test_search_forest_on_the_gpu_evaluator(weights, suite):
                 assert got.shape == want.shape and np.array_equal(got, want), t
                 info = forest.info(t)
                 assert info["evaluations"] == ref.evaluations and info["simulations"] == 6
+                assert info["move_index"] == ref.index[ref.best_move()]            # the move the search plays
         # a larger forest just runs: 512 trees, every evaluation a legal expansion
         big = wann_b200.SearchForest(np.tile(sq[:512], (1, 1)), bl[:512])
         steps, evals = big.run(ev, 3)
