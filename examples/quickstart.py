@@ -42,3 +42,11 @@ with wann_b200.PolicyEvaluator(mode="fp16") as ev:
     idx, prior, n_legal, _, flags, stats, parent = ev.eval_expand_seeded(sq[:4], black[:4], with_children=False)
     print("eval_expand_seeded(): first child visits/wins/gameover_visits/gameover_wins", stats[0, 0].tolist(),
           "| parent gained", parent[0, :4].tolist(), "win_status", int(parent[0, 4]))
+
+# 5. many searches at once: array-based trees with the reference's search semantics, one GPU call per lock step
+with wann_b200.PolicyEvaluator(mode="fp16", refine_margin=0.02) as ev, \
+        wann_b200.SearchForest(sq[:256], black[:256]) as forest:
+    steps, evals = forest.run(ev, simulations=5)
+    info = forest.info(0)
+    print("SearchForest: 256 trees, 5 simulations each:", steps, "lock steps,", evals, "evaluations; tree 0 has",
+          info["nodes"], "nodes and would play move index", info["move_index"])
