@@ -30,17 +30,19 @@ constexpr int kMaxLegal = 48;
 enum : uint8_t { kSeedWin = 1, kSeedCapture = 2, kSeedCloseToHome = 4, kSeedGameSaving = 8, kSeedDoomed = 16, kSeedEvalOne = 32 };
 
 struct Tree {
-  // ---- nodes (TreeNode.pyx:7-50): one 136-byte record per node (children of a node are contiguous,
-  // so selection walks one cache-friendly run instead of seventeen arrays) ---------------------------
+  // ---- nodes (TreeNode.pyx:7-50): one 72-byte record per node (children of a node are contiguous,
+  // so selection walks one cache-friendly run instead of seventeen arrays).  Boards are kept only for
+  // nodes that get evaluated (1 in ~23): a child's board is its parent's board plus its move. ----------
   struct Node {
     int64_t visits, wins, gv, gw;
     double uct;                                 // UCT_multiplier (a float32-rounded number when uct_f32)
     int32_t parent, first, count, height, threads;
+    int32_t board;                              // slot in `boards` (x 64 bytes), -1 until the node is evaluated
     int8_t ws;                                  // -1 None / 0 False / 1 True
     uint8_t index, black, gameover, checked, being_checked, uct_f32;
-    int8_t board[64];
   };
   std::vector<Node> nodes;
+  std::vector<int8_t> boards;
   int32_t root = 0;
   // ---- resumable state ---------------------------------------------------------------------------
   enum Phase : uint8_t { kIdle, kWaitEval, kFinished };
@@ -50,7 +52,7 @@ struct Tree {
   std::vector<int32_t> frontier;
   int64_t simulations = 0, evaluations = 0;
 
-  int32_t new_node(int32_t par, int idx, bool blk, const int8_t* board, int32_t h, double u, bool u_f32) {
+  int32_t new_node(int32_t par, int idx, bool blk, int32_t h, double u, bool u_f32) {
     Node nd;
     nd.visits = nd.wins = nd.gv = nd.gw = 0;
     nd.uct = u;
@@ -58,11 +60,27 @@ struct Tree {
     nd.ws = -1;
     nd.index = static_cast<uint8_t>(idx); nd.black = blk; nd.gameover = 0; nd.checked = 0; nd.being_checked = 0;
     nd.uct_f32 = u_f32;
-    memcpy(nd.board, board, 64);
+    nd.board = -1;
     nodes.push_back(nd);
     return static_cast<int32_t>(nodes.size()) - 1;
   }
-  void init(const int8_t* squares, bool blk, int32_t h) { root = new_node(-1, 0, blk, squares, h, 1.0, false); }
+  void init(const int8_t* squares, bool blk, int32_t h) {
+    root = new_node(-1, 0, blk, h, 1.0, false);
+    nodes[root].board = 0;
+    boards.assign(squares, squares + 64);
+  }
+  // the position of node n (materialised from its parent's on first use; parents are always expanded,
+  // hence evaluated, hence have theirs)
+  const int8_t* board_of(int32_t n) {
+    if (nodes[n].board < 0) {
+      const int32_t par = nodes[n].parent;
+      const size_t slot = boards.size() / 64;
+      boards.resize(boards.size() + 64);
+      apply_move(&boards[static_cast<size_t>(nodes[par].board) * 64], nodes[par].black, nodes[n].index, &boards[slot * 64]);
+      nodes[n].board = static_cast<int32_t>(slot);
+    }
+    return &boards[static_cast<size_t>(nodes[n].board) * 64];
+  }
 
   // ---- statistics (tree_search_utils.pyx:43-66) -------------------------------------------------
   void update_tree_wins(int32_t n, int64_t amount, bool go) {
@@ -220,14 +238,12 @@ struct Tree {
     ++evaluations;
     const bool blk = nodes[n].black;
     const int32_t base = static_cast<int32_t>(nodes.size());
-    int8_t child[64];
     for (int j = 0; j < k; ++j) {                  // get_child: created (a winner's loss propagated) before the sort
       const uint8_t f = flags[j];
       const float p = prior[j];
       const bool f32 = f & kSeedCloseToHome;
       const double u = f32 ? static_cast<double>(1.0f + p) : 1.0 + static_cast<double>(p);
-      apply_move(nodes[n].board, blk, idx[j], child);
-      const int32_t c = new_node(n, idx[j], !blk, child, nodes[n].height + 1, u, f32);
+      const int32_t c = new_node(n, idx[j], !blk, nodes[n].height + 1, u, f32);
       if (f & kSeedWin) {                          // set_game_over_values + update_tree_losses(child)
         nodes[c].gameover = nodes[c].checked = 1;
         nodes[c].ws = 0;

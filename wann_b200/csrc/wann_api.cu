@@ -1473,8 +1473,8 @@ int wann_forest_next(wann_forest* fo, int64_t max_simulations, int8_t* squares_o
   int64_t m = 0;
   for (int64_t t = 0; t < n; ++t) {
     if (node[t] < 0) continue;
-    const wann_tree::Tree& tr = fo->f.trees[t];
-    memcpy(squares_out + m * 64, tr.nodes[node[t]].board, 64);
+    wann_tree::Tree& tr = fo->f.trees[t];
+    memcpy(squares_out + m * 64, tr.board_of(node[t]), 64);
     black_out[m] = tr.nodes[node[t]].black;
     if (tree_ids != nullptr) tree_ids[m] = t;
     fo->waiting.push_back(t);
