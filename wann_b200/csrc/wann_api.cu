@@ -1469,16 +1469,22 @@ int wann_forest_next(wann_forest* fo, int64_t max_simulations, int8_t* squares_o
   const int64_t n = static_cast<int64_t>(fo->f.trees.size());
   std::vector<int32_t> node(static_cast<size_t>(n), -1);
 #pragma omp parallel for schedule(dynamic, 8)
-  for (int64_t t = 0; t < n; ++t) node[t] = fo->f.trees[t].advance(max_simulations);
-  int64_t m = 0;
   for (int64_t t = 0; t < n; ++t) {
-    if (node[t] < 0) continue;
     wann_tree::Tree& tr = fo->f.trees[t];
-    memcpy(squares_out + m * 64, tr.board_of(node[t]), 64);
-    black_out[m] = tr.nodes[node[t]].black;
-    if (tree_ids != nullptr) tree_ids[m] = t;
-    fo->waiting.push_back(t);
-    ++m;
+    node[t] = tr.advance(max_simulations);
+    if (node[t] >= 0) tr.board_of(node[t]);          // materialise the position while we are parallel
+  }
+  int64_t m = 0;
+  for (int64_t t = 0; t < n; ++t)
+    if (node[t] >= 0) fo->waiting.push_back(t);
+  m = static_cast<int64_t>(fo->waiting.size());
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < m; ++i) {
+    const int64_t t = fo->waiting[i];
+    wann_tree::Tree& tr = fo->f.trees[t];
+    memcpy(squares_out + i * 64, tr.board_of(node[t]), 64);
+    black_out[i] = tr.nodes[node[t]].black;
+    if (tree_ids != nullptr) tree_ids[i] = t;
   }
   *m_out = m;
   return WANN_OK;
