@@ -215,6 +215,12 @@ int wann_forest_apply(wann_forest* forest, const uint8_t* idx, const float* prio
  * check_for_forced_win :559-582 and choose_best_true_loser :493-557; expansion_MCTS_functions.pyx:129),
  * -1 while the root is unexpanded. */
 int wann_forest_info(wann_forest* forest, int64_t tree, int64_t out[8]);
+/* Root reuse between moves (assign_root's "Reused old tree" branch + reset_thread_flag,
+ * expansion_MCTS_functions.pyx:197-207,236-257): the child of the root reached by `move_index`
+ * becomes the root of the tree's next search (its subtree, statistics and win statuses are kept, the
+ * thread bookkeeping is cleared, the simulation count restarts).  Fails if the root has no such child. */
+int wann_forest_advance(wann_forest* forest, int64_t tree, int move_index);
+
 /* Breadth-first dump of one tree, 14 int64 per node: parent row, move index, black to move, visits,
  * wins, gameover_visits, gameover_wins, win_status, gameover, subtree_checked, subtree_being_checked,
  * threads_checking_node, number of children (-1 = not expanded), height.  Returns the number of

@@ -79,4 +79,5 @@ cdef extern from "wann_b200.h" nogil:
     int wann_forest_apply(wann_forest* forest, const uint8_t* idx, const float* prior, const uint8_t* n_legal,
                           const uint8_t* child_flags, const int32_t* child_stats, const int32_t* parent_summary)
     int wann_forest_info(wann_forest* forest, int64_t tree, int64_t* out)
+    int wann_forest_advance(wann_forest* forest, int64_t tree, int move_index)
     int64_t wann_forest_dump(wann_forest* forest, int64_t tree, int64_t* rows, int64_t capacity)

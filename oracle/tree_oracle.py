@@ -308,6 +308,24 @@ class ArrayTree(object):
             if n < 0:
                 return
 
+    # ------------------------------------------------------------------ root reuse between moves
+    def advance_root(self, move_index):
+        """assign_root's "Reused old tree" branch (expansion_MCTS_functions.pyx:236-247,253-257) followed by
+        reset_thread_flag (:197-207): the child reached by `move_index` becomes the root of the next
+        search and the thread bookkeeping of its subtree is cleared.  (The reference also cuts the tree
+        above the new root's grandparent, :259-266 -- memory housekeeping with no effect below the root.)"""
+        kid = [c for c in self.children(self.root) if self.index[c] == move_index]
+        if not kid:
+            raise KeyError("the root has no child for move index %d" % move_index)
+        self.root = kid[0]
+        stack = [self.root]
+        while stack:
+            n = stack.pop()
+            self.threads[n] = 0
+            self.being_checked[n] = False
+            if self.count[n] >= 0:
+                stack.extend(self.children(n))
+
     # ------------------------------------------------------------------ the move the search plays
     def best_move(self):
         """randomly_choose_a_winning_move (tree_search_utils.pyx:469-486; deterministic despite its name:

@@ -105,6 +105,23 @@ def main():
             # the move the search would play now (expansion_MCTS_functions.pyx:129: randomly_choose_a_winning_move,
             # deterministic despite its name) as the move index of the chosen child
             out["start%d_move%d" % (s, cp)] = np.int64(tsu.randomly_choose_a_winning_move(root)["index"])
+        # root reuse (assign_root, expansion_MCTS_functions.pyx:209-266, for the position after the move the
+        # search chose): the chosen child becomes the root of the next search, reset_thread_flag (:197-207)
+        # clears the thread bookkeeping of its subtree, 15 more simulations follow
+        best = tsu.randomly_choose_a_winning_move(root)
+        if not best["gameover"]:
+            sim2 = tsu.SimulationInfo(io.StringIO())
+            sim2.update(time_to_think=10 ** 6, start_time=time.time(), main_pid="not-this-thread")
+            new_root = mc.assign_root(best["game_board"], best["color"], root, None, ply + 2, net, sim2, lock)
+            assert new_root is best
+            sim2["root"] = new_root
+            mc.reset_thread_flag(new_root)
+            for _ in range(15):
+                mc.run_MCTS_with_expansions_simulation(new_root, 5, sim2, net, sim2["start_time"], 10 ** 6, lock)
+            out["start%d_reuse_move" % s] = np.int64(best["index"])
+            out["start%d_reuse_after15" % s] = dump(new_root)
+            out["start%d_reuse_evals" % s] = np.int64(net.calls)
+            out["start%d_reuse_next_move" % s] = np.int64(tsu.randomly_choose_a_winning_move(new_root)["index"])
         print("start", s, color, "ply", ply, "sims", done_sims, "evaluations", net.calls, "nodes",
               len(out["start%d_after%d" % (s, checkpoints[-1])]), "root win_status", root["win_status"])
     out["checkpoints"] = np.array(checkpoints)

@@ -302,6 +302,12 @@ def test_array_tree_restatement_reproduces_the_references_trees():
             assert t.evaluations == int(g["start%d_evals%d" % (s, cp)])
             assert np.array_equal(t.dump(), g["start%d_after%d" % (s, cp)]), (s, cp)
             assert t.index[t.best_move()] == int(g["start%d_move%d" % (s, cp)])      # the move the search plays
+        if s < 3:                                    # root reuse (assign_root + reset_thread_flag), 15 more simulations
+            t.advance_root(int(g["start%d_reuse_move" % s]))
+            for _ in range(15):
+                t.run_simulation()
+            assert np.array_equal(t.dump(), g["start%d_reuse_after15" % s]) and t.evaluations == int(g["start%d_reuse_evals" % s])
+            assert t.index[t.best_move()] == int(g["start%d_reuse_next_move" % s])
     p = O.synthetic_policy(O.initial_squares(), 0)
     assert p.dtype == np.float32 and len(set(p.tolist())) == 155 and abs(float(p.sum()) - 1) < 1e-2
     assert np.array_equal((np.float32(1) + p).astype(np.float64), 1.0 + p.astype(np.float64))   # 1 + p exact in float32
@@ -342,6 +348,17 @@ def test_native_search_forest_reproduces_the_references_trees(lib_built):
                 assert info["move_index"] == int(g["start%d_move%d" % (s, cp)])
         sq2, bl2, ids = forest.next(40)
         assert len(sq2) == 0 and len(ids) == 0                     # budget reached: nothing to evaluate
+        # root reuse: play the chosen move in the three open positions, search 15 simulations more
+        for s in range(3):
+            assert forest.info(s)["move_index"] == int(g["start%d_reuse_move" % s])
+            forest.advance(s, int(g["start%d_reuse_move" % s]))
+        with pytest.raises(wann_b200.WannError):
+            forest.advance(0, 154)                                 # no such child
+        forest.run(_CpuSeeds(), 15)
+        for s in range(3):
+            assert np.array_equal(forest.dump(s), g["start%d_reuse_after15" % s]), s
+            assert forest.info(s)["move_index"] == int(g["start%d_reuse_next_move" % s])
+            assert forest.info(s)["evaluations"] == int(g["start%d_reuse_evals" % s])
     with pytest.raises(wann_b200.WannError):
         f = wann_b200.SearchForest(sq, bl)
         f.next(1)

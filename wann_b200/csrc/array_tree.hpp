@@ -374,6 +374,28 @@ struct Tree {
     }
   }
 
+  // ---- root reuse between moves: assign_root's "Reused old tree" branch (expansion_MCTS_functions.pyx:
+  // 236-247,253-257) + reset_thread_flag (:197-207).  Returns false if the root has no such child.
+  bool advance_root(int move_index) {
+    if (phase == kWaitEval || nodes[root].count < 0) return false;
+    int32_t kid = -1;
+    for (int32_t c = nodes[root].first; c < nodes[root].first + nodes[root].count; ++c)
+      if (nodes[c].index == move_index) { kid = c; break; }
+    if (kid < 0) return false;
+    root = kid;
+    std::vector<int32_t> stack(1, root);
+    while (!stack.empty()) {
+      const int32_t n = stack.back();
+      stack.pop_back();
+      nodes[n].threads = 0;
+      nodes[n].being_checked = 0;
+      for (int32_t c = nodes[n].first; nodes[n].count >= 0 && c < nodes[n].first + nodes[n].count; ++c) stack.push_back(c);
+    }
+    phase = kIdle;
+    simulations = 0;                           // the budget of wann_forest_next counts per search
+    return true;
+  }
+
   // ---- the move the search plays: randomly_choose_a_winning_move (tree_search_utils.pyx:469-486;
   // deterministic despite its name), check_for_forced_win :559-582, choose_best_true_loser :493-557.
   // Num mirrors the reference's scalars: a Python float (weak) or a numpy float32 (the UCT_multiplier

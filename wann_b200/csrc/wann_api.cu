@@ -1522,6 +1522,16 @@ int wann_forest_info(wann_forest* fo, int64_t tree, int64_t out[8]) {
   return WANN_OK;
 }
 
+int wann_forest_advance(wann_forest* fo, int64_t tree, int move_index) {
+  if (fo == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size()))
+    return fail(WANN_E_INVALID, "bad argument");
+  if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
+  if (!fo->f.trees[tree].advance_root(move_index))
+    return fail(WANN_E_INVALID, "tree %lld: the root has no child for move index %d (or is mid-simulation)",
+                static_cast<long long>(tree), move_index);
+  return WANN_OK;
+}
+
 int64_t wann_forest_dump(wann_forest* fo, int64_t tree, int64_t* rows, int64_t capacity) {
   if (fo == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size())) return -1;
   return fo->f.trees[tree].dump(rows, rows ? capacity : 0);

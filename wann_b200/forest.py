@@ -80,6 +80,10 @@ class SearchForest(object):
             steps += 1
             evals += len(sq)
 
+    def advance(self, tree, move_index):
+        """Root reuse: the child reached by `move_index` becomes the root of tree's next search."""
+        L.check(self._lib.wann_forest_advance(self._f, int(tree), int(move_index)))
+
     def info(self, tree):
         out = (ctypes.c_int64 * 8)()
         L.check(self._lib.wann_forest_info(self._f, int(tree), out))
