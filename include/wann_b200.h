@@ -221,6 +221,15 @@ int wann_forest_info(wann_forest* forest, int64_t tree, int64_t out[8]);
  * thread bookkeeping is cleared, the simulation count restarts).  Fails if the root has no such child. */
 int wann_forest_advance(wann_forest* forest, int64_t tree, int move_index);
 
+/* Self-play step for the whole forest: every tree plays the move its search chose (wann_forest_info's
+ * move) -- wann_forest_advance, i.e. the game continues from the chosen child with its subtree reused;
+ * a winning move ends the game and the tree restarts from `restart_squares` (the opening position,
+ * tools/utils.pyx:518-541).  moves_out uint8 [n] (255 = root not expanded yet), finished_out uint8 [n];
+ * both optional.  Between two calls: wann_forest_next / wann_eval_expand_seeded / wann_forest_apply
+ * until the simulation budget is used up. */
+int wann_forest_play(wann_forest* forest, const int8_t* restart_squares, int restart_black,
+                     uint8_t* moves_out, uint8_t* finished_out);
+
 /* Breadth-first dump of one tree, 14 int64 per node: parent row, move index, black to move, visits,
  * wins, gameover_visits, gameover_wins, win_status, gameover, subtree_checked, subtree_being_checked,
  * threads_checking_node, number of children (-1 = not expanded), height.  Returns the number of

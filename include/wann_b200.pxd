@@ -80,4 +80,6 @@ cdef extern from "wann_b200.h" nogil:
                           const uint8_t* child_flags, const int32_t* child_stats, const int32_t* parent_summary)
     int wann_forest_info(wann_forest* forest, int64_t tree, int64_t* out)
     int wann_forest_advance(wann_forest* forest, int64_t tree, int move_index)
+    int wann_forest_play(wann_forest* forest, const int8_t* restart_squares, int restart_black,
+                         uint8_t* moves_out, uint8_t* finished_out)
     int64_t wann_forest_dump(wann_forest* forest, int64_t tree, int64_t* rows, int64_t capacity)

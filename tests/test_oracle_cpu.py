@@ -365,6 +365,48 @@ def test_native_search_forest_reproduces_the_references_trees(lib_built):
         f.next(1)                                                  # apply must follow next
 
 
+def test_search_forest_self_play_follows_the_restatement(lib_built):
+    """wann_forest_play: every tree plays its search's move and reuses the subtree; a winning move restarts
+    the game.  Three games (an open one, two near their end) stay node for node equal to the array-tree
+    restatement advanced the same way, move after move, until they end and restart."""
+    import wann_b200
+    from oracle.tree_oracle import ArrayTree
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_tree_golden.npz"))
+    pick, heights = (1, 3, 5), (14, 44, 58)
+    sq = np.stack([g["start%d_squares" % s] for s in pick])
+    bl = np.array([int(g["start%d_black" % s]) for s in pick], np.uint8)
+    models = [ArrayTree(sq[i], int(bl[i]), O.synthetic_policy, height=heights[i]) for i in range(3)]
+    done = [False] * 3
+    with wann_b200.SearchForest(sq, bl, heights=heights) as forest:
+        finished_games = 0
+        for ply in range(12):
+            forest.run(_CpuSeeds(), 6)
+            want_moves = []
+            for i, m in enumerate(models):
+                if done[i]:
+                    want_moves.append(None)
+                    continue
+                for _ in range(6):
+                    m.run_simulation()
+                assert np.array_equal(forest.dump(i), m.dump()), (ply, i)
+                want_moves.append(m.best_move())
+            moves, fin = forest.play()
+            for i, m in enumerate(models):
+                if done[i]:
+                    continue
+                c = want_moves[i]
+                assert moves[i] == m.index[c] and bool(fin[i]) == bool(m.gameover[c])
+                if m.gameover[c]:
+                    done[i] = True                                   # the forest restarted this tree from the opening
+                    assert forest.info(i)["nodes"] == 1 and np.array_equal(forest.next(0)[0], np.zeros((0, 64), np.int8))
+                else:
+                    m.advance_root(int(moves[i]))
+            finished_games += int(fin.sum())
+        assert finished_games >= 2 and done[1] and done[2]
+        root0 = forest.dump(0)
+        assert root0[0, 0] == -1 and forest.info(0)["nodes"] == len(root0)   # compacted: only the reused subtree is kept
+
+
 def test_child_seeding_oracle_vs_reference_golden(seed_golden):
     """641 positions expanded ONCE by the compiled reference tree code (expand_descendants_to_depth_wrt_NN
     -> get_child / update_child / assign_children / eval_children / update_win_status_from_children) with

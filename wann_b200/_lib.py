@@ -19,7 +19,7 @@ EXPORTS = [
     "wann_debug_profile", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
     "wann_forest_create", "wann_forest_destroy", "wann_forest_next", "wann_forest_apply", "wann_forest_info",
-    "wann_forest_dump", "wann_forest_advance", "wann_host_threads",
+    "wann_forest_dump", "wann_forest_advance", "wann_forest_play", "wann_host_threads",
 ]
 
 
@@ -63,6 +63,7 @@ def load():
     lib.wann_forest_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.wann_forest_info.argtypes = [vp, i64, vp]
     lib.wann_forest_advance.argtypes = [vp, i64, ci]
+    lib.wann_forest_play.argtypes = [vp, vp, ci, vp, vp]
     lib.wann_forest_dump.argtypes = [vp, i64, vp, i64]
     lib.wann_forest_dump.restype = i64
     lib.wann_set_weights.argtypes = [vp, ctypes.POINTER(WannWeights)]

@@ -382,15 +382,37 @@ struct Tree {
     for (int32_t c = nodes[root].first; c < nodes[root].first + nodes[root].count; ++c)
       if (nodes[c].index == move_index) { kid = c; break; }
     if (kid < 0) return false;
-    root = kid;
-    std::vector<int32_t> stack(1, root);
-    while (!stack.empty()) {
-      const int32_t n = stack.back();
-      stack.pop_back();
-      nodes[n].threads = 0;
-      nodes[n].being_checked = 0;
-      for (int32_t c = nodes[n].first; nodes[n].count >= 0 && c < nodes[n].first + nodes[n].count; ++c) stack.push_back(c);
+    // Keep only the new root's subtree (the reference drops everything above the new root's
+    // grandparent, :259-266; nothing above the root influences the search below it): breadth-first
+    // copy, so that the children of a node stay contiguous.  Thread bookkeeping is cleared on the way.
+    board_of(kid);                               // its position, before its parent disappears
+    std::vector<Node> kept;
+    std::vector<int8_t> kept_boards;
+    std::vector<int32_t> order(1, kid);
+    kept.reserve(1024);
+    for (size_t i = 0; i < order.size(); ++i) {
+      Node nd = nodes[order[i]];
+      nd.threads = 0;
+      nd.being_checked = 0;
+      if (nd.board >= 0) {
+        const int8_t* b = &boards[static_cast<size_t>(nd.board) * 64];
+        nd.board = static_cast<int32_t>(kept_boards.size() / 64);
+        kept_boards.insert(kept_boards.end(), b, b + 64);
+      }
+      if (nd.count >= 0) {
+        const int32_t new_first = static_cast<int32_t>(order.size());
+        for (int32_t c = nd.first; c < nd.first + nd.count; ++c) order.push_back(c);
+        nd.first = new_first;
+      }
+      kept.push_back(nd);
     }
+    for (size_t i = 0; i < kept.size(); ++i)     // parents: children of kept[i] are kept[first .. first + count)
+      if (kept[i].count >= 0)
+        for (int32_t c = kept[i].first; c < kept[i].first + kept[i].count; ++c) kept[c].parent = static_cast<int32_t>(i);
+    kept[0].parent = -1;
+    nodes.swap(kept);
+    boards.swap(kept_boards);
+    root = 0;
     phase = kIdle;
     simulations = 0;                           // the budget of wann_forest_next counts per search
     return true;

@@ -1532,6 +1532,30 @@ int wann_forest_advance(wann_forest* fo, int64_t tree, int move_index) {
   return WANN_OK;
 }
 
+int wann_forest_play(wann_forest* fo, const int8_t* restart_squares, int restart_black, uint8_t* moves_out,
+                     uint8_t* finished_out) {
+  if (fo == nullptr || restart_squares == nullptr) return fail(WANN_E_INVALID, "null argument");
+  if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
+  const int64_t n = static_cast<int64_t>(fo->f.trees.size());
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int64_t t = 0; t < n; ++t) {
+    wann_tree::Tree& tr = fo->f.trees[t];
+    const int32_t c = tr.best_move();
+    uint8_t mv = 255, fin = 0;
+    if (c >= 0) {
+      mv = tr.nodes[c].index;
+      if (tr.nodes[c].gameover || !tr.advance_root(mv)) {      // the move wins the game: next game
+        fin = 1;
+        tr = wann_tree::Tree();
+        tr.init(restart_squares, restart_black != 0, 0);
+      }
+    }
+    if (moves_out != nullptr) moves_out[t] = mv;
+    if (finished_out != nullptr) finished_out[t] = fin;
+  }
+  return WANN_OK;
+}
+
 int64_t wann_forest_dump(wann_forest* fo, int64_t tree, int64_t* rows, int64_t capacity) {
   if (fo == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size())) return -1;
   return fo->f.trees[tree].dump(rows, rows ? capacity : 0);

@@ -84,6 +84,25 @@ class SearchForest(object):
         """Root reuse: the child reached by `move_index` becomes the root of tree's next search."""
         L.check(self._lib.wann_forest_advance(self._f, int(tree), int(move_index)))
 
+    def play(self, restart_squares=None, restart_black=0):
+        """Every tree plays the move its search chose and continues from that child (subtree reused); a
+        winning move restarts the tree from `restart_squares` (default: the opening position).
+        -> (moves uint8 [n], finished uint8 [n])."""
+        from . import synthetic
+        rs = np.ascontiguousarray(synthetic.initial_squares() if restart_squares is None else restart_squares, np.int8)
+        moves, fin = np.empty(self.n, np.uint8), np.empty(self.n, np.uint8)
+        L.check(self._lib.wann_forest_play(self._f, rs.ctypes.data, int(restart_black), moves.ctypes.data, fin.ctypes.data))
+        return moves, fin
+
+    def self_play(self, evaluator, simulations_per_move, plies):
+        """`plies` rounds of: search `simulations_per_move` simulations in every tree, play the chosen
+        moves.  Returns (evaluations, games finished)."""
+        evals = games = 0
+        for _ in range(plies):
+            evals += self.run(evaluator, simulations_per_move)[1]
+            games += int(self.play()[1].sum())
+        return evals, games
+
     def info(self, tree):
         out = (ctypes.c_int64 * 8)()
         L.check(self._lib.wann_forest_info(self._f, int(tree), out))
