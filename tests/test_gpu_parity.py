@@ -811,6 +811,10 @@ def test_search_forest_on_the_gpu_evaluator(weights, suite):
                 info = forest.info(t)
                 assert info["evaluations"] == ref.evaluations and info["simulations"] == 6
                 assert info["move_index"] == ref.index[ref.best_move()]            # the move the search plays
+        # self-play on the real network: whole games, subtree reuse, restarts
+        with wann_b200.SearchForest(np.tile(O.initial_squares()[None], (64, 1)), np.zeros(64, np.uint8)) as sp:
+            evals, games = sp.self_play(ev, 4, 70)
+            assert evals > 64 * 70 and games >= 32             # Breakthrough games end within ~60 plies
         # a larger forest just runs: 512 trees, every evaluation a legal expansion
         big = wann_b200.SearchForest(np.tile(sq[:512], (1, 1)), bl[:512])
         steps, evals = big.run(ev, 3)

@@ -69,4 +69,18 @@ with wann_b200.PolicyEvaluator(w, mode="fp16", refine_margin=0.02) as ev:
                                           "evaluations_per_s": round(evals / wall, 1), "nodes_per_s": round(nodes / wall, 1)}
         print(T, "two half forests", rep["%d_two_half_forests" % T], flush=True)
         [f.close() for f in halves]
+    # self-play: search, play the chosen move (subtree reused), restart finished games
+    for T, spm, plies in ((1024, 8, 40), (8192, 8, 20)):
+        rs, rb = synthetic.random_positions(T, seed=5)          # games in progress: they end (and restart) at different times
+        forest = wann_b200.SearchForest(rs, rb)
+        t0 = time.perf_counter()
+        evals, games = forest.self_play(ev, spm, plies)
+        wall = time.perf_counter() - t0
+        nodes = sum(forest.info(t)["nodes"] for t in range(T))
+        rep["self_play_%d" % T] = {"trees": T, "simulations_per_move": spm, "plies": plies, "moves_played": T * plies,
+                                   "games_finished": games, "evaluations": evals, "wall_s": round(wall, 3),
+                                   "evaluations_per_s": round(evals / wall, 1), "moves_per_s": round(T * plies / wall, 1),
+                                   "nodes_alive_at_end": nodes}
+        print("self-play", rep["self_play_%d" % T], flush=True)
+        forest.close()
 open(os.path.join(ROOT, "gpurun_out", "forest.json"), "w").write(json.dumps(rep, indent=1))
