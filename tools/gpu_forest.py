@@ -22,6 +22,7 @@ with wann_b200.PolicyEvaluator(w, mode="fp16", refine_margin=0.02) as ev:
             rs, rb = synthetic.random_positions(T - 1, seed=3)
             sq[1:], bl[1:] = rs, rb
         forest = wann_b200.SearchForest(sq, bl)
+        rows = ev.pinned_rows(T)
         t_next = t_eval = t_apply = 0.0
         steps = evals = 0
         t0 = time.perf_counter()
@@ -32,7 +33,7 @@ with wann_b200.PolicyEvaluator(w, mode="fp16", refine_margin=0.02) as ev:
             t_next += c - a
             if len(s) == 0:
                 break
-            out = ev.eval_expand_seeded(s, b, with_children=False)
+            out = ev.eval_expand_seeded(s, b, with_children=False, out=rows)
             d = time.perf_counter()
             t_eval += d - c
             forest.apply(out[0], out[1], out[2], out[4], out[5], out[6])

@@ -59,6 +59,9 @@ class PolicyEvaluator(object):
         if getattr(self, "_ctx", None):
             self._lib.wann_destroy(self._ctx)
             self._ctx = None
+            for p in getattr(self, "_pinned", []):
+                self._lib.wann_host_free(p)
+            self._pinned = []
 
     __del__ = close
 
@@ -203,10 +206,11 @@ class PolicyEvaluator(object):
                                            L.MEM_HOST, None))
         return idx, pri, cnt, kids, flg
 
-    def eval_expand_seeded(self, squares, black, with_children=True):
+    def eval_expand_seeded(self, squares, black, with_children=True, out=None):
         """eval_expand + child seeding (wann_eval_expand_seeded).  -> idx, prior, n_legal,
         child_squares (or None), child_flags uint8 [n,48] (6 bits), child_stats int32 [n,48,4]
-        (visits, wins, gameover_visits, gameover_wins), parent_summary int32 [n,8]."""
+        (visits, wins, gameover_visits, gameover_wins), parent_summary int32 [n,8].
+        `out` (host path): the seven arrays to fill (e.g. pinned ones from pinned_rows), rows [:n] are used."""
         if _is_torch(squares):
             import torch
             n, dev = squares.shape[0], squares.device
@@ -221,14 +225,36 @@ class PolicyEvaluator(object):
             return idx, pri, cnt, kids, flg, st, ps
         sq, bl = self._np_in(squares, black)
         n = sq.shape[0]
-        idx, pri, cnt = np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL), np.float32), np.empty(n, np.uint8)
-        kids = np.empty((n, L.MAX_LEGAL, 64), np.int8) if with_children else None
-        flg, st, ps = np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL, 4), np.int32), np.empty((n, 8), np.int32)
+        if out is not None:
+            idx, pri, cnt, kids, flg, st, ps = [None if a is None else a[:n] for a in out]
+            with_children = with_children and kids is not None
+        else:
+            idx, pri, cnt = np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL), np.float32), np.empty(n, np.uint8)
+            kids = np.empty((n, L.MAX_LEGAL, 64), np.int8) if with_children else None
+            flg, st, ps = np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL, 4), np.int32), np.empty((n, 8), np.int32)
         L.check(self._lib.wann_eval_expand_seeded(
             self._ctx, sq.ctypes.data, bl.ctypes.data, n, idx.ctypes.data, pri.ctypes.data, cnt.ctypes.data,
             kids.ctypes.data if with_children else None, flg.ctypes.data, st.ctypes.data, ps.ctypes.data,
             L.MEM_HOST, None))
         return idx, pri, cnt, kids, flg, st, ps
+
+    def pinned_rows(self, n, with_children=False):
+        """Pinned host arrays for eval_expand_seeded(out=...) over up to n positions (wann_host_alloc):
+        the copies of a large host call then run at PCIe speed and nothing is allocated per call.
+        The arrays live as long as this evaluator."""
+        shapes = [((n, L.MAX_LEGAL), np.uint8), ((n, L.MAX_LEGAL), np.float32), ((n,), np.uint8),
+                  ((n, L.MAX_LEGAL, 64), np.int8) if with_children else None,
+                  ((n, L.MAX_LEGAL), np.uint8), ((n, L.MAX_LEGAL, 4), np.int32), ((n, 8), np.int32)]
+        return tuple(None if sh is None else self.pinned_array(*sh) for sh in shapes)
+
+    def pinned_array(self, shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = ctypes.c_void_p()
+        L.check(self._lib.wann_host_alloc(ctypes.byref(ptr), max(nbytes, 1)))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def tree_step(self, squares, black, greedy=False, seed=0, step=0, want_outputs=True):
         """In-place self-play step on torch CUDA tensors (see wann_tree_step).  Returns

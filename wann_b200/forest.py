@@ -71,11 +71,20 @@ class SearchForest(object):
         """Grow every tree by `simulations` simulations on `evaluator` (anything with
         eval_expand_seeded(squares, black, with_children=False)).  Returns (steps, evaluations)."""
         steps = evals = 0
+        out = None
+        if hasattr(evaluator, "pinned_rows"):            # pinned result rows, allocated once per evaluator
+            cache = evaluator.__dict__.setdefault("_forest_rows", {})
+            if cache.get("n", 0) < self.n:
+                cache.update(n=self.n, rows=evaluator.pinned_rows(self.n))
+            out = cache["rows"]
         while True:
             sq, bl, _ = self.next(simulations)
             if len(sq) == 0:
                 return steps, evals
-            idx, pri, cnt, _, flg, st, ps = evaluator.eval_expand_seeded(sq, bl, with_children=False)
+            if out is not None:
+                idx, pri, cnt, _, flg, st, ps = evaluator.eval_expand_seeded(sq, bl, with_children=False, out=out)
+            else:
+                idx, pri, cnt, _, flg, st, ps = evaluator.eval_expand_seeded(sq, bl, with_children=False)
             self.apply(idx, pri, cnt, flg, st, ps)
             steps += 1
             evals += len(sq)
