@@ -93,6 +93,22 @@ struct Tree {
       win = !win;
     }
   }
+  // Several updates that start at the same node, in ONE walk to the root (they are all additions, and
+  // nothing reads the statistics in between): update_tree_wins(n, w), update_tree_losses(n, l),
+  // update_tree_wins(n, wg, gameover), update_tree_losses(n, lg, gameover).  A walk up a deep tree is a
+  // chain of cache misses; an expansion needs this one instead of 2 + (winning + doomed children).
+  void propagate(int32_t n, int64_t w, int64_t l, int64_t wg, int64_t lg) {
+    while (n >= 0 && (w | l | wg | lg) != 0) {
+      Node& nd = nodes[n];
+      nd.wins += w + wg;
+      nd.visits += w + l + wg + lg;
+      nd.gw += wg;
+      nd.gv += wg + lg;
+      n = nd.parent;
+      int64_t t = w; w = l; l = t;               // a win here is a loss for the parent
+      t = wg; wg = lg; lg = t;
+    }
+  }
   void update_tree_losses(int32_t n, int64_t amount, bool go) {
     nodes[n].visits += amount;
     if (go) nodes[n].gv += amount;
@@ -238,6 +254,7 @@ struct Tree {
     ++evaluations;
     const bool blk = nodes[n].black;
     const int32_t base = static_cast<int32_t>(nodes.size());
+    int64_t up_w = 0, up_l = 0, up_wg = 0, up_lg = 0;   // what this expansion adds to n and its ancestors
     for (int j = 0; j < k; ++j) {                  // get_child: created (a winner's loss propagated) before the sort
       const uint8_t f = flags[j];
       const float p = prior[j];
@@ -247,8 +264,8 @@ struct Tree {
       if (f & kSeedWin) {                          // set_game_over_values + update_tree_losses(child)
         nodes[c].gameover = nodes[c].checked = 1;
         nodes[c].ws = 0;
-        nodes[c].gv = nodes[c].visits = 65536;
-        update_tree_losses(c, 1, true);
+        nodes[c].gv = nodes[c].visits = 65536 + 1;   // ... and its own share of update_tree_losses(child)
+        ++up_wg;                                     // the rest of it: update_tree_wins(parent, 1, gameover)
       }
     }
     crement_threads(n, -1);                        // assign_children
@@ -261,9 +278,9 @@ struct Tree {
         if (threat) {
           if (f & kSeedGameSaving) { nodes[c].visits = st[0]; nodes[c].wins = st[1]; nodes[c].gv = st[2]; nodes[c].gw = st[3]; next.push_back(c); }
           else if (f & kSeedDoomed) {              // set_game_over_values_1_step_lookahead + update_tree_wins(child)
-            nodes[c].visits = nodes[c].wins = nodes[c].gw = nodes[c].gv = 65536;
+            nodes[c].visits = nodes[c].wins = nodes[c].gw = nodes[c].gv = 65536 + 1;   // incl. update_tree_wins(child)
             nodes[c].ws = 1;
-            update_tree_wins(c, 1, true);
+            ++up_lg;                                 // -> update_tree_losses(parent, 1, gameover)
           }
         } else {
           if (!(f & kSeedWin)) { nodes[c].visits = st[0]; nodes[c].wins = st[1]; nodes[c].gv = st[2]; nodes[c].gw = st[3]; }
@@ -274,12 +291,15 @@ struct Tree {
       nodes[n].count = k;
       if (!threat) {
         for (int j = 0; j < k; ++j) next.push_back(base + j);
-        update_tree_losses(n, ev_l, false);        // eval_children
-        update_tree_wins(n, ev_w, false);
+        up_l += ev_l;                              // eval_children: update_tree_losses(n, L); update_tree_wins(n, W)
+        up_w += ev_w;
       }
+      propagate(n, up_w, up_l, up_wg, up_lg);
       update_win_status_from_children(n);
       backpropagate_num_checked_children(n);
       update_num_children_being_checked(n);
+    } else {
+      propagate(n, up_w, up_l, up_wg, up_lg);      // (children that were not attached still reported their results)
     }
   }
 
