@@ -194,6 +194,8 @@ int wann_tree_step(wann_ctx* ctx, int8_t* squares, uint8_t* black_to_move, int64
  *   (caller)           ONE wann_eval_expand_seeded call over those m rows (child_squares may be NULL);
  *   wann_forest_apply  attaches the children with the reference's seeds, propagates statistics and
  *                      win statuses, and leaves every tree ready for the next wann_forest_next.
+ * A forest is driven by ONE host thread (its entry points parallelise over the trees internally, see
+ * wann_host_threads); different forests may be driven by different threads on the same context.
  * Trees grown this way are node-for-node the trees the compiled reference grows single-threaded
  * (tests/golden/ref_tree_golden.npz).  Tie-break: children arrive ranked by prior, equal priors by
  * ascending move index (the reference's order for exact ties depends on its piece-list history). */
