@@ -388,11 +388,12 @@ def main():
         n_trees, sims = 1024, 10
         forest = SearchForest(sq_np[:n_trees], bl_np[:n_trees])
         forest.run(ev3, 1)                                          # warm-up: first expansions, lane allocation
+        nodes0 = sum(forest.info(t)["nodes"] for t in range(n_trees))
         barrier()
         t0 = time.perf_counter()
         fsteps, fevals = forest.run(ev3, sims)
         dt = time.perf_counter() - t0
-        nodes = sum(forest.info(t)["nodes"] for t in range(n_trees))
+        nodes = sum(forest.info(t)["nodes"] for t in range(n_trees)) - nodes0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         cnts = torch.tensor([fevals, nodes], dtype=torch.float64, device=dev)
         if world > 1:
