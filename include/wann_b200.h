@@ -220,7 +220,10 @@ int wann_forest_info(wann_forest* forest, int64_t tree, int64_t out[8]);
 /* Root reuse between moves (assign_root's "Reused old tree" branch + reset_thread_flag,
  * expansion_MCTS_functions.pyx:197-207,236-257): the child of the root reached by `move_index`
  * becomes the root of the tree's next search (its subtree, statistics and win statuses are kept, the
- * thread bookkeeping is cleared, the simulation count restarts).  Fails if the root has no such child. */
+ * thread bookkeeping is cleared, the simulation count restarts).  Fails if the root has no such child.
+ * If the root was never expanded (a move that is not in the tree: init_new_root, tree_builder.pyx:
+ * 809-897) it is expanded first -- the evaluations this needs are handed out by the following
+ * wann_forest_next calls like any others -- and the advance completes when they are done. */
 int wann_forest_advance(wann_forest* forest, int64_t tree, int move_index);
 
 /* Self-play step for the whole forest: every tree plays the move its search chose (wann_forest_info's

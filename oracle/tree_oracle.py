@@ -247,11 +247,13 @@ class ArrayTree(object):
             self.update_num_children_being_checked(n)
         return returned
 
-    def expand_descendants(self, leaf, depth, depth_limit):
-        """tree_builder.pyx:122-215 for a one-node frontier (what the tree always passes)."""
+    def expand_descendants(self, leaf, depth, depth_limit, no_root=False):
+        """tree_builder.pyx:122-215 for a one-node frontier (what the tree always passes).
+        no_root: sim_info['root'] is None (init_new_root runs before the root is assigned): the frontier
+        filter then ignores win statuses (:142-143,156-159)."""
         frontier = []
         while depth < depth_limit:
-            if self.ws[self.root] == -1:
+            if not no_root and self.ws[self.root] == -1:
                 if self.count[leaf] < 0 and self.ws[leaf] == -1:
                     frontier.append(leaf)
             elif self.count[leaf] < 0 and not self.gameover[leaf]:
@@ -314,6 +316,13 @@ class ArrayTree(object):
         reset_thread_flag (:197-207): the child reached by `move_index` becomes the root of the next
         search and the thread bookkeeping of its subtree is cleared.  (The reference also cuts the tree
         above the new root's grandparent, :259-266 -- memory housekeeping with no effect below the root.)"""
+        if self.count[self.root] < 0:
+            # init_new_root (tree_builder.pyx:809-897): the previous node was never expanded -- expand it
+            # now (threads_checking_node = 1, expand_descendants([parent], 0, 1) with sim_info['root'] still
+            # None), then continue as below.  (Its closing backpropagate_num_checked_children /
+            # update_win_status_from_children(new_subtree=True) only touch the parent and above.)
+            self.threads[self.root] = 1
+            self.expand_descendants(self.root, 0, 1, no_root=True)
         kid = [c for c in self.children(self.root) if self.index[c] == move_index]
         if not kid:
             raise KeyError("the root has no child for move index %d" % move_index)

@@ -122,6 +122,36 @@ def main():
             out["start%d_reuse_after15" % s] = dump(new_root)
             out["start%d_reuse_evals" % s] = np.int64(net.calls)
             out["start%d_reuse_next_move" % s] = np.int64(tsu.randomly_choose_a_winning_move(new_root)["index"])
+        # init_new_root (tree_builder.pyx:809-897): the position after a move that is NOT in the tree yet --
+        # the previous node was never expanded.  A fresh tree is searched 12 simulations, an UNEXPANDED child
+        # u of its root stands in for "our move", the opponent answers with u's lowest-index legal move:
+        # assign_root then expands u (with sim_info['root'] still None), finds the answer among u's new
+        # children and makes it the root; 10 simulations follow.
+        root3 = TreeNode(B.copy_game_board(board), list(wp), list(bp), color, 0, None, ply)
+        sim3 = tsu.SimulationInfo(io.StringIO())
+        sim3.update(time_to_think=10 ** 6, start_time=time.time(), root=root3, main_pid="not-this-thread")
+        net3 = Net()
+        for _ in range(12):
+            mc.run_MCTS_with_expansions_simulation(root3, 5, sim3, net3, sim3["start_time"], 10 ** 6, lock)
+        cands = [c for c in root3["children"] if c["children"] is None and not c["gameover"] and c["win_status"] is None]
+        if cands:
+            u = cands[-1]
+            legal = B.enumerate_legal_moves(u["game_board"], u["color"])
+            reply = min(legal, key=U.index_lookup_by_move)
+            nb = B.move_piece_update_piece_arrays(u["game_board"], reply, u["color"])[0]   # incl. the side-to-move keys
+            reply_color = "Black" if u["color"] == "White" else "White"
+            sim4 = tsu.SimulationInfo(io.StringIO())
+            sim4.update(time_to_think=10 ** 6, start_time=time.time(), main_pid="not-this-thread")
+            new_root = mc.assign_root(nb, reply_color, u, reply, ply + 2, net3, sim4, lock)
+            assert new_root["parent"] is u and new_root["index"] == U.index_lookup_by_move(reply)
+            sim4["root"] = new_root
+            mc.reset_thread_flag(new_root)
+            for _ in range(10):
+                mc.run_MCTS_with_expansions_simulation(new_root, 5, sim4, net3, sim4["start_time"], 10 ** 6, lock)
+            out["start%d_newroot_u" % s] = np.int64(u["index"])
+            out["start%d_newroot_reply" % s] = np.int64(new_root["index"])
+            out["start%d_newroot_after10" % s] = dump(new_root)
+            out["start%d_newroot_evals" % s] = np.int64(net3.calls)
         print("start", s, color, "ply", ply, "sims", done_sims, "evaluations", net.calls, "nodes",
               len(out["start%d_after%d" % (s, checkpoints[-1])]), "root win_status", root["win_status"])
     out["checkpoints"] = np.array(checkpoints)

@@ -308,6 +308,14 @@ def test_array_tree_restatement_reproduces_the_references_trees():
                 t.run_simulation()
             assert np.array_equal(t.dump(), g["start%d_reuse_after15" % s]) and t.evaluations == int(g["start%d_reuse_evals" % s])
             assert t.index[t.best_move()] == int(g["start%d_reuse_next_move" % s])
+            t2 = ArrayTree(g["start%d_squares" % s], int(g["start%d_black" % s]), O.synthetic_policy, height=height)
+            for _ in range(12):                      # a move that is not in the tree yet (init_new_root)
+                t2.run_simulation()
+            t2.advance_root(int(g["start%d_newroot_u" % s]))
+            t2.advance_root(int(g["start%d_newroot_reply" % s]))
+            for _ in range(10):
+                t2.run_simulation()
+            assert np.array_equal(t2.dump(), g["start%d_newroot_after10" % s]) and t2.evaluations == int(g["start%d_newroot_evals" % s])
     p = O.synthetic_policy(O.initial_squares(), 0)
     assert p.dtype == np.float32 and len(set(p.tolist())) == 155 and abs(float(p.sum()) - 1) < 1e-2
     assert np.array_equal((np.float32(1) + p).astype(np.float64), 1.0 + p.astype(np.float64))   # 1 + p exact in float32
@@ -359,6 +367,18 @@ def test_native_search_forest_reproduces_the_references_trees(lib_built):
             assert np.array_equal(forest.dump(s), g["start%d_reuse_after15" % s]), s
             assert forest.info(s)["move_index"] == int(g["start%d_reuse_next_move" % s])
             assert forest.info(s)["evaluations"] == int(g["start%d_reuse_evals" % s])
+    # a move that is NOT in the tree (init_new_root): 12 simulations, "our move" to an unexpanded child, the
+    # opponent's answer, 10 more simulations -- the evaluations of the late expansion come through next/apply
+    with wann_b200.SearchForest(sq[:3], bl[:3], heights=[0, 14, 31]) as forest:
+        forest.run(_CpuSeeds(), 12)
+        for s in range(3):
+            forest.advance(s, int(g["start%d_newroot_u" % s]))
+            assert forest.info(s)["nodes"] == 1                     # the unexpanded child is the whole tree now
+            forest.advance(s, int(g["start%d_newroot_reply" % s]))
+        forest.run(_CpuSeeds(), 10)
+        for s in range(3):
+            assert np.array_equal(forest.dump(s), g["start%d_newroot_after10" % s]), s
+            assert forest.info(s)["evaluations"] == int(g["start%d_newroot_evals" % s]) and forest.info(s)["simulations"] == 10
     with pytest.raises(wann_b200.WannError):
         f = wann_b200.SearchForest(sq, bl)
         f.next(1)

@@ -49,6 +49,8 @@ struct Tree {
   Phase phase = kIdle;
   int32_t ex_leaf = -1, ex_depth = 0, ex_limit = 0, pending = -1;
   bool ex_final = false;                        // the expansion run_simulation makes for a solved, childless root
+  bool ex_no_root = false;                      // init_new_root: sim_info['root'] is None while it expands
+  int pending_move = -1;                        // ... and the move to advance by once that expansion is done
   std::vector<int32_t> frontier;
   int64_t simulations = 0, evaluations = 0;
 
@@ -307,7 +309,7 @@ struct Tree {
   // node) or the expansion is over (returns -1).
   int32_t expand_run() {
     while (ex_depth < ex_limit) {
-      if (nodes[root].ws == -1) { if (nodes[ex_leaf].count < 0 && nodes[ex_leaf].ws == -1) frontier.push_back(ex_leaf); }
+      if (!ex_no_root && nodes[root].ws == -1) { if (nodes[ex_leaf].count < 0 && nodes[ex_leaf].ws == -1) frontier.push_back(ex_leaf); }
       else if (nodes[ex_leaf].count < 0 && !nodes[ex_leaf].gameover) frontier.push_back(ex_leaf);
       if (!frontier.empty()) {                     // (the reference's 0 < len < 256; a frontier has one node)
         ex_limit = 800;
@@ -355,6 +357,14 @@ struct Tree {
       if (phase == kWaitEval) {                    // continue the expansion that was interrupted
         const int32_t need = expand_run();
         if (need >= 0) return need;
+        if (pending_move >= 0) {                   // init_new_root's expansion is done: now reuse the child
+          const int mv = pending_move;
+          pending_move = -1;
+          ex_no_root = ex_final = false;
+          phase = kIdle;
+          if (!advance_root(mv)) phase = kFinished;   // (a position without that move: nothing to search)
+          continue;
+        }
         if (!ex_final) {                           // tail of run_MCTS_with_expansions_simulation
           const bool done = nodes[root].checked || nodes[root].ws != -1;
           if (done && nodes[root].count < 0) {
@@ -397,7 +407,22 @@ struct Tree {
   // ---- root reuse between moves: assign_root's "Reused old tree" branch (expansion_MCTS_functions.pyx:
   // 236-247,253-257) + reset_thread_flag (:197-207).  Returns false if the root has no such child.
   bool advance_root(int move_index) {
-    if (phase == kWaitEval || nodes[root].count < 0) return false;
+    if (phase == kWaitEval) return false;
+    if (nodes[root].count < 0) {
+      // init_new_root (tree_builder.pyx:809-897): the previous node was never expanded.  Expand it first
+      // (threads_checking_node = 1; expand_descendants([parent], 0, 1) with sim_info['root'] still None);
+      // the evaluations go through the usual next / apply cycle and the advance completes when they are
+      // done.  (Its closing backpropagate_num_checked_children / update_win_status_from_children
+      // (new_subtree=True) only touch the parent and above.)
+      if (nodes[root].gameover) return false;
+      nodes[root].threads = 1;
+      expand_begin(root, 0, 1);
+      ex_no_root = true;
+      ex_final = true;
+      pending_move = move_index;
+      phase = kWaitEval;
+      return true;
+    }
     int32_t kid = -1;
     for (int32_t c = nodes[root].first; c < nodes[root].first + nodes[root].count; ++c)
       if (nodes[c].index == move_index) { kid = c; break; }
