@@ -423,6 +423,12 @@ def test_search_forest_self_play_follows_the_restatement(lib_built):
                     m.advance_root(int(moves[i]))
             finished_games += int(fin.sum())
         assert finished_games >= 2 and done[1] and done[2]
+        # a time budget instead of a simulation count (the reference's time_to_think): when it returns every
+        # tree is between two simulations, so moves can be played
+        steps, evals = forest.run_for(_CpuSeeds(), 0.3)
+        assert steps > 0 and evals > 0 and len(forest.next(0)[0]) == 0
+        moves, fin = forest.play()
+        assert (moves != 255).all()
         root0 = forest.dump(0)
         assert root0[0, 0] == -1 and forest.info(0)["nodes"] == len(root0)   # compacted: only the reused subtree is kept
 

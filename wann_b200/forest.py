@@ -89,6 +89,29 @@ class SearchForest(object):
             steps += 1
             evals += len(sq)
 
+    def run_for(self, evaluator, seconds):
+        """Time-budgeted search, the reference's `time_to_think` (MCTS_with_expansions,
+        expansion_MCTS_functions.pyx:113-119): lock steps until `seconds` have passed, then the
+        simulations in flight are finished (no new ones start), so that every tree is between two
+        simulations when this returns.  -> (steps, evaluations)."""
+        import time
+        t_end = time.perf_counter() + float(seconds)
+        steps = evals = 0
+        budget = 1 << 60
+        while True:
+            if budget and time.perf_counter() >= t_end:
+                budget = 0                                   # drain: continue, but start nothing new
+            sq, bl, _ = self.next(budget)
+            if len(sq) == 0:
+                if budget == 0:
+                    return steps, evals
+                budget = 0
+                continue
+            idx, pri, cnt, _, flg, st, ps = evaluator.eval_expand_seeded(sq, bl, with_children=False)
+            self.apply(idx, pri, cnt, flg, st, ps)
+            steps += 1
+            evals += len(sq)
+
     def advance(self, tree, move_index):
         """Root reuse: the child reached by `move_index` becomes the root of tree's next search."""
         L.check(self._lib.wann_forest_advance(self._f, int(tree), int(move_index)))
