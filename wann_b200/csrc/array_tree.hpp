@@ -21,44 +21,12 @@
 #include <stdint.h>
 
 #include <cmath>
-#include <cstdlib>
 #include <cstring>
-#include <new>
-#include <utility>
 #include <vector>
 
 namespace wann_tree {
 
 constexpr int kMaxLegal = 48;
-
-// Growable array of trivially copyable records on realloc(): a large block grows through mremap, i.e.
-// without copying (or re-faulting) what is already there -- a std::vector doubles by allocate + copy,
-// which for millions of 72-byte nodes per second is most of the memory traffic of the tree code.
-template <typename T>
-struct PodVec {
-  T* p = nullptr;
-  size_t n = 0, cap = 0;
-  PodVec() = default;
-  PodVec(const PodVec&) = delete;
-  PodVec& operator=(const PodVec&) = delete;
-  PodVec(PodVec&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
-  PodVec& operator=(PodVec&& o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
-  ~PodVec() { free(p); }
-  size_t size() const { return n; }
-  T& operator[](size_t i) { return p[i]; }
-  const T& operator[](size_t i) const { return p[i]; }
-  void reserve(size_t want) {
-    if (want <= cap) return;
-    size_t c = cap ? cap : 64;
-    while (c < want) c *= 2;
-    T* q = static_cast<T*>(realloc(p, c * sizeof(T)));
-    if (q == nullptr) throw std::bad_alloc();
-    p = q;
-    cap = c;
-  }
-  void push_back(const T& v) { if (n == cap) reserve(n + 1); p[n++] = v; }
-  void swap(PodVec& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
-};
 enum : uint8_t { kSeedWin = 1, kSeedCapture = 2, kSeedCloseToHome = 4, kSeedGameSaving = 8, kSeedDoomed = 16, kSeedEvalOne = 32 };
 
 struct Tree {
@@ -73,7 +41,7 @@ struct Tree {
     int8_t ws;                                  // -1 None / 0 False / 1 True
     uint8_t index, black, gameover, checked, being_checked, uct_f32;
   };
-  PodVec<Node> nodes;
+  std::vector<Node> nodes;
   std::vector<int8_t> boards;
   int32_t root = 0;
   // ---- resumable state ---------------------------------------------------------------------------
@@ -83,7 +51,7 @@ struct Tree {
   bool ex_final = false;                        // the expansion run_simulation makes for a solved, childless root
   bool ex_no_root = false;                      // init_new_root: sim_info['root'] is None while it expands
   int pending_move = -1;                        // ... and the move to advance by once that expansion is done
-  std::vector<int32_t> frontier, scratch;
+  std::vector<int32_t> frontier;
   int64_t simulations = 0, evaluations = 0;
 
   int32_t new_node(int32_t par, int idx, bool blk, int32_t h, double u, bool u_f32) {
@@ -289,7 +257,6 @@ struct Tree {
     const bool blk = nodes[n].black;
     const int32_t base = static_cast<int32_t>(nodes.size());
     int64_t up_w = 0, up_l = 0, up_wg = 0, up_lg = 0;   // what this expansion adds to n and its ancestors
-    nodes.reserve(nodes.size() + static_cast<size_t>(k));
     for (int j = 0; j < k; ++j) {                  // get_child: created (a winner's loss propagated) before the sort
       const uint8_t f = flags[j];
       const float p = prior[j];
@@ -369,7 +336,7 @@ struct Tree {
   // continuation after the evaluation of `pending`
   void expand_resume(const uint8_t* idx, const float* prior, int k, const uint8_t* flags, const int32_t* stats,
                      bool threat) {
-    std::vector<int32_t>& kids = scratch;
+    std::vector<int32_t> kids;
     expand_one(pending, idx, prior, k, flags, stats, threat, kids);
     frontier.clear();
     if (ex_depth + 1 < ex_limit && !kids.empty()) {
@@ -464,7 +431,7 @@ struct Tree {
     // grandparent, :259-266; nothing above the root influences the search below it): breadth-first
     // copy, so that the children of a node stay contiguous.  Thread bookkeeping is cleared on the way.
     board_of(kid);                               // its position, before its parent disappears
-    PodVec<Node> kept;
+    std::vector<Node> kept;
     std::vector<int8_t> kept_boards;
     std::vector<int32_t> order(1, kid);
     kept.reserve(1024);
