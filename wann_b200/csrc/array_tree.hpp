@@ -67,6 +67,8 @@ struct Tree {
     return static_cast<int32_t>(nodes.size()) - 1;
   }
   void init(const int8_t* squares, bool blk, int32_t h) {
+    nodes.reserve(16384);                        // address space only (pages are touched as nodes arrive): the
+                                                 // first ~700 evaluations of a search never re-allocate / copy
     root = new_node(-1, 0, blk, h, 1.0, false);
     nodes[root].board = 0;
     boards.assign(squares, squares + 64);
@@ -434,7 +436,7 @@ struct Tree {
     std::vector<Node> kept;
     std::vector<int8_t> kept_boards;
     std::vector<int32_t> order(1, kid);
-    kept.reserve(1024);
+    kept.reserve(16384);
     for (size_t i = 0; i < order.size(); ++i) {
       Node nd = nodes[order[i]];
       nd.threads = 0;
