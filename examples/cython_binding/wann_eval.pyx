@@ -29,7 +29,7 @@ cdef class PolicyNet:
     def __cinit__(self):
         self.ctx = NULL
 
-    def __init__(self, dict weights, int device=0, int mode=W.WANN_MODE_FP16, int final_kernel=1,
+    def __init__(self, dict weights, int device=0, int mode=W.WANN_MODE_FP16C, int final_kernel=1,
                  double refine_margin=0.02):
         cdef W.wann_weights w
         cdef cnp.ndarray a

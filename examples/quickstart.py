@@ -21,13 +21,15 @@ sq, black = synthetic.random_positions(4096, seed=0)
 # 1. reference surface: list of node dicts -> ndarray [N,155] float32 (MCTS.pyx:85-127)
 nodes = [{"game_board": boards.squares_to_board(s, 0 if b else 1), "color": "Black" if b else "White"}
          for s, b in zip(sq[:8], black[:8])]
-with wann_b200.NeuralNetsCombined_128() as policy_net:
+# (no weights given -> $WANN_B200_CHECKPOINT / $WANN_B200_FROZEN_GRAPH; here: the synthetic preset, explicitly)
+weights = wann_b200.weights.synthetic("trained_like", 1, final_kernel=1)
+with wann_b200.NeuralNetsCombined_128(weights) as policy_net:
     probs = policy_net.evaluate(nodes)
     best = [boards.move_lookup_by_index(int(i), n["color"]) for i, n in zip(probs.argmax(1), nodes)]
     print("evaluate():", probs.shape, probs.dtype, "argmax moves", best[:4])
 
 # 2. array API: ranked legal children (indices in the reference's 155-move alphabet, priors)
-with wann_b200.PolicyEvaluator(mode="fp16") as ev:
+with wann_b200.PolicyEvaluator(wann_b200.weights.synthetic("trained_like", 1), mode="fp16c") as ev:
     idx, prior, n_legal = ev.eval_topk(sq, black)
     print("eval_topk(): policy moves", idx[:4, 0], "priors", np.round(prior[:4, 0], 3), "legal", n_legal[:4])
 
@@ -44,7 +46,7 @@ with wann_b200.PolicyEvaluator(mode="fp16") as ev:
           "| parent gained", parent[0, :4].tolist(), "win_status", int(parent[0, 4]))
 
 # 5. many searches at once: array-based trees with the reference's search semantics, one GPU call per lock step
-with wann_b200.PolicyEvaluator(mode="fp16", refine_margin=0.02) as ev, \
+with wann_b200.PolicyEvaluator(wann_b200.weights.synthetic("trained_like", 1), mode="fp16c", refine_margin=0.02) as ev, \
         wann_b200.SearchForest(sq[:256], black[:256]) as forest:
     steps, evals = forest.run(ev, simulations=5)
     info = forest.info(0)

@@ -55,9 +55,15 @@ enum wann_mode {
   WANN_MODE_FP32 = 1, /* CUDA-core fp32 path (accuracy mode, validation) */
   WANN_MODE_FP16 = 2, /* tcgen05 path with fp16 operands (same speed as BF16, 3 more mantissa
                          bits; activations saturate at 65504) */
-  WANN_MODE_FP32_TC = 3 /* fp32-class accuracy ON the tensor cores: operands split into fp16
+  WANN_MODE_FP32_TC = 3, /* fp32-class accuracy ON the tensor cores: operands split into fp16
                          hi + lo/4096 pairs, 3 MMAs per K-step, fp32 accumulate (about a third
                          of the BF16 throughput, ~20x the CUDA-core FP32 mode) */
+  WANN_MODE_FP16C = 4   /* "centred" fp16: the FP16 kernel at the same MMA count with its rounding error
+                         roughly halved -- activations are stored as a - c (c = calibrated per-bucket mean,
+                         the sign bit of fp16 is no longer wasted on non-negative ReLU outputs; the halo
+                         holds -c and the next bias absorbs sum(w*c)), conv1 and conv5 see their weights
+                         as fp16 hi + lo pairs in spare K / N slots.  Option "split_layers" adds lo weight
+                         stages to chosen 192->192 layers (2 MMAs per K-step there). */
 };
 
 enum wann_mem { WANN_MEM_HOST = 0, WANN_MEM_DEVICE = 1 };
@@ -127,9 +133,15 @@ int wann_eval_planes(wann_ctx* ctx, const void* planes, int planes_dtype, int64_
  * softmax-155 probabilities, sorted by prior descending (ties: ascending index), padded
  * with 255 / 0; n_legal uint8 [n].  idx[.][0] is the policy move of get_best_move
  * (board_utils.pyx:262-277).  DEVICE idx / prior buffers must be 16-byte aligned (rows are
- * written as 16-byte vectors). */
+ * written as 16-byte vectors).
+ * k: keep only the k best legal children per position -- num_top of get_top_children
+ * (board_utils.pyx:279-291), num_to_keep of the pruning branch (tree_builder.pyx:585-609,
+ * TreeNode.pyx:18).  k = 0 (like num_top = 0), or any k outside 1..47, keeps every legal child.
+ * With 1 <= k <= 47 the entries from k on are padding (255 / 0) and n_legal = min(legal moves, k),
+ * so wann_eval_expand / _expand_seeded build and seed the kept children only (the parent summary
+ * then covers the kept children, as update_win_status_from_children does after pruning). */
 int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
-                   int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal, int mem,
+                   int64_t n, int k, uint8_t* idx, float* prior, uint8_t* n_legal, int mem,
                    void* stream);
 
 /* wann_eval_topk + child construction in one call (no host round trip between them): for every
@@ -141,7 +153,7 @@ int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to
  * move_piece_update_piece_arrays (board_utils.pyx:90-131) and check_for_winning_move
  * (tree_builder.pyx:902-905). */
 int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
-                     int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal,
+                     int64_t n, int k, uint8_t* idx, float* prior, uint8_t* n_legal,
                      int8_t* child_squares, uint8_t* child_flags, int mem, void* stream);
 
 /* wann_eval_expand + CHILD SEEDING: everything the reference derives from the priors right after
@@ -164,7 +176,7 @@ int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_
  * The propagation ABOVE the parent is the tree's business.  child_squares may be NULL (seeds only).
  * DEVICE child_stats / parent_summary must be 16-byte aligned. */
 int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
-                            int64_t n, uint8_t* idx, float* prior, uint8_t* n_legal,
+                            int64_t n, int k, uint8_t* idx, float* prior, uint8_t* n_legal,
                             int8_t* child_squares, uint8_t* child_flags, int32_t* child_stats,
                             int32_t* parent_summary, int mem, void* stream);
 
@@ -252,6 +264,13 @@ int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* 
  * [4h+3][k] epilogue end (int64 [8][64]).  Host pointers; n <= chunk. */
 int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
                        int64_t n, int64_t* stamps);
+
+/* Test/inspection hook (WANN_MODE_FP16C): the calibrated centring of the context's weights --
+ * offsets[l*8 + j] = offset of the stored output of hidden layer l+1 for channel positions q with
+ * q % 8 == j (exact fp16 values), position_of[l*192 + c] = position of TF channel c in the kernel's
+ * layout, kappa[9] (optional) = what the centring of layer 4 took out of each tap product of
+ * hidden_layer/5.  The emulation in tests/ uses it to reproduce the kernel's roundings. */
+int wann_debug_centering(wann_ctx* ctx, float offsets[32], uint8_t position_of[768], float kappa[9]);
 
 /* Measurement hook: with option "time_kernels" = 1 every conv-stack kernel launch is bracketed
  * by CUDA events on its own stream; this call synchronises the device and returns

@@ -16,6 +16,7 @@ cdef extern from "wann_b200.h" nogil:
     enum: WANN_MODE_FP32
     enum: WANN_MODE_FP16
     enum: WANN_MODE_FP32_TC
+    enum: WANN_MODE_FP16C
     enum: WANN_MEM_HOST
     enum: WANN_MEM_DEVICE
     enum: WANN_PLANES_I8
@@ -43,12 +44,12 @@ cdef extern from "wann_b200.h" nogil:
                         float* probs, float* logits, int mem, void* stream)
     int wann_eval_planes(wann_ctx* ctx, const void* planes, int planes_dtype, int64_t n,
                          float* probs, float* logits, int mem, void* stream)
-    int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n,
+    int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n, int k,
                        uint8_t* idx, float* prior, uint8_t* n_legal, int mem, void* stream)
-    int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n,
+    int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n, int k,
                          uint8_t* idx, float* prior, uint8_t* n_legal, int8_t* child_squares,
                          uint8_t* child_flags, int mem, void* stream)
-    int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n,
+    int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n, int k,
                                 uint8_t* idx, float* prior, uint8_t* n_legal, int8_t* child_squares,
                                 uint8_t* child_flags, int32_t* child_stats, int32_t* parent_summary,
                                 int mem, void* stream)
@@ -58,6 +59,7 @@ cdef extern from "wann_b200.h" nogil:
                                int64_t n, int layer, float* out, int mem)
     int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
                            int64_t n, int64_t* stamps)
+    int wann_debug_centering(wann_ctx* ctx, float* offsets, uint8_t* position_of, float* kappa)
     int wann_kernel_times(wann_ctx* ctx, double* out)
     uint32_t wann_crc32c(const void* data, uint64_t nbytes, uint32_t seed)
     int wann_host_alloc(void** ptr, uint64_t nbytes)

@@ -453,6 +453,69 @@ def forward_16bit_emulated(planes, weights, fmt="bf16", return_all=False):
     return logits, probs
 
 
+def forward_fp16c_emulated(planes, weights, offsets, position_of, split_mask=0, return_all=False):
+    """Emulation of the roundings of the CENTRED fp16 tensor-core mode (WANN_MODE_FP16C,
+    wann_b200/csrc/conv_stack_tc.cuh) for the same graph as forward_fp32
+    (policy_net_utils.pyx:106-124,149-178,215-239).  offsets [4,8] / position_of [4,192] are the
+    calibrated centring of the context (wann_debug_centering): channel c of hidden layer l sits at
+    position q = position_of[l-1][c] and is stored as a' = fp16(relu(z) - offsets[l-1][q % 8]); the
+    zero padding of the next conv therefore reads -offset, and that layer's bias absorbs
+    sum(w * offset) with the TRUE fp32 weights.  hidden_layer/1 and /5 see their weights as fp16
+    hi + lo pairs (22 bits), layers in split_mask (bits 1..3 = hidden_layer/2..4) too; the other
+    layers round their weights to fp16.  Accumulation, bias and ReLU in fp32; FC/softmax in fp32."""
+    def two16(w):                     # hi + lo/4096 pair, as the kernel's conv1 / conv5 operands
+        hi = f16_round(w)
+        return hi + f16_round((w - hi) * 4096.0) / np.float32(4096.0)
+    def hilo(w):                      # hi + unscaled lo stage of a split 192->192 layer
+        hi = f16_round(w)
+        return hi + f16_round(w - hi)
+    offsets = np.asarray(offsets, np.float32)
+    position_of = np.asarray(position_of)
+    x = np.asarray(planes).astype(np.float32)        # exact in fp16
+    acts = []
+    c_prev = None
+    for i in range(1, 6):
+        w = weights["hidden_layer/%d/weights" % i].astype(np.float32)
+        b = weights["hidden_layer/%d/bias" % i].astype(np.float64)
+        if i == 1 or i == 5 or (split_mask >> (i - 1)) & 1:
+            w16 = two16(w) if i in (1, 5) else hilo(w)
+        else:
+            w16 = f16_round(w)
+        if c_prev is None:
+            z = conv2d_same_nhwc(x, w16, np.float32)
+        else:
+            n, hh, ww, cin = x.shape
+            xp = np.empty((n, hh + 2, ww + 2, cin), np.float32)
+            xp[:] = -c_prev                              # the halo holds -offset
+            xp[:, 1:-1, 1:-1, :] = x
+            kh = w16.shape[0]
+            if kh == 1:
+                z = x.reshape(-1, cin) @ w16.reshape(cin, -1)
+                z = z.reshape(n, hh, ww, -1)
+                b = b + (w.reshape(cin, -1).astype(np.float64) * c_prev[:, None].astype(np.float64)).sum(0)
+            else:
+                cols = np.concatenate([xp[:, dy:dy + hh, dx:dx + ww, :] for dy in range(3) for dx in range(3)], axis=-1)
+                z = (cols.reshape(-1, 9 * cin) @ w16.reshape(9 * cin, -1)).reshape(n, hh, ww, -1)
+                b = b + (w.astype(np.float64) * c_prev[None, None, :, None].astype(np.float64)).sum(axis=(0, 1, 2))
+        if i < 5:
+            c = offsets[i - 1][position_of[i - 1] % 8].astype(np.float32)      # per TF channel
+            t = z + (b - c.astype(np.float64)).astype(np.float32)
+            x = f16_round(np.maximum(t, -c))                                   # a' = relu(z + b') - c
+            acts.append(x + c)
+            c_prev = c
+        else:
+            x = np.maximum(z + b.astype(np.float32), 0).astype(np.float32)
+            acts.append(x)
+    h = x.reshape(-1, 64)
+    logits = h @ weights["output_layer/weights"] + weights["output_layer/bias"]
+    zz = logits - logits.max(axis=1, keepdims=True)
+    e = np.exp(zz)
+    probs = e / e.sum(axis=1, keepdims=True)
+    if return_all:
+        return logits, probs, acts
+    return logits, probs
+
+
 # ----------------------------------------------------------------------------
 # Child construction (SURVEY 8f-1): get_child / get_child_attributes
 # (monte_carlo_tree_search/tree_builder.pyx:530-537, 623-658),

@@ -504,11 +504,12 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"(from|import)\s+oracle|oracle[./\\]|liboracle|oracle_", src), f
 
 
-def test_no_cpu_fallback_without_gpu(lib_built):
+def test_no_cpu_fallback_without_gpu(lib_built, monkeypatch):
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     import wann_b200
+    monkeypatch.setenv("WANN_B200_SYNTHETIC", "1")
     with pytest.raises(wann_b200.WannError):
         wann_b200.PolicyEvaluator()
     with pytest.raises(wann_b200.WannError):
@@ -595,7 +596,7 @@ def test_multi_gpu_evaluator_shards_by_position_with_fake_devices():
             out[:] = sq[:, :1].astype(np.float32) + 1000 * self.dev          # row id + which device served it
             return (out, out * 2) if return_logits else out
 
-        def eval_topk(self, sq, bl, out=None):
+        def eval_topk(self, sq, bl, out=None, k=0):
             out[0][:] = self.dev
             out[1][:] = sq[:, :1]
             out[2][:] = 7
@@ -727,3 +728,86 @@ def test_bulk_board_conversion_equals_per_square_conversion(golden):
     bad[3]["c"] = "x"
     with pytest.raises(ValueError):
         boards.boards_to_squares([bad])
+
+
+def test_missing_checkpoint_fails_loudly_and_dual_net_bundles_load_by_scope(tmp_path, monkeypatch):
+    """(1) the reference-shaped constructors must not fall back to random weights silently
+    (the reference fails when its checkpoint is missing, policy_net_utils.pyx:68-73); (2) the dual-net
+    bundles keep their variables under 'white_net/' and 'black_net/' (policy_net_utils.pyx:22-25,43-46)."""
+    from wann_b200 import weights as W, tf_bundle
+    for k in ("WANN_B200_CHECKPOINT", "WANN_B200_FROZEN_GRAPH", "WANN_B200_SYNTHETIC"):
+        monkeypatch.delenv(k, raising=False)
+    with pytest.raises(W.MissingCheckpoint):
+        W.default_weights()
+    monkeypatch.setenv("WANN_B200_SYNTHETIC", "1")
+    assert np.array_equal(W.default_weights()["output_layer/bias"], W.synthetic("trained_like", 1)["output_layer/bias"])
+    monkeypatch.delenv("WANN_B200_SYNTHETIC")
+    white, black = W.synthetic("trained_like", 3, final_kernel=1), W.synthetic("trained_like", 4, final_kernel=1)
+    both = {"white_net/" + k: v for k, v in white.items()}
+    both.update({"black_net/" + k: v for k, v in black.items()})
+    prefix = str(tmp_path / "dual")
+    tf_bundle.save_policy_weights(prefix, both)
+    monkeypatch.setenv("WANN_B200_CHECKPOINT", prefix)
+    got_w = W.default_weights(scope="white_net/", final_kernel=1)
+    got_b = W.default_weights(scope="black_net/", final_kernel=1)
+    for k in white:
+        assert np.array_equal(got_w[k], white[k]) and np.array_equal(got_b[k], black[k])
+    assert not np.array_equal(got_w["hidden_layer/2/weights"], got_b["hidden_layer/2/weights"])
+    with pytest.raises(KeyError):
+        W.default_weights(scope="", final_kernel=1)             # no unscoped net in a dual bundle
+    single = str(tmp_path / "single")                           # a single-net bundle serves both colours
+    tf_bundle.save_policy_weights(single, white)
+    monkeypatch.setenv("WANN_B200_CHECKPOINT", single)
+    assert np.array_equal(W.default_weights(scope="black_net/", final_kernel=1)["output_layer/weights"],
+                          white["output_layer/weights"])
+
+
+def test_centred_fp16_emulation_halves_the_fp16_error():
+    """The arithmetic idea behind WANN_MODE_FP16C, on the CPU: storing ReLU outputs as a - c (c = bucket
+    mean, halo = -c, bias absorbs sum(w*c)) and giving hidden_layer/1 and /5 their weights as hi + lo
+    pairs roughly halves the error of plain fp16 operands; split layers reduce it further."""
+    from wann_b200 import weights as W
+    w = W.synthetic("trained_like", 1)
+    sq, bl = O.random_positions_fast(192, seed=11)
+    planes = O.encode_planes(sq, bl)
+    lg, pr, acts = O.forward_fp32(planes, w, return_all=True)
+    off = np.zeros((4, 8), np.float32)
+    pos = np.zeros((4, 192), np.uint8)
+    for l in range(4):                                          # the calibration of wann_api.cu, restated
+        m = acts[l].reshape(-1, 192).astype(np.float64).mean(0)
+        order = np.argsort(m, kind="stable")
+        for j in range(8):
+            pos[l][order[j * 24:(j + 1) * 24]] = 8 * np.arange(24) + j
+            off[l][j] = np.float32(np.float16(m[order[j * 24:(j + 1) * 24]].mean()))
+    rms = lambda d: float(np.sqrt((d.astype(np.float64) ** 2).mean()) / lg.std())   # noqa: E731
+    e_plain = rms(O.forward_16bit_emulated(planes, w, "fp16")[0] - lg)
+    e_zero = rms(O.forward_fp16c_emulated(planes, w, np.zeros((4, 8), np.float32), np.tile(np.arange(192, dtype=np.uint8), (4, 1)))[0] - lg)
+    e_cen = rms(O.forward_fp16c_emulated(planes, w, off, pos)[0] - lg)
+    e_split = rms(O.forward_fp16c_emulated(planes, w, off, pos, split_mask=14)[0] - lg)
+    assert e_zero < e_plain and e_cen < 0.65 * e_plain and e_split < 0.8 * e_cen, (e_plain, e_zero, e_cen, e_split)
+    assert e_cen < 1e-3
+
+
+def test_shim_turns_valid_planes_back_into_boards():
+    """sess.run(y_pred, {X: planes}) / evaluate(already_converted=True): valid P/O/E/1 planes take the
+    boards path (refinement + coalescing apply), anything else is evaluated as planes."""
+    from wann_b200 import session
+
+    class Fake(object):
+        def eval_probs(self, sq, bl):
+            return ("boards", sq.copy(), bl.copy())
+
+        def eval_planes(self, p):
+            return ("planes", p)
+    sq, bl = O.random_positions_fast(40, seed=3)
+    planes = O.encode_planes(sq, bl)
+    kind, got_sq, got_bl = session.eval_planes_as_boards(Fake(), planes)
+    assert kind == "boards" and not got_bl.any()
+    assert np.array_equal(O.encode_planes(got_sq, got_bl), planes)        # the same network input
+    assert session.eval_planes_as_boards(Fake(), planes.astype(np.float32))[0] == "boards"
+    soft = planes.astype(np.float32)
+    soft[0, 0, 0, 0] = 0.5
+    assert session.eval_planes_as_boards(Fake(), soft)[0] == "planes"
+    bad = planes.copy()
+    bad[1, 2, 3, 3] = 0
+    assert session.eval_planes_as_boards(Fake(), bad)[0] == "planes"

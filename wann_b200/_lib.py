@@ -8,7 +8,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwann_b200.so")
 
-MODE_BF16, MODE_FP32, MODE_FP16, MODE_FP32_TC = 0, 1, 2, 3
+MODE_BF16, MODE_FP32, MODE_FP16, MODE_FP32_TC, MODE_FP16C = 0, 1, 2, 3, 4
+MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "fp16": MODE_FP16, "fp32_tc": MODE_FP32_TC, "fp16c": MODE_FP16C}
 MEM_HOST, MEM_DEVICE = 0, 1
 PLANES_I8, PLANES_F32 = 0, 1
 N_MOVES, MAX_LEGAL = 155, 48
@@ -16,7 +17,7 @@ N_MOVES, MAX_LEGAL = 155, 48
 EXPORTS = [
     "wann_create", "wann_set_weights", "wann_destroy", "wann_last_error", "wann_encode", "wann_legal_mask",
     "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_eval_expand", "wann_eval_expand_seeded", "wann_tree_step", "wann_debug_activations",
-    "wann_debug_profile", "wann_kernel_times", "wann_crc32c",
+    "wann_debug_profile", "wann_debug_centering", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
     "wann_forest_create", "wann_forest_destroy", "wann_forest_next", "wann_forest_apply", "wann_forest_info",
     "wann_forest_dump", "wann_forest_advance", "wann_forest_play", "wann_host_threads",
@@ -53,9 +54,9 @@ def load():
     lib.wann_legal_mask.argtypes = [vp, vp, vp, i64, vp, ci, vp]
     lib.wann_eval_probs.argtypes = [vp, vp, vp, i64, vp, vp, ci, vp]
     lib.wann_eval_planes.argtypes = [vp, vp, ci, i64, vp, vp, ci, vp]
-    lib.wann_eval_topk.argtypes = [vp, vp, vp, i64, vp, vp, vp, ci, vp]
-    lib.wann_eval_expand.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, ci, vp]
-    lib.wann_eval_expand_seeded.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+    lib.wann_eval_topk.argtypes = [vp, vp, vp, i64, ci, vp, vp, vp, ci, vp]
+    lib.wann_eval_expand.argtypes = [vp, vp, vp, i64, ci, vp, vp, vp, vp, vp, ci, vp]
+    lib.wann_eval_expand_seeded.argtypes = [vp, vp, vp, i64, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
     lib.wann_host_threads.argtypes = [ci]
     lib.wann_forest_create.argtypes = [i64, vp, vp, vp, ctypes.POINTER(vp)]
     lib.wann_forest_destroy.argtypes = [vp]
@@ -70,6 +71,7 @@ def load():
     lib.wann_tree_step.argtypes = [vp, vp, vp, i64, ci, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp]
     lib.wann_debug_activations.argtypes = [vp, vp, vp, i64, ci, vp, ci]
     lib.wann_debug_profile.argtypes = [vp, vp, vp, i64, vp]
+    lib.wann_debug_centering.argtypes = [vp, vp, vp, vp]
     lib.wann_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 2)]
     lib.wann_crc32c.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint32]
     lib.wann_crc32c.restype = ctypes.c_uint32

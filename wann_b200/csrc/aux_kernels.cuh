@@ -156,6 +156,7 @@ struct TailParams {
   uint8_t* idx;             // [n][48] or null
   float* prior;             // [n][48]
   uint8_t* n_legal;         // [n]
+  int top_k = kMaxLegal;    // keep the best top_k legal children per position (num_top / num_to_keep of the reference)
   // margin refinement (wann_set_option "refine_margin_milli"):
   //   flagging pass: boards whose two best LEGAL priors are closer than the margin
   //                  (p2 >= p1 * refine_ratio, refine_ratio = exp(-margin)) are appended to
@@ -300,8 +301,9 @@ __device__ __forceinline__ void tail_group(const TailParams& p, const float* __r
               const float other = cp[o];
               rank += (other > me) || (other == me && o < c);
             }
-            ri[rank] = cj[c];
-            rp[rank] = me;
+            const bool keep = rank < p.top_k;       // pruned children read as padding
+            ri[rank] = keep ? cj[c] : static_cast<uint8_t>(255);
+            rp[rank] = keep ? me : 0.f;
             if (flagging && rank < 2) cp[kMaxLegal + rank] = me;   // the two best legal priors
           } else {
             ri[c] = 255;
@@ -316,7 +318,7 @@ __device__ __forceinline__ void tail_group(const TailParams& p, const float* __r
         else if (lane < 15)
           reinterpret_cast<uint4*>(p.idx + board * kMaxLegal)[lane - 12] = reinterpret_cast<const uint4*>(ri)[lane - 12];
         else if (lane == 15)
-          p.n_legal[board] = static_cast<uint8_t>(cnt);
+          p.n_legal[board] = static_cast<uint8_t>(min(cnt, p.top_k));
       }
       if (flagging && lane == 0 && cnt >= 2 && cp[kMaxLegal + 1] >= cp[kMaxLegal] * p.refine_ratio) {
         p.refine_list[atomicAdd(p.refine_count, 1)] = static_cast<int>(board);

@@ -33,7 +33,7 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_stack_split_kernel(const TcParams p) {
   constexpr uint32_t kIdescN192 = ptx::make_idesc_16bit(256, 192, true);
-  constexpr uint32_t kIdescN16 = ptx::make_idesc_16bit(256, 16, true);
+  constexpr uint32_t kIdescN32 = ptx::make_idesc_16bit(256, 32, true);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t a_base = smem_base + kOffA;
@@ -122,7 +122,7 @@ conv_stack_split_kernel(const TcParams p) {
     const uint32_t a_hi_desc = (kRowStride >> 4) | (1u << 14);
     const uint32_t b_hi_desc = (kSboB >> 4) | (1u << 14);
     const uint32_t a_lo_hi = (a_base >> 4) | ((kChunkStride >> 4) << 16);                  // tile 0: hi parts
-    const uint32_t a_lo_lo = ((a_base + kATileBytes) >> 4) | ((kChunkStride >> 4) << 16);  // tile 1: lo parts
+    const uint32_t a_lo_lo = ((a_base + kATileStride) >> 4) | ((kChunkStride >> 4) << 16);  // tile 1: lo parts
     const uint32_t b_lo_mid = (b_base >> 4) | ((kLboB >> 4) << 16);
     const uint32_t b_lo_l5 = (b_base >> 4) | ((kLboB5 >> 4) << 16);
     const uint32_t acc0 = tmem_base, acc1 = tmem_base + kC;
@@ -187,13 +187,13 @@ conv_stack_split_kernel(const TcParams p) {
         ++lstep;
       }
       if (!ok) break;
-      do {   // conv5 as a 1x1 GEMM with N = 16 (columns = the 9 taps)
+      do {   // conv5 as a 1x1 GEMM with N = 32 (columns 0..8 = the 9 taps; 16..31 unused here)
         if (!wait_bar(bar_a_ready, lstep & 1u, true, p.err, 204)) { ok = false; break; }
         ptx::tc_fence_after();
         constexpr uint32_t kCentre16 = (kYStride >> 4) + 1;
         for (uint32_t j = 0; j < 3; ++j) {
           const uint32_t ao0 = j * 8 * kChunk16 + kCentre16;
-          WANN_SPLIT_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_l5, (2 * kLboB5) >> 4, kIdescN16, j == 0, true)
+          WANN_SPLIT_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_l5, (2 * kLboB5) >> 4, kIdescN32, j == 0, true)
         }
         if (!ok) break;
         if (issuer) ptx::umma_commit<2>(bar_acc_full, 3);
@@ -209,7 +209,7 @@ conv_stack_split_kernel(const TcParams p) {
     const int row = quad * 32 + lane;
     const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
     const uint32_t cell_hi = a_base + ((y + 1) * 2 + b) * kRowStride + (x + 1) * kCell;   // tile 0
-    const uint32_t cell_lo = cell_hi + kATileBytes;                                       // tile 1
+    const uint32_t cell_lo = cell_hi + kATileStride;                                       // tile 1
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const bool signaller = (tid == kFirstEpiWarp * 32);
     const uint32_t a_ready_leader = ptx::mapa(bar_a_ready, 0);
@@ -231,7 +231,7 @@ conv_stack_split_kernel(const TcParams p) {
     ptx::pdl_wait();
     long long st = pair;
     if (st < total_st) {
-      if (chalf == 0) store_input_cell(cell_hi, load_in(board_of(st)));
+      if (chalf == 0) store_input_cell<false>(cell_hi, load_in(board_of(st)));
       signal_a_ready();
     }
     uint32_t lstep = 0;
@@ -302,7 +302,7 @@ conv_stack_split_kernel(const TcParams p) {
           const float hval = fmaxf(acc + bias_s[4 * kC], 0.f);
           if (board < n_eff) p.h5[board * 64 + y * 8 + x] = hval;
           if (st + npairs < total_st)
-            store_input_cell(cell_hi, load_in(board_of(st + npairs)));
+            store_input_cell<false>(cell_hi, load_in(board_of(st + npairs)));
         }
         signal_a_ready();
       }

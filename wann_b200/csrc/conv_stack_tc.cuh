@@ -59,15 +59,20 @@ constexpr int kYStride = 2 * kRowStride;      // 288 B: two boards interleaved p
 constexpr int kChunkStride = 9 * kYStride;    // 2592 B: y = -1..7 (y = 8 halo is next chunk's y = -1)
 constexpr int kATileBytes = kKChunks * kChunkStride;  // 62208 B per 128-row tile
 constexpr int kTilesPerCta = 2;
-constexpr int kABytes = kTilesPerCta * kATileBytes + kYStride + kCell;   // + trailing halo row
+// each tile carries its OWN trailing halo row (the y = 8 row of its last chunk + the x = 8 cell of that
+// row): in the centred mode the halo of a tile is rewritten per layer, and the two tiles of a CTA are
+// in different layers at the same time
+constexpr int kATileStride = kATileBytes + kYStride + kCell;             // 62512 B
+constexpr int kABytes = kTilesPerCta * kATileStride;
+constexpr int kHaloCells = kKChunks * 34 + 19;    // per tile: 18 (y = -1 row) + 16 (x = -1 cells) per chunk, + trailing row
 constexpr int kBoardsPerCta = 4;
 constexpr int kBoardsPerPair = 8;
 
 constexpr int kStageBytes = 96 * 64 * 2;      // 12288 B: half of [192 x 64] 16-bit
-constexpr int kStageBytesL5 = 8 * 64 * 2;     // 1024 B: half of [16 x 64] 16-bit
+constexpr int kStageBytesL5 = 16 * 64 * 2;    // 2048 B: half of [32 x 64] 16-bit (rows 0-15 = taps, 16-31 = their lo parts)
 constexpr int kStages = 8;
 constexpr int kLboB = 96 / 8 * 128;           // 1536 B between K-chunks of a stage
-constexpr int kLboB5 = 8 / 8 * 128;           // 128 B
+constexpr int kLboB5 = 16 / 8 * 128;          // 256 B
 constexpr int kSboB = 128;
 
 constexpr int kKbL1 = 3, kKbMid = 27, kKbL5 = 3;
@@ -132,6 +137,17 @@ struct TcParams {
   int fuse_tail = 0;
   TailParams tail;
   int* err_mirror = nullptr;   // host-mapped copy of err[0..5], written by the last CTA to finish
+  // weight stream geometry: stages per supertile (kKbPerSupertile + 27 per hi/lo-split layer) and the
+  // byte distance between the stage images of CTA rank 0 and 1
+  int stages_per_st = kKbPerSupertile;
+  long long img_stride = kImgBytesPerRank;
+  int split_mask = 0;          // bit l (1..3): conv(l+1)'s weights stream as hi stage + lo stage per K-block
+  // centred mode (kCen kernels): the stored activation of channel position q of conv l+1 is
+  // a' = a - cen[l][q % 8]; the halo holds -cen (so that a' + cen == 0 there) and the next layer's bias
+  // absorbs sum(w * cen).  kappa[t] = sum_k w5[t][k] * cen[3][..] corrects conv5's tap products.
+  float cen[4][8] = {};
+  float kappa[9] = {};
+  const uint8_t* dbg_unperm = nullptr;   // [4][192] channel position -> TF channel (debug dump of a permuted net)
 };
 
 // bounded mbarrier wait: returns false (and records who/where) instead of hanging the GPU
@@ -194,15 +210,33 @@ __device__ __forceinline__ uint2 load_input_cell(const TcParams& p, long long bo
   }
   return v;
 }
+// Centred mode: channels 4..7 carry the same planes scaled by 2^-12; the weight image holds
+// (w1 - fp16(w1)) * 4096 there, so conv1 sees its weights to ~22 bits at no extra MMA.
+template <bool kCen>
 __device__ __forceinline__ void store_input_cell(uint32_t cell0, uint2 v) {
-  ptx::st_shared_v4(cell0, make_uint4(v.x, v.y, 0u, 0u));
+  if (kCen) {
+    const __half2 s = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x0C00)));   // 2^-12
+    const __half2 dx = __hmul2(*reinterpret_cast<const __half2*>(&v.x), s);
+    const __half2 dy = __hmul2(*reinterpret_cast<const __half2*>(&v.y), s);
+    ptx::st_shared_v4(cell0, make_uint4(v.x, v.y, *reinterpret_cast<const uint32_t*>(&dx),
+                                        *reinterpret_cast<const uint32_t*>(&dy)));
+  } else {
+    ptx::st_shared_v4(cell0, make_uint4(v.x, v.y, 0u, 0u));
+  }
+}
+// byte offset (inside a tile) of halo cell i in [0, kHaloCells)
+__device__ __forceinline__ uint32_t halo_cell_offset(int i) {
+  if (i >= kKChunks * 34) return kKChunks * kChunkStride + (i - kKChunks * 34) * kCell;   // trailing row
+  const int q = i / 34, r = i - 34 * q;
+  return q * kChunkStride + (r < 18 ? r * kCell : kYStride + (r - 18) * kRowStride);
 }
 
-template <bool kF16>
+template <bool kF16, bool kCen>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_stack_tc_kernel(const TcParams p) {
+  static_assert(kF16 || !kCen, "the centred mode is fp16 only");
   constexpr uint32_t kIdescN192 = ptx::make_idesc_16bit(256, 192, kF16);
-  constexpr uint32_t kIdescN16 = ptx::make_idesc_16bit(256, 16, kF16);
+  constexpr uint32_t kIdescN32 = ptx::make_idesc_16bit(256, 32, kF16);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t a_base = smem_base + kOffA;
@@ -275,13 +309,14 @@ conv_stack_tc_kernel(const TcParams p) {
     // ===== weight producer: stream this CTA's half of every weight stage ====================
     if (lane == 0) {
       const uint32_t img_rank = (p.variant & 4) ? (rank ^ 1u) : rank;
-      const uint8_t* img = p.wimg + static_cast<size_t>(img_rank) * kImgBytesPerRank;
+      const uint8_t* img = p.wimg + static_cast<size_t>(img_rank) * p.img_stride;
+      const int nstages = p.stages_per_st;
       uint32_t s = 0, ph = 0;
       bool ok = true;
       for (long long st = pair; st < total_st && ok; st += npairs) {
         size_t off = 0;
-        for (int kb = 0; kb < kKbPerSupertile; ++kb) {
-          const uint32_t bytes = (kb >= kKbPerSupertile - kKbL5) ? kStageBytesL5 : kStageBytes;
+        for (int kb = 0; kb < nstages; ++kb) {
+          const uint32_t bytes = (kb >= nstages - kKbL5) ? kStageBytesL5 : kStageBytes;
           if (!wait_bar(bar_empty(s), ph ^ 1u, false, p.err, 100 + s)) { ok = false; break; }
           ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
           ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes, bar_full(s));
@@ -293,10 +328,11 @@ conv_stack_tc_kernel(const TcParams p) {
   } else if (warp == 1 && rank != 0) {
     // ===== relay (peer CTA): forward "my half of stage s has landed" to the leader ===========
     if (lane == 0) {
+      const int nstages = p.stages_per_st;
       uint32_t s = 0, ph = 0;
       bool ok = true;
       for (long long st = pair; st < total_st && ok; st += npairs) {
-        for (int kb = 0; kb < kKbPerSupertile; ++kb) {
+        for (int kb = 0; kb < nstages; ++kb) {
           if (!wait_bar(bar_full(s), ph, false, p.err, 500 + s)) { ok = false; break; }
           ptx::mbar_arrive_cluster(ptx::mapa(bar_peer_full(s), 0));
           if (++s == nst) { s = 0; ph ^= 1u; }
@@ -314,7 +350,7 @@ conv_stack_tc_kernel(const TcParams p) {
       const bool skip_mma = p.variant & 8;        // timing experiment: weight stream only
       const uint32_t a_hi = (kRowStride >> 4) | (1u << 14);
       const uint32_t b_hi = (kSboB >> 4) | (1u << 14);
-      const uint32_t a_lo = ((a_base + h * kATileBytes) >> 4) | ((kChunkStride >> 4) << 16);
+      const uint32_t a_lo = ((a_base + h * kATileStride) >> 4) | ((kChunkStride >> 4) << 16);
       const uint32_t b_lo_mid = (b_base >> 4) | ((kLboB >> 4) << 16);
       const uint32_t b_lo_l5 = (b_base >> 4) | ((kLboB5 >> 4) << 16);
       const uint32_t tmem_d = tmem_base + h * kC;
@@ -327,7 +363,7 @@ conv_stack_tc_kernel(const TcParams p) {
       // to run while half 0 sits in its epilogue (and vice versa at the start of the next layer)
       const uint32_t lookahead = (h == 1) ? min(static_cast<uint32_t>(p.skew), nst - 2u) : 0u;
       long long kb_left = 0;
-      for (long long st = pair; st < total_st; st += npairs) kb_left += kKbPerSupertile;
+      for (long long st = pair; st < total_st; st += npairs) kb_left += p.stages_per_st;
       long long* prof = (p.prof != nullptr && pair == 0) ? p.prof + 4 * h * kProfSteps : nullptr;
       // one K-block: wait for the stage, 4 (or fewer) K=16 steps, release my claim on the stage
 #define WANN_KBLOCK(NKS, A_OFF16_OF_KS, B_LO, B_KS16, IDESC, ACC_FIRST)                          \
@@ -371,6 +407,7 @@ conv_stack_tc_kernel(const TcParams p) {
           ptx::tc_fence_after();
           if (prof && lstep < kProfSteps && issuer) prof[lstep] = clock64();
           uint32_t first = 1;
+          const bool split = (p.split_mask >> layer) & 1;   // weights as hi stage + lo stage: 2 MMAs per K-step
           for (uint32_t ty = 0; ty < 3 && ok; ++ty)
             for (uint32_t tx = 0; tx < 3 && ok; ++tx) {
               const uint32_t tap16 = ty * (kYStride >> 4) + tx;
@@ -378,6 +415,7 @@ conv_stack_tc_kernel(const TcParams p) {
                 const uint32_t ao0 = j * 8 * kChunk16 + tap16;
                 WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_mid, (2 * kLboB) >> 4, kIdescN192, first)
                 first = 0;
+                if (split) WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
               }
             }
           if (!ok) break;
@@ -394,7 +432,7 @@ conv_stack_tc_kernel(const TcParams p) {
           constexpr uint32_t kCentre16 = (kYStride >> 4) + 1;
           for (uint32_t j = 0; j < 3; ++j) {
             const uint32_t ao0 = j * 8 * kChunk16 + kCentre16;
-            WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_l5, (2 * kLboB5) >> 4, kIdescN16, j == 0)
+            WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_l5, (2 * kLboB5) >> 4, kIdescN32, j == 0)
           }
           if (!ok) break;
           if (issuer) ptx::umma_commit<2>(acc_bar, 3);
@@ -417,6 +455,12 @@ conv_stack_tc_kernel(const TcParams p) {
     const uint32_t a_ready_leader0 = ptx::mapa(bar_a_ready(0), 0);
     const uint32_t a_ready_leader1 = ptx::mapa(bar_a_ready(1), 0);
     const bool profiler = (p.prof != nullptr && blockIdx.x == 0 && signaller);
+    uint32_t halo_off[4];      // centred mode: the (up to) 4 halo cells of a tile this thread rewrites per layer
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = ew * 32 + lane + i * kNumEpiWarps * 32;
+      halo_off[i] = c < kHaloCells ? halo_cell_offset(c) : 0xFFFFFFFFu;
+    }
 
     auto signal_a_ready = [&](int h) {
       ptx::fence_proxy_async_smem();
@@ -433,7 +477,7 @@ conv_stack_tc_kernel(const TcParams p) {
     if (st < total_st) {
       for (int h = 0; h < nh; ++h) {
         if (chalf == 0)
-          store_input_cell(a_base + h * kATileBytes + cell_in_tile, load_input_cell<kF16>(p, board_of(st, h), y, x));
+          store_input_cell<kCen>(a_base + h * kATileStride + cell_in_tile, load_input_cell<kF16>(p, board_of(st, h), y, x));
         signal_a_ready(h);
       }
     }
@@ -444,7 +488,7 @@ conv_stack_tc_kernel(const TcParams p) {
       for (int layer = 0; layer < 5 && ok; ++layer, ++lstep) {
         for (int h = 0; h < nh; ++h) {
           const long long board = board_of(st, h);
-          const uint32_t cell0 = a_base + h * kATileBytes + cell_in_tile;
+          const uint32_t cell0 = a_base + h * kATileStride + cell_in_tile;
           const uint32_t taddr = lane_taddr + h * kC;
           if (!wait_bar(bar_acc_full(h), lstep & 1u, true, p.err, 600 + 10 * h + layer)) { ok = false; break; }
           ptx::tc_fence_after();
@@ -454,7 +498,21 @@ conv_stack_tc_kernel(const TcParams p) {
               next_in[h] = load_input_cell<kF16>(p, board_of(st + npairs, h), y, x);
             const float* bs = bias_s + layer * kC + chalf * 96;
             float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < p.n)
-                             ? p.dbg + (board * 64 + y * 8 + x) * kC + chalf * 96 : nullptr;
+                             ? p.dbg + (board * 64 + y * 8 + x) * kC : nullptr;
+            // centred mode: store a' = max(acc + (b' - c), -c) = relu(acc + b') - c   (c by channel % 8);
+            // bias_s already holds b' - c
+            float nc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nc[j] = kCen ? -p.cen[layer][j] : 0.f;
+            // -c as packed 16-bit pairs: rounding is monotonic and -c is exact in the operand format, so
+            // fp16(max(t, -c)) == max(fp16(t), -c): one packed max per PAIR after the conversion
+            uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+            if (kCen) {
+              hv.x = ptx::pack_sat<kF16>(nc[0], nc[1]);
+              hv.y = ptx::pack_sat<kF16>(nc[2], nc[3]);
+              hv.z = ptx::pack_sat<kF16>(nc[4], nc[5]);
+              hv.w = ptx::pack_sat<kF16>(nc[6], nc[7]);
+            }
 #pragma unroll 1
             for (int ch = 0; ch < 3; ++ch) {
               uint32_t v[32];
@@ -465,29 +523,61 @@ conv_stack_tc_kernel(const TcParams p) {
                 const float4 b0 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8);
                 const float4 b1 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8 + 4);
                 uint4 o;
-                o.x = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 0]) + b0.x,
-                                           __uint_as_float(v[kc * 8 + 1]) + b0.y);
-                o.y = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 2]) + b0.z,
-                                           __uint_as_float(v[kc * 8 + 3]) + b0.w);
-                o.z = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 4]) + b1.x,
-                                           __uint_as_float(v[kc * 8 + 5]) + b1.y);
-                o.w = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
-                                           __uint_as_float(v[kc * 8 + 7]) + b1.w);
+                if (kCen) {
+                  o.x = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 0]) + b0.x,
+                                                               __uint_as_float(v[kc * 8 + 1]) + b0.y), hv.x);
+                  o.y = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 2]) + b0.z,
+                                                               __uint_as_float(v[kc * 8 + 3]) + b0.w), hv.y);
+                  o.z = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 4]) + b1.x,
+                                                               __uint_as_float(v[kc * 8 + 5]) + b1.y), hv.z);
+                  o.w = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
+                                                               __uint_as_float(v[kc * 8 + 7]) + b1.w), hv.w);
+                } else {
+                  o.x = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 0]) + b0.x,
+                                             __uint_as_float(v[kc * 8 + 1]) + b0.y);
+                  o.y = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 2]) + b0.z,
+                                             __uint_as_float(v[kc * 8 + 3]) + b0.w);
+                  o.z = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 4]) + b1.x,
+                                             __uint_as_float(v[kc * 8 + 5]) + b1.y);
+                  o.w = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
+                                             __uint_as_float(v[kc * 8 + 7]) + b1.w);
+                }
                 ptx::st_shared_v4(cell0 + (chalf * 12 + ch * 4 + kc) * kChunkStride, o);
                 if (dbg != nullptr) {
                   const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+                  const int q0 = chalf * 96 + ch * 32 + kc * 8;     // channel position of w[0]'s low half
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    dbg[ch * 32 + kc * 8 + 2 * i] = ptx::unpack16<kF16>(w[i] & 0xFFFFu);
-                    dbg[ch * 32 + kc * 8 + 2 * i + 1] = ptx::unpack16<kF16>(w[i] >> 16);
+                  for (int i = 0; i < 8; ++i) {
+                    const int q = q0 + i;
+                    const int c_tf = p.dbg_unperm != nullptr ? p.dbg_unperm[layer * kC + q] : q;
+                    dbg[c_tf] = ptx::unpack16<kF16>((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu) - nc[i];
                   }
                 }
               }
+            }
+            if (kCen) {
+              // the tile's halo must read as "activation 0" for the NEXT layer: -c of this layer's output
+              // (conv4's output: zeros -- conv5 uses the centre tap only, its stencil scratch and the next
+              // supertile's conv1 need a zero halo)
+              const uint4 hz = (layer < 3) ? hv : make_uint4(0u, 0u, 0u, 0u);
+              const uint32_t tile0 = a_base + h * kATileStride;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < 3 || halo_off[3] != 0xFFFFFFFFu) ptx::st_shared_v4(tile0 + halo_off[i], hz);
             }
           } else if (chalf == 0) {
             // conv5: column t of the accumulator is P[pixel][tap t]; out = 9-point stencil sum.
             uint32_t v[16];
             ptx::tmem_ld_x16(taddr, v);
+            if (kCen) {
+              // columns 16..24: the taps' lo weights (x 4096); kappa: what the centring took out of a4
+              uint32_t vl[16];
+              ptx::tmem_ld_x16(taddr + 16, vl);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int t = 0; t < 9; ++t)
+                v[t] = __float_as_uint(__uint_as_float(v[t]) + __uint_as_float(vl[t]) * (1.f / 4096.f) + p.kappa[t]);
+            }
             ptx::tmem_ld_wait();
             // scratch = cells of channel-chunks 2..4 at this pixel (fp32 x 4 per cell); halo = 0
             ptx::st_shared_v4(cell0 + 2 * kChunkStride, make_uint4(v[0], v[1], v[2], v[3]));
@@ -511,7 +601,7 @@ conv_stack_tc_kernel(const TcParams p) {
               ptx::mbar_arrive(bar_h5_full(h));
             }
             if (p.h5 != nullptr && board < p.n) p.h5[board * 64 + y * 8 + x] = hval;
-            if (st + npairs < total_st) store_input_cell(cell0, next_in[h]);
+            if (st + npairs < total_st) store_input_cell<kCen>(cell0, next_in[h]);
           }
           signal_a_ready(h);
           if (profiler && lstep < kProfSteps) p.prof[(4 * h + 3) * kProfSteps + lstep] = clock64();

@@ -252,6 +252,26 @@ __device__ __forceinline__ uint32_t pack_relu(float a, float b) {
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// two fp32 -> packed 16-bit pair, no ReLU (the centred mode stores signed values)
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_sat(float a, float b) {
+  uint32_t r;
+  if (kF16)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// packed max of two 16-bit pairs in the operand format
+template <bool kF16>
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  if (kF16)
+    asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  else
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 template <bool kF16>
 __device__ __forceinline__ float unpack16(uint32_t bits16) {
   if (kF16) return __half2float(__ushort_as_half(static_cast<unsigned short>(bits16)));

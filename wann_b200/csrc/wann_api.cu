@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <omp.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -167,6 +168,22 @@ struct CombineReq {
   int rc = 0; std::string err; bool done = false;
 };
 
+// Centred fp16 mode (WANN_MODE_FP16C): per conv layer 1..4 a permutation of the output channels into
+// 8 buckets of 24 by mean activation (bucket = channel position % 8 -- the halo cells of the shared
+// memory layout are shared by all 24 channel chunks, so an offset can only depend on position % 8) and
+// one offset per bucket.  Identity / zero = the plain layout.
+struct Centering {
+  uint8_t pos_of[4][192];   // TF channel -> position in the kernel's layout
+  uint8_t tf_of[4][192];    // position -> TF channel
+  float c[4][8];            // offsets (exact fp16 values) of the stored output of conv l+1
+  Centering() {
+    for (int l = 0; l < 4; ++l) {
+      for (int i = 0; i < 192; ++i) pos_of[l][i] = tf_of[l][i] = static_cast<uint8_t>(i);
+      for (int j = 0; j < 8; ++j) c[l][j] = 0.f;
+    }
+  }
+};
+
 }  // namespace
 
 struct wann_ctx {
@@ -194,7 +211,17 @@ struct wann_ctx {
   // margin refinement: boards whose two best legal priors are closer than `margin` logits are
   // re-evaluated by conv_stack_split_kernel (fp32-class); refine_ratio = exp(-margin), 0 = off
   std::atomic<float> refine_ratio{0.f};
-  float* d_bias_tc = nullptr;  // [4*192 + 1]
+  float* d_bias_tc = nullptr;  // [4*192 + 4] bias table of the context's own tensor-core kernel (centred mode: b' - c)
+  float* d_bias_plain = nullptr;   // [4*192 + 4] the TF biases (fp32_tc mode and the refinement pass)
+  // centred fp16 mode: calibrated channel buckets / offsets, conv5 tap corrections, weight stream geometry
+  Centering cen;
+  float kappa[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  uint8_t* d_unperm = nullptr;     // [4][192] channel position -> TF channel
+  std::atomic<int> split_mask{0};  // option "split_layers": conv layers (bits 1..3) whose weights stream as hi + lo
+  int stages_per_st = wann::kKbPerSupertile;
+  long long img_stride = wann::kImgBytesPerRank;
+  size_t wimg_capacity = 0;
+  std::vector<float> host_w[12];   // copy of the weights (images are rebuilt when split_layers changes)
   WeightsGate weights_gate;       // evaluations are readers, wann_set_weights the writer
   Lane lanes[kLanes];
   std::mutex mu;
@@ -220,15 +247,41 @@ namespace {
 
 using namespace wann;
 
+float f16_value(float v) {
+  const uint16_t h = f32_to_f16(v);
+  __half hh;
+  memcpy(&hh, &h, 2);
+  return __half2float(hh);
+}
+
+struct ImageOpts {
+  bool f16 = false;
+  bool exact15 = false;     // conv1: lo parts (x 4096) in input channels 4..7; conv5: lo parts (x 4096) in rows 16..24
+  int split_mask = 0;       // bit l (1..3): conv(l+1) K-blocks stream a lo stage (w - fp16(w), unscaled) after the hi stage
+  const Centering* cen = nullptr;
+};
+
+int stages_per_supertile(int split_mask) {
+  int n = kKbPerSupertile;
+  for (int l = 1; l <= 3; ++l) n += ((split_mask >> l) & 1) * kKbMid;
+  return n;
+}
+size_t image_bytes_per_rank(int split_mask) {
+  return static_cast<size_t>(stages_per_supertile(split_mask) - kKbL5) * kStageBytes + kKbL5 * kStageBytesL5;
+}
+
 // Build the shared-memory stage images of operand B (see conv_stack_tc.cuh).
 // Element (n, k) of a stage lives at (k/8)*LBO + (n/8)*128 + (n%8)*16 + (k%8)*2 bytes.
-void build_weight_image(const wann_weights& w, bool f16, std::vector<uint8_t>& img) {
-  img.assign(2 * static_cast<size_t>(kImgBytesPerRank), 0);
+void build_weight_image(const wann_weights& w, const ImageOpts& o, std::vector<uint8_t>& img) {
+  static const Centering identity;
+  const Centering& cen = o.cen ? *o.cen : identity;
+  const size_t per_rank = image_bytes_per_rank(o.split_mask);
+  img.assign(2 * per_rank, 0);
   for (int rank = 0; rank < 2; ++rank) {
-    uint8_t* base = img.data() + static_cast<size_t>(rank) * kImgBytesPerRank;
+    uint8_t* base = img.data() + static_cast<size_t>(rank) * per_rank;
     size_t off = 0;
     auto put = [&](uint8_t* stage, int lbo, int n, int k, float v) {
-      const uint16_t h = f16 ? f32_to_f16(v) : f32_to_bf16(v);
+      const uint16_t h = o.f16 ? f32_to_f16(v) : f32_to_bf16(v);
       memcpy(stage + (k / 8) * lbo + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2, &h, 2);
     };
     // conv1: k-block kb holds taps 4kb..4kb+3, 16 k per tap (4 real input planes)
@@ -238,32 +291,40 @@ void build_weight_image(const wann_weights& w, bool f16, std::vector<uint8_t>& i
         if (tap >= 9) continue;
         for (int c = 0; c < 4; ++c)
           for (int nl = 0; nl < 96; ++nl) {
-            const int co = rank * 96 + nl;
-            put(base + off, kLboB, nl, ks * 16 + c, w.conv_w[0][(tap * 4 + c) * 192 + co]);
+            const int co = cen.tf_of[0][rank * 96 + nl];
+            const float v = w.conv_w[0][(tap * 4 + c) * 192 + co];
+            put(base + off, kLboB, nl, ks * 16 + c, v);
+            if (o.exact15) put(base + off, kLboB, nl, ks * 16 + 4 + c, (v - f16_value(v)) * 4096.f);
           }
       }
-    // conv2..4: k-block kb = tap*3 + j holds input channels 64j..64j+63 of tap
-    for (int layer = 1; layer <= 3; ++layer)
-      for (int kb = 0; kb < kKbMid; ++kb, off += kStageBytes) {
+    // conv2..4: k-block kb = tap*3 + j holds input channel positions 64j..64j+63 of tap
+    for (int layer = 1; layer <= 3; ++layer) {
+      const bool split = (o.split_mask >> layer) & 1;
+      for (int kb = 0; kb < kKbMid; ++kb) {
         const int tap = kb / 3, j = kb % 3;
-        for (int k = 0; k < 64; ++k)
-          for (int nl = 0; nl < 96; ++nl) {
-            const int co = rank * 96 + nl, ci = j * 64 + k;
-            put(base + off, kLboB, nl, k, w.conv_w[layer][(static_cast<size_t>(tap) * 192 + ci) * 192 + co]);
-          }
+        for (int part = 0; part < (split ? 2 : 1); ++part, off += kStageBytes)
+          for (int k = 0; k < 64; ++k)
+            for (int nl = 0; nl < 96; ++nl) {
+              const int co = cen.tf_of[layer][rank * 96 + nl], ci = cen.tf_of[layer - 1][j * 64 + k];
+              const float v = w.conv_w[layer][(static_cast<size_t>(tap) * 192 + ci) * 192 + co];
+              put(base + off, kLboB, nl, k, part == 0 ? v : v - f16_value(v));
+            }
       }
-    // conv5 as a 1x1 GEMM whose N index is the TAP: row n = tap (9 real of 16)
+    }
+    // conv5 as a 1x1 GEMM whose N index is the TAP: rows 0..8 (CTA rank 0) = the taps, rows 16..24
+    // (CTA rank 1) = their lo parts x 4096 (exact15 only)
     for (int j = 0; j < kKbL5; ++j, off += kStageBytesL5)
-      for (int nl = 0; nl < 8; ++nl) {
-        const int tap = rank * 8 + nl;
+      for (int nl = 0; nl < 16; ++nl) {
+        const int tap = nl;
         for (int k = 0; k < 64; ++k) {
-          const int ci = j * 64 + k;
+          const int ci = cen.tf_of[3][j * 64 + k];
           float v = 0.f;
           if (w.final_kernel == 3) {
             if (tap < 9) v = w.conv_w[4][tap * 192 + ci];
           } else if (tap == 4) {
             v = w.conv_w[4][ci];
           }
+          if (rank == 1) v = o.exact15 ? (v - f16_value(v)) * 4096.f : 0.f;
           put(base + off, kLboB5, nl, k, v);
         }
       }
@@ -274,7 +335,9 @@ void build_weight_image(const wann_weights& w, bool f16, std::vector<uint8_t>& i
 // stage is followed by the lo stage (conv_stack_split.cuh).
 void build_weight_image_split(const wann_weights& w, std::vector<uint8_t>& img) {
   std::vector<uint8_t> hi_img, lo_img;
-  build_weight_image(w, true, hi_img);
+  ImageOpts fo;
+  fo.f16 = true;
+  build_weight_image(w, fo, hi_img);
   // residuals: same layout, value (w - float(hi)) * 4096 -- build by transforming the weights
   std::vector<float> res[5];
   const size_t k5 = static_cast<size_t>(w.final_kernel) * w.final_kernel;
@@ -290,7 +353,7 @@ void build_weight_image_split(const wann_weights& w, std::vector<uint8_t>& img) 
     }
     r.conv_w[l] = res[l].data();
   }
-  build_weight_image(r, true, lo_img);
+  build_weight_image(r, fo, lo_img);
   img.assign(2 * static_cast<size_t>(kSplitImgBytesPerRank), 0);
   for (int rank = 0; rank < 2; ++rank) {
     const uint8_t* h = hi_img.data() + static_cast<size_t>(rank) * kImgBytesPerRank;
@@ -396,6 +459,204 @@ void release_lane(wann_ctx* ctx, Lane* l) {
   ctx->cv.notify_one();
 }
 
+bool is_tc16(int mode) { return mode == WANN_MODE_BF16 || mode == WANN_MODE_FP16 || mode == WANN_MODE_FP16C; }
+
+wann_weights host_weights_view(const wann_ctx* ctx) {
+  wann_weights w = {};
+  for (int i = 0; i < 5; ++i) { w.conv_w[i] = ctx->host_w[2 * i].data(); w.conv_b[i] = ctx->host_w[2 * i + 1].data(); }
+  w.fc_w = ctx->host_w[10].data();
+  w.fc_b = ctx->host_w[11].data();
+  w.final_kernel = ctx->final_kernel;
+  return w;
+}
+
+// Stage image + bias table (+ the centred mode's tap corrections and channel table) of the context's own
+// tensor-core kernel, for the given centring.
+int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) {
+  const bool centred = ctx->mode == WANN_MODE_FP16C;
+  const int split_mask = centred ? ctx->split_mask.load() : 0;
+  std::vector<uint8_t> img;
+  if (ctx->mode == WANN_MODE_FP32_TC) {
+    build_weight_image_split(w, img);
+  } else {
+    ImageOpts o;
+    o.f16 = ctx->mode != WANN_MODE_BF16;
+    o.exact15 = centred;
+    o.split_mask = split_mask;
+    o.cen = &cen;
+    build_weight_image(w, o, img);
+  }
+  if (ctx->d_wimg != nullptr && ctx->wimg_capacity < img.size()) { cudaFree(ctx->d_wimg); ctx->d_wimg = nullptr; }
+  if (ctx->d_wimg == nullptr) { CU(cudaMalloc(&ctx->d_wimg, img.size())); ctx->wimg_capacity = img.size(); }
+  CU(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+  ctx->stages_per_st = stages_per_supertile(split_mask);
+  ctx->img_stride = static_cast<long long>(img.size() / 2);
+  // bias table: conv1..4 by channel POSITION, then b5.  Centred: b'[n] - c, where
+  // b'[n] = b[n] + sum_{tap,k} W[tap][k][n] * c_prev[k] (true fp32 weights, summed in double) gives back
+  // what subtracting c_prev from the layer's input took away (halo cells hold -c_prev, so the sum runs
+  // over all 9 taps for every pixel).
+  std::vector<float> bias(4 * 192 + 4, 0.f);
+  for (int l = 0; l < 4; ++l)
+    for (int q = 0; q < 192; ++q) {
+      const int n = cen.tf_of[l][q];
+      double b = w.conv_b[l][n];
+      if (centred && l >= 1)
+        for (int tap = 0; tap < 9; ++tap)
+          for (int k = 0; k < 192; ++k)
+            b += static_cast<double>(w.conv_w[l][(static_cast<size_t>(tap) * 192 + k) * 192 + n]) *
+                 cen.c[l - 1][cen.pos_of[l - 1][k] % 8];
+      bias[l * 192 + q] = static_cast<float>(b - (centred ? cen.c[l][q % 8] : 0.f));
+    }
+  bias[4 * 192] = w.conv_b[4][0];
+  for (int t = 0; t < 9; ++t) {
+    double kp = 0;
+    if (centred)
+      for (int k = 0; k < 192; ++k) {
+        const double c = cen.c[3][cen.pos_of[3][k] % 8];
+        if (w.final_kernel == 3) kp += static_cast<double>(w.conv_w[4][t * 192 + k]) * c;
+        else if (t == 4) kp += static_cast<double>(w.conv_w[4][k]) * c;
+      }
+    ctx->kappa[t] = static_cast<float>(kp);
+  }
+  if (ctx->d_bias_tc == nullptr) CU(cudaMalloc(&ctx->d_bias_tc, bias.size() * 4));
+  CU(cudaMemcpy(ctx->d_bias_tc, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  if (centred) {
+    if (ctx->d_unperm == nullptr) CU(cudaMalloc(&ctx->d_unperm, 4 * 192));
+    CU(cudaMemcpy(ctx->d_unperm, cen.tf_of, 4 * 192, cudaMemcpyHostToDevice));
+  }
+  ctx->cen = cen;
+  return WANN_OK;
+}
+
+void fill_tc_params(const wann_ctx* ctx, TcParams& p) {
+  p.wimg = ctx->d_wimg;
+  p.bias = ctx->d_bias_tc;
+  p.stages_per_st = ctx->stages_per_st;
+  p.img_stride = ctx->img_stride;
+  if (ctx->mode == WANN_MODE_FP16C) {
+    p.split_mask = (ctx->stages_per_st == kKbPerSupertile) ? 0 : ctx->split_mask.load();
+    memcpy(p.cen, ctx->cen.c, sizeof p.cen);
+    memcpy(p.kappa, ctx->kappa, sizeof p.kappa);
+    p.dbg_unperm = ctx->d_unperm;
+  }
+}
+
+// Calibration positions of the centred mode: seeded random legal play-outs from the opening, cut at a
+// random ply (the rules of board_utils.pyx:331-400; a game that reaches the far rank restarts).
+void calibration_positions(int n, std::vector<int8_t>& squares, std::vector<uint8_t>& black) {
+  squares.assign(static_cast<size_t>(n) * 64, 0);
+  black.assign(n, 0);
+  uint64_t state = 0x57414E4E42323030ull;
+  auto rnd = [&]() {
+    uint64_t z = (state += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  for (int g = 0; g < n; ++g) {
+    int8_t sq[64];
+    int blk = 0;
+    auto reset = [&]() { for (int i = 0; i < 64; ++i) sq[i] = i < 16 ? 1 : (i >= 48 ? 2 : 0); blk = 0; };
+    reset();
+    const int plies = static_cast<int>(rnd() % 60);
+    for (int ply = 0; ply < plies; ++ply) {
+      int from[48], to[48], cnt = 0;
+      const int own = blk ? 2 : 1, dir = blk ? -8 : 8;
+      for (int i = 0; i < 64; ++i) {
+        if (sq[i] != own) continue;
+        const int r = i / 8, f = i % 8, t = i + dir;
+        if ((blk && r == 0) || (!blk && r == 7)) continue;
+        if (sq[t] == 0) { from[cnt] = i; to[cnt++] = t; }
+        if (f > 0 && sq[t - 1] != own) { from[cnt] = i; to[cnt++] = t - 1; }
+        if (f < 7 && sq[t + 1] != own) { from[cnt] = i; to[cnt++] = t + 1; }
+      }
+      if (cnt == 0) break;
+      const int m = static_cast<int>(rnd() % static_cast<uint64_t>(cnt));
+      const int tr = to[m] / 8;
+      if ((blk && tr == 0) || (!blk && tr == 7)) break;      // keep the pre-terminal position
+      sq[to[m]] = sq[from[m]];
+      sq[from[m]] = 0;
+      blk ^= 1;
+    }
+    memcpy(squares.data() + static_cast<size_t>(g) * 64, sq, 64);
+    black[g] = static_cast<uint8_t>(blk);
+  }
+}
+
+__global__ void channel_partial_sums_kernel(const float* __restrict__ act, long long rows, float* __restrict__ partial) {
+  const int c = threadIdx.x;                 // 192 threads: one channel each, coalesced rows
+  float acc = 0.f;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) acc += act[r * 192 + c];
+  partial[blockIdx.x * 192 + c] = acc;
+}
+
+// Centred mode calibration: run the (not yet centred) kernel on the built-in positions, take the mean
+// post-ReLU activation of every channel of conv1..4, sort the channels of a layer into 8 buckets of 24
+// and give every bucket the fp16-rounded mean of its channel means as offset.  Deterministic: fixed
+// positions, fixed summation order.
+int calibrate_centering(wann_ctx* ctx, Centering* out) {
+  constexpr int kN = 1024, kBlocks = 128;
+  std::vector<int8_t> sq;
+  std::vector<uint8_t> bl;
+  calibration_positions(kN, sq, bl);
+  int8_t* d_sq = nullptr; uint8_t* d_bl = nullptr; float* d_act = nullptr; float* d_part = nullptr; int* d_err = nullptr;
+  cudaStream_t stream = nullptr;
+  int rc = WANN_OK;
+  auto body = [&]() -> int {
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&d_sq, kN * 64));
+    CU(cudaMalloc(&d_bl, kN));
+    CU(cudaMalloc(&d_act, static_cast<size_t>(kN) * 64 * 192 * 4));
+    CU(cudaMalloc(&d_part, kBlocks * 192 * 4));
+    CU(cudaMalloc(&d_err, 8 * sizeof(int)));
+    CU(cudaMemsetAsync(d_err, 0, 8 * sizeof(int), stream));
+    CU(cudaMemcpyAsync(d_sq, sq.data(), kN * 64, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(d_bl, bl.data(), kN, cudaMemcpyHostToDevice, stream));
+    Centering cen;
+    for (int l = 0; l < 4; ++l) {
+      TcParams p = {};
+      fill_tc_params(ctx, p);
+      p.squares = d_sq; p.black = d_bl; p.n = kN; p.err = d_err; p.halves = 2; p.skew = ctx->skew;
+      p.dbg = d_act; p.dbg_layer = l + 1;
+      const int npairs = std::min(ctx->sm_count / 2, kN / kBoardsPerPair);
+      conv_stack_tc_kernel<true, true><<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
+      channel_partial_sums_kernel<<<kBlocks, 192, 0, stream>>>(d_act, static_cast<long long>(kN) * 64, d_part);
+      std::vector<float> part(kBlocks * 192);
+      int herr[8];
+      CU(cudaMemcpyAsync(part.data(), d_part, part.size() * 4, cudaMemcpyDeviceToHost, stream));
+      CU(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      CU(cudaGetLastError());
+      if (herr[0] != 0) return fail(WANN_E_KERNEL, "calibration: conv_stack_tc watchdog, wait site %d", herr[0]);
+      double mean[192];
+      for (int c = 0; c < 192; ++c) {
+        double a = 0;
+        for (int b = 0; b < kBlocks; ++b) a += part[b * 192 + c];
+        mean[c] = a / (static_cast<double>(kN) * 64);
+      }
+      int order[192];
+      for (int c = 0; c < 192; ++c) order[c] = c;
+      std::stable_sort(order, order + 192, [&](int a, int b) { return mean[a] < mean[b]; });
+      for (int j = 0; j < 8; ++j) {
+        double m = 0;
+        for (int i = 0; i < 24; ++i) {
+          const int c = order[j * 24 + i], q = 8 * i + j;
+          m += mean[c];
+          cen.pos_of[l][c] = static_cast<uint8_t>(q);
+          cen.tf_of[l][q] = static_cast<uint8_t>(c);
+        }
+        cen.c[l][j] = f16_value(static_cast<float>(m / 24));
+      }
+    }
+    *out = cen;
+    return WANN_OK;
+  };
+  rc = body();
+  if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+  cudaFree(d_sq); cudaFree(d_bl); cudaFree(d_act); cudaFree(d_part); cudaFree(d_err);
+  return rc;
+}
+
 // (Re)build every device-side form of the weights: the fp32 TF-layout tensors (fp32 mode, FC of the
 // tail), the tensor-core stage images and the bias vector.  Buffers are allocated on first use and
 // overwritten afterwards (wann_set_weights); the caller guarantees that no evaluation is in flight.
@@ -412,26 +673,38 @@ int upload_weights(wann_ctx* ctx, const wann_weights& w) {
     int rc = up(&ctx->d_conv_w[i], w.conv_w[i], wsz[i]);
     if (rc == WANN_OK) rc = up(&ctx->d_conv_b[i], w.conv_b[i], bsz[i]);
     if (rc != WANN_OK) return rc;
+    if (w.conv_w[i] != ctx->host_w[2 * i].data()) {       // (not when re-uploading the context's own copy)
+      ctx->host_w[2 * i].assign(w.conv_w[i], w.conv_w[i] + wsz[i]);
+      ctx->host_w[2 * i + 1].assign(w.conv_b[i], w.conv_b[i] + bsz[i]);
+    }
   }
   int rc = up(&ctx->d_fc_w, w.fc_w, 64 * kMoves);
   if (rc == WANN_OK) rc = up(&ctx->d_fc_b, w.fc_b, kMoves);
   if (rc != WANN_OK) return rc;
-  std::vector<uint8_t> img;
-  if (ctx->mode == WANN_MODE_FP32_TC) build_weight_image_split(w, img);
-  else build_weight_image(w, ctx->mode == WANN_MODE_FP16, img);
-  if (ctx->d_wimg == nullptr) CU(cudaMalloc(&ctx->d_wimg, img.size()));
-  CU(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
-  if (ctx->mode != WANN_MODE_FP32_TC) {   // the refinement pass's fp16 hi/lo split image
+  if (w.fc_w != ctx->host_w[10].data()) {
+    ctx->host_w[10].assign(w.fc_w, w.fc_w + 64 * kMoves);
+    ctx->host_w[11].assign(w.fc_b, w.fc_b + kMoves);
+  }
+  std::vector<float> bias(4 * 192 + 4, 0.f);
+  for (int l = 0; l < 4; ++l) memcpy(bias.data() + l * 192, w.conv_b[l], 192 * 4);
+  bias[4 * 192] = w.conv_b[4][0];
+  if (ctx->d_bias_plain == nullptr) CU(cudaMalloc(&ctx->d_bias_plain, bias.size() * 4));
+  CU(cudaMemcpy(ctx->d_bias_plain, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  if (ctx->mode != WANN_MODE_FP32) {
+    Centering cen;                       // identity: the plain layout
+    rc = upload_tc_image(ctx, w, cen);
+    if (rc == WANN_OK && ctx->mode == WANN_MODE_FP16C) {
+      rc = calibrate_centering(ctx, &cen);
+      if (rc == WANN_OK) rc = upload_tc_image(ctx, w, cen);
+    }
+    if (rc != WANN_OK) return rc;
+  }
+  if (is_tc16(ctx->mode)) {   // the refinement pass's fp16 hi/lo split image
     std::vector<uint8_t> simg;
     build_weight_image_split(w, simg);
     if (ctx->d_wimg_split == nullptr) CU(cudaMalloc(&ctx->d_wimg_split, simg.size()));
     CU(cudaMemcpy(ctx->d_wimg_split, simg.data(), simg.size(), cudaMemcpyHostToDevice));
   }
-  std::vector<float> bias(4 * 192 + 4, 0.f);
-  for (int l = 0; l < 4; ++l) memcpy(bias.data() + l * 192, w.conv_b[l], 192 * 4);
-  bias[4 * 192] = w.conv_b[4][0];
-  if (ctx->d_bias_tc == nullptr) CU(cudaMalloc(&ctx->d_bias_tc, bias.size() * 4));
-  CU(cudaMemcpy(ctx->d_bias_tc, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   return WANN_OK;
 }
 
@@ -447,6 +720,7 @@ struct ChunkIO {   // device pointers for one chunk
   uint8_t* nlegal = nullptr;
   float* dbg = nullptr;
   int dbg_layer = 0;
+  int top_k = kMaxLegal;
   long long* prof = nullptr;
   int8_t* children = nullptr;
   uint8_t* cflags = nullptr;
@@ -459,8 +733,7 @@ struct ChunkIO {   // device pointers for one chunk
 
 bool refine_active(const wann_ctx* ctx, const ChunkIO& io, float refine_ratio) {
   return (io.probs != nullptr || io.logits != nullptr || io.idx != nullptr) && refine_ratio > 0.f &&
-         io.squares != nullptr && io.dbg == nullptr && io.prof == nullptr &&
-         (ctx->mode == WANN_MODE_BF16 || ctx->mode == WANN_MODE_FP16);
+         io.squares != nullptr && io.dbg == nullptr && io.prof == nullptr && is_tc16(ctx->mode);
 }
 
 // Refinement pass 2: the flagged boards (ws.d_rlist[0 .. d_err[4])) again, fp32-class (fp16 hi/lo
@@ -473,7 +746,7 @@ int enqueue_refine_pass(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const Chun
   int* d_rcount = ws.d_err + 4;
   TcParams p = {};
   p.squares = io.squares; p.black = io.black; p.n = n; p.wimg = ctx->d_wimg_split;
-  p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5r; p.err = ws.d_err; p.halves = 2;
+  p.bias = ctx->d_bias_plain; p.h5 = ws.d_h5r; p.err = ws.d_err; p.halves = 2;
   p.gather = ws.d_rlist; p.n_dev = d_rcount;
   const long long total_st = (m + kSplitBoardsPerPair - 1) / kSplitBoardsPerPair;
   const int npairs = static_cast<int>(std::min<long long>(ctx->sm_count / 2, total_st));
@@ -481,7 +754,7 @@ int enqueue_refine_pass(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const Chun
   TailParams t2;
   t2.h5 = ws.d_h5r; t2.squares = io.squares; t2.black = io.black; t2.n = n;
   t2.fc_w = ctx->d_fc_w; t2.fc_b = ctx->d_fc_b; t2.probs = io.probs; t2.logits = io.logits;
-  t2.idx = io.idx; t2.prior = io.prior; t2.n_legal = io.nlegal;
+  t2.idx = io.idx; t2.prior = io.prior; t2.n_legal = io.nlegal; t2.top_k = io.top_k;
   t2.gather = ws.d_rlist; t2.n_dev = d_rcount;
   if (io.err_mirror != nullptr) { t2.err_src = ws.d_err; t2.err_dst = io.err_mirror; }
   const long long groups = (m + kTailBoards - 1) / kTailBoards;
@@ -500,11 +773,11 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   uint64_t launches = 0;
   // ---- the tail (FC-155 -> softmax -> legal gather -> rank) and the refinement set-up ---------
   const bool want_tail = io.probs != nullptr || io.logits != nullptr || io.idx != nullptr;
-  const bool tc16 = ctx->mode == WANN_MODE_BF16 || ctx->mode == WANN_MODE_FP16;
+  const bool tc16 = is_tc16(ctx->mode);
   TailParams t;
   t.h5 = ws.d_h5; t.squares = io.squares; t.black = io.black; t.n = n;
   t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
-  t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal;
+  t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal; t.top_k = io.top_k;
   const float refine_ratio = ctx->refine_ratio.load();
   const bool refine = refine_active(ctx, io, refine_ratio);
   int* d_rcount = ws.d_err + 4;     // [0] flagged boards of this chunk, [1] running total
@@ -527,7 +800,8 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   if (ctx->mode != WANN_MODE_FP32) {
     TcParams p;
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
-    p.n = n; p.wimg = ctx->d_wimg; p.skew = ctx->skew; p.bias = ctx->d_bias_tc; p.h5 = ws.d_h5;
+    fill_tc_params(ctx, p);
+    p.n = n; p.skew = ctx->skew; p.h5 = ws.d_h5;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
     if (fused) {
       p.fuse_tail = 1;
@@ -562,8 +836,9 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       if (ctx->mode == WANN_MODE_FP32_TC) CU(cudaLaunchKernelEx(&cfg, conv_stack_split_kernel, p));
-      else if (ctx->mode == WANN_MODE_FP16) CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<true>, p));
-      else CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<false>, p));
+      else if (ctx->mode == WANN_MODE_FP16C) CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<true, true>, p));
+      else if (ctx->mode == WANN_MODE_FP16) CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<true, false>, p));
+      else CU(cudaLaunchKernelEx(&cfg, conv_stack_tc_kernel<false, false>, p));
     }
     if (t0 != nullptr) {
       CU(cudaEventRecord(t1, stream));
@@ -673,7 +948,11 @@ struct EvalArgs {
   uint8_t* nlegal = nullptr;
   float* dbg = nullptr;
   int dbg_layer = 0;
+  int top_k = kMaxLegal;          // ranked children kept per position
 };
+
+// the k argument of the C ABI: 0 (or anything outside 1..47) = every legal child
+int clamp_top_k(int k) { return (k >= 1 && k < kMaxLegal) ? k : kMaxLegal; }
 
 int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void* stream_v) {
   const long long cap = lane->slot[0].cap * (ctx->mode == WANN_MODE_FP32 ? 1 : kDevChunkMul);
@@ -696,6 +975,7 @@ int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void*
     io.nlegal = a.nlegal ? a.nlegal + off : nullptr;
     io.dbg = a.dbg ? a.dbg + off * 64 * dbg_c : nullptr;
     io.dbg_layer = a.dbg_layer;
+    io.top_k = a.top_k;
     io.children = a.children ? a.children + off * kMaxLegal * 64 : nullptr;
     io.cflags = a.cflags ? a.cflags + off * kMaxLegal : nullptr;
     io.cstats = a.cstats ? a.cstats + off * kMaxLegal * 4 : nullptr;
@@ -757,6 +1037,7 @@ int eval_host_small(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
   io.logits = a.logits ? reinterpret_cast<float*>(z_logits) : nullptr;
   if (a.idx) { io.idx = z_idx; io.prior = reinterpret_cast<float*>(z_prior); io.nlegal = z_nlegal; }
   io.err_mirror = z_err;
+  io.top_k = a.top_k;
   // margin refinement: the host is about to synchronise anyway, so it reads the number of flagged
   // boards itself and launches pass 2 only when there are any (98 % of batch-1 calls: none)
   io.allow_defer = true;
@@ -788,7 +1069,11 @@ int eval_host_small(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
 // HOST memory: chunked, double-buffered over the lane's two slots so that the H2D copy of
 // chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
 int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
-  if (ctx->zero_copy && n <= kZeroCopyMax && a.dbg == nullptr && a.children == nullptr && a.cstats == nullptr &&
+  // (the zero-copy path runs the whole call as ONE chunk on the slot's workspaces: only when it fits them
+  // -- the "chunk" option may be as small as 8)
+  const long long zc_cap = std::min<long long>(
+      kZeroCopyMax, lane->slot[0].cap * (ctx->mode == WANN_MODE_FP32 ? 1 : kDevChunkMul));
+  if (ctx->zero_copy && n <= zc_cap && a.dbg == nullptr && a.children == nullptr && a.cstats == nullptr &&
       (a.probs != nullptr || a.logits != nullptr || a.idx != nullptr))
     return eval_host_small(ctx, lane, a, n);
   const long long cap = lane->slot[0].cap;
@@ -809,6 +1094,7 @@ int eval_host(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n) {
       if (rc != WANN_OK) return rc;
     }
     ChunkIO io;
+    io.top_k = a.top_k;
     if (a.squares) {
       CU(cudaMemcpyAsync(s.d_squares, a.squares + off * 64, m * 64, cudaMemcpyHostToDevice, s.stream));
       CU(cudaMemcpyAsync(s.d_black, a.black + off, m, cudaMemcpyHostToDevice, s.stream));
@@ -982,7 +1268,7 @@ int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* strea
   ReaderScope weights_scope(bypass ? nullptr : &ctx->weights_gate);   // (a combined call runs under its leader's)
   if (!bypass) ctx->stats[2] += 1;
   if (!bypass && ctx->coalesce && mem == WANN_MEM_HOST && a.squares != nullptr && a.dbg == nullptr &&
-      a.children == nullptr && a.cstats == nullptr && n <= kCombineMaxCall)
+      a.children == nullptr && a.cstats == nullptr && a.top_k == kMaxLegal && n <= kCombineMaxCall)
     return run_combined(ctx, a, n);
   Lane* lane = nullptr;
   int rc = acquire_lane(ctx, &lane);
@@ -1007,7 +1293,9 @@ const char* wann_last_error(void) { return g_err.c_str(); }
 int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx) {
   if (out_ctx == nullptr || w == nullptr) return fail(WANN_E_INVALID, "null argument");
   *out_ctx = nullptr;
-  if (mode != WANN_MODE_BF16 && mode != WANN_MODE_FP32 && mode != WANN_MODE_FP16 && mode != WANN_MODE_FP32_TC) return fail(WANN_E_INVALID, "bad mode %d", mode);
+  if (mode != WANN_MODE_BF16 && mode != WANN_MODE_FP32 && mode != WANN_MODE_FP16 && mode != WANN_MODE_FP32_TC &&
+      mode != WANN_MODE_FP16C)
+    return fail(WANN_E_INVALID, "bad mode %d", mode);
   if (w->final_kernel != 3 && w->final_kernel != 1)
     return fail(WANN_E_INVALID, "final_kernel must be 3 or 1");
   for (int i = 0; i < 5; ++i)
@@ -1032,14 +1320,13 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
   ctx->mode = mode;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->final_kernel = w->final_kernel;
-  int rc = upload_weights(ctx, *w);
-  if (rc == WANN_OK) {
+  int rc = WANN_OK;
+  {
+    e = cudaFuncSetAttribute(conv_stack_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_stack_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               kSmemBytes);
+      e = cudaFuncSetAttribute(conv_stack_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_stack_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               kSmemBytes);
+      e = cudaFuncSetAttribute(conv_stack_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_stack_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e == cudaSuccess)
@@ -1055,8 +1342,9 @@ int wann_create(const wann_weights* w, int device, int mode, wann_ctx** out_ctx)
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(expand_children_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) rc = fail(WANN_E_CUDA, "weight upload / kernel attributes: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) rc = fail(WANN_E_CUDA, "kernel attributes: %s", cudaGetErrorString(e));
   }
+  if (rc == WANN_OK) rc = upload_weights(ctx, *w);   // (the centred mode calibrates here: kernels run)
   if (rc != WANN_OK) {
     wann_destroy(ctx);
     return rc;
@@ -1101,6 +1389,7 @@ int wann_destroy(wann_ctx* ctx) {
   }
   for (int i = 0; i < 5; ++i) { cudaFree(ctx->d_conv_w[i]); cudaFree(ctx->d_conv_b[i]); }
   cudaFree(ctx->d_fc_w); cudaFree(ctx->d_fc_b); cudaFree(ctx->d_wimg); cudaFree(ctx->d_wimg_split); cudaFree(ctx->d_bias_tc);
+  cudaFree(ctx->d_bias_plain); cudaFree(ctx->d_unperm);
   delete ctx;
   return WANN_OK;
 }
@@ -1127,18 +1416,18 @@ int wann_eval_planes(wann_ctx* ctx, const void* planes, int planes_dtype, int64_
   return run_eval(ctx, a, n, mem, stream);
 }
 
-int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, uint8_t* idx,
+int wann_eval_topk(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, int k, uint8_t* idx,
                    float* prior, uint8_t* n_legal, int mem, void* stream) {
   if ((idx == nullptr || prior == nullptr || n_legal == nullptr) && n > 0)
     return fail(WANN_E_INVALID, "null output buffer");
   if (squares == nullptr && n > 0) return fail(WANN_E_INVALID, "squares is null");
   if (n < 0) return fail(WANN_E_INVALID, "negative n");
   EvalArgs a;
-  a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
+  a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal; a.top_k = clamp_top_k(k);
   return run_eval(ctx, a, n, mem, stream);
 }
 
-int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, uint8_t* idx,
+int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, int k, uint8_t* idx,
                      float* prior, uint8_t* n_legal, int8_t* child_squares, uint8_t* child_flags, int mem,
                      void* stream) {
   if ((idx == nullptr || prior == nullptr || n_legal == nullptr || child_squares == nullptr ||
@@ -1148,11 +1437,11 @@ int wann_eval_expand(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
   if (n < 0) return fail(WANN_E_INVALID, "negative n");
   EvalArgs a;
   a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
-  a.children = child_squares; a.cflags = child_flags;
+  a.children = child_squares; a.cflags = child_flags; a.top_k = clamp_top_k(k);
   return run_eval(ctx, a, n, mem, stream);
 }
 
-int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, uint8_t* idx,
+int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, int k, uint8_t* idx,
                             float* prior, uint8_t* n_legal, int8_t* child_squares, uint8_t* child_flags,
                             int32_t* child_stats, int32_t* parent_summary, int mem, void* stream) {
   if ((idx == nullptr || prior == nullptr || n_legal == nullptr || child_flags == nullptr ||
@@ -1166,6 +1455,7 @@ int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t*
   EvalArgs a;
   a.squares = squares; a.black = black; a.idx = idx; a.prior = prior; a.nlegal = n_legal;
   a.children = child_squares; a.cflags = child_flags; a.cstats = child_stats; a.psum = parent_summary;
+  a.top_k = clamp_top_k(k);
   return run_eval(ctx, a, n, mem, stream);
 }
 
@@ -1353,6 +1643,16 @@ int wann_kernel_times(wann_ctx* ctx, double out[2]) {
   return WANN_OK;
 }
 
+int wann_debug_centering(wann_ctx* ctx, float offsets[32], uint8_t position_of[768], float kappa[9]) {
+  if (ctx == nullptr || offsets == nullptr || position_of == nullptr) return fail(WANN_E_INVALID, "null argument");
+  if (ctx->mode != WANN_MODE_FP16C) return fail(WANN_E_INVALID, "centring exists in the fp16c mode only");
+  ReaderScope weights_scope(&ctx->weights_gate);
+  memcpy(offsets, ctx->cen.c, 32 * sizeof(float));
+  memcpy(position_of, ctx->cen.pos_of, 768);
+  if (kappa != nullptr) memcpy(kappa, ctx->kappa, 9 * sizeof(float));
+  return WANN_OK;
+}
+
 // CRC-32C (Castagnoli), the checksum of TF-V2 checkpoint bundles (model.index entries).
 uint32_t wann_crc32c(const void* data, uint64_t bytes, uint32_t seed) {
   static uint32_t table[8][256];
@@ -1415,12 +1715,31 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "refine_margin_micro") == 0) {
     // margin in 1e-6 logit units; 0 switches the refinement pass off
     if (value < 0 || value > 20000000) return fail(WANN_E_INVALID, "refine margin out of range");
-    if (value > 0 && ctx->mode != WANN_MODE_BF16 && ctx->mode != WANN_MODE_FP16)
+    if (value > 0 && !is_tc16(ctx->mode))
       return fail(WANN_E_INVALID, "margin refinement applies to the bf16/fp16 tensor-core modes");
     ctx->refine_ratio = value == 0 ? 0.f : expf(-static_cast<float>(value) * 1e-6f);
     return WANN_OK;
   }
   if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
+  if (strcmp(key, "split_layers") == 0) {
+    // centred mode: bit l (1..3) makes conv(l+1) stream its weights as fp16 hi + lo stages (2 MMAs per
+    // K-step in that layer: the layer's weight rounding error disappears); rebuilds the stage image
+    if (ctx->mode != WANN_MODE_FP16C) return fail(WANN_E_INVALID, "split_layers applies to the fp16c mode");
+    if (value < 0 || (value & ~14ll)) return fail(WANN_E_INVALID, "split_layers is a mask of bits 1..3");
+    DeviceGuard dev_guard(ctx->device);
+    CU(dev_guard.status);
+    ctx->weights_gate.writer_enter();
+    int rc = WANN_OK;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = fail(WANN_E_CUDA, "device synchronise: %s", cudaGetErrorString(e));
+    else {
+      ctx->split_mask = static_cast<int>(value);
+      const Centering cen = ctx->cen;
+      rc = upload_tc_image(ctx, host_weights_view(ctx), cen);
+    }
+    ctx->weights_gate.writer_exit();
+    return rc;
+  }
   if (strcmp(key, "chunk") == 0) {
     if (value < 8 || value > (1 << 20)) return fail(WANN_E_INVALID, "chunk out of range");
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -1537,18 +1856,26 @@ int wann_forest_play(wann_forest* fo, const int8_t* restart_squares, int restart
   if (fo == nullptr || restart_squares == nullptr) return fail(WANN_E_INVALID, "null argument");
   if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
   const int64_t n = static_cast<int64_t>(fo->f.trees.size());
+  for (int64_t t = 0; t < n; ++t)      // a tree that is mid-expansion cannot move: finish the next / apply cycle first
+    if (fo->f.trees[t].phase == wann_tree::Tree::kWaitEval)
+      return fail(WANN_E_INVALID, "tree %lld is waiting for an evaluation: run wann_forest_next / _apply until "
+                  "wann_forest_next returns no rows before wann_forest_play", static_cast<long long>(t));
 #pragma omp parallel for schedule(dynamic, 8)
   for (int64_t t = 0; t < n; ++t) {
     wann_tree::Tree& tr = fo->f.trees[t];
     const int32_t c = tr.best_move();
     uint8_t mv = 255, fin = 0;
+    bool restart = false;
     if (c >= 0) {
       mv = tr.nodes[c].index;
-      if (tr.nodes[c].gameover || !tr.advance_root(mv)) {      // the move wins the game: next game
-        fin = 1;
-        tr = wann_tree::Tree();
-        tr.init(restart_squares, restart_black != 0, 0);
-      }
+      restart = tr.nodes[c].gameover || !tr.advance_root(mv);   // the move wins the game: next game
+    } else {
+      restart = true;            // a root without children (never searched, or a finished game): start a new game
+    }
+    if (restart) {
+      fin = 1;
+      tr = wann_tree::Tree();
+      tr.init(restart_squares, restart_black != 0, 0);
     }
     if (moves_out != nullptr) moves_out[t] = mv;
     if (finished_out != nullptr) finished_out[t] = fin;

@@ -22,7 +22,7 @@ class PolicyEvaluator(object):
         self.final_kernel = final_kernel
         w, cw = self._c_weights(weights, final_kernel)
         self._keep = w
-        self.mode = {"bf16": L.MODE_BF16, "fp32": L.MODE_FP32, "fp16": L.MODE_FP16, "fp32_tc": L.MODE_FP32_TC}[mode] if isinstance(mode, str) else int(mode)
+        self.mode = L.MODES[mode] if isinstance(mode, str) else int(mode)
         self.device = int(device)
         ctx = ctypes.c_void_p()
         L.check(lib.wann_create(ctypes.byref(cw), self.device, self.mode, ctypes.byref(ctx)))
@@ -78,6 +78,14 @@ class PolicyEvaluator(object):
         """bf16/fp16 modes: re-evaluate, inside the same call, every position whose two best legal
         moves are closer than `margin_logits` with fp32-class arithmetic (0 switches it off)."""
         self.set_option("refine_margin_micro", int(round(float(margin_logits) * 1e6)))
+
+    def centering(self):
+        """fp16c mode: (offsets [4,8], position_of [4,192], kappa [9]) of the calibrated centring."""
+        off = np.zeros((4, 8), np.float32)
+        pos = np.zeros((4, 192), np.uint8)
+        kap = np.zeros(9, np.float32)
+        L.check(self._lib.wann_debug_centering(self._ctx, off.ctypes.data, pos.ctypes.data, kap.ctypes.data))
+        return off, pos, kap
 
     def stats(self):
         arr = (ctypes.c_uint64 * 8)()
@@ -152,8 +160,10 @@ class PolicyEvaluator(object):
                                            logits.ctypes.data if return_logits else None, L.MEM_HOST, None))
         return (probs, logits) if return_logits else probs
 
-    def eval_topk(self, squares, black, out=None):
-        """-> idx uint8 [n,48], prior float32 [n,48], n_legal uint8 [n] (sorted, descending)."""
+    def eval_topk(self, squares, black, out=None, k=0):
+        """-> idx uint8 [n,48], prior float32 [n,48], n_legal uint8 [n] (sorted, descending).
+        k: keep the k best legal children only (num_top of get_top_children, board_utils.pyx:279-291);
+        0 = all."""
         if _is_torch(squares):
             import torch
             n = squares.shape[0]
@@ -163,7 +173,7 @@ class PolicyEvaluator(object):
                        torch.empty((n, L.MAX_LEGAL), dtype=torch.float32, device=dev),
                        torch.empty((n,), dtype=torch.uint8, device=dev))
             idx, pri, cnt = out
-            L.check(self._lib.wann_eval_topk(self._ctx, squares.data_ptr(), black.data_ptr(), n, idx.data_ptr(),
+            L.check(self._lib.wann_eval_topk(self._ctx, squares.data_ptr(), black.data_ptr(), n, int(k), idx.data_ptr(),
                                              pri.data_ptr(), cnt.data_ptr(), L.MEM_DEVICE,
                                              self._torch_stream(squares)))
             return idx, pri, cnt
@@ -173,11 +183,11 @@ class PolicyEvaluator(object):
             out = (np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL), np.float32),
                    np.empty(n, np.uint8))
         idx, pri, cnt = out
-        L.check(self._lib.wann_eval_topk(self._ctx, sq.ctypes.data, bl.ctypes.data, n, idx.ctypes.data,
+        L.check(self._lib.wann_eval_topk(self._ctx, sq.ctypes.data, bl.ctypes.data, n, int(k), idx.ctypes.data,
                                          pri.ctypes.data, cnt.ctypes.data, L.MEM_HOST, None))
         return idx, pri, cnt
 
-    def eval_expand(self, squares, black):
+    def eval_expand(self, squares, black, k=0):
         """eval_topk + device-side child construction.  -> idx, prior, n_legal, child_squares int8
         [n,48,64], child_flags uint8 [n,48] (bit0 win, bit1 capture).  numpy in -> numpy out,
         torch CUDA tensors in -> torch CUDA tensors out (children stay on the device, ready to be
@@ -190,7 +200,7 @@ class PolicyEvaluator(object):
             cnt = torch.empty((n,), dtype=torch.uint8, device=dev)
             kids = torch.empty((n, L.MAX_LEGAL, 64), dtype=torch.int8, device=dev)
             flg = torch.empty((n, L.MAX_LEGAL), dtype=torch.uint8, device=dev)
-            L.check(self._lib.wann_eval_expand(self._ctx, squares.data_ptr(), black.data_ptr(), n, idx.data_ptr(),
+            L.check(self._lib.wann_eval_expand(self._ctx, squares.data_ptr(), black.data_ptr(), n, int(k), idx.data_ptr(),
                                                pri.data_ptr(), cnt.data_ptr(), kids.data_ptr(), flg.data_ptr(),
                                                L.MEM_DEVICE, self._torch_stream(squares)))
             return idx, pri, cnt, kids, flg
@@ -201,12 +211,12 @@ class PolicyEvaluator(object):
         cnt = np.empty(n, np.uint8)
         kids = np.empty((n, L.MAX_LEGAL, 64), np.int8)
         flg = np.empty((n, L.MAX_LEGAL), np.uint8)
-        L.check(self._lib.wann_eval_expand(self._ctx, sq.ctypes.data, bl.ctypes.data, n, idx.ctypes.data,
+        L.check(self._lib.wann_eval_expand(self._ctx, sq.ctypes.data, bl.ctypes.data, n, int(k), idx.ctypes.data,
                                            pri.ctypes.data, cnt.ctypes.data, kids.ctypes.data, flg.ctypes.data,
                                            L.MEM_HOST, None))
         return idx, pri, cnt, kids, flg
 
-    def eval_expand_seeded(self, squares, black, with_children=True, out=None):
+    def eval_expand_seeded(self, squares, black, with_children=True, out=None, k=0):
         """eval_expand + child seeding (wann_eval_expand_seeded).  -> idx, prior, n_legal,
         child_squares (or None), child_flags uint8 [n,48] (6 bits), child_stats int32 [n,48,4]
         (visits, wins, gameover_visits, gameover_wins), parent_summary int32 [n,8].
@@ -219,7 +229,7 @@ class PolicyEvaluator(object):
             kids = mk((n, L.MAX_LEGAL, 64), torch.int8) if with_children else None
             flg, st, ps = mk((n, L.MAX_LEGAL), torch.uint8), mk((n, L.MAX_LEGAL, 4), torch.int32), mk((n, 8), torch.int32)
             L.check(self._lib.wann_eval_expand_seeded(
-                self._ctx, squares.data_ptr(), black.data_ptr(), n, idx.data_ptr(), pri.data_ptr(), cnt.data_ptr(),
+                self._ctx, squares.data_ptr(), black.data_ptr(), n, int(k), idx.data_ptr(), pri.data_ptr(), cnt.data_ptr(),
                 kids.data_ptr() if with_children else None, flg.data_ptr(), st.data_ptr(), ps.data_ptr(),
                 L.MEM_DEVICE, self._torch_stream(squares)))
             return idx, pri, cnt, kids, flg, st, ps
@@ -233,7 +243,7 @@ class PolicyEvaluator(object):
             kids = np.empty((n, L.MAX_LEGAL, 64), np.int8) if with_children else None
             flg, st, ps = np.empty((n, L.MAX_LEGAL), np.uint8), np.empty((n, L.MAX_LEGAL, 4), np.int32), np.empty((n, 8), np.int32)
         L.check(self._lib.wann_eval_expand_seeded(
-            self._ctx, sq.ctypes.data, bl.ctypes.data, n, idx.ctypes.data, pri.ctypes.data, cnt.ctypes.data,
+            self._ctx, sq.ctypes.data, bl.ctypes.data, n, int(k), idx.ctypes.data, pri.ctypes.data, cnt.ctypes.data,
             kids.ctypes.data if with_children else None, flg.ctypes.data, st.ctypes.data, ps.ctypes.data,
             L.MEM_HOST, None))
         return idx, pri, cnt, kids, flg, st, ps

@@ -116,7 +116,7 @@ class MultiGpuEvaluator(object):
         self._run(n, work)
         return probs
 
-    def eval_topk(self, squares, black, out=None):
+    def eval_topk(self, squares, black, out=None, k=0):
         sq, bl = PolicyEvaluator._np_in(squares, black)
         n = sq.shape[0]
         if out is None:
@@ -125,7 +125,7 @@ class MultiGpuEvaluator(object):
         idx, pri, cnt = out
 
         def work(ev, lo, hi):
-            ev.eval_topk(sq[lo:hi], bl[lo:hi], out=(idx[lo:hi], pri[lo:hi], cnt[lo:hi]))
+            ev.eval_topk(sq[lo:hi], bl[lo:hi], out=(idx[lo:hi], pri[lo:hi], cnt[lo:hi]), k=k)
         self._run(n, work)
         return idx, pri, cnt
 

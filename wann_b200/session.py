@@ -53,7 +53,7 @@ class Session(object):
         if planes.shape[1:] != (8, 8, 4):
             raise ValueError("Cannot feed value of shape %s for placeholder of shape (?, 8, 8, 4)"
                              % (planes.shape,))
-        return self._nets[fetches.net].eval_planes(planes)
+        return eval_planes_as_boards(self._nets[fetches.net], planes)
 
     def evaluator(self, net):
         return self._nets[net]
@@ -71,24 +71,41 @@ class Session(object):
         self.close()
 
 
-# Default arithmetic of the shim: fp16 operands on the tensor cores (logits within 1.5e-3 of the
-# fp32 graph at the bf16 mode's speed) plus the margin-refinement pass, which re-evaluates the
-# ~2 % of positions whose two best legal moves are within 0.02 logits with fp32-class arithmetic:
+def eval_planes_as_boards(ev, planes):
+    """sess.run(y_pred, {X: planes}) / evaluate(already_converted=True) (MCTS.pyx:103-104).  Planes that
+    are a valid P/O/E/1 encoding (tools/utils.pyx:842-865) are turned back into side-to-move boards --
+    the encoding is invertible, and a side-to-move board IS a White-to-move board -- and go through
+    eval_probs, so that they get the same treatment as every other input form (margin refinement,
+    coalescing of concurrent small calls) and bit-identical outputs; anything else (soft or malformed
+    planes) is evaluated as given."""
+    p = np.asarray(planes)
+    if p.size and p.ndim == 4:
+        own, opp, emp, one = p[..., 0], p[..., 1], p[..., 2], p[..., 3]
+        if ((own == 0) | (own == 1)).all() and ((opp == 0) | (opp == 1)).all() and \
+                ((emp == 0) | (emp == 1)).all() and (one == 1).all() and (own + opp + emp == 1).all():
+            sq = (own + 2 * opp).astype(np.int8).reshape(-1, 64)
+            return ev.eval_probs(sq, np.zeros(sq.shape[0], np.uint8))
+    return ev.eval_planes(p)
+
+
+# Default arithmetic of the shim: the CENTRED fp16 mode on the tensor cores (logits within 1e-3 of the
+# fp32 graph, profiles/r02_accuracy_fp16c.json) plus the margin-refinement pass, which re-evaluates
+# the ~2 % of positions whose two best legal moves are within 0.02 logits with fp32-class arithmetic:
 # the policy move (get_best_move, board_utils.pyx:262-277) then equals the fp32 graph's on every
-# one of 100,000 test positions (profiles/r01_accuracy_100k_with_refinement.json).
+# one of 100,000 test positions.
 # Override per call (mode=..., refine_margin=...) or with WANN_B200_MODE / WANN_B200_REFINE_MARGIN.
-DEFAULT_MODE = os.environ.get("WANN_B200_MODE", "fp16")
+DEFAULT_MODE = os.environ.get("WANN_B200_MODE", "fp16c")
 DEFAULT_REFINE_MARGIN = float(os.environ.get("WANN_B200_REFINE_MARGIN", "0.02"))
 
 
-def _make(weights, device, mode, final_kernel, refine_margin=None):
+def _make(weights, device, mode, final_kernel, refine_margin=None, scope=""):
     mode = DEFAULT_MODE if mode is None else mode
     if refine_margin is None:
-        refine_margin = DEFAULT_REFINE_MARGIN if mode in ("fp16", "bf16") else 0.0
+        refine_margin = DEFAULT_REFINE_MARGIN if mode in ("fp16", "bf16", "fp16c") else 0.0
     # coalesce=True: the reference calls evaluate concurrently from its ThreadPool(10) + main
     # thread, each with a single node (expansion_MCTS_functions.pyx:105-119); concurrent small
     # calls are merged into one launch inside the C++ runtime.
-    w = weights if weights is not None else W.default_weights(final_kernel=final_kernel)
+    w = weights if weights is not None else W.default_weights(scope=scope, final_kernel=final_kernel)
     if isinstance(device, (list, tuple)):          # one process, several GPUs: host batches are sharded by position
         from .multi import MultiGpuEvaluator
         return MultiGpuEvaluator(w, devices=list(device), mode=mode, final_kernel=final_kernel, coalesce=True,
@@ -104,10 +121,13 @@ def instantiate_session(weights=None, device=0, mode=None, refine_margin=None):
 
 
 def _both(weights_white, weights_black, device, mode, final_kernel, refine_margin=None):
-    white = _make(weights_white, device, mode, final_kernel, refine_margin)
-    black = white if weights_black is None and weights_white is None else \
-        _make(weights_black if weights_black is not None else weights_white, device, mode, final_kernel,
-              refine_margin)
+    # policy_net_utils.pyx:22-25,43-46: the dual-net checkpoints keep their variables under the
+    # 'white_net/' and 'black_net/' scopes; with explicit weights, one dict may serve both colours
+    white = _make(weights_white, device, mode, final_kernel, refine_margin, scope="white_net/")
+    if weights_black is None and weights_white is not None:
+        black = white
+    else:
+        black = _make(weights_black, device, mode, final_kernel, refine_margin, scope="black_net/")
     sess = Session({"white_net": white, "black_net": black})
     return (sess, _Endpoint("white_net", "y_pred"), _Endpoint("white_net", "X"),
             _Endpoint("black_net", "y_pred"), _Endpoint("black_net", "X"))
@@ -153,7 +173,7 @@ class NeuralNetsCombined_128(object):
     def evaluate(self, game_nodes, player_color=None, is_player=True, already_converted=False):
         ev = self._net(is_player)
         if already_converted:                                   # MCTS.pyx:103-104
-            return ev.eval_planes(np.asarray(game_nodes))
+            return eval_planes_as_boards(ev, np.asarray(game_nodes))
         if player_color is not None:                            # MCTS.pyx:98-99: one board + colour
             sq = boards.board_to_squares(game_nodes)[None]
             bl = np.array([boards.color_is_black(player_color)], np.uint8)
@@ -168,11 +188,12 @@ class NeuralNetsCombined_128(object):
                          len(game_nodes))
         return sq, bl
 
-    def evaluate_children(self, game_nodes, is_player=True):
+    def evaluate_children(self, game_nodes, is_player=True, num_top=0):
         """Fused variant for callers that only need the ranked legal priors
-        (what enumerate_update_and_prune consumes, tree_builder.pyx:428-445)."""
+        (what enumerate_update_and_prune consumes, tree_builder.pyx:428-445).  num_top keeps the best
+        num_top legal children (get_top_children's argument, board_utils.pyx:279-291; 0 = all)."""
         sq, bl = self._nodes_to_arrays(game_nodes)
-        return self._net(is_player).eval_topk(sq, bl)
+        return self._net(is_player).eval_topk(sq, bl, k=num_top)
 
     def __enter__(self):
         return self

@@ -65,18 +65,36 @@ def validate(w, final_kernel=3):
     return out
 
 
+class MissingCheckpoint(FileNotFoundError):
+    """No weights were given and no checkpoint is configured."""
+
+
 def default_weights(scope="", final_kernel=3):
     """Weights used when the reference-shaped constructors are called with no arguments
-    (the reference hard-codes its checkpoint path, policy_net_utils.pyx:69).  Order:
-    $WANN_B200_CHECKPOINT (TF-V2 bundle prefix, CRC-verified), else $WANN_B200_FROZEN_GRAPH
-    (frozen GraphDef .pb, tf_graphdef.py), else the synthetic
-    'trained_like' preset (seed from $WANN_B200_SEED, default 1)."""
+    (the reference hard-codes its checkpoint path, policy_net_utils.pyx:69, and fails when the
+    checkpoint is missing).  Order: $WANN_B200_CHECKPOINT (TF-V2 bundle prefix, CRC-verified; `scope`
+    = 'white_net/' / 'black_net/' for the dual-net bundles of policy_net_utils.pyx:22-25, falling
+    back to the unscoped names when the bundle holds a single net), else $WANN_B200_FROZEN_GRAPH
+    (frozen GraphDef .pb, tf_graphdef.py).  Synthetic weights are used ONLY on explicit request
+    ($WANN_B200_SYNTHETIC=1: the 'trained_like' preset, seed from $WANN_B200_SEED, default 1);
+    otherwise a missing checkpoint raises MissingCheckpoint -- a drop-in that silently played on
+    random weights would be a trap."""
     prefix = os.environ.get("WANN_B200_CHECKPOINT")
     if prefix:
         from . import tf_bundle
+        if scope:
+            names = tf_bundle.read_index(prefix + ".index")
+            if not any(k.startswith(scope) for k in names):
+                scope = ""                        # a single-net bundle serves both colours
         return tf_bundle.load_policy_weights(prefix, scope=scope, final_kernel=final_kernel)
     frozen = os.environ.get("WANN_B200_FROZEN_GRAPH")
     if frozen:                                    # a frozen GraphDef (.pb) of the same architecture
         from . import tf_graphdef
         return tf_graphdef.load_frozen_weights(frozen, final_kernel=final_kernel)
-    return synthetic("trained_like", int(os.environ.get("WANN_B200_SEED", "1")), final_kernel)
+    if os.environ.get("WANN_B200_SYNTHETIC") == "1":
+        return synthetic("trained_like", int(os.environ.get("WANN_B200_SEED", "1")), final_kernel)
+    raise MissingCheckpoint(
+        "no policy-net weights: pass weights=..., or set WANN_B200_CHECKPOINT (TF-V2 bundle prefix, e.g. "
+        ".../policy_net_model/model) or WANN_B200_FROZEN_GRAPH (.pb).  The reference repository does not ship "
+        "its weight shard (policy_net_model/model.data-00000-of-00001); WANN_B200_SYNTHETIC=1 asks for the "
+        "synthetic 'trained_like' preset explicitly (tests, benchmarks).")
