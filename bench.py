@@ -13,12 +13,22 @@ collective on the data path).  The smaller configs (1 / 256 / 1024 positions) ar
 cases; their throughput (and the rest of the sweep, per-GPU batch sizes, whole-job
 positions/s) is listed under "sweep_positions_per_s" for information.
 
+Arithmetic of every number in the line unless a key says otherwise (`arithmetic` in `config`): the
+configuration that meets north_star's accuracy gates on 100,000 positions
+(tests/test_gpu_parity.py::test_centred_fp16_mode_meets_the_north_star_gates_on_100k_positions):
+mode fp16c (centred fp16 operands, fp32 accumulate), split_layers = 8 (hidden_layer/4's weights as
+fp16 hi + lo stages), no refinement pass (one kernel launch per evaluation).  Faster, less accurate
+modes -- and the same mode with margin refinement, which makes the policy move equal the fp32
+graph's on all 100,000 positions -- are extra keys under `modes`.
+
 `value`  : whole-job positions/s, inputs resident in HBM, device pointers through the C ABI.
 `e2e`    : same metric through the public host-buffer API (wann_eval_topk with pinned host
            arrays): every step copies its 65 B/position inputs H2D and its 241 B/position ranked
            priors D2H inside the timed region.
-`roofline`: conv_stack_tc kernel, algorithmic FLOPs per launch / CUDA-event time of the launch,
-           against the measured cuBLAS bf16 peak in MEASURED_PEAKS.json.
+`roofline`: conv_stack_tc kernel, ALGORITHMIC FLOPs per launch (the extra MMAs of a split layer are
+           overhead, not counted) / CUDA-event time of the launch, against the measured cuBLAS bf16
+           peak in MEASURED_PEAKS.json: the burst figure when the timed region is shorter than 1 s,
+           else the sustained one; `sustained` repeats the measurement over >= 3 s.
 """
 import argparse
 import json
@@ -67,7 +77,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -232,10 +242,12 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32_tc"])
+    ap.add_argument("--mode", default="fp16c", choices=["bf16", "fp16", "fp16c", "fp32_tc"])
+    ap.add_argument("--split-layers", type=int, default=None, help="fp16c: mask of hidden layers (bits 1..3) with hi+lo weights; default 8")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--refine-margin", type=float, default=0.02)
+    ap.add_argument("--refine-margin", type=float, default=None, help="logits; default 0 (no refinement pass)")
+    ap.add_argument("--sustained-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "ours" else 0)
@@ -265,7 +277,17 @@ def main():
               file=sys.stderr)
 
     B = args.batch
-    ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode=args.mode)
+    split_layers = (8 if args.mode == "fp16c" else 0) if args.split_layers is None else args.split_layers
+    refine_margin = 0.0 if args.refine_margin is None else args.refine_margin
+    ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode=args.mode,
+                                   refine_margin=refine_margin)
+    if split_layers:
+        ev.set_option("split_layers", split_layers)
+    arithmetic = {"bf16": "bf16 operands, fp32 accumulate", "fp16": "fp16 operands, fp32 accumulate",
+                  "fp32_tc": "fp16 hi/lo split operands (3 MMAs per K-step), fp32 accumulate",
+                  "fp16c": "centred fp16 operands (a - bucket mean; conv1/conv5 weights hi+lo), fp32 accumulate"}[args.mode]
+    arithmetic += "; split_layers=%d; margin refinement %.3g logit (fp32-class re-evaluation of near-ties)" % (
+        split_layers, refine_margin)
     for opt in os.environ.get("WANN_BENCH_OPTIONS", "").split(","):      # experiments: "skew=5,fuse_tail=0"
         if "=" in opt:
             ev.set_option(opt.split("=")[0].strip(), int(opt.split("=")[1]))
@@ -290,31 +312,50 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (`value`) --------------------------------
+    def timed_device_run(evaluator, steps, first):
+        """K steps between barriers, CUDA events on the launching stream, clocks sampled meanwhile,
+        conv-stack kernel bracketed by its own events (option time_kernels).  Max over ranks."""
+        evaluator.set_option("time_kernels", 1)
+        evaluator.kernel_times()
+        l0 = evaluator.stats()["kernel_launches"]
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            k = (first + i) % POOL_SETS
+            evaluator.eval_topk(sq_pool[k * B:(k + 1) * B], bl_pool[k * B:(k + 1) * B], out=outs[k])
+        e1.record()
+        barrier()
+        ms_local = e0.elapsed_time(e1)
+        clk = sampler.stop()
+        n_launch = evaluator.stats()["kernel_launches"] - l0
+        k_ms, k_launches = evaluator.kernel_times()
+        evaluator.set_option("time_kernels", 0)
+        tt = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return dict(ms=float(tt.item()), ms_local=ms_local, clocks=clk, launches=n_launch, conv_ms=k_ms,
+                    conv_launches=max(k_launches, 1), steps=steps)
+
+    def roofline_of(run, peak, peak_kind):
+        per_launch_pos = B * run["steps"] / run["conv_launches"]
+        ach = FLOP_PER_POS_CONV * per_launch_pos / (run["conv_ms"] / run["conv_launches"] * 1e-3) / 1e12
+        return ach, per_launch_pos
+
     for i in range(args.warmup):
         step(i)
     barrier()
-    ev.set_option("time_kernels", 1)
-    ev.kernel_times()
-    launches0 = ev.stats()["kernel_launches"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    launches = ev.stats()["kernel_launches"] - launches0
-    conv_ms, conv_launches = ev.kernel_times()
-    ev.set_option("time_kernels", 0)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    main_run = timed_device_run(ev, args.steps, args.warmup)
+    ms, ms_max, clocks, launches = main_run["ms_local"], main_run["ms"], main_run["clocks"], main_run["launches"]
+    conv_ms, conv_launches = main_run["conv_ms"], main_run["conv_launches"]
     value = n_gpus * B * args.steps / (ms_max * 1e-3)
+    # the same measurement over >= 3 s back to back: what the power-capped clock sustains
+    sustained_run = None
+    if args.sustained_seconds > 0:
+        s_steps = max(args.steps, int(np.ceil(args.sustained_seconds * 1e3 / (ms_max / args.steps))))
+        sustained_run = timed_device_run(ev, s_steps, args.warmup + args.steps)
 
     # ---------------- end to end through the host-buffer API (`e2e`) ----------------------
     h_sq = torch.from_numpy(sq_np[:B].copy()).pin_memory()
@@ -383,8 +424,8 @@ def main():
         from wann_b200 import SearchForest
         from wann_b200.forest import host_threads
         host_threads(max(1, (os.cpu_count() or 1) // max(1, world)))      # torchrun exports OMP_NUM_THREADS=1
-        ev3 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode="fp16",
-                                        refine_margin=args.refine_margin)
+        ev3 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode="fp16c",
+                                        refine_margin=0.02)
         n_trees, sims = 1024, 10
         forest = SearchForest(sq_np[:n_trees], bl_np[:n_trees])
         forest.run(ev3, 1)                                          # warm-up: first expansions, lane allocation
@@ -406,33 +447,43 @@ def main():
         forest.close()
         ev3.close()
 
-    # ---------------- fp16 operands + margin refinement: the configuration that meets north_star's
-    # top-1 >= 99.9 % gate (profiles/*accuracy*.json) -- same workload, device resident
-    refined = None
+    # ---------------- the other arithmetic modes on the same workload (device resident, short runs):
+    # faster and less accurate (bf16, fp16, fp16c without the split layer), or slower and more accurate
+    modes = None
     if not args.no_sweep:
-        ev2 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode="fp16",
-                                        refine_margin=args.refine_margin)
-        for i in range(3):
-            ev2.eval_topk(sq_pool[i * B:(i + 1) * B], bl_pool[i * B:(i + 1) * B], out=outs[i])
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        rsteps = max(3, min(args.steps, 50))
-        a.record()
-        for i in range(rsteps):
-            k = (3 + i) % POOL_SETS
-            ev2.eval_topk(sq_pool[k * B:(k + 1) * B], bl_pool[k * B:(k + 1) * B], out=outs[k])
-        b.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ev2.eval_topk(sq_np[:B], bl_np[:B])                      # host calls read the device-side counter back:
-        r0 = ev2.stats()["refined_positions"]                    # the first drains the timed loop's total,
-        ev2.eval_topk(sq_np[:B], bl_np[:B])                      # the second counts one batch
-        frac = (ev2.stats()["refined_positions"] - r0) / float(B)
-        refined = {"mode": "fp16", "refine_margin_logits": args.refine_margin, "refined_fraction": round(frac, 5),
+        modes = {}
+        for name, mode, split, margin in (("bf16", "bf16", 0, 0.0), ("fp16", "fp16", 0, 0.0),
+                                          ("fp16+refine0.02", "fp16", 0, 0.02), ("fp16c", "fp16c", 0, 0.0),
+                                          ("fp16c+refine0.01", "fp16c", 0, 0.01),
+                                          ("fp16c+split8+refine0.01", "fp16c", 8, 0.01),
+                                          ("fp16c+split14", "fp16c", 14, 0.0)):
+            ev2 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode=mode,
+                                            refine_margin=margin)
+            if split:
+                ev2.set_option("split_layers", split)
+            for i in range(3):
+                ev2.eval_topk(sq_pool[i * B:(i + 1) * B], bl_pool[i * B:(i + 1) * B], out=outs[i])
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rsteps = max(3, min(args.steps, 40))
+            a.record()
+            for i in range(rsteps):
+                k = (3 + i) % POOL_SETS
+                ev2.eval_topk(sq_pool[k * B:(k + 1) * B], bl_pool[k * B:(k + 1) * B], out=outs[k])
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rec = {"mode": mode, "split_layers": split, "refine_margin_logits": margin,
                    "value": n_gpus * B * rsteps / (float(t.item()) * 1e-3), "unit": UNIT, "steps": rsteps}
-        ev2.close()
+            if margin:
+                ev2.eval_topk(sq_np[:B], bl_np[:B])                  # host calls read the device-side counter back:
+                r0 = ev2.stats()["refined_positions"]                # the first drains the timed loop's total,
+                ev2.eval_topk(sq_np[:B], bl_np[:B])                  # the second counts one batch
+                rec["refined_fraction"] = round((ev2.stats()["refined_positions"] - r0) / float(B), 5)
+            modes[name] = rec
+            ev2.close()
 
     # ---------------- the HBM-bound byte kernels beside the path (north_star: "achieved HBM GB/s for
     # encode and epilogue"): encode 65 B -> 256 B, legal mask 65 B -> 155 B per position, device resident
@@ -467,6 +518,38 @@ def main():
                                  "achieved_gbs": round(nbk * bpp / sec / 1e9, 1),
                                  "frac": round(nbk * bpp / sec / 1e9 / hbm_peak, 4)}
         del d_planes, d_mask
+        # child construction (65+49 B in, 3,120 B out per position) and child seeding (65+48+192+1 B in,
+        # 768+48+32 B out) on already-ranked positions (wann_expand_ranked)
+        nck = min(pool_n, 1 << 17)
+        d_idx = torch.empty((nck, 48), dtype=torch.uint8, device=dev)
+        d_pri = torch.empty((nck, 48), dtype=torch.float32, device=dev)
+        d_cnt = torch.empty((nck,), dtype=torch.uint8, device=dev)
+        ev.eval_topk(sq_pool[:nck], bl_pool[:nck], out=(d_idx, d_pri, d_cnt))
+        d_kids = torch.empty((nck, 48, 64), dtype=torch.int8, device=dev)
+        d_flg = torch.empty((nck, 48), dtype=torch.uint8, device=dev)
+        d_st = torch.empty((nck, 48, 4), dtype=torch.int32, device=dev)
+        d_ps = torch.empty((nck, 8), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        for name, kids_t, st_t, bpp in (("expand_children_kernel", d_kids, None, 65 + 49 + 48 * 64 + 48),
+                                        ("seed_children_kernel", None, d_st, 65 + 48 + 192 + 1 + 768 + 48 + 32)):
+            call = lambda: L.check(ev._lib.wann_expand_ranked(   # noqa: E731
+                ev._ctx, sq_pool.data_ptr(), bl_pool.data_ptr(), nck, d_idx.data_ptr(), d_pri.data_ptr(), d_cnt.data_ptr(),
+                kids_t.data_ptr() if kids_t is not None else None, d_flg.data_ptr(),
+                st_t.data_ptr() if st_t is not None else None, d_ps.data_ptr() if st_t is not None else None, s1))
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                call()
+            b.record()
+            torch.cuda.synchronize()
+            sec = a.elapsed_time(b) / 10 * 1e-3
+            hbm_kernels[name] = {"positions": nck, "bytes_per_position": bpp, "us": round(sec * 1e6, 2),
+                                 "achieved_gbs": round(nck * bpp / sec / 1e9, 1),
+                                 "frac": round(nck * bpp / sec / 1e9 / hbm_peak, 4)}
+        del d_kids, d_st
 
     # ---------------- optional: counters gathered with NCCL, sweep, CPU baseline ----------
     counters = gather_counters([B * args.steps, int(ms * 1e6)], device=dev)
@@ -475,7 +558,7 @@ def main():
     # whole-job positions/s from the max-over-ranks CUDA-event time
     sweep = {}
     if not args.no_sweep:
-        for nb in (1, 64, 256, 1024, 4096, 8192, 16384, 65536):
+        for nb in (1, 4, 16, 64, 256, 1024, 4096, 8192, 16384, 65536):   # policy_net_metrics.py:39-100
             o = tuple(x[:nb] for x in outs[0])
             for _ in range(3):
                 ev.eval_topk(sq_pool[:nb], bl_pool[:nb], out=o)
@@ -497,41 +580,72 @@ def main():
 
     if rank == 0:
         burst, sustained, src = peaks()
-        per_launch_pos = B * args.steps / max(conv_launches, 1)
-        achieved = FLOP_PER_POS_CONV * per_launch_pos / (conv_ms / max(conv_launches, 1) * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         summ = os.path.join(ROOT, "profiles", "ncu_summary.json")
         if os.path.exists(summ):
-            traffic = json.load(open(summ)).get("conv_stack_tc", {}).get("dram_bytes_per_launch")
+            rec = json.load(open(summ)).get("conv_stack_tc", {})
+            traffic = rec.get("dram_bytes_per_launch")
+            traffic_src = ("profiles/ncu_summary.json: %s (static value from the committed ncu --set full "
+                           "capture, NOT measured in this run)" % rec.get("source", "r01 capture, bf16 mode"))
+
+        def roof(run):
+            ach, per_launch = roofline_of(run, None, None)
+            short = run["ms"] < 1000.0
+            peak = burst if short else sustained
+            return {"bound": "tensor", "kernel": "conv_stack_tc_kernel<%s>" % args.mode, "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak,
+                    "peak_kind": "%s cuBLAS bf16 %s" % (src, "burst (timed region %.2f s < 1 s)" % (run["ms"] * 1e-3) if short
+                                                        else "sustained (timed region %.2f s)" % (run["ms"] * 1e-3)),
+                    "frac_of_burst_peak": ach / burst, "frac_of_sustained_peak": ach / sustained,
+                    "burst_peak": burst, "sustained_peak": sustained,
+                    "flop_per_position": FLOP_PER_POS_CONV,
+                    "flop_note": "algorithmic FLOPs of conv1..conv5; the second MMA per K-step of a split layer "
+                                 "(split_layers=%d) and the refinement pass are overhead and not counted" % split_layers,
+                    "positions_per_launch": per_launch,
+                    "kernel_ms_per_launch": run["conv_ms"] / run["conv_launches"],
+                    "kernel_share_of_step": run["conv_ms"] / run["ms_local"]}
+        roofline = roof(main_run)
+        roofline["traffic"] = traffic
+        roofline["traffic_source"] = traffic_src
+        sustained_rec = None
+        if sustained_run is not None:
+            sustained_rec = {"value": n_gpus * B * sustained_run["steps"] / (sustained_run["ms"] * 1e-3), "unit": UNIT,
+                             "steps": sustained_run["steps"], "seconds": sustained_run["ms"] * 1e-3,
+                             "clocks": sustained_run["clocks"], "roofline": roof(sustained_run)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16" if args.mode in ("fp16", "fp16c", "fp32_tc") else "bf16",
+            "data": "synthetic",
             "config": {"workload": "configs[3] batch sweep, top batch: %d positions per GPU per step, "
                                    "full path encode->conv stack->FC->softmax->legal gather+sort "
                                    "(ranked child priors out)" % B,
+                       "mode": args.mode, "split_layers": split_layers, "refine_margin_logits": refine_margin,
+                       "arithmetic": arithmetic,
+                       "accuracy": "this configuration on 100,000 positions vs the fp32 graph: see profiles/r02_accuracy_fp16c.json "
+                                   "and tests/test_gpu_parity.py::test_centred_fp16_mode_meets_the_north_star_gates_on_100k_positions",
                        "weights": "synthetic trained_like seed 1 (reference weight shard absent)",
                        "positions": "seeded random legal play-out positions",
                        "l2": "inputs/outputs rotate over %d buffer sets (%.0f MB) > 126 MB L2; 2 MB of "
                              "weights stay L2-resident by design" % (POOL_SETS, POOL_SETS * B * (IN_BYTES + OUT_BYTES) / 1e6),
                        "parallelism": "replicas x%d, leaf batches sharded per GPU, no collective" % n_gpus},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * IN_BYTES,
-                    "d2h_bytes_per_step": B * OUT_BYTES, "api": "wann_eval_topk(WANN_MEM_HOST), pinned buffers"},
+                    "d2h_bytes_per_step": B * OUT_BYTES, "api": "wann_eval_topk(WANN_MEM_HOST), pinned buffers",
+                    "mode": args.mode, "split_layers": split_layers, "refine_margin_logits": refine_margin,
+                    "note": "may exceed `value`: the host path runs 16,384-position chunks double-buffered on two "
+                            "streams (copies hidden under the kernels), the power-capped kernel is faster per position "
+                            "at 16,384 than at 65,536 positions per launch (see sweep_positions_per_s), and `value` "
+                            "is taken with per-launch event bracketing (time_kernels) on"},
             "e2e_probs": {"value": e2e_probs_value, "unit": UNIT, "h2d_bytes_per_step": B * IN_BYTES,
-                          "d2h_bytes_per_step": B * 155 * 4,
+                          "d2h_bytes_per_step": B * 155 * 4, "mode": args.mode,
                           "api": "wann_eval_probs(WANN_MEM_HOST): full [N,155] rows, the reference's evaluate() output"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv_stack_tc_kernel", "achieved": achieved,
-                         "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                         "peak_kind": "%s cuBLAS bf16, sustained (kernel timed inside a long step)" % src,
-                         "frac_of_burst_peak": achieved / burst, "burst_peak": burst,
-                         "flop_per_position": FLOP_PER_POS_CONV, "positions_per_launch": per_launch_pos,
-                         "kernel_ms_per_launch": conv_ms / max(conv_launches, 1),
-                         "kernel_share_of_step": conv_ms / ms, "traffic": traffic},
+            "roofline": roofline,
+            "sustained": sustained_rec,
             "sweep_positions_per_s": sweep,
             "config5_game_trees": trees,
-            "fp16_margin_refined": refined,
+            "modes": modes,
             "config5_search_forest": forest_line,
             "hbm_kernels": hbm_kernels,
             "per_rank_counters": counters.tolist(),

@@ -180,6 +180,19 @@ int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t*
                             int8_t* child_squares, uint8_t* child_flags, int32_t* child_stats,
                             int32_t* parent_summary, int mem, void* stream);
 
+/* The child half of wann_eval_expand_seeded on its own, for positions whose ranked children are
+ * already known (idx / prior / n_legal as written by wann_eval_topk): child boards and flags
+ * (get_child_attributes + move_piece_update_piece_arrays + check_for_winning_move,
+ * tree_builder.pyx:623-658,902-905, board_utils.pyx:90-131) when child_squares != NULL, and the
+ * child seeds / parent summary (update_child, assign_children, eval_children,
+ * tree_search_utils.pyx:963-1071, tree_builder.pyx:538-620) when child_stats != NULL.  DEVICE
+ * pointers only, 16-byte aligned; enqueued on `stream` (NULL = the legacy default stream, then a
+ * synchronize).  Also what bench.py times to report these two kernels' HBM bandwidth. */
+int wann_expand_ranked(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n,
+                       const uint8_t* idx, const float* prior, const uint8_t* n_legal,
+                       int8_t* child_squares, uint8_t* child_flags, int32_t* child_stats,
+                       int32_t* parent_summary, void* stream);
+
 /* One self-play style step for n independent games, entirely on the device (BASELINE config 5:
  * independent game trees, each contributing one leaf per step): evaluate the positions, pick ONE
  * child per game -- greedy != 0: the policy move (get_best_move, board_utils.pyx:262-277);

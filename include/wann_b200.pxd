@@ -53,6 +53,10 @@ cdef extern from "wann_b200.h" nogil:
                                 uint8_t* idx, float* prior, uint8_t* n_legal, int8_t* child_squares,
                                 uint8_t* child_flags, int32_t* child_stats, int32_t* parent_summary,
                                 int mem, void* stream)
+    int wann_expand_ranked(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move, int64_t n,
+                           const uint8_t* idx, const float* prior, const uint8_t* n_legal,
+                           int8_t* child_squares, uint8_t* child_flags, int32_t* child_stats,
+                           int32_t* parent_summary, void* stream)
     int wann_tree_step(wann_ctx* ctx, int8_t* squares, uint8_t* black_to_move, int64_t n, int greedy,
                        uint64_t seed, uint64_t step, uint8_t* chosen_idx, uint8_t* finished, void* stream)
     int wann_debug_activations(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,

@@ -180,7 +180,7 @@ def test_centred_fp16_mode_meets_the_north_star_gates_on_100k_positions(weights)
     """north_star: logits and probabilities within 1e-3 relative of the fp32 graph, top-1 >= 99.9 % on a
     fixed suite of random legal positions -- measured on 100,000 positions against the fp32 mode (itself
     within 1e-5 of the CPU oracle, test_fp32_mode_matches_oracle_1e5), for the benchmark's configuration
-    (fp16c, split_layers = 8, refinement margin 0.01 logit) and for the plain centred mode."""
+    (fp16c, split_layers = 8, no refinement pass), the same with margin refinement, and the plain centred mode."""
     import wann_b200
     from wann_b200 import synthetic
     sq, bl = synthetic.random_positions(100000, seed=20260601)
@@ -196,12 +196,15 @@ def test_centred_fp16_mode_meets_the_north_star_gates_on_100k_positions(weights)
                     pmed=np.median(np.abs(p - p32) / p32),
                     prow=np.median(np.linalg.norm(p - p32, axis=1) / np.linalg.norm(p32, axis=1)),
                     top1=(idx[:, 0] == i32[:, 0]).mean(), counts=np.array_equal(cnt, c32))
-    with wann_b200.PolicyEvaluator(weights, mode="fp16c", refine_margin=0.01) as ev:
+    with wann_b200.PolicyEvaluator(weights, mode="fp16c") as ev:
         ev.set_option("split_layers", 8)
         m = measure(ev)
-        assert m["maxnorm"] <= 1e-3 and m["relrms"] <= 1e-3, m       # logits
-        assert m["pmed"] <= 1e-3 and m["prow"] <= 1e-3, m            # probabilities
-        assert m["top1"] >= 0.999 and m["counts"], m                 # policy move (measured: 100 %)
+        assert m["maxnorm"] <= 1e-3 and m["relrms"] <= 1e-3, m       # logits (measured 7.0e-4 / 5.2e-4)
+        assert m["pmed"] <= 1e-3 and m["prow"] <= 1e-3, m            # probabilities (measured 9.4e-4 / 8.8e-4)
+        assert m["top1"] >= 0.999 and m["counts"], m                 # policy move (measured 99.946 %)
+        ev.set_refine_margin(0.01)                                    # + margin refinement: every policy move agrees
+        m = measure(ev)
+        assert m["maxnorm"] <= 1e-3 and m["pmed"] <= 1e-3 and m["top1"] == 1.0, m
     with wann_b200.PolicyEvaluator(weights, mode="fp16c") as ev:      # no split, no refinement: full speed
         m = measure(ev)
         assert m["maxnorm"] <= 1e-3 and m["relrms"] <= 1e-3 and m["top1"] >= 0.999, m

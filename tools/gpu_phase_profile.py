@@ -10,7 +10,10 @@ n = int(os.environ.get("N", "8192"))
 sq, bl = synthetic.random_positions(min(n, 2048), seed=5)
 reps = (n + len(sq) - 1) // len(sq)
 sq = np.tile(sq, (reps, 1))[:n]; bl = np.tile(bl, reps)[:n]
-ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), mode="bf16")
+ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), mode=os.environ.get("MODE", "bf16"))
+if os.environ.get("SPLIT"):
+    ev.set_option("split_layers", int(os.environ["SPLIT"]))
+print("mode", os.environ.get("MODE", "bf16"), "split_layers", os.environ.get("SPLIT", "0"))
 for variant in [int(v) for v in os.environ.get("VARIANTS", "0").split(",")]:
   ev.set_option("variant", variant & 0xFFFF)
   ev.set_option("skew", variant >> 16)

@@ -16,7 +16,7 @@ N_MOVES, MAX_LEGAL = 155, 48
 
 EXPORTS = [
     "wann_create", "wann_set_weights", "wann_destroy", "wann_last_error", "wann_encode", "wann_legal_mask",
-    "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_eval_expand", "wann_eval_expand_seeded", "wann_tree_step", "wann_debug_activations",
+    "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_eval_expand", "wann_eval_expand_seeded", "wann_expand_ranked", "wann_tree_step", "wann_debug_activations",
     "wann_debug_profile", "wann_debug_centering", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
     "wann_forest_create", "wann_forest_destroy", "wann_forest_next", "wann_forest_apply", "wann_forest_info",
@@ -57,6 +57,7 @@ def load():
     lib.wann_eval_topk.argtypes = [vp, vp, vp, i64, ci, vp, vp, vp, ci, vp]
     lib.wann_eval_expand.argtypes = [vp, vp, vp, i64, ci, vp, vp, vp, vp, vp, ci, vp]
     lib.wann_eval_expand_seeded.argtypes = [vp, vp, vp, i64, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
+    lib.wann_expand_ranked.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.wann_host_threads.argtypes = [ci]
     lib.wann_forest_create.argtypes = [i64, vp, vp, vp, ctypes.POINTER(vp)]
     lib.wann_forest_destroy.argtypes = [vp]

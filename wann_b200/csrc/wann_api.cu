@@ -1459,6 +1459,38 @@ int wann_eval_expand_seeded(wann_ctx* ctx, const int8_t* squares, const uint8_t*
   return run_eval(ctx, a, n, mem, stream);
 }
 
+int wann_expand_ranked(wann_ctx* ctx, const int8_t* squares, const uint8_t* black, int64_t n, const uint8_t* idx,
+                       const float* prior, const uint8_t* n_legal, int8_t* child_squares, uint8_t* child_flags,
+                       int32_t* child_stats, int32_t* parent_summary, void* stream_v) {
+  if (ctx == nullptr) return fail(WANN_E_INVALID, "null context");
+  if (n < 0) return fail(WANN_E_INVALID, "negative n");
+  if (n == 0) return WANN_OK;
+  if (!squares || !black || !idx || !prior || !n_legal || !child_flags)
+    return fail(WANN_E_INVALID, "null buffer");
+  if (child_squares == nullptr && child_stats == nullptr) return fail(WANN_E_INVALID, "nothing to produce");
+  if (child_stats != nullptr && parent_summary == nullptr) return fail(WANN_E_INVALID, "child_stats needs parent_summary");
+  if ((reinterpret_cast<uintptr_t>(child_squares) | reinterpret_cast<uintptr_t>(child_stats) |
+       reinterpret_cast<uintptr_t>(parent_summary) | reinterpret_cast<uintptr_t>(idx) |
+       reinterpret_cast<uintptr_t>(prior)) & 15u)
+    return fail(WANN_E_INVALID, "device buffers must be 16-byte aligned");
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int eb = static_cast<int>(std::min<long long>((n + 7) / 8, 16ll * ctx->sm_count));
+  if (child_squares != nullptr) {
+    expand_children_kernel<<<eb, 256, 0, stream>>>(squares, black, idx, n_legal, n, child_squares, child_flags);
+    ctx->stats[1] += 1;
+  }
+  if (child_stats != nullptr) {
+    seed_children_kernel<<<eb, 256, 0, stream>>>(squares, black, idx, prior, n_legal, n, child_stats, child_flags,
+                                                 parent_summary);
+    ctx->stats[1] += 1;
+  }
+  CU(cudaGetLastError());
+  if (stream_v == nullptr) CU(cudaStreamSynchronize(stream));
+  return WANN_OK;
+}
+
 int wann_tree_step(wann_ctx* ctx, int8_t* squares, uint8_t* black, int64_t n, int greedy, uint64_t seed,
                    uint64_t step, uint8_t* chosen_idx, uint8_t* finished, void* stream_v) {
   if (ctx == nullptr) return fail(WANN_E_INVALID, "null context");
