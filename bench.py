@@ -416,35 +416,44 @@ def main():
                                "us_per_step": round(float(t.item()) * 1e3 / tsteps, 2),
                                "positions_per_s": round(n_gpus * n_trees * tsteps / (float(t.item()) * 1e-3), 1)}
 
-    # ---------------- configs[4] with the REFERENCE'S OWN SEARCH per tree: a forest of native array trees
-    # (wann_forest_*, node-for-node the compiled reference's trees) advancing in lock step, one
-    # wann_eval_expand_seeded call per step (host buffers), 1,024 trees per GPU
+    # ---------------- configs[4] with the REFERENCE'S OWN SEARCH per tree: a forest of array trees
+    # (node-for-node the compiled reference's trees), 1,024 trees per GPU (and 8,192), the headline arithmetic.
+    # DEVICE-RESIDENT forest: trees in HBM, one warp per tree, each
+    # lock step = tree kernel -> conv stack -> child seeding -> tree kernel on one stream (wann_forest_run);
+    # and, for comparison, the HOST forest (OpenMP tree code, one host-buffer evaluation call per step).
     forest_line = None
     if not args.no_sweep:
         from wann_b200 import SearchForest
         from wann_b200.forest import host_threads
         host_threads(max(1, (os.cpu_count() or 1) // max(1, world)))      # torchrun exports OMP_NUM_THREADS=1
-        ev3 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode="fp16c",
-                                        refine_margin=0.02)
-        n_trees, sims = 1024, 10
-        forest = SearchForest(sq_np[:n_trees], bl_np[:n_trees])
-        forest.run(ev3, 1)                                          # warm-up: first expansions, lane allocation
-        nodes0 = sum(forest.info(t)["nodes"] for t in range(n_trees))
-        barrier()
-        t0 = time.perf_counter()
-        fsteps, fevals = forest.run(ev3, sims)
-        dt = time.perf_counter() - t0
-        nodes = sum(forest.info(t)["nodes"] for t in range(n_trees)) - nodes0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        cnts = torch.tensor([fevals, nodes], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
-        forest_line = {"trees_per_gpu": n_trees, "simulations_per_tree": sims - 1, "lock_steps": fsteps,
-                       "evaluations": int(cnts[0].item()), "tree_nodes": int(cnts[1].item()),
-                       "evaluations_per_s": round(float(cnts[0].item()) / float(t.item()), 1),
-                       "host_threads_per_rank": host_threads()}
-        forest.close()
+        ev3 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode="fp16c")
+        ev3.set_option("split_layers", 8)                 # the headline arithmetic (one launch per evaluation)
+        forest_line = {"arithmetic": "fp16c, split_layers=8, no refinement pass"}
+        for key, n_trees, resident, sims in (("device_resident", 1024, True, 24), ("device_resident_8192", 8192, True, 12),
+                                             ("host", 1024, False, 10)):
+            fsq, fbl = sq_np[:n_trees], bl_np[:n_trees]
+            forest = SearchForest(fsq, fbl, evaluator=ev3, device_resident=resident, node_capacity=16384)
+            forest.run(ev3, 1)                                          # warm-up: first expansions, lane allocation
+            barrier()
+            t0 = time.perf_counter()
+            fsteps, fevals = forest.run(ev3, sims)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            sample = range(0, n_trees, max(1, n_trees // 64))
+            nodes = float(np.mean([forest.info(t)["nodes"] for t in sample])) * n_trees
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            cnts = torch.tensor([fevals, nodes], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
+            forest_line[key] = {"trees_per_gpu": n_trees, "simulations_per_tree": sims - 1, "lock_steps": fsteps,
+                                "evaluations": int(cnts[0].item()), "tree_nodes_estimate": int(cnts[1].item()),
+                                "evaluations_per_s": round(float(cnts[0].item()) / float(t.item()), 1),
+                                "us_per_lock_step": round(dt * 1e6 / max(fsteps, 1), 1)}
+            if not resident:
+                forest_line[key]["host_threads_per_rank"] = host_threads()
+            forest.close()
+        forest_line["evaluations_per_s"] = forest_line["device_resident"]["evaluations_per_s"]
         ev3.close()
 
     # ---------------- the other arithmetic modes on the same workload (device resident, short runs):

@@ -232,12 +232,32 @@ typedef struct wann_forest wann_forest;
 int wann_forest_create(int64_t n_trees, const int8_t* squares, const uint8_t* black_to_move,
                        const int32_t* heights /* ply of each root, may be NULL */, wann_forest** out);
 int wann_forest_destroy(wann_forest* forest);
+/* The same forest, DEVICE-RESIDENT: tree headers, node records (72 B) and evaluated positions live in
+ * the context's GPU memory, `node_capacity` nodes per tree (0 = 16,384; fixed -- a tree that fills its
+ * arena stops and reports finished = 2 in wann_forest_info).  The tree code is the host forest's,
+ * compiled for the device (array_tree.hpp): one warp per tree, so the trees are node for node the
+ * same.  Such a forest is driven by wann_forest_run and wann_forest_play only; _info / _dump copy the
+ * tree back.  Destroy it before its context. */
+int wann_forest_create_device(wann_ctx* ctx, int64_t n_trees, const int8_t* squares,
+                              const uint8_t* black_to_move, const int32_t* heights, int32_t node_capacity,
+                              wann_forest** out);
+/* The search loop inside the library (expansion_MCTS_functions.pyx:105-119 for many trees at once):
+ * every tree does max_simulations simulations.  Host forest: wann_forest_next -> one
+ * wann_eval_expand_seeded -> wann_forest_apply per lock step, pinned rows.  Device forest: per lock step
+ * forest_next_kernel -> conv stack + fused tail -> seed_children_kernel -> forest_apply_kernel are
+ * enqueued on one stream, the number of requested rows stays on the device, and the host only looks
+ * at the per-step row counts every 8 steps.  out[0] = lock steps, out[1] = evaluations (optional). */
+int wann_forest_run(wann_ctx* ctx, wann_forest* forest, int64_t max_simulations, int64_t out[2]);
+/* Inspection hook (device-resident forests): the last 64 lock steps, oldest first, out int64 [64][5]:
+ * rows requested, then the clock64 cycles the trees spent in forest_next_kernel (sum over trees, max)
+ * and in forest_apply_kernel (sum, max). */
+int wann_forest_debug_cycles(wann_forest* forest, int64_t* out);
 int wann_forest_next(wann_forest* forest, int64_t max_simulations, int8_t* squares_out,
                      uint8_t* black_out, int64_t* tree_ids, int64_t* m_out);
 int wann_forest_apply(wann_forest* forest, const uint8_t* idx, const float* prior, const uint8_t* n_legal,
                       const uint8_t* child_flags, const int32_t* child_stats, const int32_t* parent_summary);
 /* out[8] = nodes, simulations, evaluations, root visits, root wins, root win_status (-1/0/1),
- * finished (root subtree checked), and the move the search would play now: the move index of the
+ * finished (1 = root subtree checked, 2 = a device tree whose arena is full), and the move the search would play now: the move index of the
  * child chosen by randomly_choose_a_winning_move (tree_search_utils.pyx:469-486 with
  * check_for_forced_win :559-582 and choose_best_true_loser :493-557; expansion_MCTS_functions.pyx:129),
  * -1 while the root is unexpanded. */

@@ -1090,3 +1090,55 @@ def test_checkpoint_bundle_and_frozen_graph_load_into_the_session(tmp_path, monk
     sess, y_pred, X = wann_b200.instantiate_session()
     assert np.array_equal(sess.run(y_pred, feed_dict={X: O.encode_planes(nodes_sq, nodes_bl)}), want)
     sess.close()
+
+
+@pytest.mark.parametrize("mode,margin", [("fp16c", 0.02), ("bf16", 0.0)])
+def test_device_resident_forest_equals_the_host_forest(mode, margin, weights, suite):
+    """SURVEY 8f-2 moved onto the GPU: the device-resident forest (array_tree.hpp compiled for the device,
+    one warp per tree, lock steps enqueued on one stream by wann_forest_run) grows node for node the trees
+    of the host forest -- themselves pinned to the compiled reference's trees
+    (test_native_search_forest_reproduces_the_references_trees) -- on the same evaluator, through
+    searches, self-play moves with subtree reuse, and restarts of finished games."""
+    import wann_b200
+    sq, bl = suite
+    n = 96
+    with wann_b200.PolicyEvaluator(weights, mode=mode, refine_margin=margin) as ev:
+        host = wann_b200.SearchForest(sq[:n], bl[:n])
+        dev = wann_b200.SearchForest(sq[:n], bl[:n], evaluator=ev, device_resident=True, node_capacity=65536)
+        host.native_run = False                                  # the Python next/eval/apply loop
+        steps_h, evals_h = host.run(ev, 6)
+        steps_d, evals_d = dev.run(ev, 6)
+        assert evals_d == evals_h and evals_h > 6 * n and steps_d >= steps_h   # (a device tree yields its step after an evaluation-free simulation)
+        for t in range(n):
+            assert np.array_equal(dev.dump(t), host.dump(t)), t
+            assert dev.info(t) == host.info(t)
+        host.native_run = True                                   # wann_forest_run on a host forest
+        for ply in range(4):                                     # self-play: move, reuse the subtree, search on
+            mh, fh = host.play()
+            md, fd = dev.play()
+            assert np.array_equal(mh, md) and np.array_equal(fh, fd)
+            assert host.run(ev, 3)[1] == dev.run(ev, 3)[1]
+        for t in range(0, n, 7):
+            assert np.array_equal(dev.dump(t), host.dump(t)), t
+        # near-finished games: winning moves restart the tree from the opening
+        late_sq, late_bl = O.random_positions_fast(4000, seed=5)
+        pieces = (late_sq != 0).sum(1)
+        pick = np.argsort(pieces)[:32]
+        host2 = wann_b200.SearchForest(late_sq[pick], late_bl[pick])
+        dev2 = wann_b200.SearchForest(late_sq[pick], late_bl[pick], evaluator=ev, device_resident=True, node_capacity=65536)
+        finished = 0
+        for ply in range(6):
+            assert host2.run(ev, 4)[1] == dev2.run(ev, 4)[1]
+            mh, fh = host2.play()
+            md, fd = dev2.play()
+            assert np.array_equal(mh, md) and np.array_equal(fh, fd)
+            finished += int(fd.sum())
+        for t in range(32):
+            assert np.array_equal(dev2.dump(t), host2.dump(t)), t
+        # a tree that fills its arena stops cleanly (finished == 2), the others carry on
+        tiny = wann_b200.SearchForest(sq[:8], bl[:8], evaluator=ev, device_resident=True, node_capacity=256)
+        tiny.run(ev, 50)
+        infos = [tiny.info(t) for t in range(8)]
+        assert all(i["nodes"] <= 256 for i in infos) and any(i["finished"] == 2 for i in infos)
+        for f in (host, dev, host2, dev2, tiny):
+            f.close()

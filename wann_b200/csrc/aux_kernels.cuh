@@ -167,7 +167,8 @@ struct TailParams {
   int* refine_count = nullptr;
   float refine_ratio = 0.f;
   const int* gather = nullptr;
-  const int* n_dev = nullptr;
+  const int* n_dev = nullptr;      // device-side position count: min(n, max(0, *n_dev - n_dev_off)) positions
+  long long n_dev_off = 0;
   // zero-copy small calls: the slot's device-side watchdog / refinement record is mirrored into
   // host-mapped memory by the last kernel of the call (saves a D2H copy on the latency path)
   const int* err_src = nullptr;
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(kTailWarps * 32) tail_kernel(const TailParams 
   extern __shared__ float tsm[];
   // refinement pass: the board count lives on the device (this launch is never made under PDL, so
   // the flagging pass has completed); CTAs without work leave before touching the FC weights
-  const long long n_eff = (p.n_dev != nullptr) ? min(p.n, static_cast<long long>(*p.n_dev)) : p.n;
+  const long long n_eff = (p.n_dev != nullptr) ? max(0ll, min(p.n, static_cast<long long>(*p.n_dev) - p.n_dev_off)) : p.n;
   if (p.err_dst != nullptr && blockIdx.x == 0 && threadIdx.x < 8) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     p.err_dst[threadIdx.x] = p.err_src[threadIdx.x];
@@ -470,7 +471,10 @@ __global__ void __launch_bounds__(256) seed_children_kernel(const int8_t* __rest
                                                             const float* __restrict__ prior,
                                                             const uint8_t* __restrict__ n_legal, long long n,
                                                             int32_t* __restrict__ stats, uint8_t* __restrict__ flags,
-                                                            int32_t* __restrict__ parent) {
+                                                            int32_t* __restrict__ parent,
+                                                            const int* __restrict__ n_dev = nullptr,
+                                                            long long n_dev_off = 0) {
+  if (n_dev != nullptr) n = max(0ll, min(n, static_cast<long long>(*n_dev) - n_dev_off));
   __shared__ int8_t brd[8][64];
   __shared__ int8_t tab[64];        // lanes index the table divergently: shared memory, not the constant cache
   if (threadIdx.x < 64) tab[threadIdx.x] = kEvalTable[threadIdx.x];

@@ -57,7 +57,7 @@ conv_stack_split_kernel(const TcParams p) {
   const int npairs = gridDim.x >> 1;
   // refinement pass: the number of boards is only known on the device (written by the tail kernel
   // launched before us on the same stream, never under programmatic dependent launch)
-  const long long n_eff = (p.n_dev != nullptr) ? min(p.n, static_cast<long long>(*p.n_dev)) : p.n;
+  const long long n_eff = effective_n(p);
   const long long total_st = (n_eff + kSplitBoardsPerPair - 1) / kSplitBoardsPerPair;
   if (pair >= total_st) return;   // both CTAs of the pair leave together, before any cluster traffic
 
@@ -225,7 +225,7 @@ conv_stack_split_kernel(const TcParams p) {
     };
     auto load_in = [&](long long board) {
       if (board >= n_eff) return make_uint2(0u, 0u);
-      return load_input_cell<true>(p, p.gather != nullptr ? static_cast<long long>(p.gather[board]) : board, y, x);
+      return load_input_cell<true>(p, p.n, p.gather != nullptr ? static_cast<long long>(p.gather[board]) : board, y, x);
     };
 
     ptx::pdl_wait();

@@ -131,7 +131,11 @@ struct TcParams {
   // margin refinement pass (conv_stack_split_kernel only): evaluate the boards gather[0..*n_dev)
   // of `squares` and write their h5 rows COMPACTLY (row i <- board gather[i]); both null otherwise
   const int* gather = nullptr;
+  // device-side position count (both kernels): evaluate min(n, max(0, *n_dev - n_dev_off)) positions -- the
+  // refinement pass's flagged boards, or the rows a device-resident search forest asked for this step.
+  // Read at kernel start: such a launch is never made under programmatic dependent launch.
   const int* n_dev = nullptr;
+  long long n_dev_off = 0;
   // fused tail (conv_stack_tc_kernel only): when fuse_tail != 0 the tail warps produce tail.probs /
   // logits / idx / prior / n_legal (and the refinement flags) themselves and h5 may be null
   int fuse_tail = 0;
@@ -184,10 +188,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // (tools/utils.pyx:563-600: Black sees the board rotated by 180 degrees; :842-865: P/O/E/bias
 // planes).  Split into a global-memory load (issued early, during the conv4 epilogue, so that its
 // latency is off the conv5 -> conv1 critical chain) and the shared-memory store.
+__device__ __forceinline__ long long effective_n(const TcParams& p) {
+  if (p.n_dev == nullptr) return p.n;
+  return max(0ll, min(p.n, static_cast<long long>(*p.n_dev) - p.n_dev_off));
+}
 template <bool kF16>
-__device__ __forceinline__ uint2 load_input_cell(const TcParams& p, long long board, int y, int x) {
+__device__ __forceinline__ uint2 load_input_cell(const TcParams& p, long long n_tot, long long board, int y, int x) {
   uint2 v = make_uint2(0u, 0u);
-  if (board < p.n) {
+  if (board < n_tot) {
     const int sq = y * 8 + x;
     if (p.squares != nullptr) {
       const int8_t* b64 = p.squares + board * 64;
@@ -265,7 +273,8 @@ conv_stack_tc_kernel(const TcParams p) {
   // over the SM pairs, and each 5-layer chain has the tensor pipe to itself (lower latency)
   const int nh = (p.halves == 1) ? 1 : 2;
   const int boards_per_pair = 4 * nh;
-  const long long total_st = (p.n + boards_per_pair - 1) / boards_per_pair;
+  const long long n_tot = effective_n(p);
+  const long long total_st = (n_tot + boards_per_pair - 1) / boards_per_pair;
   constexpr uint32_t nst = kStages;
 
   // ---- one-time setup ---------------------------------------------------------------------
@@ -477,7 +486,7 @@ conv_stack_tc_kernel(const TcParams p) {
     if (st < total_st) {
       for (int h = 0; h < nh; ++h) {
         if (chalf == 0)
-          store_input_cell<kCen>(a_base + h * kATileStride + cell_in_tile, load_input_cell<kF16>(p, board_of(st, h), y, x));
+          store_input_cell<kCen>(a_base + h * kATileStride + cell_in_tile, load_input_cell<kF16>(p, n_tot, board_of(st, h), y, x));
         signal_a_ready(h);
       }
     }
@@ -495,9 +504,9 @@ conv_stack_tc_kernel(const TcParams p) {
           if (profiler && lstep < kProfSteps) p.prof[(4 * h + 2) * kProfSteps + lstep] = clock64();
           if (layer < 4) {
             if (layer == 3 && chalf == 0 && st + npairs < total_st)   // prefetch next supertile's input
-              next_in[h] = load_input_cell<kF16>(p, board_of(st + npairs, h), y, x);
+              next_in[h] = load_input_cell<kF16>(p, n_tot, board_of(st + npairs, h), y, x);
             const float* bs = bias_s + layer * kC + chalf * 96;
-            float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < p.n)
+            float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < n_tot)
                              ? p.dbg + (board * 64 + y * 8 + x) * kC : nullptr;
             // centred mode: store a' = max(acc + (b' - c), -c) = relu(acc + b') - c   (c by channel % 8);
             // bias_s already holds b' - c
@@ -600,7 +609,7 @@ conv_stack_tc_kernel(const TcParams p) {
               h5s[(h * 2 + b) * 64 + y * 8 + x] = hval;
               ptx::mbar_arrive(bar_h5_full(h));
             }
-            if (p.h5 != nullptr && board < p.n) p.h5[board * 64 + y * 8 + x] = hval;
+            if (p.h5 != nullptr && board < n_tot) p.h5[board * 64 + y * 8 + x] = hval;
             if (st + npairs < total_st) store_input_cell<kCen>(cell0, next_in[h]);
           }
           signal_a_ready(h);
@@ -634,7 +643,7 @@ conv_stack_tc_kernel(const TcParams p) {
         uint32_t tcount = 0;
         for (long long st = pair; st < total_st; st += npairs, ++tcount) {
           const long long board0 = st * boards_per_pair + static_cast<int>(rank) * (2 * nh) + h * 2;
-          const int nb = static_cast<int>(max(0ll, min(2ll, p.n - board0)));
+          const int nb = static_cast<int>(max(0ll, min(2ll, n_tot - board0)));
           const long long dst[2] = {board0, board0 + 1};
           if (p.tail.squares != nullptr) {
 #pragma unroll

@@ -721,6 +721,8 @@ struct ChunkIO {   // device pointers for one chunk
   float* dbg = nullptr;
   int dbg_layer = 0;
   int top_k = kMaxLegal;
+  const int* n_dev = nullptr;   // device-side row count (device-resident forest): rows [0, *n_dev - n_dev_off) of this chunk
+  long long n_dev_off = 0;
   long long* prof = nullptr;
   int8_t* children = nullptr;
   uint8_t* cflags = nullptr;
@@ -778,6 +780,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
   t.h5 = ws.d_h5; t.squares = io.squares; t.black = io.black; t.n = n;
   t.fc_w = ctx->d_fc_w; t.fc_b = ctx->d_fc_b; t.probs = io.probs; t.logits = io.logits;
   t.idx = io.idx; t.prior = io.prior; t.n_legal = io.nlegal; t.top_k = io.top_k;
+  t.n_dev = io.n_dev; t.n_dev_off = io.n_dev_off;
   const float refine_ratio = ctx->refine_ratio.load();
   const bool refine = refine_active(ctx, io, refine_ratio);
   int* d_rcount = ws.d_err + 4;     // [0] flagged boards of this chunk, [1] running total
@@ -802,6 +805,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
     p.squares = io.squares; p.black = io.black; p.planes = io.planes; p.planes_f32 = io.planes_f32;
     fill_tc_params(ctx, p);
     p.n = n; p.skew = ctx->skew; p.h5 = ws.d_h5;
+    p.n_dev = io.n_dev; p.n_dev_off = io.n_dev_off;
     p.dbg = io.dbg; p.dbg_layer = io.dbg_layer; p.variant = ctx->variant; p.err = ws.d_err; p.prof = io.prof;
     if (fused) {
       p.fuse_tail = 1;
@@ -831,8 +835,9 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       const int pdl = ctx->pdl.load();
+      // (a kernel that reads its position count from device memory must not start before its predecessor ends)
       attr[0].val.programmaticStreamSerializationAllowed =
-          (pdl > 0 || (pdl < 0 && total_st <= 2ll * (ctx->sm_count / 2))) ? 1 : 0;
+          (io.n_dev == nullptr && (pdl > 0 || (pdl < 0 && total_st <= 2ll * (ctx->sm_count / 2)))) ? 1 : 0;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       if (ctx->mode == WANN_MODE_FP32_TC) CU(cudaLaunchKernelEx(&cfg, conv_stack_split_kernel, p));
@@ -882,7 +887,7 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
       cfg.stream = stream;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = ctx->pdl.load() > 0 ? 1 : 0;
+      attr[0].val.programmaticStreamSerializationAllowed = (io.n_dev == nullptr && ctx->pdl.load() > 0) ? 1 : 0;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       CU(cudaLaunchKernelEx(&cfg, tail_kernel, t));
@@ -901,12 +906,12 @@ int enqueue_eval(wann_ctx* ctx, Slot& ws, cudaStream_t stream, const ChunkIO& io
     if (io.cstats != nullptr) {
       const int eb = static_cast<int>(std::min<long long>((n + 7) / 8, 16ll * ctx->sm_count));
       seed_children_kernel<<<eb, 256, 0, stream>>>(io.squares, io.black, io.idx, io.prior, io.nlegal, n, io.cstats,
-                                                   io.cflags, io.psum);
+                                                   io.cflags, io.psum, io.n_dev, io.n_dev_off);
       ++launches;
     }
   }
   CU(cudaGetLastError());
-  ctx->stats[0] += static_cast<uint64_t>(n);
+  if (io.n_dev == nullptr) ctx->stats[0] += static_cast<uint64_t>(n);   // (device-side counts are added by their owner)
   ctx->stats[1] += launches;
   return WANN_OK;
 }
@@ -949,6 +954,7 @@ struct EvalArgs {
   float* dbg = nullptr;
   int dbg_layer = 0;
   int top_k = kMaxLegal;          // ranked children kept per position
+  const int* n_dev = nullptr;     // optional device-side count of valid rows (<= n)
 };
 
 // the k argument of the C ABI: 0 (or anything outside 1..47) = every legal child
@@ -976,6 +982,8 @@ int eval_device(wann_ctx* ctx, Lane* lane, const EvalArgs& a, long long n, void*
     io.dbg = a.dbg ? a.dbg + off * 64 * dbg_c : nullptr;
     io.dbg_layer = a.dbg_layer;
     io.top_k = a.top_k;
+    io.n_dev = a.n_dev;
+    io.n_dev_off = off;
     io.children = a.children ? a.children + off * kMaxLegal * 64 : nullptr;
     io.cflags = a.cflags ? a.cflags + off * kMaxLegal : nullptr;
     io.cstats = a.cstats ? a.cstats + off * kMaxLegal * 4 : nullptr;
@@ -1786,10 +1794,164 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
 
 // ---------------------------------------------------------------------------------------------
 // Forest of array-based search trees (array_tree.hpp): host-side, no context needed.
+}  // extern "C"
+
+// Device-resident forest: the trees (headers + node / board arenas) live in HBM; a lock step is
+// forest_next_kernel -> conv stack (+ fused tail) -> seed_children_kernel -> forest_apply_kernel on one
+// stream, the number of requested rows staying on the device.  One warp per tree, lane 0 walks it.
+struct DeviceForest {
+  wann_ctx* ctx = nullptr;
+  int64_t n = 0;
+  int32_t cap_nodes = 0, cap_boards = 0;
+  wann_tree::Tree* d_trees = nullptr;
+  wann_tree::Tree::Node* d_nodes = nullptr;     // [2][n][cap_nodes]: arena + the one advance_root compacts into
+  int8_t* d_boards = nullptr;                   // [2][n][cap_boards][64]
+  int8_t* d_sq = nullptr; uint8_t* d_bl = nullptr; int32_t* d_ids = nullptr;
+  uint8_t* d_idx = nullptr; float* d_prior = nullptr; uint8_t* d_nlegal = nullptr; uint8_t* d_cflags = nullptr;
+  int32_t* d_cstats = nullptr; int32_t* d_psum = nullptr;
+  int* d_counts = nullptr;                      // [2][kForestHist] rows requested by each of the last steps; trees that yielded
+  int* h_counts = nullptr;                      // pinned copy
+  int8_t* d_restart = nullptr;                  // [64] + colour: wann_forest_play's new-game position
+  uint8_t* d_moves = nullptr; uint8_t* d_fin = nullptr; int* d_flag = nullptr;
+  unsigned long long* d_cycles = nullptr;       // [kForestHist][4]: per lock step, clock64 cycles of the trees in the tree
+                                                // kernels: next sum, next max, apply sum, apply max
+  cudaStream_t stream = nullptr;
+  int64_t steps = 0;
+};
+constexpr int kForestHist = 64, kForestBurst = 8;
+
 struct wann_forest {
   wann_tree::Forest f;
   std::vector<int64_t> waiting;      // trees whose rows were handed out by the last wann_forest_next
+  DeviceForest* dev = nullptr;       // non-null: the trees live on the GPU (wann_forest_create_device)
 };
+
+namespace {
+
+__global__ void forest_init_kernel(wann_tree::Tree* trees, long long n, const int8_t* __restrict__ squares,
+                                   const uint8_t* __restrict__ black, const int32_t* __restrict__ heights) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t >= n) return;
+  wann_tree::Tree tr = trees[t];
+  tr.init_in_place(squares + t * 64, black[t] != 0, heights != nullptr ? heights[t] : 0);
+  trees[t] = tr;
+}
+
+// every tree runs to its next evaluation (or to the end of its simulation budget); the requested
+// positions are appended to squares_out / black_out / ids (order = arrival: the evaluation of a row does
+// not depend on its place in the batch)
+__global__ void __launch_bounds__(128) forest_next_kernel(wann_tree::Tree* trees, long long n, long long max_sims,
+                                                          int8_t* __restrict__ squares_out, uint8_t* __restrict__ black_out,
+                                                          int32_t* __restrict__ ids, int* count, unsigned long long* cycles) {
+  // one WARP per tree: all lanes run the tree code on identical state (array_tree.hpp, "DEVICE execution model")
+  const long long t = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  if (t >= n) return;
+  const int lane = threadIdx.x & 31;
+  const long long c0 = clock64();
+  wann_tree::Tree tr = trees[t];
+  int32_t node = tr.advance(max_sims, 1);
+  if (node == -2 && lane == 0) atomicAdd(count + kForestHist, 1);      // more to do, nothing to evaluate this step
+  const int8_t* b = node >= 0 ? tr.board_of(node) : nullptr;
+  if (node >= 0 && b == nullptr) {             // no room for the position: the tree stops (overflow is set)
+    tr.phase = wann_tree::Tree::kFinished;
+    tr.pending = -1;
+    node = -1;
+  }
+  __syncwarp();
+  if (node >= 0) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(count, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (lane < 4) reinterpret_cast<int4*>(squares_out + static_cast<long long>(slot) * 64)[lane] = reinterpret_cast<const int4*>(b)[lane];
+    if (lane == 0) {
+      black_out[slot] = tr.nodes[node].black;
+      ids[slot] = static_cast<int32_t>(t);
+    }
+  }
+  if (lane == 0) {
+    trees[t] = tr;
+    const unsigned long long dc = static_cast<unsigned long long>(clock64() - c0);
+    atomicAdd(cycles, dc);
+    atomicMax(cycles + 1, dc);
+  }
+}
+
+__global__ void __launch_bounds__(128) forest_apply_kernel(wann_tree::Tree* trees, const int32_t* __restrict__ ids,
+                                                           const int* __restrict__ count, const uint8_t* __restrict__ idx,
+                                                           const float* __restrict__ prior, const uint8_t* __restrict__ n_legal,
+                                                           const uint8_t* __restrict__ cflags, const int32_t* __restrict__ cstats,
+                                                           const int32_t* __restrict__ psum, unsigned long long* cycles, int* count_next,
+                                                           unsigned long long* cycles_next) {
+  const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  if (blockIdx.x == 0 && threadIdx.x < 5) {      // the next step's row counter and statistics start from zero
+    if (threadIdx.x == 4) { count_next[0] = 0; count_next[kForestHist] = 0; } else cycles_next[threadIdx.x] = 0ull;
+  }
+  if (i >= *count) return;
+  const long long c0 = clock64();
+  const int32_t t = ids[i];
+  wann_tree::Tree tr = trees[t];
+  tr.expand_resume(idx + i * kMaxLegal, prior + i * kMaxLegal, min(static_cast<int>(n_legal[i]), kMaxLegal),
+                   cflags + i * kMaxLegal, cstats + i * kMaxLegal * 4, psum[i * 8 + 5] != 0);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    trees[t] = tr;
+    const unsigned long long dc = static_cast<unsigned long long>(clock64() - c0);
+    atomicAdd(cycles + 2, dc);
+    atomicMax(cycles + 3, dc);
+  }
+}
+
+__global__ void __launch_bounds__(128) forest_play_kernel(wann_tree::Tree* trees, long long n, const int8_t* __restrict__ restart,
+                                                          uint8_t* __restrict__ moves, uint8_t* __restrict__ fin, int* flag) {
+  const long long t = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  if (t >= n) return;
+  wann_tree::Tree tr = trees[t];
+  if (tr.phase == wann_tree::Tree::kWaitEval) { atomicExch(flag, static_cast<int>(t) + 1); return; }
+  uint8_t mv, f;
+  tr.play(restart, restart[64] != 0, mv, f);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    moves[t] = mv;
+    fin[t] = f;
+    trees[t] = tr;
+  }
+}
+
+void free_device_forest(DeviceForest* d) {
+  if (d == nullptr) return;
+  if (d->stream) { cudaStreamSynchronize(d->stream); cudaStreamDestroy(d->stream); }
+  cudaFree(d->d_trees); cudaFree(d->d_nodes); cudaFree(d->d_boards); cudaFree(d->d_sq); cudaFree(d->d_bl);
+  cudaFree(d->d_ids); cudaFree(d->d_idx); cudaFree(d->d_prior); cudaFree(d->d_nlegal); cudaFree(d->d_cflags);
+  cudaFree(d->d_cstats); cudaFree(d->d_psum); cudaFree(d->d_counts); cudaFree(d->d_restart); cudaFree(d->d_moves);
+  cudaFree(d->d_fin); cudaFree(d->d_flag); cudaFree(d->d_cycles);
+  if (d->h_counts) cudaFreeHost(d->h_counts);
+  delete d;
+}
+
+// host copy of one device tree (header + the used part of its arenas), owning its buffers
+int download_tree(DeviceForest* d, int64_t t, wann_tree::Tree* out) {
+  CU(cudaStreamSynchronize(d->stream));
+  wann_tree::Tree h;
+  CU(cudaMemcpy(&h, d->d_trees + t, sizeof h, cudaMemcpyDeviceToHost));
+  wann_tree::Tree r = h;
+  r.owns = 1;
+  r.alt_nodes = nullptr;
+  r.alt_boards = nullptr;
+  r.cap_nodes = std::max(h.n_nodes, 1);
+  r.cap_boards = std::max(h.n_boards, 1);
+  r.nodes = static_cast<wann_tree::Tree::Node*>(malloc(sizeof(wann_tree::Tree::Node) * static_cast<size_t>(r.cap_nodes)));
+  r.boards = static_cast<int8_t*>(malloc(static_cast<size_t>(r.cap_boards) * 64));
+  if (r.nodes == nullptr || r.boards == nullptr) { free(r.nodes); free(r.boards); return fail(WANN_E_INVALID, "out of host memory"); }
+  cudaError_t e = cudaMemcpy(r.nodes, h.nodes, sizeof(wann_tree::Tree::Node) * static_cast<size_t>(h.n_nodes), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(r.boards, h.boards, static_cast<size_t>(h.n_boards) * 64, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(r.nodes); free(r.boards); return fail(WANN_E_CUDA, "tree download: %s", cudaGetErrorString(e)); }
+  *out = r;
+  return WANN_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int wann_host_threads(int n) {
   if (n > 0) omp_set_num_threads(n);
@@ -1808,8 +1970,226 @@ int wann_forest_create(int64_t n, const int8_t* squares, const uint8_t* black, c
 }
 
 int wann_forest_destroy(wann_forest* fo) {
+  if (fo != nullptr && fo->dev != nullptr) {
+    DeviceGuard dev_guard(fo->dev->ctx->device);
+    free_device_forest(fo->dev);
+  }
   delete fo;
   return WANN_OK;
+}
+
+int wann_forest_create_device(wann_ctx* ctx, int64_t n, const int8_t* squares, const uint8_t* black,
+                              const int32_t* heights, int32_t node_capacity, wann_forest** out) {
+  if (ctx == nullptr || out == nullptr || n <= 0 || squares == nullptr || black == nullptr)
+    return fail(WANN_E_INVALID, "bad argument");
+  if (node_capacity <= 0) node_capacity = 16384;
+  if (node_capacity < 256) return fail(WANN_E_INVALID, "node_capacity must be at least 256");
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
+  wann_forest* fo = new wann_forest();
+  DeviceForest* d = new DeviceForest();
+  fo->dev = d;
+  d->ctx = ctx;
+  d->n = n;
+  d->cap_nodes = node_capacity;
+  d->cap_boards = std::max(64, node_capacity / 8);      // a node gets a board when it is evaluated: 1 in ~23
+  auto body = [&]() -> int {
+    using Node = wann_tree::Tree::Node;
+    const size_t nn = static_cast<size_t>(n);
+    CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&d->d_trees, nn * sizeof(wann_tree::Tree)));
+    CU(cudaMalloc(&d->d_nodes, 2 * nn * d->cap_nodes * sizeof(Node)));
+    CU(cudaMalloc(&d->d_boards, 2 * nn * d->cap_boards * 64));
+    CU(cudaMalloc(&d->d_sq, nn * 64));
+    CU(cudaMalloc(&d->d_bl, nn));
+    CU(cudaMalloc(&d->d_ids, nn * sizeof(int32_t)));
+    CU(cudaMalloc(&d->d_idx, nn * kMaxLegal));
+    CU(cudaMalloc(&d->d_prior, nn * kMaxLegal * 4));
+    CU(cudaMalloc(&d->d_nlegal, nn));
+    CU(cudaMalloc(&d->d_cflags, nn * kMaxLegal));
+    CU(cudaMalloc(&d->d_cstats, nn * kMaxLegal * 4 * sizeof(int32_t)));
+    CU(cudaMalloc(&d->d_psum, nn * 8 * sizeof(int32_t)));
+    CU(cudaMalloc(&d->d_counts, 2 * kForestHist * sizeof(int)));
+    CU(cudaMallocHost(&d->h_counts, 2 * kForestHist * sizeof(int)));
+    CU(cudaMalloc(&d->d_restart, 80));
+    CU(cudaMalloc(&d->d_moves, nn));
+    CU(cudaMalloc(&d->d_fin, nn));
+    CU(cudaMalloc(&d->d_flag, sizeof(int)));
+    CU(cudaMalloc(&d->d_cycles, kForestHist * 4 * sizeof(unsigned long long)));
+    std::vector<wann_tree::Tree> hdr(nn);
+    for (size_t t = 0; t < nn; ++t) {
+      wann_tree::Tree& tr = hdr[t];
+      tr.nodes = d->d_nodes + t * d->cap_nodes;
+      tr.alt_nodes = d->d_nodes + (nn + t) * d->cap_nodes;
+      tr.boards = d->d_boards + t * d->cap_boards * 64;
+      tr.alt_boards = d->d_boards + (nn + t) * d->cap_boards * 64;
+      tr.cap_nodes = d->cap_nodes;
+      tr.cap_boards = d->cap_boards;
+      tr.owns = 0;
+    }
+    CU(cudaMemcpyAsync(d->d_trees, hdr.data(), nn * sizeof(wann_tree::Tree), cudaMemcpyHostToDevice, d->stream));
+    int32_t* d_h = nullptr;
+    // the root positions go through the step buffers (d_sq / d_bl hold n rows)
+    CU(cudaMemcpyAsync(d->d_sq, squares, nn * 64, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaMemcpyAsync(d->d_bl, black, nn, cudaMemcpyHostToDevice, d->stream));
+    if (heights != nullptr) {
+      CU(cudaMalloc(&d_h, nn * sizeof(int32_t)));
+      CU(cudaMemcpyAsync(d_h, heights, nn * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
+    }
+    forest_init_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, d->stream>>>(d->d_trees, n, d->d_sq, d->d_bl, d_h);
+    cudaError_t e = cudaStreamSynchronize(d->stream);
+    cudaFree(d_h);
+    if (e != cudaSuccess) return fail(WANN_E_CUDA, "forest init: %s", cudaGetErrorString(e));
+    return WANN_OK;
+  };
+  int rc = body();
+  if (rc != WANN_OK) {
+    free_device_forest(d);
+    delete fo;
+    return rc;
+  }
+  *out = fo;
+  return WANN_OK;
+}
+
+// Search: every tree does `max_simulations` simulations (run_MCTS_with_expansions_simulation,
+// expansion_MCTS_functions.pyx:300-350); out[0] = lock steps, out[1] = evaluations.
+int wann_forest_run(wann_ctx* ctx, wann_forest* fo, int64_t max_simulations, int64_t out[2]) {
+  if (ctx == nullptr || fo == nullptr) return fail(WANN_E_INVALID, "null argument");
+  if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
+  int64_t steps = 0, evals = 0;
+  if (fo->dev == nullptr) {
+    // host forest: next -> ONE wann_eval_expand_seeded over the requested rows -> apply, until no tree asks
+    const int64_t n = static_cast<int64_t>(fo->f.trees.size());
+    if (n == 0) { if (out) out[0] = out[1] = 0; return WANN_OK; }
+    int8_t* sq = nullptr; uint8_t* bl = nullptr; uint8_t* idx = nullptr; float* prior = nullptr; uint8_t* nl = nullptr;
+    uint8_t* fl = nullptr; int32_t* st = nullptr; int32_t* ps = nullptr;
+    DeviceGuard dev_guard(ctx->device);
+    CU(dev_guard.status);
+    auto body = [&]() -> int {
+      CU(cudaMallocHost(&sq, n * 64)); CU(cudaMallocHost(&bl, n)); CU(cudaMallocHost(&idx, n * kMaxLegal));
+      CU(cudaMallocHost(&prior, n * kMaxLegal * 4)); CU(cudaMallocHost(&nl, n)); CU(cudaMallocHost(&fl, n * kMaxLegal));
+      CU(cudaMallocHost(&st, n * kMaxLegal * 16)); CU(cudaMallocHost(&ps, n * 32));
+      while (true) {
+        int64_t m = 0;
+        int rc = wann_forest_next(fo, max_simulations, sq, bl, nullptr, &m);
+        if (rc != WANN_OK) return rc;
+        if (m == 0) break;
+        rc = wann_eval_expand_seeded(ctx, sq, bl, m, 0, idx, prior, nl, nullptr, fl, st, ps, WANN_MEM_HOST, nullptr);
+        if (rc == WANN_OK) rc = wann_forest_apply(fo, idx, prior, nl, fl, st, ps);
+        if (rc != WANN_OK) { fo->waiting.clear(); return rc; }
+        ++steps;
+        evals += m;
+      }
+      return WANN_OK;
+    };
+    int rc = body();
+    cudaFreeHost(sq); cudaFreeHost(bl); cudaFreeHost(idx); cudaFreeHost(prior); cudaFreeHost(nl); cudaFreeHost(fl);
+    cudaFreeHost(st); cudaFreeHost(ps);
+    if (out) { out[0] = steps; out[1] = evals; }
+    return rc;
+  }
+  DeviceForest* d = fo->dev;
+  if (d->ctx != ctx) return fail(WANN_E_INVALID, "the forest was created on another context");
+  DeviceGuard dev_guard(ctx->device);
+  CU(dev_guard.status);
+  ReaderScope weights_scope(&ctx->weights_gate);
+  Lane* lane = nullptr;
+  int rc = acquire_lane(ctx, &lane);
+  if (rc != WANN_OK) return rc;
+  lane_wait(lane, d->stream);
+  auto body = [&]() -> int {
+    const long long n = d->n;
+    const unsigned blocks = static_cast<unsigned>((n * 32 + 127) / 128);
+    const long long cap = lane->slot[0].cap * (ctx->mode == WANN_MODE_FP32 ? 1 : kDevChunkMul);
+    Slot& ws = lane->slot[0];
+    // development aid: WANN_FOREST_TIMING=1 brackets the phases of the first 48 lock steps with CUDA events
+    const bool timing = getenv("WANN_FOREST_TIMING") != nullptr;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() {
+      if (timing && evs.size() < 48 * 4 + 1) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, d->stream);
+        evs.push_back(e);
+      }
+    };
+    // the row counter and the cycle statistics of a step are zeroed by the apply kernel of the step before
+    // (nothing touches them in between); the very first step of a run is zeroed here
+    CU(cudaMemsetAsync(d->d_counts + (d->steps % kForestHist), 0, sizeof(int), d->stream));
+    CU(cudaMemsetAsync(d->d_counts + kForestHist + (d->steps % kForestHist), 0, sizeof(int), d->stream));
+    CU(cudaMemsetAsync(d->d_cycles + (d->steps % kForestHist) * 4, 0, 4 * sizeof(unsigned long long), d->stream));
+    mark();
+    double host_enqueue_us = 0, host_wait_us = 0;
+    long long bursts = 0;
+    while (true) {
+      const int first = static_cast<int>(d->steps % kForestHist);
+      const double tq0 = omp_get_wtime();
+      for (int b = 0; b < kForestBurst; ++b, ++d->steps) {
+        int* cnt = d->d_counts + (d->steps % kForestHist);
+        unsigned long long* cyc = d->d_cycles + (d->steps % kForestHist) * 4;
+        int* cnt_next = d->d_counts + ((d->steps + 1) % kForestHist);
+        unsigned long long* cyc_next = d->d_cycles + ((d->steps + 1) % kForestHist) * 4;
+        forest_next_kernel<<<blocks, 128, 0, d->stream>>>(d->d_trees, n, max_simulations, d->d_sq, d->d_bl, d->d_ids, cnt, cyc);
+        mark();
+        for (long long off = 0; off < n; off += cap) {
+          const long long m = std::min(cap, n - off);
+          ChunkIO io;
+          io.squares = d->d_sq + off * 64; io.black = d->d_bl + off;
+          io.idx = d->d_idx + off * kMaxLegal; io.prior = d->d_prior + off * kMaxLegal; io.nlegal = d->d_nlegal + off;
+          io.cflags = d->d_cflags + off * kMaxLegal; io.cstats = d->d_cstats + off * kMaxLegal * 4; io.psum = d->d_psum + off * 8;
+          io.n_dev = cnt; io.n_dev_off = off;
+          int r = enqueue_eval(ctx, ws, d->stream, io, m);
+          if (r != WANN_OK) return r;
+        }
+        mark();
+        forest_apply_kernel<<<blocks, 128, 0, d->stream>>>(d->d_trees, d->d_ids, cnt, d->d_idx, d->d_prior, d->d_nlegal,
+                                                          d->d_cflags, d->d_cstats, d->d_psum, cyc, cnt_next, cyc_next);
+        mark();
+        mark();
+        ctx->stats[1] += 2;
+      }
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(d->h_counts, d->d_counts, 2 * kForestHist * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+      CU(copy_device_err(ctx, ws, d->stream));
+      const double tq1 = omp_get_wtime();
+      CU(cudaStreamSynchronize(d->stream));
+      host_enqueue_us += (tq1 - tq0) * 1e6;
+      host_wait_us += (omp_get_wtime() - tq1) * 1e6;
+      ++bursts;
+      int r = check_device_err(ctx, ws);
+      if (r != WANN_OK) return r;
+      bool done = false;
+      for (int b = 0; b < kForestBurst; ++b) {
+        const int c = d->h_counts[(first + b) % kForestHist], busy = d->h_counts[kForestHist + (first + b) % kForestHist];
+        if (c > 0) { ++steps; evals += c; }
+        else if (busy == 0) done = true;                           // no tree asked or yielded: none will again
+      }
+      if (done) break;
+    }
+    if (timing && evs.size() > 8) {
+      double ph[4] = {0, 0, 0, 0};
+      const size_t nst = (evs.size() - 1) / 4;
+      for (size_t i = 0; i < nst; ++i)
+        for (int k = 0; k < 4; ++k) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, evs[4 * i + k], evs[4 * i + k + 1]);
+          ph[k] += ms * 1e3 / nst;
+        }
+      fprintf(stderr, "[wann_forest_run] %zu steps, us per step: next %.1f  eval(+seed) %.1f  apply %.1f  (gap %.1f); host per "
+              "burst of %d steps: enqueue %.1f us, wait %.1f us\n", nst, ph[0], ph[1], ph[2], ph[3], kForestBurst,
+              host_enqueue_us / bursts, host_wait_us / bursts);
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    return WANN_OK;
+  };
+  rc = body();
+  if (rc != WANN_OK) cudaStreamSynchronize(d->stream);
+  lane->last_valid = false;
+  release_lane(ctx, lane);
+  ctx->stats[0] += static_cast<uint64_t>(evals);
+  if (out) { out[0] = steps; out[1] = evals; }
+  return rc;
 }
 
 int wann_forest_next(wann_forest* fo, int64_t max_simulations, int8_t* squares_out, uint8_t* black_out,
@@ -1817,6 +2197,7 @@ int wann_forest_next(wann_forest* fo, int64_t max_simulations, int8_t* squares_o
   if (fo == nullptr || squares_out == nullptr || black_out == nullptr || m_out == nullptr)
     return fail(WANN_E_INVALID, "null argument");
   if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
+  if (fo->dev != nullptr) return fail(WANN_E_INVALID, "a device-resident forest is driven by wann_forest_run");
   const int64_t n = static_cast<int64_t>(fo->f.trees.size());
   std::vector<int32_t> node(static_cast<size_t>(n), -1);
 #pragma omp parallel for schedule(dynamic, 8)
@@ -1844,6 +2225,7 @@ int wann_forest_next(wann_forest* fo, int64_t max_simulations, int8_t* squares_o
 int wann_forest_apply(wann_forest* fo, const uint8_t* idx, const float* prior, const uint8_t* n_legal,
                       const uint8_t* child_flags, const int32_t* child_stats, const int32_t* parent_summary) {
   if (fo == nullptr) return fail(WANN_E_INVALID, "null forest");
+  if (fo->dev != nullptr) return fail(WANN_E_INVALID, "a device-resident forest is driven by wann_forest_run");
   const int64_t m = static_cast<int64_t>(fo->waiting.size());
   if (m > 0 && (!idx || !prior || !n_legal || !child_flags || !child_stats || !parent_summary))
     return fail(WANN_E_INVALID, "null argument");
@@ -1858,16 +2240,24 @@ int wann_forest_apply(wann_forest* fo, const uint8_t* idx, const float* prior, c
 }
 
 int wann_forest_info(wann_forest* fo, int64_t tree, int64_t out[8]) {
-  if (fo == nullptr || out == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size()))
+  if (fo == nullptr || out == nullptr || tree < 0 ||
+      tree >= (fo->dev ? fo->dev->n : static_cast<int64_t>(fo->f.trees.size())))
     return fail(WANN_E_INVALID, "bad argument");
-  const wann_tree::Tree& tr = fo->f.trees[tree];
-  out[0] = static_cast<int64_t>(tr.nodes.size());
+  wann_tree::Tree copy;
+  if (fo->dev != nullptr) {                      // a host copy of the device tree answers the query
+    DeviceGuard dev_guard(fo->dev->ctx->device);
+    int rc = download_tree(fo->dev, tree, &copy);
+    if (rc != WANN_OK) return rc;
+  }
+  struct Release { wann_tree::Tree* t; ~Release() { if (t->owns) t->release(); } } release_copy{&copy};
+  const wann_tree::Tree& tr = fo->dev ? copy : fo->f.trees[tree];
+  out[0] = static_cast<int64_t>(tr.n_nodes);
   out[1] = tr.simulations;
   out[2] = tr.evaluations;
   out[3] = tr.nodes[tr.root].visits;
   out[4] = tr.nodes[tr.root].wins;
   out[5] = tr.nodes[tr.root].ws;
-  out[6] = tr.phase == wann_tree::Tree::kFinished;
+  out[6] = tr.phase == wann_tree::Tree::kFinished ? (tr.overflow ? 2 : 1) : 0;   // 2: stopped because its arena is full
   const int32_t mv = tr.best_move();       // randomly_choose_a_winning_move (tree_search_utils.pyx:469-486)
   out[7] = mv >= 0 ? tr.nodes[mv].index : -1;
   return WANN_OK;
@@ -1875,7 +2265,7 @@ int wann_forest_info(wann_forest* fo, int64_t tree, int64_t out[8]) {
 
 int wann_forest_advance(wann_forest* fo, int64_t tree, int move_index) {
   if (fo == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size()))
-    return fail(WANN_E_INVALID, "bad argument");
+    return fail(WANN_E_INVALID, fo != nullptr && fo->dev != nullptr ? "device-resident forests move with wann_forest_play" : "bad argument");
   if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
   if (!fo->f.trees[tree].advance_root(move_index))
     return fail(WANN_E_INVALID, "tree %lld: the root has no child for move index %d (or is mid-simulation)",
@@ -1887,6 +2277,27 @@ int wann_forest_play(wann_forest* fo, const int8_t* restart_squares, int restart
                      uint8_t* finished_out) {
   if (fo == nullptr || restart_squares == nullptr) return fail(WANN_E_INVALID, "null argument");
   if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
+  if (fo->dev != nullptr) {
+    DeviceForest* d = fo->dev;
+    DeviceGuard dev_guard(d->ctx->device);
+    CU(dev_guard.status);
+    int8_t rs[80] = {0};
+    memcpy(rs, restart_squares, 64);
+    rs[64] = restart_black != 0;
+    int flag = 0;
+    CU(cudaMemcpyAsync(d->d_restart, rs, 80, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaMemsetAsync(d->d_flag, 0, sizeof(int), d->stream));
+    forest_play_kernel<<<static_cast<unsigned>((d->n * 32 + 127) / 128), 128, 0, d->stream>>>(
+        d->d_trees, d->n, d->d_restart, d->d_moves, d->d_fin, d->d_flag);
+    CU(cudaGetLastError());
+    if (moves_out != nullptr) CU(cudaMemcpyAsync(moves_out, d->d_moves, d->n, cudaMemcpyDeviceToHost, d->stream));
+    if (finished_out != nullptr) CU(cudaMemcpyAsync(finished_out, d->d_fin, d->n, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaMemcpyAsync(&flag, d->d_flag, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    if (flag != 0)
+      return fail(WANN_E_INVALID, "tree %d is waiting for an evaluation: finish wann_forest_run before wann_forest_play", flag - 1);
+    return WANN_OK;
+  }
   const int64_t n = static_cast<int64_t>(fo->f.trees.size());
   for (int64_t t = 0; t < n; ++t)      // a tree that is mid-expansion cannot move: finish the next / apply cycle first
     if (fo->f.trees[t].phase == wann_tree::Tree::kWaitEval)
@@ -1894,29 +2305,42 @@ int wann_forest_play(wann_forest* fo, const int8_t* restart_squares, int restart
                   "wann_forest_next returns no rows before wann_forest_play", static_cast<long long>(t));
 #pragma omp parallel for schedule(dynamic, 8)
   for (int64_t t = 0; t < n; ++t) {
-    wann_tree::Tree& tr = fo->f.trees[t];
-    const int32_t c = tr.best_move();
     uint8_t mv = 255, fin = 0;
-    bool restart = false;
-    if (c >= 0) {
-      mv = tr.nodes[c].index;
-      restart = tr.nodes[c].gameover || !tr.advance_root(mv);   // the move wins the game: next game
-    } else {
-      restart = true;            // a root without children (never searched, or a finished game): start a new game
-    }
-    if (restart) {
-      fin = 1;
-      tr = wann_tree::Tree();
-      tr.init(restart_squares, restart_black != 0, 0);
-    }
+    fo->f.trees[t].play(restart_squares, restart_black != 0, mv, fin);
     if (moves_out != nullptr) moves_out[t] = mv;
     if (finished_out != nullptr) finished_out[t] = fin;
   }
   return WANN_OK;
 }
 
+int wann_forest_debug_cycles(wann_forest* fo, int64_t* out) {
+  if (fo == nullptr || fo->dev == nullptr || out == nullptr) return fail(WANN_E_INVALID, "needs a device-resident forest");
+  DeviceGuard dev_guard(fo->dev->ctx->device);
+  CU(cudaStreamSynchronize(fo->dev->stream));
+  // rows: the last kForestHist lock steps, oldest first: rows requested, next sum, next max, apply sum, apply max
+  DeviceForest* d = fo->dev;
+  std::vector<unsigned long long> cyc(kForestHist * 4);
+  std::vector<int> cnt(kForestHist);
+  CU(cudaMemcpy(cyc.data(), d->d_cycles, cyc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(cnt.data(), d->d_counts, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < kForestHist; ++i) {
+    const int slot = static_cast<int>((d->steps + i) % kForestHist);
+    out[i * 5] = cnt[slot];
+    for (int k = 0; k < 4; ++k) out[i * 5 + 1 + k] = static_cast<int64_t>(cyc[slot * 4 + k]);
+  }
+  return WANN_OK;
+}
+
 int64_t wann_forest_dump(wann_forest* fo, int64_t tree, int64_t* rows, int64_t capacity) {
-  if (fo == nullptr || tree < 0 || tree >= static_cast<int64_t>(fo->f.trees.size())) return -1;
+  if (fo == nullptr || tree < 0 || tree >= (fo->dev ? fo->dev->n : static_cast<int64_t>(fo->f.trees.size()))) return -1;
+  if (fo->dev != nullptr) {
+    DeviceGuard dev_guard(fo->dev->ctx->device);
+    wann_tree::Tree copy;
+    if (download_tree(fo->dev, tree, &copy) != WANN_OK) return -1;
+    const int64_t r = copy.dump(rows, rows ? capacity : 0);
+    copy.release();
+    return r;
+  }
   return fo->f.trees[tree].dump(rows, rows ? capacity : 0);
 }
 

@@ -7,7 +7,11 @@ the trees live in the C++ runtime as flat arrays; each step
     forest.apply(rows)                               # children + seeds attached, statistics propagated
 
 What a tree does between two evaluations is exactly what one thread of the reference's search does
-(expansion_MCTS_functions.pyx:300-350, tree_search_utils.pyx, tree_builder.pyx), see array_tree.hpp."""
+(expansion_MCTS_functions.pyx:300-350, tree_search_utils.pyx, tree_builder.pyx), see array_tree.hpp.
+
+SearchForest(..., evaluator=ev, device_resident=True) keeps the trees in the evaluator's GPU memory:
+`run` is then ONE C call (wann_forest_run) whose lock steps -- tree kernels, conv stack, child seeding --
+are enqueued on one stream with no host round trip; the trees are the same, node for node."""
 import ctypes
 
 import numpy as np
@@ -25,15 +29,25 @@ def host_threads(n=0):
 
 
 class SearchForest(object):
-    def __init__(self, squares, black_to_move, heights=None):
+    def __init__(self, squares, black_to_move, heights=None, evaluator=None, device_resident=False,
+                 node_capacity=16384):
         self._lib = L.load()
         sq = np.ascontiguousarray(squares, np.int8).reshape(-1, 64)
         bl = np.ascontiguousarray(black_to_move, np.uint8).reshape(-1)
         self.n = sq.shape[0]
         h = None if heights is None else np.ascontiguousarray(heights, np.int32).reshape(-1)
         ptr = ctypes.c_void_p()
-        L.check(self._lib.wann_forest_create(self.n, sq.ctypes.data, bl.ctypes.data,
-                                             None if h is None else h.ctypes.data, ctypes.byref(ptr)))
+        self.device_resident = bool(device_resident)
+        self._owner = evaluator                      # a device forest lives in (and dies before) its evaluator's context
+        if self.device_resident:
+            if evaluator is None or not hasattr(evaluator, "_ctx"):
+                raise ValueError("a device-resident forest needs the PolicyEvaluator whose GPU holds it")
+            L.check(self._lib.wann_forest_create_device(evaluator._ctx, self.n, sq.ctypes.data, bl.ctypes.data,
+                                                        None if h is None else h.ctypes.data, int(node_capacity),
+                                                        ctypes.byref(ptr)))
+        else:
+            L.check(self._lib.wann_forest_create(self.n, sq.ctypes.data, bl.ctypes.data,
+                                                 None if h is None else h.ctypes.data, ctypes.byref(ptr)))
         self._f = ptr
         self._sq = np.empty((self.n, 64), np.int8)
         self._bl = np.empty(self.n, np.uint8)
@@ -70,6 +84,11 @@ class SearchForest(object):
     def run(self, evaluator, simulations):
         """Grow every tree by `simulations` simulations on `evaluator` (anything with
         eval_expand_seeded(squares, black, with_children=False)).  Returns (steps, evaluations)."""
+        if self.device_resident or (hasattr(evaluator, "_ctx") and getattr(self, "native_run", True)):
+            # the whole search in the library: wann_forest_run (device forests: no host round trip per step)
+            out2 = (ctypes.c_int64 * 2)()
+            L.check(self._lib.wann_forest_run(evaluator._ctx, self._f, int(simulations), out2))
+            return int(out2[0]), int(out2[1])
         steps = evals = 0
         out = None
         if hasattr(evaluator, "pinned_rows"):            # pinned result rows, allocated once per evaluator
@@ -134,6 +153,13 @@ class SearchForest(object):
             evals += self.run(evaluator, simulations_per_move)[1]
             games += int(self.play()[1].sum())
         return evals, games
+
+    def debug_cycles(self):
+        """device-resident forests: the last 64 lock steps, int64 [64, 5] = rows requested, cycles in the
+        next kernel (sum over trees, max), cycles in the apply kernel (sum, max)."""
+        out = np.zeros((64, 5), np.int64)
+        L.check(self._lib.wann_forest_debug_cycles(self._f, out.ctypes.data))
+        return out
 
     def info(self, tree):
         out = (ctypes.c_int64 * 8)()
