@@ -23,7 +23,7 @@
  *     (the `player_color` / node['color'] argument, MCTS.pyx:98-102).
  *   - move indices are the reference's 155-way alphabet (tools/utils.pyx:69-114,605-641),
  *     in the side-to-move frame; 154 = 'no-move'.
- *   - DEVICE buffers are read and written as vectors: `squares` must be 8-byte aligned and every
+ *   - DEVICE buffers are read and written as vectors: `squares` must be 16-byte aligned and every
  *     output buffer 16-byte aligned (anything from cudaMalloc / a torch tensor, and any row slice
  *     of such a buffer, is); misaligned device pointers are refused with WANN_E_INVALID.
  *   - there is NO CPU fallback: without an sm_100 device wann_create fails.

@@ -42,10 +42,34 @@ t = timed(lambda: L.check(lib.wann_encode(ctx, sq_t.data_ptr(), bl_t.data_ptr(),
 rep["encode_kernel"] = {"bytes_per_position": 65 + 256, "seconds": t, "gbs": N * 321 / t / 1e9}
 t = timed(lambda: L.check(lib.wann_legal_mask(ctx, sq_t.data_ptr(), bl_t.data_ptr(), N, mask.data_ptr(), L.MEM_DEVICE, stream)))
 rep["legal_mask_kernel"] = {"bytes_per_position": 65 + 155, "seconds": t, "gbs": N * 220 / t / 1e9}
-for k in ("encode_kernel", "legal_mask_kernel"):
+M = min(N, 1 << 17)
+idx = torch.empty((M, 48), dtype=torch.uint8, device=dev); pri = torch.empty((M, 48), dtype=torch.float32, device=dev)
+cnt = torch.empty((M,), dtype=torch.uint8, device=dev)
+ev.eval_topk(sq_t[:M], bl_t[:M], out=(idx, pri, cnt))
+kids = torch.empty((M, 48, 64), dtype=torch.int8, device=dev); flg = torch.empty((M, 48), dtype=torch.uint8, device=dev)
+st = torch.empty((M, 48, 4), dtype=torch.int32, device=dev); ps = torch.empty((M, 8), dtype=torch.int32, device=dev)
+t = timed(lambda: L.check(lib.wann_expand_ranked(ctx, sq_t.data_ptr(), bl_t.data_ptr(), M, idx.data_ptr(), pri.data_ptr(), cnt.data_ptr(),
+                                                 kids.data_ptr(), flg.data_ptr(), None, None, stream)))
+rep["expand_children_kernel"] = {"positions": M, "bytes_per_position": 65 + 49 + 3072 + 48, "seconds": t, "gbs": M * 3234 / t / 1e9}
+t = timed(lambda: L.check(lib.wann_expand_ranked(ctx, sq_t.data_ptr(), bl_t.data_ptr(), M, idx.data_ptr(), pri.data_ptr(), cnt.data_ptr(),
+                                                 None, flg.data_ptr(), st.data_ptr(), ps.data_ptr(), stream)))
+rep["seed_children_kernel"] = {"positions": M, "bytes_per_position": 65 + 48 + 192 + 1 + 768 + 48 + 32, "seconds": t, "gbs": M * 1154 / t / 1e9}
+# context for the write-heavy kernels: what this GPU does for a pure write (fill) and a pure read (sum) of 1 GiB
+big = torch.empty(1 << 28, dtype=torch.int32, device=dev)
+t = timed(lambda: big.fill_(7)); rep["reference_fill_gbs"] = big.numel() * 4 / t / 1e9
+t = timed(lambda: big.sum()); rep["reference_read_sum_gbs"] = big.numel() * 4 / t / 1e9
+half = big[:1 << 27]; other = big[1 << 27:]
+t = timed(lambda: other.copy_(half)); rep["reference_copy_gbs"] = half.numel() * 8 / t / 1e9
+del big
+# bit-exactness of what was just timed, on a sample, against the oracle
+from oracle import oracle as O
+k = 3000
+assert (planes[:k].cpu().numpy() == O.encode_planes(sq_t[:k].cpu().numpy(), bl_t[:k].cpu().numpy())).all()
+assert (mask[:k].cpu().numpy().astype(bool) == O.legal_mask(sq_t[:k].cpu().numpy(), bl_t[:k].cpu().numpy())).all()
+assert (mask[N - k:].cpu().numpy().astype(bool) == O.legal_mask(sq_t[N - k:].cpu().numpy(), bl_t[N - k:].cpu().numpy())).all()
+rep["bit_exact_vs_oracle"] = True
+for k in ("encode_kernel", "legal_mask_kernel", "expand_children_kernel", "seed_children_kernel"):
     rep[k]["frac_of_hbm_peak"] = rep[k]["gbs"] / peak
-    rep[k]["positions_per_s"] = N / rep[k]["seconds"]
-rep["note"] = ("expand_children_kernel / seed_children_kernel run behind an evaluation: their durations come from the ncu "
-               "launch list (tools/gpu_byte_kernels_ncu.py, profiles/r01_ncu_byte_kernels.csv)")
+    rep[k]["positions_per_s"] = rep[k].get("positions", N) / rep[k]["seconds"]
 print(json.dumps(rep, indent=1))
 open(os.path.join(ROOT, "gpurun_out", "byte_kernels.json"), "w").write(json.dumps(rep, indent=1))

@@ -24,26 +24,47 @@ __device__ __forceinline__ int pov_square(const int8_t* sq64, int blk, int i) {
 
 // One thread per FOUR squares: one 4-byte load (for Black the mirrored word, bytes reversed: the
 // 180-degree rotation of tools/utils.pyx:563-600) and one 16-byte store of the four P/O/E/1 cells.
-// HBM-bound: 65 B in, 256 B out per position.
+// HBM-bound: 65 B in, 256 B out per position.  Four grid-stride items per thread are in flight at once
+// (loads first, then the stores): with one item per iteration the ~10 KB of reads a full SM keeps in
+// flight did not cover the memory latency (4.5 TB/s; profiles/r02_byte_kernels.json has the new figure).
+__device__ __forceinline__ uint4 encode_four_squares(uint32_t w, int blk) {
+  if (blk) w = __byte_perm(w, 0u, 0x0123);            // reverse the four squares
+  uint32_t out[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int sq = (w >> (8 * k)) & 0xFF;
+    if (blk && sq) sq = 3 - sq;                       // Black sees its own pieces as "player"
+    out[k] = (sq == 1 ? 1u : 0u) | (sq == 2 ? 0x100u : 0u) | (sq == 0 ? 0x10000u : 0u) | 0x1000000u;
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+template <int kUnroll, bool kStream>
 __global__ void __launch_bounds__(256) encode_kernel(const int8_t* __restrict__ squares,
                                                      const uint8_t* __restrict__ black, long long n,
                                                      int8_t* __restrict__ planes) {
   const long long total = n * 16;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long board = i >> 4;
-    const int q = static_cast<int>(i & 15);
-    const int blk = black[board];
-    uint32_t w = reinterpret_cast<const uint32_t*>(squares + board * 64)[blk ? 15 - q : q];
-    if (blk) w = __byte_perm(w, 0u, 0x0123);          // reverse the four squares
-    uint32_t out[4];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < total; i0 += kUnroll * stride) {
+    uint32_t w[kUnroll];
+    int blk[kUnroll];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int sq = (w >> (8 * k)) & 0xFF;
-      if (blk && sq) sq = 3 - sq;                       // Black sees its own pieces as "player"
-      out[k] = (sq == 1 ? 1u : 0u) | (sq == 2 ? 0x100u : 0u) | (sq == 0 ? 0x10000u : 0u) | 0x1000000u;
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        const long long board = i >> 4;
+        blk[u] = __ldg(black + board);
+        w[u] = __ldg(reinterpret_cast<const uint32_t*>(squares) + i);     // independent of the colour: for Black the
+      }                                                                    // OUTPUT cell is the mirrored one
     }
-    reinterpret_cast<uint4*>(planes)[i] = make_uint4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        const long long o = blk[u] ? (i | 15) - (i & 15) : i;             // cell 15 - q of the same board
+        if (kStream) __stcs(reinterpret_cast<uint4*>(planes) + o, encode_four_squares(w[u], blk[u]));
+        else reinterpret_cast<uint4*>(planes)[o] = encode_four_squares(w[u], blk[u]);
+      }
+    }
   }
 }
 
@@ -64,18 +85,26 @@ __device__ __forceinline__ bool move_is_legal(const int8_t* pov, int idx) {
   return d == 0 ? (t == 0) : (t != 1);
 }
 
-// One THREAD per board, bitboards in registers:
-//   * the 64 squares are read as eight 8-byte words; SWAR byte-equality tests (exact for any byte
-//     value) and a multiply-compress turn them into 64-bit "white / black / empty" boards; Black's
-//     point of view is the bit-reversed board with the colours swapped (the 180-degree rotation of
-//     tools/utils.pyx:563-600; a stray value 3 reads as empty for Black, as in pov_square);
+// One THREAD per board, bitboards in registers; all global traffic as coalesced 16-byte vectors:
+//   * a warp loads its 32 boards (2 KB) with four 16-byte loads per lane into shared memory (80-byte pitch:
+//     conflict-free both ways) and every lane reads its own board back as four 16-byte words;
+//   * SWAR byte-equality tests (exact for any byte value) and a multiply-compress turn them into 64-bit
+//     "white / black / empty" boards; Black's point of view is the bit-reversed board with the colours
+//     swapped (the 180-degree rotation of tools/utils.pyx:563-600; a stray value 3 reads as empty for
+//     Black, as in pov_square);
 //   * legality for all 154 moves is three shifts: forward = player & (empty >> 8), the diagonals
 //     = player & ~(player >> 7 | 9) off the edge files (board_utils.pyx:331-400);
-//   * the move alphabet order (22 indices per rank: F0 R0 | L1 F1 R1 | ... | L7 F7,
-//     tools/utils.pyx:605-641) is walked once per thread, the 155 mask bytes go to the warp's
-//     shared-memory block, and the warp writes its 32 x 155 contiguous bytes as 16-byte vectors.
-// ~22 warp instructions per board instead of ~200: HBM-bound.  65 B in, 155 B out per position.
+//   * the 155 mask bytes of a board are built IN REGISTERS as 39 packed words: per rank the three 8-bit
+//     rows (left / forward / right) are spread to bytes with a multiply (bit i -> byte i), interleaved to
+//     the move alphabet's order (22 indices per rank: F0 R0 | L1 F1 R1 | ... | L7 F7,
+//     tools/utils.pyx:605-641) with byte permutes, and shifted to the row's byte offset; the row is then
+//     shifted once more by its own alignment (155 * lane mod 4) and written with WORD stores into the warp's
+//     packed 4,960-byte block (a word shared by two rows is written by the lower row, which fetches the
+//     upper row's bytes with a shuffle), and the block leaves as 16-byte vectors.
+//   The first version wrote the 155 bytes of a board with 155 byte stores per lane: shared-memory store
+//   bound (2.8 TB/s = 0.43 of the HBM copy peak).  65 B in, 155 B out per position.
 constexpr int kMaskWarps = 4;
+constexpr int kMaskInPitch = 80;
 __device__ __forceinline__ uint64_t swar_eq_flags(uint64_t w, uint64_t pattern) {   // 0x80 in every byte == pattern's
   const uint64_t x = w ^ pattern;
   const uint64_t t = (x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full;
@@ -84,61 +113,119 @@ __device__ __forceinline__ uint64_t swar_eq_flags(uint64_t w, uint64_t pattern) 
 __device__ __forceinline__ uint64_t swar_compress(uint64_t flags) {   // byte c's 0x80 flag -> bit c
   return ((flags >> 7) * 0x0102040810204080ull) >> 56;
 }
+// bit i (i < 4) of x -> byte i (0 / 1)
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
 
 __global__ void __launch_bounds__(kMaskWarps * 32) legal_mask_kernel(const int8_t* __restrict__ squares,
                                                                     const uint8_t* __restrict__ black,
                                                                     long long n, uint8_t* __restrict__ mask) {
-  __shared__ __align__(16) uint8_t out_s[kMaskWarps][32 * kMoves];
+  __shared__ __align__(16) uint8_t in_s[kMaskWarps][32 * kMaskInPitch];
+  __shared__ __align__(16) uint32_t out_s[kMaskWarps][32 * kMoves / 4];      // 1,240 words
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long long base = (blockIdx.x * static_cast<long long>(kMaskWarps) + w) * 32; base < n;
        base += static_cast<long long>(gridDim.x) * kMaskWarps * 32) {
+    const int nvalid = static_cast<int>(min(32ll, n - base));
     const long long board = base + lane;
-    if (board < n) {
-      const uint2* src = reinterpret_cast<const uint2*>(squares + board * 64);
-      uint64_t white = 0, blackbb = 0, e0 = 0, t3 = 0;
+    // ---- the warp's boards: global -> shared, coalesced --------------------------------------------
+    const uint4* src = reinterpret_cast<const uint4*>(squares + base * 64);
+    uint4 chunk[4];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const uint2 v = src[r];
-        const uint64_t wd = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
-        white |= swar_compress(swar_eq_flags(wd, 0x0101010101010101ull)) << (8 * r);
-        blackbb |= swar_compress(swar_eq_flags(wd, 0x0202020202020202ull)) << (8 * r);
-        e0 |= swar_compress(swar_eq_flags(wd, 0ull)) << (8 * r);
-        t3 |= swar_compress(swar_eq_flags(wd, 0x0303030303030303ull)) << (8 * r);
-      }
-      const bool blk = black[board] != 0;
-      const uint64_t player = blk ? __brevll(blackbb) : white;
-      const uint64_t empty = blk ? __brevll(e0 | t3) : e0;
-      constexpr uint64_t kRows06 = 0x00FFFFFFFFFFFFFFull, kFileA = 0x0101010101010101ull;
-      const uint64_t fwd = player & (empty >> 8) & kRows06;
-      const uint64_t lft = player & ~(player >> 7) & ~kFileA & kRows06;          // d = -1: to = from + 7
-      const uint64_t rgt = player & ~(player >> 9) & ~(kFileA << 7) & kRows06;   // d = +1: to = from + 9
-      uint8_t* row = &out_s[w][lane * kMoves];
+    for (int j = 0; j < 4; ++j) {
+      const int q = j * 32 + lane;
+      chunk[j] = q < nvalid * 4 ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const bool blk = board < n && __ldg(black + board) != 0;
 #pragma unroll
-      for (int r = 0; r < 7; ++r) {
-        const uint32_t f = static_cast<uint32_t>(fwd >> (8 * r)) & 0xFFu;
-        const uint32_t l = static_cast<uint32_t>(lft >> (8 * r)) & 0xFFu;
-        const uint32_t g = static_cast<uint32_t>(rgt >> (8 * r)) & 0xFFu;
-        uint8_t* o = row + 22 * r;
-        o[0] = f & 1u;
-        o[1] = g & 1u;
-#pragma unroll
-        for (int c = 1; c < 7; ++c) {
-          o[3 * c - 1] = (l >> c) & 1u;
-          o[3 * c] = (f >> c) & 1u;
-          o[3 * c + 1] = (g >> c) & 1u;
-        }
-        o[20] = (l >> 7) & 1u;
-        o[21] = (f >> 7) & 1u;
-      }
-      row[154] = 0;                                   // 'no-move' is never a legal child
+    for (int j = 0; j < 4; ++j) {
+      const int q = j * 32 + lane;
+      *reinterpret_cast<uint4*>(&in_s[w][kMaskInPitch * (q >> 2) + 16 * (q & 3)]) = chunk[j];
     }
     __syncwarp();
-    const int nvalid = static_cast<int>(min(32ll, n - base));
+    // 4 squares per 32-bit word: a byte of y1 is zero where the mover's piece stands, a byte of y2 where the
+    // square is empty (for Black: 0, or a stray 3 -- pov_square reads 3 - 3 = 0); zero bytes -> 0x80 flags
+    // (exact for any byte value), 4 flags -> 4 bits with one multiply
+    const uint32_t pcode = blk ? 0x02020202u : 0x01010101u;
+    uint32_t pl[2] = {0u, 0u}, em[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint4 v = *reinterpret_cast<const uint4*>(&in_s[w][kMaskInPitch * lane + 16 * k]);
+      const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int wi = 4 * k + t;
+        const uint32_t x = xs[t];
+        const uint32_t y1 = x ^ pcode;
+        const uint32_t y2 = blk ? (((x ^ (x >> 1)) & 0x01010101u) | (x & 0xFCFCFCFCu)) : x;
+        const uint32_t z1 = ~(((y1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y1) & 0x80808080u;
+        const uint32_t z2 = ~(((y2 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y2) & 0x80808080u;
+        pl[wi >> 3] |= (((z1 >> 7) * 0x01020408u) >> 24) << (4 * (wi & 7));
+        em[wi >> 3] |= (((z2 >> 7) * 0x01020408u) >> 24) << (4 * (wi & 7));
+      }
+    }
+    const uint64_t pl64 = static_cast<uint64_t>(pl[0]) | (static_cast<uint64_t>(pl[1]) << 32);
+    const uint64_t em64 = static_cast<uint64_t>(em[0]) | (static_cast<uint64_t>(em[1]) << 32);
+    const uint64_t player = blk ? __brevll(pl64) : pl64;
+    const uint64_t empty = blk ? __brevll(em64) : em64;
+    constexpr uint64_t kRows06 = 0x00FFFFFFFFFFFFFFull, kFileA = 0x0101010101010101ull;
+    uint64_t fwd = player & (empty >> 8) & kRows06;
+    uint64_t lft = player & ~(player >> 7) & ~kFileA & kRows06;          // d = -1: to = from + 7
+    uint64_t rgt = player & ~(player >> 9) & ~(kFileA << 7) & kRows06;   // d = +1: to = from + 9
+    if (board >= n) fwd = lft = rgt = 0;
+    // ---- the row of 155 bytes as 39 packed words (byte 155 = pad) -----------------------------------
+    // per rank: T[r] = the 24 bytes L0 F0 G0 L1 F1 G1 ... L7 F7 G7; L0 and G7 are always 0, bytes 1..22 are
+    // the rank's 22 row bytes
+    uint32_t T[7][6];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const uint32_t f = static_cast<uint32_t>(fwd >> (8 * r)) & 0xFFu;
+      const uint32_t l = static_cast<uint32_t>(lft >> (8 * r)) & 0xFFu;
+      const uint32_t g = static_cast<uint32_t>(rgt >> (8 * r)) & 0xFFu;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t L = spread4(l >> (4 * hh)), F = spread4(f >> (4 * hh)), G = spread4(g >> (4 * hh));
+        T[r][3 * hh + 0] = __byte_perm(__byte_perm(L, F, 0x0140), G, 0x2410);      // L0 F0 G0 L1
+        T[r][3 * hh + 1] = __byte_perm(__byte_perm(F, G, 0x0251), L, 0x2610);      // F1 G1 L2 F2
+        T[r][3 * hh + 2] = __byte_perm(__byte_perm(G, L, 0x0372), F, 0x2710);      // G2 L3 F3 G3
+      }
+    }
+    // row word j = row bytes 4j .. 4j+3: a funnel shift inside a rank's 24 bytes, OR (where the word crosses
+    // into the next rank) that rank's first word shifted -- the always-zero L0 / G7 bytes make the ORs safe
+    uint32_t U[40];
+#pragma unroll
+    for (int j = 0; j < 39; ++j) {
+      const int b0 = 4 * j, r = b0 / 22, m0 = b0 % 22 + 1, a = m0 / 4, sh = m0 % 4;
+      uint32_t v = 0u;
+      if (r < 7) {
+        const uint32_t lo = T[r][a], hi = a + 1 < 6 ? T[r][a + 1] : 0u;
+        v = sh == 0 ? lo : __funnelshift_r(lo, hi, 8 * sh);
+        const int cnt = 23 - m0 < 4 ? 23 - m0 : 4;            // bytes of this word that belong to rank r
+        if (cnt < 4 && r + 1 < 7) v |= T[r + 1][0] << (8 * (cnt - 1));
+      }
+      U[j] = v;
+    }
+    U[39] = 0u;
+    U[38] &= 0x00FFFFFFu;                             // (byte 155 is the pad; byte 154 = 'no-move' = 0 already)
+    // ---- into the warp's packed block, word stores ---------------------------------------------------
+    const int s_me = (kMoves * lane) & 3, w0 = (kMoves * lane) >> 2;
+    const int s_next = (kMoves * (lane + 1)) & 3;
+    const int j_last = (s_me + kMoves - 1) >> 2;      // 38 or 39
+    const uint32_t head = U[0] << (8 * s_me);         // my first bytes, in the position they have in the shared word
+    uint32_t next_head = __shfl_down_sync(0xffffffffu, head, 1);
+    if (lane == 31 || s_next == 0) next_head = 0u;
+#pragma unroll
+    for (int j = 0; j < 40; ++j) {
+      const uint32_t lo = j > 0 ? U[j - 1] : 0u, hi = j < 39 ? U[j] : 0u;
+      uint32_t v = __funnelshift_l(lo, hi, 8 * s_me);
+      if (j == j_last) v |= next_head;
+      if (j <= j_last && (j > 0 || s_me == 0)) out_s[w][w0 + j] = v;
+    }
+    __syncwarp();
+    // ---- shared -> global, 16-byte vectors ------------------------------------------------------------
     const int bytes = nvalid * kMoves;
-    uint8_t* dst = mask + base * kMoves;              // base is a multiple of 32 -> 32-byte aligned if mask is
-    const uint8_t* srcb = out_s[w];
+    uint8_t* dst = mask + base * kMoves;              // base is a multiple of 32 -> 16-byte aligned if mask is
+    const uint8_t* srcb = reinterpret_cast<const uint8_t*>(out_s[w]);
     for (int i = lane; i < bytes / 16; i += 32)
-      reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(srcb)[i];
+      __stcs(reinterpret_cast<uint4*>(dst) + i, reinterpret_cast<const uint4*>(srcb)[i]);
     for (int i = (bytes & ~15) + lane; i < bytes; i += 32) dst[i] = srcb[i];
     __syncwarp();
   }

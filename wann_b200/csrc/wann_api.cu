@@ -1566,8 +1566,8 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
       ((reinterpret_cast<uintptr_t>(squares) & 3u) || (reinterpret_cast<uintptr_t>(out) & 15u)))
     return fail(WANN_E_INVALID, "device squares must be 4-byte and planes 16-byte aligned");
   if (mem == WANN_MEM_DEVICE && is_mask &&
-      ((reinterpret_cast<uintptr_t>(squares) & 7u) || (reinterpret_cast<uintptr_t>(out) & 15u)))
-    return fail(WANN_E_INVALID, "device squares must be 8-byte and the mask buffer 16-byte aligned");
+      ((reinterpret_cast<uintptr_t>(squares) | reinterpret_cast<uintptr_t>(out)) & 15u))
+    return fail(WANN_E_INVALID, "device squares and the mask buffer must be 16-byte aligned");
   DeviceGuard dev_guard(ctx->device);
   CU(dev_guard.status);
   Lane* lane = nullptr;
@@ -1596,8 +1596,19 @@ static int run_bytes(wann_ctx* ctx, const int8_t* squares, const uint8_t* black,
         const int blocks = static_cast<int>(std::min<long long>((m + per_block - 1) / per_block, 11ll * ctx->sm_count));
         legal_mask_kernel<<<blocks, kMaskWarps * 32, 0, stream>>>(dsq, dbl, m, dout);
       } else {
-        const int blocks = static_cast<int>(std::min<long long>((m * 16 + 255) / 256, 16ll * ctx->sm_count));
-        encode_kernel<<<blocks, 256, 0, stream>>>(dsq, dbl, m, reinterpret_cast<int8_t*>(dout));
+        // (experiments: option "variant" bits 8-10 = unroll / store kind, bits 12-15 = blocks per SM)
+        const int var = ctx->variant.load();
+        const int per_sm = ((var >> 12) & 15) ? ((var >> 12) & 15) : 16;
+        const int blocks = static_cast<int>(std::min<long long>((m * 16 + 255) / 256, static_cast<long long>(per_sm) * ctx->sm_count));
+        int8_t* po = reinterpret_cast<int8_t*>(dout);
+        switch ((var >> 8) & 7) {
+          case 1: encode_kernel<2, true><<<blocks, 256, 0, stream>>>(dsq, dbl, m, po); break;
+          case 2: encode_kernel<8, true><<<blocks, 256, 0, stream>>>(dsq, dbl, m, po); break;
+          case 3: encode_kernel<4, false><<<blocks, 256, 0, stream>>>(dsq, dbl, m, po); break;
+          case 4: encode_kernel<8, false><<<blocks, 256, 0, stream>>>(dsq, dbl, m, po); break;
+          case 5: encode_kernel<1, false><<<blocks, 256, 0, stream>>>(dsq, dbl, m, po); break;
+          default: encode_kernel<4, true><<<blocks, 256, 0, stream>>>(dsq, dbl, m, po); break;
+        }
       }
       CU(cudaGetLastError());
       ctx->stats[1] += 1;
