@@ -73,8 +73,8 @@ for split in (0, 14):
 # 2. accuracy + throughput per configuration
 for name, mode, split, margin in (("fp16", "fp16", 0, 0.0), ("fp16c", "fp16c", 0, 0.0), ("fp16c+refine0.02", "fp16c", 0, 0.02),
                                   ("fp16c+refine0.01", "fp16c", 0, 0.01),
-                                  ("fp16c_split4", "fp16c", 8, 0.0), ("fp16c_split34", "fp16c", 12, 0.0),
-                                  ("fp16c_split234", "fp16c", 14, 0.0), ("fp16c_split234+refine0.01", "fp16c", 14, 0.01), ("bf16", "bf16", 0, 0.0)):
+                                  ("fp16c+split_layers8", "fp16c", 8, 0.0), ("fp16c+split_layers12", "fp16c", 12, 0.0),
+                                  ("fp16c+split_layers14", "fp16c", 14, 0.0), ("fp16c+split_layers14+refine0.01", "fp16c", 14, 0.01), ("bf16", "bf16", 0, 0.0)):
     with wann_b200.PolicyEvaluator(w, mode=mode, refine_margin=margin) as ev:
         if split:
             ev.set_option("split_layers", split)
