@@ -811,3 +811,32 @@ def test_shim_turns_valid_planes_back_into_boards():
     bad = planes.copy()
     bad[1, 2, 3, 3] = 0
     assert session.eval_planes_as_boards(Fake(), bad)[0] == "planes"
+
+
+def test_forest_play_refuses_mid_expansion_and_restarts_unsearched_trees(lib_built):
+    """wann_forest_play (1) must not treat a tree that is waiting for an evaluation as a won game
+    (it returns WANN_E_INVALID and leaves every tree alone), and (2) restarts a tree whose root has no
+    children (never searched, or a finished game) instead of leaving it stuck with move 255."""
+    import wann_b200
+    from wann_b200 import _lib as L
+    sq, bl = O.random_positions_fast(3, seed=21)
+    with wann_b200.SearchForest(sq, bl) as forest:
+        moves, fin = forest.play()                                  # nothing searched yet: all three restart
+        assert (moves == 255).all() and (fin == 1).all()
+        assert all(forest.info(t)["nodes"] == 1 for t in range(3))
+        s, b, ids = forest.next(2)                                  # every tree now waits for its first evaluation
+        assert len(s) == 3
+        before = [forest.dump(t).copy() for t in range(3)]
+        with pytest.raises(L.WannError):
+            forest.play()
+        # (the pending rows are still owed: apply them, then the trees can move)
+        idx, pri, cnt = O.ranked_children(np.stack([O.synthetic_policy(x, int(c)) for x, c in zip(s, b)]), O.legal_mask(s, b))
+        seeds, flags, parent = O.seed_children(s, b, idx, pri, cnt)
+        parent8 = np.zeros((3, 8), np.int32)
+        parent8[:, :6] = parent
+        for t in range(3):
+            assert np.array_equal(forest.dump(t), before[t])
+        forest.apply(idx, pri, cnt, flags, seeds, parent8)
+        forest.run(_CpuSeeds(), 2)
+        moves, fin = forest.play()
+        assert (moves != 255).all()
