@@ -453,7 +453,29 @@ def main():
             if not resident:
                 forest_line[key]["host_threads_per_rank"] = host_threads()
             forest.close()
-        forest_line["evaluations_per_s"] = forest_line["device_resident"]["evaluations_per_s"]
+            # steady state (configs[4]: "each GPU serving its own leaf batches at steady state"): every tree keeps
+            # searching -- a budget of lock steps instead of simulations, as the reference's search has a time budget
+            forest = SearchForest(fsq, fbl, evaluator=ev3, device_resident=resident, node_capacity=32768)
+            forest.run_steps(ev3, 40)
+            barrier()
+            t0 = time.perf_counter()
+            ssteps, sevals = forest.run_steps(ev3, 150)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            forest.run(ev3, 0)                                          # finish the simulations in flight
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            cnts = torch.tensor([sevals], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(cnts, op=dist.ReduceOp.SUM)
+            forest_line[key]["steady_state"] = {"lock_steps": ssteps, "evaluations": int(cnts[0].item()),
+                                                "evaluations_per_s": round(float(cnts[0].item()) / float(t.item()), 1),
+                                                "rows_per_step": round(sevals / max(ssteps, 1), 1),
+                                                "us_per_lock_step": round(dt * 1e6 / max(ssteps, 1), 1)}
+            forest.close()
+        forest_line["evaluations_per_s"] = forest_line["device_resident"]["steady_state"]["evaluations_per_s"]
+        forest_line["note"] = ("evaluations_per_s = the device-resident forest of 1,024 trees per GPU at steady state; the "
+                               "fixed-simulation runs beside it end with ever fewer active trees per lock step")
         ev3.close()
 
     # ---------------- the other arithmetic modes on the same workload (device resident, short runs):

@@ -248,6 +248,12 @@ int wann_forest_create_device(wann_ctx* ctx, int64_t n_trees, const int8_t* squa
  * enqueued on one stream, the number of requested rows stays on the device, and the host only looks
  * at the per-step row counts every 8 steps.  out[0] = lock steps, out[1] = evaluations (optional). */
 int wann_forest_run(wann_ctx* ctx, wann_forest* forest, int64_t max_simulations, int64_t out[2]);
+/* The same with a budget of lock steps (the reference's search thinks for a fixed TIME, `time_to_think`,
+ * expansion_MCTS_functions.pyx:113-119, not for a fixed number of simulations): returns after
+ * max_lock_steps steps even if trees are mid-simulation.  wann_forest_run(ctx, forest, 0, ...) afterwards
+ * finishes the simulations in flight without starting new ones, so that moves can be played. */
+int wann_forest_run_steps(wann_ctx* ctx, wann_forest* forest, int64_t max_simulations, int64_t max_lock_steps,
+                          int64_t out[2]);
 /* Inspection hook (device-resident forests): the last 64 lock steps, oldest first, out int64 [64][5]:
  * rows requested, then the clock64 cycles the trees spent in forest_next_kernel (sum over trees, max)
  * and in forest_apply_kernel (sum, max). */

@@ -83,6 +83,8 @@ cdef extern from "wann_b200.h" nogil:
     int wann_forest_create_device(wann_ctx* ctx, int64_t n_trees, const int8_t* squares, const uint8_t* black_to_move,
                                   const int32_t* heights, int32_t node_capacity, wann_forest** out)
     int wann_forest_run(wann_ctx* ctx, wann_forest* forest, int64_t max_simulations, int64_t* out)
+    int wann_forest_run_steps(wann_ctx* ctx, wann_forest* forest, int64_t max_simulations, int64_t max_lock_steps,
+                              int64_t* out)
     int wann_forest_debug_cycles(wann_forest* forest, int64_t* out)
     int wann_forest_next(wann_forest* forest, int64_t max_simulations, int8_t* squares_out, uint8_t* black_out,
                          int64_t* tree_ids, int64_t* m_out)

@@ -1142,3 +1142,36 @@ def test_device_resident_forest_equals_the_host_forest(mode, margin, weights, su
         assert all(i["nodes"] <= 256 for i in infos) and any(i["finished"] == 2 for i in infos)
         for f in (host, dev, host2, dev2, tiny):
             f.close()
+
+
+def test_forest_step_budget_and_drain(weights, suite):
+    """wann_forest_run_steps: a budget of lock steps (the reference's search has a time budget,
+    expansion_MCTS_functions.pyx:113-119) may leave trees mid-simulation; draining with a simulation budget
+    of 0 finishes them, after which moves can be played.  Host and device forests stay identical."""
+    import wann_b200
+    sq, bl = suite
+    n = 48
+    with wann_b200.PolicyEvaluator(weights, mode="fp16c") as ev:
+        host = wann_b200.SearchForest(sq[:n], bl[:n])
+        dev = wann_b200.SearchForest(sq[:n], bl[:n], evaluator=ev, device_resident=True, node_capacity=32768)
+        for forest in (host, dev):
+            steps, evals = forest.run_steps(ev, 25)
+            assert steps == 25 and evals > 20 * n                 # (nearly) every tree asks every step
+        with pytest.raises(wann_b200.WannError):                  # trees are mid-simulation
+            dev.play()
+        # the two drivers order evaluation-free simulations differently (a device tree yields its step), so the
+        # forests are compared after both have completed the same number of simulations
+        sims = max(host.info(t)["simulations"] for t in range(n)) + 2
+        host.run(ev, sims)
+        dev.run(ev, sims)
+        for t in range(n):
+            assert np.array_equal(dev.dump(t), host.dump(t)), t
+        dev.run(ev, 0)
+        mh, fh = host.play()
+        md, fd = dev.play()
+        assert np.array_equal(mh, md) and (md != 255).all()
+        s, e = dev.run_for(ev, 0.05)                               # time budget + drain
+        assert e > 0
+        dev.play()
+        host.close()
+        dev.close()

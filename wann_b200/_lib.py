@@ -19,7 +19,7 @@ EXPORTS = [
     "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_eval_expand", "wann_eval_expand_seeded", "wann_expand_ranked", "wann_tree_step", "wann_debug_activations",
     "wann_debug_profile", "wann_debug_centering", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
-    "wann_forest_create", "wann_forest_create_device", "wann_forest_run", "wann_forest_debug_cycles", "wann_forest_destroy", "wann_forest_next", "wann_forest_apply", "wann_forest_info",
+    "wann_forest_create", "wann_forest_create_device", "wann_forest_run", "wann_forest_run_steps", "wann_forest_debug_cycles", "wann_forest_destroy", "wann_forest_next", "wann_forest_apply", "wann_forest_info",
     "wann_forest_dump", "wann_forest_advance", "wann_forest_play", "wann_host_threads",
 ]
 
@@ -62,6 +62,7 @@ def load():
     lib.wann_forest_create.argtypes = [i64, vp, vp, vp, ctypes.POINTER(vp)]
     lib.wann_forest_create_device.argtypes = [vp, i64, vp, vp, vp, ctypes.c_int32, ctypes.POINTER(vp)]
     lib.wann_forest_run.argtypes = [vp, vp, i64, vp]
+    lib.wann_forest_run_steps.argtypes = [vp, vp, i64, i64, vp]
     lib.wann_forest_debug_cycles.argtypes = [vp, vp]
     lib.wann_forest_destroy.argtypes = [vp]
     lib.wann_forest_next.argtypes = [vp, i64, vp, vp, vp, ctypes.POINTER(i64)]

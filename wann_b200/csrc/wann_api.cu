@@ -1912,6 +1912,12 @@ __global__ void __launch_bounds__(128) forest_apply_kernel(wann_tree::Tree* tree
   }
 }
 
+// a tree that is mid-expansion cannot move: the caller checks ALL trees before any of them plays
+__global__ void forest_waiting_kernel(const wann_tree::Tree* trees, long long n, int* flag) {
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t < n && trees[t].phase == wann_tree::Tree::kWaitEval) atomicExch(flag, static_cast<int>(t) + 1);
+}
+
 __global__ void __launch_bounds__(128) forest_play_kernel(wann_tree::Tree* trees, long long n, const int8_t* __restrict__ restart,
                                                           uint8_t* __restrict__ moves, uint8_t* __restrict__ fin, int* flag) {
   const long long t = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -2066,7 +2072,15 @@ int wann_forest_create_device(wann_ctx* ctx, int64_t n, const int8_t* squares, c
 // Search: every tree does `max_simulations` simulations (run_MCTS_with_expansions_simulation,
 // expansion_MCTS_functions.pyx:300-350); out[0] = lock steps, out[1] = evaluations.
 int wann_forest_run(wann_ctx* ctx, wann_forest* fo, int64_t max_simulations, int64_t out[2]) {
+  return wann_forest_run_steps(ctx, fo, max_simulations, INT64_MAX, out);
+}
+
+// ... with a budget of lock steps as well (the reference's search is time-budgeted, `time_to_think`,
+// expansion_MCTS_functions.pyx:113-119): stops after max_lock_steps steps even if trees are mid-simulation;
+// a following wann_forest_run(ctx, forest, 0, ...) finishes the simulations in flight without starting new ones.
+int wann_forest_run_steps(wann_ctx* ctx, wann_forest* fo, int64_t max_simulations, int64_t max_lock_steps, int64_t out[2]) {
   if (ctx == nullptr || fo == nullptr) return fail(WANN_E_INVALID, "null argument");
+  if (max_lock_steps <= 0) { if (out) out[0] = out[1] = 0; return WANN_OK; }
   if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
   int64_t steps = 0, evals = 0;
   if (fo->dev == nullptr) {
@@ -2081,7 +2095,7 @@ int wann_forest_run(wann_ctx* ctx, wann_forest* fo, int64_t max_simulations, int
       CU(cudaMallocHost(&sq, n * 64)); CU(cudaMallocHost(&bl, n)); CU(cudaMallocHost(&idx, n * kMaxLegal));
       CU(cudaMallocHost(&prior, n * kMaxLegal * 4)); CU(cudaMallocHost(&nl, n)); CU(cudaMallocHost(&fl, n * kMaxLegal));
       CU(cudaMallocHost(&st, n * kMaxLegal * 16)); CU(cudaMallocHost(&ps, n * 32));
-      while (true) {
+      while (steps < max_lock_steps) {
         int64_t m = 0;
         int rc = wann_forest_next(fo, max_simulations, sq, bl, nullptr, &m);
         if (rc != WANN_OK) return rc;
@@ -2133,10 +2147,13 @@ int wann_forest_run(wann_ctx* ctx, wann_forest* fo, int64_t max_simulations, int
     mark();
     double host_enqueue_us = 0, host_wait_us = 0;
     long long bursts = 0;
+    int64_t launched = 0;
     while (true) {
       const int first = static_cast<int>(d->steps % kForestHist);
       const double tq0 = omp_get_wtime();
-      for (int b = 0; b < kForestBurst; ++b, ++d->steps) {
+      const int burst = static_cast<int>(std::min<int64_t>(kForestBurst, max_lock_steps - launched));
+      launched += burst;
+      for (int b = 0; b < burst; ++b, ++d->steps) {
         int* cnt = d->d_counts + (d->steps % kForestHist);
         unsigned long long* cyc = d->d_cycles + (d->steps % kForestHist) * 4;
         int* cnt_next = d->d_counts + ((d->steps + 1) % kForestHist);
@@ -2170,8 +2187,8 @@ int wann_forest_run(wann_ctx* ctx, wann_forest* fo, int64_t max_simulations, int
       ++bursts;
       int r = check_device_err(ctx, ws);
       if (r != WANN_OK) return r;
-      bool done = false;
-      for (int b = 0; b < kForestBurst; ++b) {
+      bool done = launched >= max_lock_steps;
+      for (int b = 0; b < burst; ++b) {
         const int c = d->h_counts[(first + b) % kForestHist], busy = d->h_counts[kForestHist + (first + b) % kForestHist];
         if (c > 0) { ++steps; evals += c; }
         else if (busy == 0) done = true;                           // no tree asked or yielded: none will again
@@ -2298,6 +2315,11 @@ int wann_forest_play(wann_forest* fo, const int8_t* restart_squares, int restart
     int flag = 0;
     CU(cudaMemcpyAsync(d->d_restart, rs, 80, cudaMemcpyHostToDevice, d->stream));
     CU(cudaMemsetAsync(d->d_flag, 0, sizeof(int), d->stream));
+    forest_waiting_kernel<<<static_cast<unsigned>((d->n + 255) / 256), 256, 0, d->stream>>>(d->d_trees, d->n, d->d_flag);
+    CU(cudaMemcpyAsync(&flag, d->d_flag, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    if (flag != 0)
+      return fail(WANN_E_INVALID, "tree %d is waiting for an evaluation: finish wann_forest_run before wann_forest_play", flag - 1);
     forest_play_kernel<<<static_cast<unsigned>((d->n * 32 + 127) / 128), 128, 0, d->stream>>>(
         d->d_trees, d->n, d->d_restart, d->d_moves, d->d_fin, d->d_flag);
     CU(cudaGetLastError());

@@ -108,6 +108,14 @@ class SearchForest(object):
             steps += 1
             evals += len(sq)
 
+    def run_steps(self, evaluator, lock_steps, simulations=1 << 60):
+        """Exactly `lock_steps` lock steps (fewer if every tree finishes `simulations` first), trees may be
+        left mid-simulation (wann_forest_run_steps): the steady state of BASELINE config 5, every tree
+        contributing a leaf per step.  -> (steps, evaluations)."""
+        out2 = (ctypes.c_int64 * 2)()
+        L.check(self._lib.wann_forest_run_steps(evaluator._ctx, self._f, int(simulations), int(lock_steps), out2))
+        return int(out2[0]), int(out2[1])
+
     def run_for(self, evaluator, seconds):
         """Time-budgeted search, the reference's `time_to_think` (MCTS_with_expansions,
         expansion_MCTS_functions.pyx:113-119): lock steps until `seconds` have passed, then the
@@ -116,6 +124,14 @@ class SearchForest(object):
         import time
         t_end = time.perf_counter() + float(seconds)
         steps = evals = 0
+        if self.device_resident or (hasattr(evaluator, "_ctx") and getattr(self, "native_run", True)):
+            while time.perf_counter() < t_end:
+                s, e = self.run_steps(evaluator, 32)
+                steps, evals = steps + s, evals + e
+                if s == 0:
+                    break
+            s, e = self.run(evaluator, 0)                        # drain: finish what is in flight, start nothing new
+            return steps + s, evals + e
         budget = 1 << 60
         while True:
             if budget and time.perf_counter() >= t_end:
