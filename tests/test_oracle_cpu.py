@@ -270,7 +270,7 @@ def test_cython_binding_compiles_against_the_header(lib_built, tmp_path):
     without a GPU the class fails loudly (no CPU fallback)."""
     pytest.importorskip("Cython")
     mod = _build_cython_binding(tmp_path)
-    assert mod.abi_version() == 100
+    assert mod.abi_version() == 200
     import re
     hdr = open(os.path.join(ROOT, "include", "wann_b200.h")).read()
     pxd = open(os.path.join(ROOT, "include", "wann_b200.pxd")).read()
@@ -492,7 +492,7 @@ def test_library_loads_and_exports_every_declared_symbol(lib_built):
         assert hasattr(lib, name), "library does not export %s" % name
     from wann_b200 import _lib
     assert set(_lib.EXPORTS) == declared
-    assert _lib.load().wann_version() >= 100
+    assert _lib.load().wann_version() >= 200
 
 
 def test_product_never_imports_the_oracle():

@@ -645,7 +645,20 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
           cen.pos_of[l][c] = static_cast<uint8_t>(q);
           cen.tf_of[l][q] = static_cast<uint8_t>(c);
         }
-        cen.c[l][j] = f16_value(static_cast<float>(m / 24));
+        float cj = f16_value(static_cast<float>(m / 24));
+        // development knob: keep only the top WANN_B200_OFFSET_BITS mantissa bits of the offset (0 = a power of
+        // two): about half of all stored activations are the clamped zeros, i.e. exactly -offset, and an operand
+        // with few mantissa bits toggles less of the tensor core's multiplier array
+        if (const char* ob = getenv("WANN_B200_OFFSET_BITS")) {
+          const int bits = atoi(ob);
+          if (bits >= 0 && bits < 10 && cj > 0.f) {
+            int e;
+            const float fr = frexpf(cj, &e);                       // cj = fr * 2^e, fr in [0.5, 1)
+            const float q = static_cast<float>(1 << (bits + 1));
+            cj = f16_value(ldexpf(roundf(fr * q) / q, e));
+          }
+        }
+        cen.c[l][j] = cj;
       }
     }
     *out = cen;
@@ -1294,7 +1307,7 @@ int run_eval(wann_ctx* ctx, const EvalArgs& a, long long n, int mem, void* strea
 // =============================================================================================
 extern "C" {
 
-int wann_version(void) { return 100; }
+int wann_version(void) { return 200; }
 
 const char* wann_last_error(void) { return g_err.c_str(); }
 
@@ -1812,6 +1825,7 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
 // stream, the number of requested rows staying on the device.  One warp per tree, lane 0 walks it.
 struct DeviceForest {
   wann_ctx* ctx = nullptr;
+  int device = 0;                               // (kept here: the forest may be destroyed after its context)
   int64_t n = 0;
   int32_t cap_nodes = 0, cap_boards = 0;
   wann_tree::Tree* d_trees = nullptr;
@@ -1988,7 +2002,7 @@ int wann_forest_create(int64_t n, const int8_t* squares, const uint8_t* black, c
 
 int wann_forest_destroy(wann_forest* fo) {
   if (fo != nullptr && fo->dev != nullptr) {
-    DeviceGuard dev_guard(fo->dev->ctx->device);
+    DeviceGuard dev_guard(fo->dev->device);
     free_device_forest(fo->dev);
   }
   delete fo;
@@ -2007,6 +2021,7 @@ int wann_forest_create_device(wann_ctx* ctx, int64_t n, const int8_t* squares, c
   DeviceForest* d = new DeviceForest();
   fo->dev = d;
   d->ctx = ctx;
+  d->device = ctx->device;
   d->n = n;
   d->cap_nodes = node_capacity;
   d->cap_boards = std::max(64, node_capacity / 8);      // a node gets a board when it is evaluated: 1 in ~23
@@ -2273,7 +2288,7 @@ int wann_forest_info(wann_forest* fo, int64_t tree, int64_t out[8]) {
     return fail(WANN_E_INVALID, "bad argument");
   wann_tree::Tree copy;
   if (fo->dev != nullptr) {                      // a host copy of the device tree answers the query
-    DeviceGuard dev_guard(fo->dev->ctx->device);
+    DeviceGuard dev_guard(fo->dev->device);
     int rc = download_tree(fo->dev, tree, &copy);
     if (rc != WANN_OK) return rc;
   }
@@ -2307,7 +2322,7 @@ int wann_forest_play(wann_forest* fo, const int8_t* restart_squares, int restart
   if (!fo->waiting.empty()) return fail(WANN_E_INVALID, "wann_forest_apply must follow wann_forest_next");
   if (fo->dev != nullptr) {
     DeviceForest* d = fo->dev;
-    DeviceGuard dev_guard(d->ctx->device);
+    DeviceGuard dev_guard(d->device);
     CU(dev_guard.status);
     int8_t rs[80] = {0};
     memcpy(rs, restart_squares, 64);
@@ -2348,7 +2363,7 @@ int wann_forest_play(wann_forest* fo, const int8_t* restart_squares, int restart
 
 int wann_forest_debug_cycles(wann_forest* fo, int64_t* out) {
   if (fo == nullptr || fo->dev == nullptr || out == nullptr) return fail(WANN_E_INVALID, "needs a device-resident forest");
-  DeviceGuard dev_guard(fo->dev->ctx->device);
+  DeviceGuard dev_guard(fo->dev->device);
   CU(cudaStreamSynchronize(fo->dev->stream));
   // rows: the last kForestHist lock steps, oldest first: rows requested, next sum, next max, apply sum, apply max
   DeviceForest* d = fo->dev;
@@ -2367,7 +2382,7 @@ int wann_forest_debug_cycles(wann_forest* fo, int64_t* out) {
 int64_t wann_forest_dump(wann_forest* fo, int64_t tree, int64_t* rows, int64_t capacity) {
   if (fo == nullptr || tree < 0 || tree >= (fo->dev ? fo->dev->n : static_cast<int64_t>(fo->f.trees.size()))) return -1;
   if (fo->dev != nullptr) {
-    DeviceGuard dev_guard(fo->dev->ctx->device);
+    DeviceGuard dev_guard(fo->dev->device);
     wann_tree::Tree copy;
     if (download_tree(fo->dev, tree, &copy) != WANN_OK) return -1;
     const int64_t r = copy.dump(rows, rows ? capacity : 0);
