@@ -1175,3 +1175,23 @@ def test_forest_step_budget_and_drain(weights, suite):
         dev.play()
         host.close()
         dev.close()
+
+
+def test_expand_ranked_equals_the_fused_call(ev_bf16, suite):
+    """wann_expand_ranked: child construction and seeding on their own, from ranked children that are already
+    on the device, give what wann_eval_expand_seeded gives in one call (and hence the oracle's, bit for bit)."""
+    import torch
+    sq, bl = suite
+    n = 500
+    dev = torch.device("cuda", ev_bf16.device)
+    dsq, dbl = torch.from_numpy(sq[:n]).to(dev), torch.from_numpy(bl[:n]).to(dev)
+    idx, pri, cnt, kids, flg, st, ps = ev_bf16.eval_expand_seeded(dsq, dbl)
+    k2, f2, s2, p2 = ev_bf16.expand_ranked(dsq, dbl, idx, pri, cnt)
+    torch.cuda.synchronize()
+    for a, b in ((kids, k2), (flg, f2), (st, s2), (ps, p2)):
+        assert torch.equal(a, b)
+    k3, f3, _, _ = ev_bf16.expand_ranked(dsq, dbl, idx, pri, cnt, with_seeds=False)      # children only: 2 flag bits
+    torch.cuda.synchronize()
+    assert torch.equal(k3, kids) and torch.equal(f3 & 3, flg & 3)
+    wk, wf = O.expand_children(sq[:n], bl[:n], idx.cpu().numpy(), cnt.cpu().numpy())
+    assert np.array_equal(k3.cpu().numpy(), wk) and np.array_equal(f3.cpu().numpy(), wf)

@@ -248,6 +248,22 @@ class PolicyEvaluator(object):
             L.MEM_HOST, None))
         return idx, pri, cnt, kids, flg, st, ps
 
+    def expand_ranked(self, squares, black, idx, prior, n_legal, with_children=True, with_seeds=True):
+        """Child boards / child seeds for positions whose ranked children are already known (the outputs of
+        eval_topk): wann_expand_ranked, torch CUDA tensors only.  -> child_squares (or None), child_flags,
+        child_stats (or None), parent_summary (or None)."""
+        import torch
+        n, dev = squares.shape[0], squares.device
+        kids = torch.empty((n, L.MAX_LEGAL, 64), dtype=torch.int8, device=dev) if with_children else None
+        flg = torch.empty((n, L.MAX_LEGAL), dtype=torch.uint8, device=dev)
+        st = torch.empty((n, L.MAX_LEGAL, 4), dtype=torch.int32, device=dev) if with_seeds else None
+        ps = torch.empty((n, 8), dtype=torch.int32, device=dev) if with_seeds else None
+        L.check(self._lib.wann_expand_ranked(
+            self._ctx, squares.data_ptr(), black.data_ptr(), n, idx.data_ptr(), prior.data_ptr(), n_legal.data_ptr(),
+            kids.data_ptr() if with_children else None, flg.data_ptr(), st.data_ptr() if with_seeds else None,
+            ps.data_ptr() if with_seeds else None, self._torch_stream(squares)))
+        return kids, flg, st, ps
+
     def pinned_rows(self, n, with_children=False):
         """Pinned host arrays for eval_expand_seeded(out=...) over up to n positions (wann_host_alloc):
         the copies of a large host call then run at PCIe speed and nothing is allocated per call.

@@ -129,13 +129,13 @@ class MultiGpuEvaluator(object):
         self._run(n, work)
         return idx, pri, cnt
 
-    def eval_expand_seeded(self, squares, black, with_children=True):
+    def eval_expand_seeded(self, squares, black, with_children=True, k=0):
         sq, bl = PolicyEvaluator._np_in(squares, black)
         n = sq.shape[0]
         parts, lock = {}, threading.Lock()
 
         def work(ev, lo, hi):
-            res = ev.eval_expand_seeded(sq[lo:hi], bl[lo:hi], with_children=with_children)
+            res = ev.eval_expand_seeded(sq[lo:hi], bl[lo:hi], with_children=with_children, k=k)
             with lock:
                 parts[lo] = res
         self._run(n, work)
