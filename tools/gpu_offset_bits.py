@@ -16,11 +16,8 @@ with wann_b200.PolicyEvaluator(w, mode="fp32") as ev:
 dev = torch.device("cuda", 0)
 B = 65536
 bsq = torch.from_numpy(np.tile(sq, (4, 1))[:B]).to(dev); bbl = torch.from_numpy(np.tile(bl, 4)[:B]).to(dev)
-for bits in (None, 3, 2, 1, 0):
-    if bits is None:
-        os.environ.pop("WANN_B200_OFFSET_BITS", None)
-    else:
-        os.environ["WANN_B200_OFFSET_BITS"] = str(bits)
+for bits in [int(x) for x in os.environ.get("ZERO_BUCKETS", "0,2,3,4,5,6").split(",")]:
+    os.environ["WANN_B200_ZERO_BUCKETS"] = str(bits)
     with wann_b200.PolicyEvaluator(w, mode="fp16c") as ev:
         ev.set_option("split_layers", int(os.environ.get("SPLIT", "8")))
         p, l = ev.eval_probs(sq, bl, return_logits=True)
@@ -41,6 +38,6 @@ for bits in (None, 3, 2, 1, 0):
         rows = [r.split(",") for r in smi.stdout.read().strip().splitlines()]
         clk = np.median([float(r[0]) for r in rows[3:]]) if len(rows) > 4 else -1
         pw = np.median([float(r[1]) for r in rows[3:]]) if len(rows) > 4 else -1
-        print("offset bits %s: logits maxnorm %.2e relrms %.2e pmed %.2e | sustained %.2f M pos/s over %.1f s, %.0f MHz, %.0f W | offsets %s" % (
+        print("zero buckets %s: logits maxnorm %.2e relrms %.2e pmed %.2e | sustained %.2f M pos/s over %.1f s, %.0f MHz, %.0f W | offsets %s" % (
             bits, acc[0], acc[1], acc[2], B * steps / (a.elapsed_time(b) * 1e-3) / 1e6, a.elapsed_time(b) * 1e-3, clk, pw,
             np.round(ev.centering()[0][1], 4).tolist()), flush=True)

@@ -658,6 +658,14 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
             cj = f16_value(ldexpf(roundf(fr * q) / q, e));
           }
         }
+        // The two lowest-mean buckets keep offset 0: their clamped activations stay exact zeros (an operand of 0
+        // toggles nothing in the tensor core's multiplier array -- measured +2 % sustained throughput under the
+        // power cap) and, being small, they contribute next to nothing to the rounding error (probability
+        // median 9.39e-4 -> 9.41e-4).  WANN_B200_ZERO_BUCKETS overrides the count for experiments
+        // (3: +2.6 % / 9.5e-4, 4: +3.4 % / 1.0e-3; tools/gpu_offset_bits.py).
+        int zero_buckets = 2;
+        if (const char* zb = getenv("WANN_B200_ZERO_BUCKETS")) zero_buckets = atoi(zb);
+        if (j < zero_buckets) cj = 0.f;
         cen.c[l][j] = cj;
       }
     }
