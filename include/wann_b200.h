@@ -62,8 +62,9 @@ enum wann_mode {
                          roughly halved -- activations are stored as a - c (c = calibrated per-bucket mean,
                          the sign bit of fp16 is no longer wasted on non-negative ReLU outputs; the halo
                          holds -c and the next bias absorbs sum(w*c)), conv1 and conv5 see their weights
-                         as fp16 hi + lo pairs in spare K / N slots.  Option "split_layers" adds lo weight
-                         stages to chosen 192->192 layers (2 MMAs per K-step there). */
+                         as fp16 hi + lo pairs in spare K / N slots.  Options "split_layers", "lo_n" and
+                         "lo_kgroups" add lo weight stages for the block of chosen 192->192 layers whose
+                         rounding error matters most (wann_set_option). */
 };
 
 enum wann_mem { WANN_MEM_HOST = 0, WANN_MEM_DEVICE = 1 };
@@ -305,11 +306,11 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
                        int64_t n, int64_t* stamps);
 
 /* Test/inspection hook (WANN_MODE_FP16C): the calibrated centring of the context's weights --
- * offsets[l*8 + j] = offset of the stored output of hidden layer l+1 for channel positions q with
- * q % 8 == j (exact fp16 values), position_of[l*192 + c] = position of TF channel c in the kernel's
+ * offsets[l*24 + (q/64)*8 + q%8] = offset of the stored output of hidden layer l+1 at channel position q
+ * (exact fp16 values), position_of[l*192 + c] = position of TF channel c in the kernel's
  * layout, kappa[9] (optional) = what the centring of layer 4 took out of each tap product of
  * hidden_layer/5.  The emulation in tests/ uses it to reproduce the kernel's roundings. */
-int wann_debug_centering(wann_ctx* ctx, float offsets[32], uint8_t position_of[768], float kappa[9]);
+int wann_debug_centering(wann_ctx* ctx, float offsets[96], uint8_t position_of[768], float kappa[9]);
 
 /* Measurement hook: with option "time_kernels" = 1 every conv-stack kernel launch is bracketed
  * by CUDA events on its own stream; this call synchronises the device and returns
@@ -346,7 +347,15 @@ int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]);
  * positions where 16-bit operand rounding can flip the policy move of get_best_move
  * (board_utils.pyx:262-277) -- are evaluated a second time in the same call by the fp32-class
  * split kernel (WANN_MODE_FP32_TC arithmetic) and every output row of theirs is overwritten.
- * Needs board inputs (squares); plane inputs are not refined. */
+ * Needs board inputs (squares); plane inputs are not refined.
+ * "split_layers" / "lo_n" / "lo_kgroups" (WANN_MODE_FP16C; defaults 0 / 64 / 1): partial hi/lo weight split.
+ * The calibration orders the channels of every hidden layer by activation variance, so the weight
+ * rounding error of a 192->192 layer is concentrated in its leading input positions (the first of the three
+ * 64-channel K-groups carries ~70 % of the input variance) and leading output positions.  In the layers of
+ * the mask split_layers (bit l = hidden_layer/(l+1), l = 1..3) every K-block of the first lo_kgroups groups
+ * streams a second stage w - fp16(w) for the output positions [0, lo_n) and a second MMA with N = lo_n runs
+ * against it: split_layers = 14, lo_n = 64, lo_kgroups = 1 costs +11 % MMAs and meets the 1e-3 gates;
+ * lo_n = 192, lo_kgroups = 3 removes a layer's weight error completely (+33 % MMAs per layer). */
 int wann_set_option(wann_ctx* ctx, const char* key, int64_t value);
 
 /* Library/ABI version (major*100+minor). */

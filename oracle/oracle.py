@@ -453,16 +453,18 @@ def forward_16bit_emulated(planes, weights, fmt="bf16", return_all=False):
     return logits, probs
 
 
-def forward_fp16c_emulated(planes, weights, offsets, position_of, split_mask=0, return_all=False):
+def forward_fp16c_emulated(planes, weights, offsets, position_of, split_mask=0, lo_n=192, lo_kgroups=3,
+                           return_all=False):
     """Emulation of the roundings of the CENTRED fp16 tensor-core mode (WANN_MODE_FP16C,
     wann_b200/csrc/conv_stack_tc.cuh) for the same graph as forward_fp32
-    (policy_net_utils.pyx:106-124,149-178,215-239).  offsets [4,8] / position_of [4,192] are the
+    (policy_net_utils.pyx:106-124,149-178,215-239).  offsets [4,24] / position_of [4,192] are the
     calibrated centring of the context (wann_debug_centering): channel c of hidden layer l sits at
-    position q = position_of[l-1][c] and is stored as a' = fp16(relu(z) - offsets[l-1][q % 8]); the
-    zero padding of the next conv therefore reads -offset, and that layer's bias absorbs
+    position q = position_of[l-1][c] and is stored as a' = fp16(relu(z) - offsets[l-1][(q // 64) * 8 + q % 8]);
+    the zero padding of the next conv therefore reads -offset, and that layer's bias absorbs
     sum(w * offset) with the TRUE fp32 weights.  hidden_layer/1 and /5 see their weights as fp16
-    hi + lo pairs (22 bits), layers in split_mask (bits 1..3 = hidden_layer/2..4) too; the other
-    layers round their weights to fp16.  Accumulation, bias and ReLU in fp32; FC/softmax in fp32."""
+    hi + lo pairs (22 bits); in the layers of split_mask (bits 1..3 = hidden_layer/2..4) the block
+    [input positions < 64 * lo_kgroups] x [output positions < lo_n] too; all other weights are rounded
+    to fp16.  Accumulation, bias and ReLU in fp32; FC/softmax in fp32."""
     def two16(w):                     # hi + lo/4096 pair, as the kernel's conv1 / conv5 operands
         hi = f16_round(w)
         return hi + f16_round((w - hi) * 4096.0) / np.float32(4096.0)
@@ -477,10 +479,15 @@ def forward_fp16c_emulated(planes, weights, offsets, position_of, split_mask=0, 
     for i in range(1, 6):
         w = weights["hidden_layer/%d/weights" % i].astype(np.float32)
         b = weights["hidden_layer/%d/bias" % i].astype(np.float64)
-        if i == 1 or i == 5 or (split_mask >> (i - 1)) & 1:
-            w16 = two16(w) if i in (1, 5) else hilo(w)
+        if i == 1 or i == 5:
+            w16 = two16(w)
         else:
             w16 = f16_round(w)
+            if (split_mask >> (i - 1)) & 1:
+                k_in = position_of[i - 2] < 64 * lo_kgroups          # inputs of layer i = outputs of layer i-1
+                k_out = position_of[i - 1] < lo_n
+                blk = np.ix_(range(w.shape[0]), range(w.shape[1]), np.nonzero(k_in)[0], np.nonzero(k_out)[0])
+                w16[blk] = hilo(w)[blk]
         if c_prev is None:
             z = conv2d_same_nhwc(x, w16, np.float32)
         else:
@@ -498,7 +505,8 @@ def forward_fp16c_emulated(planes, weights, offsets, position_of, split_mask=0, 
                 z = (cols.reshape(-1, 9 * cin) @ w16.reshape(9 * cin, -1)).reshape(n, hh, ww, -1)
                 b = b + (w.astype(np.float64) * c_prev[None, None, :, None].astype(np.float64)).sum(axis=(0, 1, 2))
         if i < 5:
-            c = offsets[i - 1][position_of[i - 1] % 8].astype(np.float32)      # per TF channel
+            q = position_of[i - 1].astype(np.int64)
+            c = offsets[i - 1][(q // 64) * 8 + q % 8].astype(np.float32)       # per TF channel
             t = z + (b - c.astype(np.float64)).astype(np.float32)
             x = f16_round(np.maximum(t, -c))                                   # a' = relu(z + b') - c
             acts.append(x + c)

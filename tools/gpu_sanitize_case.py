@@ -14,7 +14,7 @@ w = W.synthetic("trained_like", 1)
 for mode, margin in (("bf16", 0.0), ("fp32", 0.0), ("fp16c", 0.05), ("fp32_tc", 0.0)):
     with wann_b200.PolicyEvaluator(w, mode=mode, chunk=32, refine_margin=margin) as ev:
         if mode == "fp16c":
-            ev.set_option("split_layers", 8)
+            ev.set_option("split_layers", 14)
         p, l = ev.eval_probs(sq, bl, return_logits=True)
         out = ev.eval_expand(sq, bl)
         ev.eval_expand_seeded(sq[:33], bl[:33], k=5)

@@ -57,14 +57,26 @@ constexpr int kCell = 16;                     // bytes per (pixel, channel-chunk
 constexpr int kRowStride = 9 * kCell;         // 144 B: x = -1..7 (x = 8 halo is next row's x = -1)
 constexpr int kYStride = 2 * kRowStride;      // 288 B: two boards interleaved per y
 constexpr int kChunkStride = 9 * kYStride;    // 2592 B: y = -1..7 (y = 8 halo is next chunk's y = -1)
-constexpr int kATileBytes = kKChunks * kChunkStride;  // 62208 B per 128-row tile
 constexpr int kTilesPerCta = 2;
-// each tile carries its OWN trailing halo row (the y = 8 row of its last chunk + the x = 8 cell of that
-// row): in the centred mode the halo of a tile is rewritten per layer, and the two tiles of a CTA are
-// in different layers at the same time
-constexpr int kATileStride = kATileBytes + kYStride + kCell;             // 62512 B
+// The 24 chunks of a tile form 3 GROUPS of 8 (= the 64-channel K-blocks of the weight stream).  Every group
+// carries its OWN trailing halo row (the y = 8 row of its last chunk + the x = 8 cell of that row), so that
+// no halo cell is shared between groups (centred mode: a halo cell holds -offset, and offsets differ per
+// group) or between the two tiles of a CTA (which are in different layers at the same time).
+constexpr int kGroupChunks = 8;
+constexpr int kGroups = kKChunks / kGroupChunks;                         // 3
+constexpr int kGroupGap = kYStride + kCell;                              // 304 B
+constexpr int kGroupStride = kGroupChunks * kChunkStride + kGroupGap;    // 21040 B
+constexpr int kATileStride = kGroups * kGroupStride;                     // 63120 B per 128-row tile
 constexpr int kABytes = kTilesPerCta * kATileStride;
-constexpr int kHaloCells = kKChunks * 34 + 19;    // per tile: 18 (y = -1 row) + 16 (x = -1 cells) per chunk, + trailing row
+constexpr int kHaloCells = kKChunks * 34 + kGroups * 19;   // per tile: 18 (y = -1 row) + 16 (x = -1 cells) per chunk, + a trailing row per group
+constexpr int kCenBuckets = kGroups * 8;      // centred mode: one offset per (group, channel position % 8)
+// lo weight stages (partial hi/lo split): a (tap, j) block is [lo_n / 2 rows x 64 k] = 64 * lo_n bytes per CTA;
+// a stage carries as many consecutive blocks as fit a ring slot
+__host__ __device__ constexpr uint32_t lo_blocks_per_stage(int lo_n) {
+  return (12288 / (64 * lo_n)) > 0 ? static_cast<uint32_t>(12288 / (64 * lo_n)) : 1u;
+}
+// byte offset of channel chunk q inside a tile
+__host__ __device__ constexpr int chunk_off(int q) { return q * kChunkStride + (q / kGroupChunks) * kGroupGap; }
 constexpr int kBoardsPerCta = 4;
 constexpr int kBoardsPerPair = 8;
 
@@ -88,7 +100,7 @@ constexpr int kBiasFloats = 4 * kC + 4;
 
 // shared memory carve-up (bytes from the 128-aligned base)
 constexpr int kOffA = 0;
-constexpr int kOffB = (kOffA + kABytes + 127) / 128 * 128;
+constexpr int kOffB = (kOffA + kABytes + 15) / 16 * 16;    // SWIZZLE_NONE operands and bulk copies need 16-byte alignment only
 constexpr int kOffBias = kOffB + kStages * kStageBytes;
 constexpr int kOffBar = kOffBias + kBiasFloats * 4;
 constexpr int kNumBars = 3 * kStages + 8;
@@ -145,11 +157,18 @@ struct TcParams {
   // byte distance between the stage images of CTA rank 0 and 1
   int stages_per_st = kKbPerSupertile;
   long long img_stride = kImgBytesPerRank;
-  int split_mask = 0;          // bit l (1..3): conv(l+1)'s weights stream as hi stage + lo stage per K-block
+  // hi/lo weight split: in conv(l+1), bit l (1..3) of split_mask, every K-block (tap, j) with j < lo_kgroups
+  // streams a second stage -- the lo parts w - fp16(w) of output positions [0, lo_n) x its 64 input
+  // positions -- and the issuer runs the same A descriptors against it with N = lo_n: the weight rounding
+  // error of that block of the layer disappears.  (Channel positions are sorted by activation variance,
+  // so the leading positions are the ones whose weight error matters.)
+  int split_mask = 0;
+  int lo_n = 192;              // multiple of 16, 16..192
+  int lo_kgroups = 3;          // 1..3
   // centred mode (kCen kernels): the stored activation of channel position q of conv l+1 is
-  // a' = a - cen[l][q % 8]; the halo holds -cen (so that a' + cen == 0 there) and the next layer's bias
-  // absorbs sum(w * cen).  kappa[t] = sum_k w5[t][k] * cen[3][..] corrects conv5's tap products.
-  float cen[4][8] = {};
+  // a' = a - cen[l][(q / 64) * 8 + q % 8]; the halo holds -cen (so that a' + cen == 0 there) and the next
+  // layer's bias absorbs sum(w * cen).  kappa[t] = sum_k w5[t][k] * cen[3][..] corrects conv5's tap products.
+  float cen[4][kCenBuckets] = {};
   float kappa[9] = {};
   const uint8_t* dbg_unperm = nullptr;   // [4][192] channel position -> TF channel (debug dump of a permuted net)
 };
@@ -232,11 +251,14 @@ __device__ __forceinline__ void store_input_cell(uint32_t cell0, uint2 v) {
     ptx::st_shared_v4(cell0, make_uint4(v.x, v.y, 0u, 0u));
   }
 }
-// byte offset (inside a tile) of halo cell i in [0, kHaloCells)
+// byte offset (inside a tile) of halo cell i in [0, kHaloCells), with the cell's group in bits 0..1
 __device__ __forceinline__ uint32_t halo_cell_offset(int i) {
-  if (i >= kKChunks * 34) return kKChunks * kChunkStride + (i - kKChunks * 34) * kCell;   // trailing row
+  if (i >= kKChunks * 34) {                                   // the trailing rows of the groups
+    const int t = i - kKChunks * 34, g = t / 19, r = t - 19 * g;
+    return static_cast<uint32_t>(g * kGroupStride + kGroupChunks * kChunkStride + r * kCell) | g;
+  }
   const int q = i / 34, r = i - 34 * q;
-  return q * kChunkStride + (r < 18 ? r * kCell : kYStride + (r - 18) * kRowStride);
+  return static_cast<uint32_t>(chunk_off(q) + (r < 18 ? r * kCell : kYStride + (r - 18) * kRowStride)) | (q / kGroupChunks);
 }
 
 template <bool kF16, bool kCen>
@@ -319,19 +341,35 @@ conv_stack_tc_kernel(const TcParams p) {
     if (lane == 0) {
       const uint32_t img_rank = (p.variant & 4) ? (rank ^ 1u) : rank;
       const uint8_t* img = p.wimg + static_cast<size_t>(img_rank) * p.img_stride;
-      const int nstages = p.stages_per_st;
       uint32_t s = 0, ph = 0;
       bool ok = true;
+      size_t off = 0;
+      auto stage = [&](uint32_t bytes) {
+        if (!ok) return;
+        if (!wait_bar(bar_empty(s), ph ^ 1u, false, p.err, 100 + s)) { ok = false; return; }
+        ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
+        ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes, bar_full(s));
+        off += bytes;
+        if (++s == nst) { s = 0; ph ^= 1u; }
+      };
+      const uint32_t lo_block = 64u * static_cast<uint32_t>(p.lo_n);      // [lo_n / 2 rows x 64 k] 16-bit
+      const uint32_t bps = lo_blocks_per_stage(p.lo_n);
       for (long long st = pair; st < total_st && ok; st += npairs) {
-        size_t off = 0;
-        for (int kb = 0; kb < nstages; ++kb) {
-          const uint32_t bytes = (kb >= nstages - kKbL5) ? kStageBytesL5 : kStageBytes;
-          if (!wait_bar(bar_empty(s), ph ^ 1u, false, p.err, 100 + s)) { ok = false; break; }
-          ptx::mbar_arrive_expect_tx(bar_full(s), bytes);
-          ptx::bulk_g2s(b_base + s * kStageBytes, img + off, bytes, bar_full(s));
-          off += bytes;
-          if (++s == nst) { s = 0; ph ^= 1u; }
+        off = 0;
+        for (int kb = 0; kb < kKbL1; ++kb) stage(kStageBytes);
+        for (int layer = 1; layer <= 3; ++layer) {
+          const int lo_j = ((p.split_mask >> layer) & 1) ? p.lo_kgroups : 0;
+          uint32_t pend = 0;
+          for (int tap = 0; tap < 9; ++tap)
+            for (int j = 0; j < 3; ++j) {
+              stage(kStageBytes);
+              if (j < lo_j && (++pend == bps || (tap == 8 && j == lo_j - 1))) {
+                stage(pend * lo_block);
+                pend = 0;
+              }
+            }
         }
+        for (int kb = 0; kb < kKbL5; ++kb) stage(kStageBytesL5);
       }
     }
   } else if (warp == 1 && rank != 0) {
@@ -362,9 +400,15 @@ conv_stack_tc_kernel(const TcParams p) {
       const uint32_t a_lo = ((a_base + h * kATileStride) >> 4) | ((kChunkStride >> 4) << 16);
       const uint32_t b_lo_mid = (b_base >> 4) | ((kLboB >> 4) << 16);
       const uint32_t b_lo_l5 = (b_base >> 4) | ((kLboB5 >> 4) << 16);
+      // lo stages: [lo_n / 2 rows x 64 k] per CTA, LBO = 8 * lo_n bytes, K-step = 2 LBO = lo_n sixteen-byte units
+      const uint32_t lo_n = static_cast<uint32_t>(p.lo_n);
+      const uint32_t b_lo_lo = (b_base >> 4) | (((8u * lo_n) >> 4) << 16);
+      const uint32_t idesc_lo = ptx::make_idesc_16bit(256, p.lo_n, kF16);
+      const uint32_t lo_bps = lo_blocks_per_stage(p.lo_n);
       const uint32_t tmem_d = tmem_base + h * kC;
       const uint32_t acc_bar = bar_acc_full(h), ready_bar = bar_a_ready(h);
       constexpr uint32_t kChunk16 = kChunkStride >> 4;          // 162
+      constexpr uint32_t kGroup16 = kGroupStride >> 4;          // 1315
       constexpr uint32_t kStage16 = kStageBytes >> 4;           // 768
       uint32_t s = 0, ph = 0, lstep = 0;
       bool ok = true;
@@ -375,7 +419,8 @@ conv_stack_tc_kernel(const TcParams p) {
       for (long long st = pair; st < total_st; st += npairs) kb_left += p.stages_per_st;
       long long* prof = (p.prof != nullptr && pair == 0) ? p.prof + 4 * h * kProfSteps : nullptr;
       // one K-block: wait for the stage, 4 (or fewer) K=16 steps, release my claim on the stage
-#define WANN_KBLOCK(NKS, A_OFF16_OF_KS, B_LO, B_KS16, IDESC, ACC_FIRST)                          \
+      // one weight stage: wait for it (WANN_STAGE_BEGIN), issue the MMAs, release my claim on it (WANN_STAGE_END)
+#define WANN_STAGE_BEGIN                                                                          \
       {                                                                                           \
         if (lookahead != 0 && kb_left > lookahead) {   /* half 1 trails the stream by d stages */ \
           const uint32_t s2 = (s + lookahead >= nst) ? s + lookahead - nst : s + lookahead;       \
@@ -385,7 +430,13 @@ conv_stack_tc_kernel(const TcParams p) {
         --kb_left;                                                                                \
         if (!wait_bar(bar_full(s), ph, false, p.err, 300 + s) ||                                 \
             !wait_bar(bar_peer_full(s), ph, true, p.err, 400 + s)) { ok = false; break; }       \
-        ptx::tc_fence_after();                                                                    \
+        ptx::tc_fence_after();
+#define WANN_STAGE_END                                                                            \
+        if (issuer) ptx::umma_commit<2>(bar_empty(s), 3);   /* my claim, in BOTH CTAs */          \
+        if (++s == nst) { s = 0; ph ^= 1u; }                                                  \
+      }
+#define WANN_KBLOCK(NKS, A_OFF16_OF_KS, B_LO, B_KS16, IDESC, ACC_FIRST)                          \
+      WANN_STAGE_BEGIN                                                                            \
         const uint32_t blo = (B_LO) + s * kStage16;                                               \
         _Pragma("unroll") for (int ks = 0; ks < (NKS); ++ks) {                                   \
           const uint32_t ao = (A_OFF16_OF_KS);                                                    \
@@ -393,9 +444,7 @@ conv_stack_tc_kernel(const TcParams p) {
           if (issuer && !skip_mma)                                                                \
             ptx::umma_bf16_2cta(tmem_d, a_lo + ao, a_hi, blo + ks * (B_KS16), b_hi, (IDESC), acc); \
         }                                                                                         \
-        if (issuer) ptx::umma_commit<2>(bar_empty(s), 3);   /* my claim, in BOTH CTAs */          \
-        if (++s == nst) { s = 0; ph ^= 1u; }                                                  \
-      }
+      WANN_STAGE_END
       for (long long st = pair; st < total_st && ok; st += npairs) {
         // ---- conv1: 9 taps x K=16 (4 real planes); K-block kb holds taps 4kb..4kb+3
         do {
@@ -416,15 +465,33 @@ conv_stack_tc_kernel(const TcParams p) {
           ptx::tc_fence_after();
           if (prof && lstep < kProfSteps && issuer) prof[lstep] = clock64();
           uint32_t first = 1;
-          const bool split = (p.split_mask >> layer) & 1;   // weights as hi stage + lo stage: 2 MMAs per K-step
+          // hi/lo split: the blocks (tap, j < lo_j) also have lo weights; they arrive lo_bps blocks per stage,
+          // right after the hi stage of the last block, and run with N = lo_n against the same A descriptors
+          const uint32_t lo_j = ((p.split_mask >> layer) & 1) ? static_cast<uint32_t>(p.lo_kgroups) : 0u;
+          uint32_t pend = 0, first_blk = 0;
           for (uint32_t ty = 0; ty < 3 && ok; ++ty)
             for (uint32_t tx = 0; tx < 3 && ok; ++tx) {
               const uint32_t tap16 = ty * (kYStride >> 4) + tx;
               for (uint32_t j = 0; j < 3; ++j) {
-                const uint32_t ao0 = j * 8 * kChunk16 + tap16;
+                const uint32_t ao0 = j * kGroup16 + tap16;
                 WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_mid, (2 * kLboB) >> 4, kIdescN192, first)
                 first = 0;
-                if (split) WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
+                if (j < lo_j && (++pend == lo_bps || (ty == 2 && tx == 2 && j == lo_j - 1))) {
+                  // one lo stage = the blocks first_blk .. first_blk + pend - 1 (block index = tap * lo_j + j)
+                  WANN_STAGE_BEGIN
+                  const uint32_t blo = b_lo_lo + s * kStage16;
+                  for (uint32_t b = 0; b < pend; ++b) {
+                    const uint32_t blk = first_blk + b, btap = blk / lo_j, bj = blk - btap * lo_j;
+                    const uint32_t bao = bj * kGroup16 + (btap / 3u) * (kYStride >> 4) + (btap % 3u);
+                    _Pragma("unroll") for (uint32_t ks = 0; ks < 4; ++ks)
+                      if (issuer && !skip_mma)
+                        ptx::umma_bf16_2cta(tmem_d, a_lo + bao + ks * 2 * kChunk16, a_hi,
+                                            blo + b * 4u * lo_n + ks * lo_n, b_hi, idesc_lo, 1u);
+                  }
+                  WANN_STAGE_END
+                  first_blk += pend;
+                  pend = 0;
+                }
               }
             }
           if (!ok) break;
@@ -440,7 +507,7 @@ conv_stack_tc_kernel(const TcParams p) {
           if (prof && lstep < kProfSteps && issuer) prof[lstep] = clock64();
           constexpr uint32_t kCentre16 = (kYStride >> 4) + 1;
           for (uint32_t j = 0; j < 3; ++j) {
-            const uint32_t ao0 = j * 8 * kChunk16 + kCentre16;
+            const uint32_t ao0 = j * kGroup16 + kCentre16;
             WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_l5, (2 * kLboB5) >> 4, kIdescN32, j == 0)
           }
           if (!ok) break;
@@ -450,6 +517,8 @@ conv_stack_tc_kernel(const TcParams p) {
         } while (false);
       }
 #undef WANN_KBLOCK
+#undef WANN_STAGE_BEGIN
+#undef WANN_STAGE_END
     }
   } else if (warp < kFirstTailWarp) {
     // ===== epilogue warps: all 8 serve half 0, then half 1, alternately =======================
@@ -508,22 +577,29 @@ conv_stack_tc_kernel(const TcParams p) {
             const float* bs = bias_s + layer * kC + chalf * 96;
             float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < n_tot)
                              ? p.dbg + (board * 64 + y * 8 + x) * kC : nullptr;
-            // centred mode: store a' = max(acc + (b' - c), -c) = relu(acc + b') - c   (c by channel % 8);
-            // bias_s already holds b' - c
-            float nc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) nc[j] = kCen ? -p.cen[layer][j] : 0.f;
+            // centred mode: store a' = max(acc + (b' - c), -c) = relu(acc + b') - c   (c by chunk group and
+            // channel % 8); bias_s already holds b' - c.
             // -c as packed 16-bit pairs: rounding is monotonic and -c is exact in the operand format, so
             // fp16(max(t, -c)) == max(fp16(t), -c): one packed max per PAIR after the conversion
-            uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-            if (kCen) {
-              hv.x = ptx::pack_sat<kF16>(nc[0], nc[1]);
-              hv.y = ptx::pack_sat<kF16>(nc[2], nc[3]);
-              hv.z = ptx::pack_sat<kF16>(nc[4], nc[5]);
-              hv.w = ptx::pack_sat<kF16>(nc[6], nc[7]);
-            }
+            auto packed_neg_offsets = [&](int g) {
+              const float* c = p.cen[layer] + 8 * g;
+              return make_uint4(ptx::pack_sat<kF16>(-c[0], -c[1]), ptx::pack_sat<kF16>(-c[2], -c[3]),
+                                ptx::pack_sat<kF16>(-c[4], -c[5]), ptx::pack_sat<kF16>(-c[6], -c[7]));
+            };
 #pragma unroll 1
             for (int ch = 0; ch < 3; ++ch) {
+              const int qc0 = chalf * 12 + ch * 4;              // this pass writes chunks qc0..qc0+3: one group
+              const int grp = qc0 / kGroupChunks;
+              const uint32_t cell_q0 = cell0 + qc0 * kChunkStride + grp * kGroupGap;
+              uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+              float nc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (kCen) {
+                hv = packed_neg_offsets(grp);
+                if (dbg != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) nc[j] = -p.cen[layer][8 * grp + j];
+                }
+              }
               uint32_t v[32];
               ptx::tmem_ld_x32(taddr + chalf * 96 + ch * 32, v);
               ptx::tmem_ld_wait();
@@ -551,7 +627,7 @@ conv_stack_tc_kernel(const TcParams p) {
                   o.w = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
                                              __uint_as_float(v[kc * 8 + 7]) + b1.w);
                 }
-                ptx::st_shared_v4(cell0 + (chalf * 12 + ch * 4 + kc) * kChunkStride, o);
+                ptx::st_shared_v4(cell_q0 + kc * kChunkStride, o);
                 if (dbg != nullptr) {
                   const uint32_t w[4] = {o.x, o.y, o.z, o.w};
                   const int q0 = chalf * 96 + ch * 32 + kc * 8;     // channel position of w[0]'s low half
@@ -568,11 +644,17 @@ conv_stack_tc_kernel(const TcParams p) {
               // the tile's halo must read as "activation 0" for the NEXT layer: -c of this layer's output
               // (conv4's output: zeros -- conv5 uses the centre tap only, its stencil scratch and the next
               // supertile's conv1 need a zero halo)
-              const uint4 hz = (layer < 3) ? hv : make_uint4(0u, 0u, 0u, 0u);
+              const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+              uint4 hz[kGroups];
+#pragma unroll
+              for (int g = 0; g < kGroups; ++g) hz[g] = (layer < 3) ? packed_neg_offsets(g) : zero4;
               const uint32_t tile0 = a_base + h * kATileStride;
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                if (i < 3 || halo_off[3] != 0xFFFFFFFFu) ptx::st_shared_v4(tile0 + halo_off[i], hz);
+                if (i < 3 || halo_off[3] != 0xFFFFFFFFu) {
+                  const uint32_t g = halo_off[i] & 3u;
+                  ptx::st_shared_v4(tile0 + (halo_off[i] & ~15u), g == 0 ? hz[0] : (g == 1 ? hz[1] : hz[2]));
+                }
             }
           } else if (chalf == 0) {
             // conv5: column t of the accumulator is P[pixel][tap t]; out = 9-point stencil sum.

@@ -168,18 +168,22 @@ struct CombineReq {
   int rc = 0; std::string err; bool done = false;
 };
 
-// Centred fp16 mode (WANN_MODE_FP16C): per conv layer 1..4 a permutation of the output channels into
-// 8 buckets of 24 by mean activation (bucket = channel position % 8 -- the halo cells of the shared
-// memory layout are shared by all 24 channel chunks, so an offset can only depend on position % 8) and
-// one offset per bucket.  Identity / zero = the plain layout.
+// Centred fp16 mode (WANN_MODE_FP16C): per conv layer 1..4 a permutation of the output channels and one offset
+// per BUCKET of 8 channels.  Positions are sorted by activation variance (descending) into the 3 groups of 64
+// that are the K-blocks of the next layer's weight stream -- the group whose weight rounding error matters
+// most comes first, which is what the partial hi/lo split (options "split_layers", "lo_n", "lo_kgroups")
+// relies on; inside a group, bucket = channel position % 8 (the halo cells of the shared-memory layout are
+// shared by the 8 channel chunks of a group, so an offset can only depend on the group and position % 8),
+// filled by ascending mean activation.  Identity / zero = the plain layout.
+inline int cen_bucket(int q) { return (q / 64) * 8 + (q % 8); }
 struct Centering {
   uint8_t pos_of[4][192];   // TF channel -> position in the kernel's layout
   uint8_t tf_of[4][192];    // position -> TF channel
-  float c[4][8];            // offsets (exact fp16 values) of the stored output of conv l+1
+  float c[4][wann::kCenBuckets];   // offsets (exact fp16 values) of the stored output of conv l+1, by cen_bucket(position)
   Centering() {
     for (int l = 0; l < 4; ++l) {
       for (int i = 0; i < 192; ++i) pos_of[l][i] = tf_of[l][i] = static_cast<uint8_t>(i);
-      for (int j = 0; j < 8; ++j) c[l][j] = 0.f;
+      for (int j = 0; j < wann::kCenBuckets; ++j) c[l][j] = 0.f;
     }
   }
 };
@@ -218,6 +222,9 @@ struct wann_ctx {
   float kappa[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint8_t* d_unperm = nullptr;     // [4][192] channel position -> TF channel
   std::atomic<int> split_mask{0};  // option "split_layers": conv layers (bits 1..3) whose weights stream as hi + lo
+  std::atomic<int> lo_n{64};       // option "lo_n": the lo stages cover output positions [0, lo_n) ...
+  std::atomic<int> lo_kgroups{1};  // option "lo_kgroups": ... and the first lo_kgroups 64-channel input groups of every tap
+  int img_lo_n = 192, img_lo_kgroups = 3;   // what the uploaded stage image was built with
   int stages_per_st = wann::kKbPerSupertile;
   long long img_stride = wann::kImgBytesPerRank;
   size_t wimg_capacity = 0;
@@ -257,17 +264,25 @@ float f16_value(float v) {
 struct ImageOpts {
   bool f16 = false;
   bool exact15 = false;     // conv1: lo parts (x 4096) in input channels 4..7; conv5: lo parts (x 4096) in rows 16..24
-  int split_mask = 0;       // bit l (1..3): conv(l+1) K-blocks stream a lo stage (w - fp16(w), unscaled) after the hi stage
+  int split_mask = 0;       // bit l (1..3): conv(l+1) K-blocks (tap, j < lo_kgroups) stream a lo stage (w - fp16(w),
+                            // unscaled, output positions [0, lo_n)) after the hi stage
+  int lo_n = 192;
+  int lo_kgroups = 3;
   const Centering* cen = nullptr;
 };
 
-int stages_per_supertile(int split_mask) {
-  int n = kKbPerSupertile;
-  for (int l = 1; l <= 3; ++l) n += ((split_mask >> l) & 1) * kKbMid;
+int split_layer_count(int split_mask) {
+  int n = 0;
+  for (int l = 1; l <= 3; ++l) n += (split_mask >> l) & 1;
   return n;
 }
-size_t image_bytes_per_rank(int split_mask) {
-  return static_cast<size_t>(stages_per_supertile(split_mask) - kKbL5) * kStageBytes + kKbL5 * kStageBytesL5;
+int stages_per_supertile(int split_mask, int lo_n, int lo_kgroups) {
+  const int bps = static_cast<int>(lo_blocks_per_stage(lo_n));        // (tap, j) lo blocks per stage
+  return kKbPerSupertile + split_layer_count(split_mask) * ((9 * lo_kgroups + bps - 1) / bps);
+}
+size_t image_bytes_per_rank(int split_mask, int lo_n, int lo_kgroups) {
+  return static_cast<size_t>(kKbPerSupertile - kKbL5) * kStageBytes + kKbL5 * kStageBytesL5 +
+         static_cast<size_t>(split_layer_count(split_mask)) * 9 * lo_kgroups * 64 * lo_n;
 }
 
 // Build the shared-memory stage images of operand B (see conv_stack_tc.cuh).
@@ -275,7 +290,7 @@ size_t image_bytes_per_rank(int split_mask) {
 void build_weight_image(const wann_weights& w, const ImageOpts& o, std::vector<uint8_t>& img) {
   static const Centering identity;
   const Centering& cen = o.cen ? *o.cen : identity;
-  const size_t per_rank = image_bytes_per_rank(o.split_mask);
+  const size_t per_rank = image_bytes_per_rank(o.split_mask, o.lo_n, o.lo_kgroups);
   img.assign(2 * per_rank, 0);
   for (int rank = 0; rank < 2; ++rank) {
     uint8_t* base = img.data() + static_cast<size_t>(rank) * per_rank;
@@ -299,16 +314,33 @@ void build_weight_image(const wann_weights& w, const ImageOpts& o, std::vector<u
       }
     // conv2..4: k-block kb = tap*3 + j holds input channel positions 64j..64j+63 of tap
     for (int layer = 1; layer <= 3; ++layer) {
-      const bool split = (o.split_mask >> layer) & 1;
+      const int lo_j = ((o.split_mask >> layer) & 1) ? o.lo_kgroups : 0;
+      const int bps = static_cast<int>(lo_blocks_per_stage(o.lo_n));
+      int pend_tap[16], pend_j[16], pend = 0;
+      auto weight = [&](int tap, int j, int out_pos, int k) {
+        const int co = cen.tf_of[layer][out_pos], ci = cen.tf_of[layer - 1][j * 64 + k];
+        return w.conv_w[layer][(static_cast<size_t>(tap) * 192 + ci) * 192 + co];
+      };
       for (int kb = 0; kb < kKbMid; ++kb) {
         const int tap = kb / 3, j = kb % 3;
-        for (int part = 0; part < (split ? 2 : 1); ++part, off += kStageBytes)
-          for (int k = 0; k < 64; ++k)
-            for (int nl = 0; nl < 96; ++nl) {
-              const int co = cen.tf_of[layer][rank * 96 + nl], ci = cen.tf_of[layer - 1][j * 64 + k];
-              const float v = w.conv_w[layer][(static_cast<size_t>(tap) * 192 + ci) * 192 + co];
-              put(base + off, kLboB, nl, k, part == 0 ? v : v - f16_value(v));
-            }
+        for (int k = 0; k < 64; ++k)
+          for (int nl = 0; nl < 96; ++nl) put(base + off, kLboB, nl, k, weight(tap, j, rank * 96 + nl, k));
+        off += kStageBytes;
+        if (j < lo_j) {
+          pend_tap[pend] = tap; pend_j[pend] = j; ++pend;
+          if (pend == bps || (tap == 8 && j == lo_j - 1)) {
+            // one lo stage = the pending (tap, j) blocks, [lo_n / 2 rows x 64 k] each: an N = lo_n MMA takes
+            // columns [0, lo_n / 2) from CTA rank 0 and [lo_n / 2, lo_n) from rank 1
+            const int half = o.lo_n / 2;
+            for (int b = 0; b < pend; ++b, off += static_cast<size_t>(64) * o.lo_n)
+              for (int k = 0; k < 64; ++k)
+                for (int nl = 0; nl < half; ++nl) {
+                  const float v = weight(pend_tap[b], pend_j[b], rank * half + nl, k);
+                  put(base + off, 8 * o.lo_n, nl, k, v - f16_value(v));
+                }
+            pend = 0;
+          }
+        }
       }
     }
     // conv5 as a 1x1 GEMM whose N index is the TAP: rows 0..8 (CTA rank 0) = the taps, rows 16..24
@@ -475,6 +507,7 @@ wann_weights host_weights_view(const wann_ctx* ctx) {
 int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) {
   const bool centred = ctx->mode == WANN_MODE_FP16C;
   const int split_mask = centred ? ctx->split_mask.load() : 0;
+  const int lo_n = ctx->lo_n.load(), lo_kgroups = ctx->lo_kgroups.load();
   std::vector<uint8_t> img;
   if (ctx->mode == WANN_MODE_FP32_TC) {
     build_weight_image_split(w, img);
@@ -483,14 +516,18 @@ int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) 
     o.f16 = ctx->mode != WANN_MODE_BF16;
     o.exact15 = centred;
     o.split_mask = split_mask;
+    o.lo_n = lo_n;
+    o.lo_kgroups = lo_kgroups;
     o.cen = &cen;
     build_weight_image(w, o, img);
   }
   if (ctx->d_wimg != nullptr && ctx->wimg_capacity < img.size()) { cudaFree(ctx->d_wimg); ctx->d_wimg = nullptr; }
   if (ctx->d_wimg == nullptr) { CU(cudaMalloc(&ctx->d_wimg, img.size())); ctx->wimg_capacity = img.size(); }
   CU(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
-  ctx->stages_per_st = stages_per_supertile(split_mask);
+  ctx->stages_per_st = (ctx->mode == WANN_MODE_FP32_TC) ? kKbPerSupertile : stages_per_supertile(split_mask, lo_n, lo_kgroups);
   ctx->img_stride = static_cast<long long>(img.size() / 2);
+  ctx->img_lo_n = lo_n;
+  ctx->img_lo_kgroups = lo_kgroups;
   // bias table: conv1..4 by channel POSITION, then b5.  Centred: b'[n] - c, where
   // b'[n] = b[n] + sum_{tap,k} W[tap][k][n] * c_prev[k] (true fp32 weights, summed in double) gives back
   // what subtracting c_prev from the layer's input took away (halo cells hold -c_prev, so the sum runs
@@ -504,15 +541,15 @@ int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) 
         for (int tap = 0; tap < 9; ++tap)
           for (int k = 0; k < 192; ++k)
             b += static_cast<double>(w.conv_w[l][(static_cast<size_t>(tap) * 192 + k) * 192 + n]) *
-                 cen.c[l - 1][cen.pos_of[l - 1][k] % 8];
-      bias[l * 192 + q] = static_cast<float>(b - (centred ? cen.c[l][q % 8] : 0.f));
+                 cen.c[l - 1][cen_bucket(cen.pos_of[l - 1][k])];
+      bias[l * 192 + q] = static_cast<float>(b - (centred ? cen.c[l][cen_bucket(q)] : 0.f));
     }
   bias[4 * 192] = w.conv_b[4][0];
   for (int t = 0; t < 9; ++t) {
     double kp = 0;
     if (centred)
       for (int k = 0; k < 192; ++k) {
-        const double c = cen.c[3][cen.pos_of[3][k] % 8];
+        const double c = cen.c[3][cen_bucket(cen.pos_of[3][k])];
         if (w.final_kernel == 3) kp += static_cast<double>(w.conv_w[4][t * 192 + k]) * c;
         else if (t == 4) kp += static_cast<double>(w.conv_w[4][k]) * c;
       }
@@ -535,6 +572,9 @@ void fill_tc_params(const wann_ctx* ctx, TcParams& p) {
   p.img_stride = ctx->img_stride;
   if (ctx->mode == WANN_MODE_FP16C) {
     p.split_mask = (ctx->stages_per_st == kKbPerSupertile) ? 0 : ctx->split_mask.load();
+    p.lo_n = ctx->img_lo_n;
+    p.lo_kgroups = ctx->img_lo_kgroups;
+    static_assert(sizeof p.cen == sizeof ctx->cen.c, "centring tables");
     memcpy(p.cen, ctx->cen.c, sizeof p.cen);
     memcpy(p.kappa, ctx->kappa, sizeof p.kappa);
     p.dbg_unperm = ctx->d_unperm;
@@ -585,15 +625,20 @@ void calibration_positions(int n, std::vector<int8_t>& squares, std::vector<uint
 
 __global__ void channel_partial_sums_kernel(const float* __restrict__ act, long long rows, float* __restrict__ partial) {
   const int c = threadIdx.x;                 // 192 threads: one channel each, coalesced rows
-  float acc = 0.f;
-  for (long long r = blockIdx.x; r < rows; r += gridDim.x) acc += act[r * 192 + c];
-  partial[blockIdx.x * 192 + c] = acc;
+  float acc = 0.f, acc2 = 0.f;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float a = act[r * 192 + c];
+    acc += a;
+    acc2 += a * a;
+  }
+  partial[blockIdx.x * 384 + c] = acc;               // sum
+  partial[blockIdx.x * 384 + 192 + c] = acc2;        // sum of squares
 }
 
-// Centred mode calibration: run the (not yet centred) kernel on the built-in positions, take the mean
-// post-ReLU activation of every channel of conv1..4, sort the channels of a layer into 8 buckets of 24
-// and give every bucket the fp16-rounded mean of its channel means as offset.  Deterministic: fixed
-// positions, fixed summation order.
+// Centred mode calibration: run the (not yet centred) kernel on the built-in positions, take mean and variance
+// of the post-ReLU activation of every channel of conv1..4, sort the channels of a layer by variance into the
+// 3 groups of 64 (highest first), the channels of a group by mean into 8 buckets of 8, and give every bucket
+// the fp16-rounded mean of its channel means as offset.  Deterministic: fixed positions, fixed summation order.
 int calibrate_centering(wann_ctx* ctx, Centering* out) {
   constexpr int kN = 1024, kBlocks = 128;
   std::vector<int8_t> sq;
@@ -607,7 +652,7 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
     CU(cudaMalloc(&d_sq, kN * 64));
     CU(cudaMalloc(&d_bl, kN));
     CU(cudaMalloc(&d_act, static_cast<size_t>(kN) * 64 * 192 * 4));
-    CU(cudaMalloc(&d_part, kBlocks * 192 * 4));
+    CU(cudaMalloc(&d_part, kBlocks * 384 * 4));
     CU(cudaMalloc(&d_err, 8 * sizeof(int)));
     CU(cudaMemsetAsync(d_err, 0, 8 * sizeof(int), stream));
     CU(cudaMemcpyAsync(d_sq, sq.data(), kN * 64, cudaMemcpyHostToDevice, stream));
@@ -621,53 +666,65 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
       const int npairs = std::min(ctx->sm_count / 2, kN / kBoardsPerPair);
       conv_stack_tc_kernel<true, true><<<2 * npairs, kThreads, kSmemBytes, stream>>>(p);
       channel_partial_sums_kernel<<<kBlocks, 192, 0, stream>>>(d_act, static_cast<long long>(kN) * 64, d_part);
-      std::vector<float> part(kBlocks * 192);
+      std::vector<float> part(kBlocks * 384);
       int herr[8];
       CU(cudaMemcpyAsync(part.data(), d_part, part.size() * 4, cudaMemcpyDeviceToHost, stream));
       CU(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, stream));
       CU(cudaStreamSynchronize(stream));
       CU(cudaGetLastError());
       if (herr[0] != 0) return fail(WANN_E_KERNEL, "calibration: conv_stack_tc watchdog, wait site %d", herr[0]);
-      double mean[192];
+      double mean[192], var[192];
+      const double rows = static_cast<double>(kN) * 64;
       for (int c = 0; c < 192; ++c) {
-        double a = 0;
-        for (int b = 0; b < kBlocks; ++b) a += part[b * 192 + c];
-        mean[c] = a / (static_cast<double>(kN) * 64);
+        double a = 0, a2 = 0;
+        for (int b = 0; b < kBlocks; ++b) { a += part[b * 384 + c]; a2 += part[b * 384 + 192 + c]; }
+        mean[c] = a / rows;
+        var[c] = a2 / rows - mean[c] * mean[c];
       }
       int order[192];
       for (int c = 0; c < 192; ++c) order[c] = c;
-      std::stable_sort(order, order + 192, [&](int a, int b) { return mean[a] < mean[b]; });
-      for (int j = 0; j < 8; ++j) {
-        double m = 0;
-        for (int i = 0; i < 24; ++i) {
-          const int c = order[j * 24 + i], q = 8 * i + j;
-          m += mean[c];
-          cen.pos_of[l][c] = static_cast<uint8_t>(q);
-          cen.tf_of[l][q] = static_cast<uint8_t>(c);
-        }
-        float cj = f16_value(static_cast<float>(m / 24));
-        // development knob: keep only the top WANN_B200_OFFSET_BITS mantissa bits of the offset (0 = a power of
-        // two): about half of all stored activations are the clamped zeros, i.e. exactly -offset, and an operand
-        // with few mantissa bits toggles less of the tensor core's multiplier array
-        if (const char* ob = getenv("WANN_B200_OFFSET_BITS")) {
-          const int bits = atoi(ob);
-          if (bits >= 0 && bits < 10 && cj > 0.f) {
-            int e;
-            const float fr = frexpf(cj, &e);                       // cj = fr * 2^e, fr in [0.5, 1)
-            const float q = static_cast<float>(1 << (bits + 1));
-            cj = f16_value(ldexpf(roundf(fr * q) / q, e));
+      std::stable_sort(order, order + 192, [&](int a, int b) { return var[a] > var[b]; });
+      struct Bucket { double mean; int l, j; };
+      std::vector<Bucket> buckets;
+      for (int g = 0; g < 3; ++g) {
+        int* grp = order + 64 * g;
+        std::stable_sort(grp, grp + 64, [&](int a, int b) { return mean[a] < mean[b]; });
+        for (int j = 0; j < 8; ++j) {
+          int* bk = grp + 8 * j;                               // bucket j of the group: 8 channels of similar mean,
+          std::stable_sort(bk, bk + 8, [&](int a, int b) { return var[a] > var[b]; });   // the most variable first
+          double m = 0;
+          for (int i = 0; i < 8; ++i) {
+            const int c = bk[i], q = 64 * g + 8 * i + j;
+            m += mean[c];
+            cen.pos_of[l][c] = static_cast<uint8_t>(q);
+            cen.tf_of[l][q] = static_cast<uint8_t>(c);
           }
+          float cj = f16_value(static_cast<float>(m / 8));
+          // development knob: keep only the top WANN_B200_OFFSET_BITS mantissa bits of the offset (0 = a power of
+          // two): about half of all stored activations are the clamped zeros, i.e. exactly -offset, and an operand
+          // with few mantissa bits toggles less of the tensor core's multiplier array
+          if (const char* ob = getenv("WANN_B200_OFFSET_BITS")) {
+            const int bits = atoi(ob);
+            if (bits >= 0 && bits < 10 && cj > 0.f) {
+              int e;
+              const float fr = frexpf(cj, &e);                       // cj = fr * 2^e, fr in [0.5, 1)
+              const float q = static_cast<float>(1 << (bits + 1));
+              cj = f16_value(ldexpf(roundf(fr * q) / q, e));
+            }
+          }
+          cen.c[l][8 * g + j] = cj;
+          buckets.push_back({m / 8, l, 8 * g + j});
         }
-        // The two lowest-mean buckets keep offset 0: their clamped activations stay exact zeros (an operand of 0
-        // toggles nothing in the tensor core's multiplier array -- measured +2 % sustained throughput under the
-        // power cap) and, being small, they contribute next to nothing to the rounding error (probability
-        // median 9.39e-4 -> 9.41e-4).  WANN_B200_ZERO_BUCKETS overrides the count for experiments
-        // (3: +2.6 % / 9.5e-4, 4: +3.4 % / 1.0e-3; tools/gpu_offset_bits.py).
-        int zero_buckets = 2;
-        if (const char* zb = getenv("WANN_B200_ZERO_BUCKETS")) zero_buckets = atoi(zb);
-        if (j < zero_buckets) cj = 0.f;
-        cen.c[l][j] = cj;
       }
+      // The lowest-mean half of the buckets keeps offset 0: their clamped activations stay exact zeros (an
+      // operand of 0 toggles nothing in the tensor core's multiplier array -- under the power cap 12 zero buckets
+      // of 24 run 3.7 % faster than none, 1,515 -> 1,570 MHz) and, being small, they contribute little to the
+      // rounding error (probability median 8.9e-4 -> 9.0e-4; 15: 9.8e-4, 18: 1.05e-3).
+      // WANN_B200_ZERO_BUCKETS overrides the count (of 24) for experiments (tools/gpu_partial_split.py).
+      int zero_buckets = 12;
+      if (const char* zb = getenv("WANN_B200_ZERO_BUCKETS")) zero_buckets = atoi(zb);
+      std::stable_sort(buckets.begin(), buckets.end(), [](const Bucket& a, const Bucket& b) { return a.mean < b.mean; });
+      for (int i = 0; i < zero_buckets && i < static_cast<int>(buckets.size()); ++i) cen.c[l][buckets[i].j] = 0.f;
     }
     *out = cen;
     return WANN_OK;
@@ -1715,11 +1772,11 @@ int wann_kernel_times(wann_ctx* ctx, double out[2]) {
   return WANN_OK;
 }
 
-int wann_debug_centering(wann_ctx* ctx, float offsets[32], uint8_t position_of[768], float kappa[9]) {
+int wann_debug_centering(wann_ctx* ctx, float offsets[96], uint8_t position_of[768], float kappa[9]) {
   if (ctx == nullptr || offsets == nullptr || position_of == nullptr) return fail(WANN_E_INVALID, "null argument");
   if (ctx->mode != WANN_MODE_FP16C) return fail(WANN_E_INVALID, "centring exists in the fp16c mode only");
   ReaderScope weights_scope(&ctx->weights_gate);
-  memcpy(offsets, ctx->cen.c, 32 * sizeof(float));
+  memcpy(offsets, ctx->cen.c, 4 * kCenBuckets * sizeof(float));
   memcpy(position_of, ctx->cen.pos_of, 768);
   if (kappa != nullptr) memcpy(kappa, ctx->kappa, 9 * sizeof(float));
   return WANN_OK;
@@ -1793,11 +1850,17 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
     return WANN_OK;
   }
   if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
-  if (strcmp(key, "split_layers") == 0) {
-    // centred mode: bit l (1..3) makes conv(l+1) stream its weights as fp16 hi + lo stages (2 MMAs per
-    // K-step in that layer: the layer's weight rounding error disappears); rebuilds the stage image
-    if (ctx->mode != WANN_MODE_FP16C) return fail(WANN_E_INVALID, "split_layers applies to the fp16c mode");
-    if (value < 0 || (value & ~14ll)) return fail(WANN_E_INVALID, "split_layers is a mask of bits 1..3");
+  if (strcmp(key, "split_layers") == 0 || strcmp(key, "lo_n") == 0 || strcmp(key, "lo_kgroups") == 0) {
+    // centred mode, partial hi/lo weight split: in the conv layers of "split_layers" (bit l = conv(l+1), l = 1..3)
+    // every K-block (tap, j < "lo_kgroups") streams a lo stage w - fp16(w) for the output positions [0, "lo_n")
+    // and runs a second, N = lo_n MMA per K-step against it: the weight rounding error of that block of the layer
+    // disappears.  Positions are sorted by activation variance, so the leading block carries most of the error
+    // (lo_n = 192, lo_kgroups = 3: the whole layer).  Rebuilds the stage image.
+    if (ctx->mode != WANN_MODE_FP16C) return fail(WANN_E_INVALID, "%s applies to the fp16c mode", key);
+    if (key[0] == 's' && (value < 0 || (value & ~14ll))) return fail(WANN_E_INVALID, "split_layers is a mask of bits 1..3");
+    if (strcmp(key, "lo_n") == 0 && (value < 16 || value > 192 || value % 16))
+      return fail(WANN_E_INVALID, "lo_n is a multiple of 16 in 16..192");
+    if (strcmp(key, "lo_kgroups") == 0 && (value < 1 || value > 3)) return fail(WANN_E_INVALID, "lo_kgroups is 1..3");
     DeviceGuard dev_guard(ctx->device);
     CU(dev_guard.status);
     ctx->weights_gate.writer_enter();
@@ -1805,7 +1868,9 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) rc = fail(WANN_E_CUDA, "device synchronise: %s", cudaGetErrorString(e));
     else {
-      ctx->split_mask = static_cast<int>(value);
+      if (key[0] == 's') ctx->split_mask = static_cast<int>(value);
+      else if (strcmp(key, "lo_n") == 0) ctx->lo_n = static_cast<int>(value);
+      else ctx->lo_kgroups = static_cast<int>(value);
       const Centering cen = ctx->cen;
       rc = upload_tc_image(ctx, host_weights_view(ctx), cen);
     }

@@ -80,8 +80,9 @@ class PolicyEvaluator(object):
         self.set_option("refine_margin_micro", int(round(float(margin_logits) * 1e6)))
 
     def centering(self):
-        """fp16c mode: (offsets [4,8], position_of [4,192], kappa [9]) of the calibrated centring."""
-        off = np.zeros((4, 8), np.float32)
+        """fp16c mode: (offsets [4,24] by (position // 64) * 8 + position % 8, position_of [4,192], kappa [9])
+        of the calibrated centring."""
+        off = np.zeros((4, 24), np.float32)
         pos = np.zeros((4, 192), np.uint8)
         kap = np.zeros(9, np.float32)
         L.check(self._lib.wann_debug_centering(self._ctx, off.ctypes.data, pos.ctypes.data, kap.ctypes.data))
