@@ -16,10 +16,9 @@ positions/s) is listed under "sweep_positions_per_s" for information.
 Arithmetic of every number in the line unless a key says otherwise (`arithmetic` in `config`): the
 configuration that meets north_star's accuracy gates on 100,000 positions
 (tests/test_gpu_parity.py::test_centred_fp16_mode_meets_the_north_star_gates_on_100k_positions):
-mode fp16c (centred fp16 operands, fp32 accumulate), split_layers = 14 with lo_n = 64, lo_kgroups = 1 (the
-partial hi/lo weight split: in hidden_layer/2..4 the weights of the 64 highest-variance input channels x
-64 leading output channels also stream their fp16 lo parts, +11 % MMAs), no refinement pass (one kernel
-launch per evaluation).  Faster, less accurate
+mode fp16c as created: centred fp16 operands, fp32 accumulate, the weights of the 192->192 layers rounded to
+fp16 with error compensation against the calibration inputs' second moments (GPTQ-style, wann_b200/csrc/gptq.hpp),
+ONE MMA per K-step (the MMA count of the bf16 kernel), no refinement pass (one kernel launch per evaluation).  Faster, less accurate
 modes -- and the same mode with margin refinement, which makes the policy move equal the fp32
 graph's on all 100,000 positions -- are extra keys under `modes`.
 
@@ -245,7 +244,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fp16c", choices=["bf16", "fp16", "fp16c", "fp32_tc"])
-    ap.add_argument("--split-layers", type=int, default=None, help="fp16c: mask of hidden layers (bits 1..3) with hi+lo weights; default 14")
+    ap.add_argument("--split-layers", type=int, default=None, help="fp16c: mask of hidden layers (bits 1..3) with lo weight stages; default 0")
+    ap.add_argument("--gptq", type=int, default=1, help="fp16c: data-aware weight rounding (default 1)")
     ap.add_argument("--lo-n", type=int, default=64, help="fp16c: output positions covered by the lo stages")
     ap.add_argument("--lo-kgroups", type=int, default=1, help="fp16c: 64-channel input groups covered by the lo stages")
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -281,17 +281,20 @@ def main():
               file=sys.stderr)
 
     B = args.batch
-    split_layers = (14 if args.mode == "fp16c" else 0) if args.split_layers is None else args.split_layers
+    split_layers = 0 if args.split_layers is None else args.split_layers
     refine_margin = 0.0 if args.refine_margin is None else args.refine_margin
     ev = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode=args.mode,
                                    refine_margin=refine_margin)
+    if args.mode == "fp16c" and not args.gptq:
+        ev.set_option("gptq", 0)
     if split_layers:
         ev.set_option("lo_n", args.lo_n)
         ev.set_option("lo_kgroups", args.lo_kgroups)
         ev.set_option("split_layers", split_layers)
     arithmetic = {"bf16": "bf16 operands, fp32 accumulate", "fp16": "fp16 operands, fp32 accumulate",
                   "fp32_tc": "fp16 hi/lo split operands (3 MMAs per K-step), fp32 accumulate",
-                  "fp16c": "centred fp16 operands (a - bucket mean; conv1/conv5 weights hi+lo), fp32 accumulate"}[args.mode]
+                  "fp16c": "centred fp16 operands (a - bucket mean; conv1/conv5 weights hi+lo; 192->192 weights rounded with "
+                           "error compensation, gptq=%d), fp32 accumulate" % args.gptq}[args.mode]
     arithmetic += "; split_layers=%d (lo_n=%d, lo_kgroups=%d); margin refinement %.3g logit (fp32-class re-evaluation of near-ties)" % (
         split_layers, args.lo_n, args.lo_kgroups, refine_margin)
     for opt in os.environ.get("WANN_BENCH_OPTIONS", "").split(","):      # experiments: "skew=5,fuse_tail=0"
@@ -433,8 +436,7 @@ def main():
         from wann_b200.forest import host_threads
         host_threads(max(1, (os.cpu_count() or 1) // max(1, world)))      # torchrun exports OMP_NUM_THREADS=1
         ev3 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode="fp16c")
-        ev3.set_option("split_layers", 14)                # the headline arithmetic (one launch per evaluation)
-        forest_line = {"arithmetic": "fp16c, split_layers=14 (lo_n=64, lo_kgroups=1), no refinement pass"}
+        forest_line = {"arithmetic": "fp16c as created (the headline arithmetic), no refinement pass"}
         for key, n_trees, resident, sims in (("device_resident", 1024, True, 24), ("device_resident_8192", 8192, True, 12),
                                              ("host", 1024, False, 10)):
             fsq, fbl = sq_np[:n_trees], bl_np[:n_trees]
@@ -485,20 +487,22 @@ def main():
         ev3.close()
 
     # ---------------- the other arithmetic modes on the same workload (device resident, short runs):
-    # faster and less accurate (bf16, fp16, fp16c without the split layer), or slower and more accurate
+    # faster and less accurate (bf16, fp16), or slower (margin refinement, lo weight stages: what the headline
+    # mode needed before its weights were rounded with error compensation)
     modes = None
     if not args.no_sweep:
         modes = {}
         for name, mode, split, margin in (("bf16", "bf16", 0, 0.0), ("fp16", "fp16", 0, 0.0),
-                                          ("fp16+refine0.02", "fp16", 0, 0.02), ("fp16c", "fp16c", 0, 0.0),
+                                          ("fp16+refine0.02", "fp16", 0, 0.02),
                                           ("fp16c+refine0.01", "fp16c", 0, 0.01),
-                                          ("fp16c+split14+refine0.01", "fp16c", 14, 0.01),
-                                          ("fp16c+split14+lo_n96", "fp16c", 14 | 96 << 8, 0.0),
-                                          ("fp16c+fullsplit8", "fp16c", 8 | 192 << 8 | 3 << 16, 0.0),
-                                          ("fp16c+fullsplit14", "fp16c", 14 | 192 << 8 | 3 << 16, 0.0)):
+                                          ("fp16c+rtn", "fp16c", 0, 0.0),               # round-to-nearest weights
+                                          ("fp16c+rtn+split14", "fp16c", 14, 0.0),      # + partial hi/lo split
+                                          ("fp16c+rtn+fullsplit8", "fp16c", 8 | 192 << 8 | 3 << 16, 0.0)):
             split, lo_n, lo_kg = split & 255, (split >> 8) & 255 or 64, (split >> 16) or 1
             ev2 = wann_b200.PolicyEvaluator(W.synthetic("trained_like", 1), device=local_rank, mode=mode,
                                             refine_margin=margin)
+            if "+rtn" in name:
+                ev2.set_option("gptq", 0)
             if split:
                 ev2.set_option("lo_n", lo_n)
                 ev2.set_option("lo_kgroups", lo_kg)
@@ -517,7 +521,8 @@ def main():
             t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rec = {"mode": mode, "split_layers": split, "lo_n": lo_n if split else 0, "lo_kgroups": lo_kg if split else 0,
+            rec = {"mode": mode, "gptq": int(mode == "fp16c" and "+rtn" not in name), "split_layers": split,
+                   "lo_n": lo_n if split else 0, "lo_kgroups": lo_kg if split else 0,
                    "refine_margin_logits": margin,
                    "value": n_gpus * B * rsteps / (float(t.item()) * 1e-3), "unit": UNIT, "steps": rsteps}
             if margin:
@@ -668,7 +673,7 @@ def main():
                        "mode": args.mode, "split_layers": split_layers, "lo_n": args.lo_n if split_layers else 0,
                        "lo_kgroups": args.lo_kgroups if split_layers else 0, "refine_margin_logits": refine_margin,
                        "arithmetic": arithmetic,
-                       "accuracy": "this configuration on 100,000 positions vs the fp32 graph: see profiles/r02_accuracy_partial_split.json "
+                       "accuracy": "this configuration on 100,000 positions vs the fp32 graph: see profiles/r02_accuracy_gptq.json "
                                    "and tests/test_gpu_parity.py::test_centred_fp16_mode_meets_the_north_star_gates_on_100k_positions",
                        "weights": "synthetic trained_like seed 1 (reference weight shard absent)",
                        "positions": "seeded random legal play-out positions",

@@ -312,6 +312,19 @@ int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* blac
  * hidden_layer/5.  The emulation in tests/ uses it to reproduce the kernel's roundings. */
 int wann_debug_centering(wann_ctx* ctx, float offsets[96], uint8_t position_of[768], float kappa[9]);
 
+/* Test/inspection hook (bf16 / fp16 / fp16c modes): the weights of hidden_layer/`layer` (2..4) exactly as the
+ * tensor-core kernel multiplies them, fp32 HWIO [3,3,192,192]: the 16-bit operand value, hi + lo where a lo
+ * stage covers the entry, and -- WANN_MODE_FP16C with option "gptq" (default) -- the result of the data-aware
+ * rounding (wann_b200/csrc/gptq.hpp) instead of round-to-nearest.  The emulation in tests/ is fed with it. */
+int wann_debug_effective_weights(wann_ctx* ctx, int layer, float* out);
+
+/* Host utility (no device, no context): the sequential error-compensated rounding of gptq.hpp on its own.
+ * H [n][n] symmetric second-moment matrix of the inputs, W [rows][n] weights (in/out: rounded to fp16 values,
+ * except where exact[r*n + k] != 0: those entries keep fp32 precision), damp = ridge as a fraction of
+ * mean(diag H) (the calibration uses 0.01).  Exists so that the rounding can be tested against its numpy
+ * restatement (oracle/oracle.py gptq_round) without a GPU. */
+int wann_gptq_round(const float* H, int n, float* W, int rows, const uint8_t* exact, double damp);
+
 /* Measurement hook: with option "time_kernels" = 1 every conv-stack kernel launch is bracketed
  * by CUDA events on its own stream; this call synchronises the device and returns
  * out[0] = summed kernel milliseconds, out[1] = number of launches since the last call. */
@@ -348,6 +361,10 @@ int wann_get_stats(wann_ctx* ctx, uint64_t stats[8]);
  * (board_utils.pyx:262-277) -- are evaluated a second time in the same call by the fp32-class
  * split kernel (WANN_MODE_FP32_TC arithmetic) and every output row of theirs is overwritten.
  * Needs board inputs (squares); plane inputs are not refined.
+ * "gptq" (WANN_MODE_FP16C, default 1): the weights of the three 192->192 layers are rounded to fp16 with
+ * error compensation against the second moments of the layer's inputs on 512 built-in calibration positions
+ * (GPTQ-style, wann_b200/csrc/gptq.hpp) instead of to nearest: their rounding error all but disappears from
+ * the output at no run-time cost (probability median error 1.0e-3 -> 7.3e-4); 0 = round to nearest.
  * "split_layers" / "lo_n" / "lo_kgroups" (WANN_MODE_FP16C; defaults 0 / 64 / 1): partial hi/lo weight split.
  * The calibration orders the channels of every hidden layer by activation variance, so the weight
  * rounding error of a 192->192 layer is concentrated in its leading input positions (the first of the three

@@ -64,6 +64,8 @@ cdef extern from "wann_b200.h" nogil:
     int wann_debug_profile(wann_ctx* ctx, const int8_t* squares, const uint8_t* black_to_move,
                            int64_t n, int64_t* stamps)
     int wann_debug_centering(wann_ctx* ctx, float* offsets, uint8_t* position_of, float* kappa)
+    int wann_debug_effective_weights(wann_ctx* ctx, int layer, float* out)
+    int wann_gptq_round(const float* H, int n, float* W, int rows, const uint8_t* exact, double damp)
     int wann_kernel_times(wann_ctx* ctx, double* out)
     uint32_t wann_crc32c(const void* data, uint64_t nbytes, uint32_t seed)
     int wann_host_alloc(void** ptr, uint64_t nbytes)

@@ -453,8 +453,29 @@ def forward_16bit_emulated(planes, weights, fmt="bf16", return_all=False):
     return logits, probs
 
 
+def gptq_round(H, W, damp=0.01, exact=None):
+    """numpy restatement of wann_b200/csrc/gptq.hpp (the GPTQ / optimal-brain-quantisation sequential rounding):
+    H [n,n] second moments of a layer's inputs, W [rows,n] its weights.  Column k of every row is rounded to
+    fp16 (kept as is where exact[r,k]); the error is pushed onto the columns j > k along
+    U[k,j] / U[k,k], (H + damp * mean(diag H) * I)^-1 = U^T U, U upper triangular.  -> rounded copy of W (float64)."""
+    H = np.asarray(H, np.float64)
+    n = H.shape[0]
+    Hd = 0.5 * (H + H.T) + damp * np.trace(H) / n * np.eye(n)
+    U = np.linalg.cholesky(np.linalg.inv(Hd)).T.copy()        # inv = L L^T = U^T U with U = L^T
+    W = np.array(W, np.float64)
+    for k in range(n):
+        q = f16_round(W[:, k]).astype(np.float64)
+        if exact is not None:
+            q = np.where(exact[:, k] != 0, W[:, k].astype(np.float32).astype(np.float64), q)
+        err = (W[:, k] - q) / U[k, k]
+        W[:, k] = q
+        if k + 1 < n:
+            W[:, k + 1:] -= err[:, None] * U[k, k + 1:][None, :]
+    return W
+
+
 def forward_fp16c_emulated(planes, weights, offsets, position_of, split_mask=0, lo_n=192, lo_kgroups=3,
-                           return_all=False):
+                           return_all=False, w_eff=None):
     """Emulation of the roundings of the CENTRED fp16 tensor-core mode (WANN_MODE_FP16C,
     wann_b200/csrc/conv_stack_tc.cuh) for the same graph as forward_fp32
     (policy_net_utils.pyx:106-124,149-178,215-239).  offsets [4,24] / position_of [4,192] are the
@@ -464,7 +485,10 @@ def forward_fp16c_emulated(planes, weights, offsets, position_of, split_mask=0, 
     sum(w * offset) with the TRUE fp32 weights.  hidden_layer/1 and /5 see their weights as fp16
     hi + lo pairs (22 bits); in the layers of split_mask (bits 1..3 = hidden_layer/2..4) the block
     [input positions < 64 * lo_kgroups] x [output positions < lo_n] too; all other weights are rounded
-    to fp16.  Accumulation, bias and ReLU in fp32; FC/softmax in fp32."""
+    to fp16.  w_eff (optional): {layer: [3,3,192,192]} the weights hidden_layer/2..4 are multiplied with, as the
+    context reports them (wann_debug_effective_weights) -- the fp16c mode rounds them with error compensation
+    (gptq_round), which only the context's calibration data determines.  Accumulation, bias and ReLU in fp32;
+    FC/softmax in fp32."""
     def two16(w):                     # hi + lo/4096 pair, as the kernel's conv1 / conv5 operands
         hi = f16_round(w)
         return hi + f16_round((w - hi) * 4096.0) / np.float32(4096.0)
@@ -481,6 +505,8 @@ def forward_fp16c_emulated(planes, weights, offsets, position_of, split_mask=0, 
         b = weights["hidden_layer/%d/bias" % i].astype(np.float64)
         if i == 1 or i == 5:
             w16 = two16(w)
+        elif w_eff is not None and i in w_eff:
+            w16 = np.asarray(w_eff[i], np.float32)
         else:
             w16 = f16_round(w)
             if (split_mask >> (i - 1)) & 1:

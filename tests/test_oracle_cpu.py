@@ -799,6 +799,39 @@ def test_centred_fp16_emulation_halves_the_fp16_error():
     assert e_cen < 1e-3
 
 
+def test_data_aware_weight_rounding_equals_its_restatement(lib_built):
+    """wann_gptq_round (wann_b200/csrc/gptq.hpp, host code) against oracle.gptq_round on a small layer with
+    strongly correlated inputs: same rounded weights, every unprotected entry an fp16 value within 2 ulp of the
+    largest weight, and an output error energy far below round-to-nearest's -- also on held-out inputs."""
+    from wann_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(5)
+    n, rows, rank = 96, 24, 6
+    F = rng.normal(size=(n, rank)) * rng.uniform(0.3, 2.0, size=rank)
+    draw = lambda m: rng.normal(size=(m, rank)) @ F.T + 0.05 * rng.normal(size=(m, n)) + 0.2   # noqa: E731
+    X, X2 = draw(4 * n), draw(4 * n)
+    H = (X.T @ X / X.shape[0]).astype(np.float32)
+    W = (rng.normal(size=(rows, n)) * 0.034).astype(np.float32)
+    exact = (rng.random((rows, n)) < 0.1).astype(np.uint8)
+    ref = O.gptq_round(H, W, 0.01, exact)
+    Wc = W.copy()
+    L.check(lib.wann_gptq_round(H.ctypes.data, n, Wc.ctypes.data, rows, exact.ctypes.data, 0.01))
+    assert (ref.astype(np.float32) == Wc).mean() > 0.99
+    free = exact == 0
+    assert np.array_equal(Wc[free], Wc[free].astype(np.float16).astype(np.float32))
+    assert np.array_equal(Wc[~free], W[~free]) or np.abs(Wc[~free] - W[~free]).max() < 1e-4   # compensation only
+    rtn = np.where(free, O.f16_round(W), W).astype(np.float64)
+    # the weights move about as far as round-to-nearest moves them (just not independently of each other)
+    assert np.abs(Wc - W).max() <= 2 * float(np.spacing(np.float16(np.abs(W).max())))
+    assert np.sqrt(((Wc - W)[free] ** 2).mean()) < 2 * np.sqrt(((rtn - W)[free] ** 2).mean())
+    energy = lambda Q, Z: float((((W - Q) @ Z.T) ** 2).mean())       # noqa: E731
+    assert energy(Wc, X) < 0.1 * energy(rtn, X) and energy(Wc, X2) < 0.2 * energy(rtn, X2)
+    # a matrix that is not positive definite is refused
+    bad = -np.eye(4, dtype=np.float32)
+    w4 = np.ones((1, 4), np.float32)
+    assert lib.wann_gptq_round(bad.ctypes.data, 4, w4.ctypes.data, 1, None, 0.0) != 0
+
+
 def test_shim_turns_valid_planes_back_into_boards():
     """sess.run(y_pred, {X: planes}) / evaluate(already_converted=True): valid P/O/E/1 planes take the
     boards path (refinement + coalescing apply), anything else is evaluated as planes."""

@@ -10,7 +10,7 @@ w = W.synthetic("trained_like", 1)
 for T in [int(x) for x in os.environ.get("TREES", "1024,8192").split(",")]:
     sq, bl = synthetic.random_positions(T, seed=3)
     with wann_b200.PolicyEvaluator(w, mode="fp16c") as ev:
-        ev.set_option("split_layers", int(os.environ.get("SPLIT", "14")))
+        ev.set_option("split_layers", int(os.environ.get("SPLIT", "0")))
         f = wann_b200.SearchForest(sq, bl, evaluator=ev, device_resident=True, node_capacity=32768)
         f.run_steps(ev, 60)
         os.environ["WANN_FOREST_TIMING"] = "1"

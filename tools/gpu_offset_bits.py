@@ -19,7 +19,7 @@ bsq = torch.from_numpy(np.tile(sq, (4, 1))[:B]).to(dev); bbl = torch.from_numpy(
 for bits in [int(x) for x in os.environ.get("ZERO_BUCKETS", "0,2,3,4,5,6").split(",")]:
     os.environ["WANN_B200_ZERO_BUCKETS"] = str(bits)
     with wann_b200.PolicyEvaluator(w, mode="fp16c") as ev:
-        ev.set_option("split_layers", int(os.environ.get("SPLIT", "14")))
+        ev.set_option("split_layers", int(os.environ.get("SPLIT", "0")))
         p, l = ev.eval_probs(sq, bl, return_logits=True)
         d = np.abs(l - l32)
         acc = (d.max() / np.abs(l32).max(), np.sqrt((d.astype(np.float64) ** 2).mean()) / l32.std(), np.median(np.abs(p - p32) / p32))

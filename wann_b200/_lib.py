@@ -17,7 +17,7 @@ N_MOVES, MAX_LEGAL = 155, 48
 EXPORTS = [
     "wann_create", "wann_set_weights", "wann_destroy", "wann_last_error", "wann_encode", "wann_legal_mask",
     "wann_eval_probs", "wann_eval_planes", "wann_eval_topk", "wann_eval_expand", "wann_eval_expand_seeded", "wann_expand_ranked", "wann_tree_step", "wann_debug_activations",
-    "wann_debug_profile", "wann_debug_centering", "wann_kernel_times", "wann_crc32c",
+    "wann_debug_profile", "wann_debug_centering", "wann_debug_effective_weights", "wann_gptq_round", "wann_kernel_times", "wann_crc32c",
     "wann_host_alloc", "wann_host_free", "wann_get_stats", "wann_set_option", "wann_version",
     "wann_forest_create", "wann_forest_create_device", "wann_forest_run", "wann_forest_run_steps", "wann_forest_debug_cycles", "wann_forest_destroy", "wann_forest_next", "wann_forest_apply", "wann_forest_info",
     "wann_forest_dump", "wann_forest_advance", "wann_forest_play", "wann_host_threads",
@@ -77,6 +77,8 @@ def load():
     lib.wann_debug_activations.argtypes = [vp, vp, vp, i64, ci, vp, ci]
     lib.wann_debug_profile.argtypes = [vp, vp, vp, i64, vp]
     lib.wann_debug_centering.argtypes = [vp, vp, vp, vp]
+    lib.wann_debug_effective_weights.argtypes = [vp, ci, vp]
+    lib.wann_gptq_round.argtypes = [vp, ci, vp, ci, vp, ctypes.c_double]
     lib.wann_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 2)]
     lib.wann_crc32c.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint32]
     lib.wann_crc32c.restype = ctypes.c_uint32

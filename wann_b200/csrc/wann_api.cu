@@ -23,6 +23,7 @@
 #include "conv_stack_tc.cuh"
 #include "conv_stack_split.cuh"
 #include "array_tree.hpp"
+#include "gptq.hpp"
 
 namespace {
 
@@ -225,6 +226,12 @@ struct wann_ctx {
   std::atomic<int> lo_n{64};       // option "lo_n": the lo stages cover output positions [0, lo_n) ...
   std::atomic<int> lo_kgroups{1};  // option "lo_kgroups": ... and the first lo_kgroups 64-channel input groups of every tap
   int img_lo_n = 192, img_lo_kgroups = 3;   // what the uploaded stage image was built with
+  // data-aware weight rounding (gptq.hpp; option "gptq", fp16c mode, default on): per 192->192 layer the
+  // factor U of the inverse second-moment matrix of its calibration inputs (kept: re-rounding after a change
+  // of the split options needs no new calibration), and the weights the kernel actually multiplies
+  std::atomic<bool> gptq{true};
+  std::vector<double> gptq_u[3];
+  std::vector<float> w_eff[3];     // [9][192][192] HWIO: effective weights of hidden_layer/2..4 (wann_debug_effective_weights)
   int stages_per_st = wann::kKbPerSupertile;
   long long img_stride = wann::kImgBytesPerRank;
   size_t wimg_capacity = 0;
@@ -509,6 +516,46 @@ int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) 
   const int split_mask = centred ? ctx->split_mask.load() : 0;
   const int lo_n = ctx->lo_n.load(), lo_kgroups = ctx->lo_kgroups.load();
   std::vector<uint8_t> img;
+  // the weights the image is built from: the true ones, or -- 192->192 layers of the centred mode -- the ones
+  // rounded with error compensation (entries covered by a lo stage stay unrounded: the image splits them hi + lo)
+  wann_weights wi = w;
+  for (int l = 0; l < 3; ++l) {
+    std::vector<float>& we = ctx->w_eff[l];
+    const float* src = w.conv_w[l + 1];
+    we.assign(src, src + static_cast<size_t>(9) * 192 * 192);
+    const bool lo_layer = centred && ((split_mask >> (l + 1)) & 1);
+    auto covered = [&](int ci, int co) {
+      return lo_layer && cen.pos_of[l][ci] < 64 * lo_kgroups && cen.pos_of[l + 1][co] < lo_n;
+    };
+    if (centred && ctx->gptq.load() && !ctx->gptq_u[l].empty()) {
+      constexpr int K = 9 * 192;
+      std::vector<double> W(static_cast<size_t>(192) * K);
+      std::vector<uint8_t> exact(static_cast<size_t>(192) * K, 0);
+      for (int k = 0; k < K; ++k)
+        for (int co = 0; co < 192; ++co) {
+          W[static_cast<size_t>(co) * K + k] = src[static_cast<size_t>(k) * 192 + co];
+          exact[static_cast<size_t>(co) * K + k] = covered(k % 192, co);
+        }
+      wann_gptq::round_rows(ctx->gptq_u[l].data(), K, W.data(), 192, exact.data());
+      for (int k = 0; k < K; ++k)
+        for (int co = 0; co < 192; ++co) we[static_cast<size_t>(k) * 192 + co] = static_cast<float>(W[static_cast<size_t>(co) * K + k]);
+      wi.conv_w[l + 1] = we.data();
+    } else if (ctx->mode != WANN_MODE_FP32_TC) {
+      // round to nearest: record what the kernel multiplies (16-bit value, or hi + lo where a lo stage covers it)
+      for (int k = 0; k < 9 * 192; ++k)
+        for (int co = 0; co < 192; ++co) {
+          float& v = we[static_cast<size_t>(k) * 192 + co];
+          if (ctx->mode == WANN_MODE_BF16) {
+            const uint16_t h = f32_to_bf16(v);
+            const uint32_t u = static_cast<uint32_t>(h) << 16;
+            memcpy(&v, &u, 4);
+          } else {
+            const float hi = f16_value(v);
+            v = covered(k % 192, co) ? hi + f16_value(v - hi) : hi;
+          }
+        }
+    }
+  }
   if (ctx->mode == WANN_MODE_FP32_TC) {
     build_weight_image_split(w, img);
   } else {
@@ -519,7 +566,7 @@ int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) 
     o.lo_n = lo_n;
     o.lo_kgroups = lo_kgroups;
     o.cen = &cen;
-    build_weight_image(w, o, img);
+    build_weight_image(wi, o, img);
   }
   if (ctx->d_wimg != nullptr && ctx->wimg_capacity < img.size()) { cudaFree(ctx->d_wimg); ctx->d_wimg = nullptr; }
   if (ctx->d_wimg == nullptr) { CU(cudaMalloc(&ctx->d_wimg, img.size())); ctx->wimg_capacity = img.size(); }
@@ -635,6 +682,61 @@ __global__ void channel_partial_sums_kernel(const float* __restrict__ act, long 
   partial[blockIdx.x * 384 + 192 + c] = acc2;        // sum of squares
 }
 
+// Second-moment matrix H = E[x x^T] of the inputs of a 192->192 conv layer (gptq.hpp): x[tap * 192 + c] =
+// the CENTRED stored activation a - off[c] of TF channel c at the pixel's 3x3 neighbour `tap`, -off[c] outside
+// the board (what the shared-memory halo holds).  One block per 64 x 64 tile of the upper triangle (a tile =
+// one tap x one 64-channel group), 256 threads x 4 x 4 outputs, fp32 accumulation over n_pos * 64 pixels.
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ act, const float* __restrict__ off,
+                                                   int n_pos, float* __restrict__ H) {
+  const int bi = blockIdx.x, bj = blockIdx.y;
+  if (bj < bi) return;
+  __shared__ __align__(16) float As[32][64];
+  __shared__ __align__(16) float Bs[32][64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int samples = n_pos * 64;
+  for (int s0 = 0; s0 < samples; s0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = threadIdx.x + 256 * r, sl = idx >> 6, ch = idx & 63;
+      const int smp = s0 + sl, pos = smp >> 6, y = (smp >> 3) & 7, x = smp & 7;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const int b = which ? bj : bi, tap = b / 3, c = (b % 3) * 64 + ch;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        float v = -off[c];
+        if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) v += act[(static_cast<size_t>(pos) * 64 + yy * 8 + xx) * 192 + c];
+        (which ? Bs : As)[sl][ch] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int sl = 0; sl < 32; ++sl) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[sl][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[sl][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float inv = 1.f / static_cast<float>(samples);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = bi * 64 + ty * 4 + i, gj = bj * 64 + tx * 4 + j;
+      H[static_cast<size_t>(gi) * 1728 + gj] = acc[i][j] * inv;
+      H[static_cast<size_t>(gj) * 1728 + gi] = acc[i][j] * inv;
+    }
+}
+
 // Centred mode calibration: run the (not yet centred) kernel on the built-in positions, take mean and variance
 // of the post-ReLU activation of every channel of conv1..4, sort the channels of a layer by variance into the
 // 3 groups of 64 (highest first), the channels of a group by mean into 8 buckets of 8, and give every bucket
@@ -645,10 +747,17 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
   std::vector<uint8_t> bl;
   calibration_positions(kN, sq, bl);
   int8_t* d_sq = nullptr; uint8_t* d_bl = nullptr; float* d_act = nullptr; float* d_part = nullptr; int* d_err = nullptr;
+  float* d_gram = nullptr; float* d_off = nullptr;
+  constexpr int kGramPositions = 512, kGramDim = 9 * 192;
+  const bool want_gptq = ctx->gptq.load();
   cudaStream_t stream = nullptr;
   int rc = WANN_OK;
   auto body = [&]() -> int {
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (want_gptq) {
+      CU(cudaMalloc(&d_gram, static_cast<size_t>(kGramDim) * kGramDim * 4));
+      CU(cudaMalloc(&d_off, 192 * 4));
+    }
     CU(cudaMalloc(&d_sq, kN * 64));
     CU(cudaMalloc(&d_bl, kN));
     CU(cudaMalloc(&d_act, static_cast<size_t>(kN) * 64 * 192 * 4));
@@ -725,13 +834,28 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
       if (const char* zb = getenv("WANN_B200_ZERO_BUCKETS")) zero_buckets = atoi(zb);
       std::stable_sort(buckets.begin(), buckets.end(), [](const Bucket& a, const Bucket& b) { return a.mean < b.mean; });
       for (int i = 0; i < zero_buckets && i < static_cast<int>(buckets.size()); ++i) cen.c[l][buckets[i].j] = 0.f;
+      // data-aware weight rounding of the NEXT layer (hidden_layer/(l+2)): second moments of its centred inputs
+      // on the device, the factor of their inverse on the host
+      if (l < 3) ctx->gptq_u[l].clear();
+      if (want_gptq && l < 3) {
+        float off_tf[192];
+        for (int c = 0; c < 192; ++c) off_tf[c] = cen.c[l][cen_bucket(cen.pos_of[l][c])];
+        CU(cudaMemcpyAsync(d_off, off_tf, sizeof off_tf, cudaMemcpyHostToDevice, stream));
+        gram_kernel<<<dim3(27, 27), 256, 0, stream>>>(d_act, d_off, kGramPositions, d_gram);
+        std::vector<float> H(static_cast<size_t>(kGramDim) * kGramDim);
+        CU(cudaMemcpyAsync(H.data(), d_gram, H.size() * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaGetLastError());
+        if (!wann_gptq::inverse_factor(H.data(), kGramDim, 0.01, ctx->gptq_u[l]))
+          return fail(WANN_E_INVALID, "calibration: the second-moment matrix of hidden_layer/%d's inputs is not positive definite", l + 2);
+      }
     }
     *out = cen;
     return WANN_OK;
   };
   rc = body();
   if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
-  cudaFree(d_sq); cudaFree(d_bl); cudaFree(d_act); cudaFree(d_part); cudaFree(d_err);
+  cudaFree(d_sq); cudaFree(d_bl); cudaFree(d_act); cudaFree(d_part); cudaFree(d_err); cudaFree(d_gram); cudaFree(d_off);
   return rc;
 }
 
@@ -770,6 +894,7 @@ int upload_weights(wann_ctx* ctx, const wann_weights& w) {
   CU(cudaMemcpy(ctx->d_bias_plain, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   if (ctx->mode != WANN_MODE_FP32) {
     Centering cen;                       // identity: the plain layout
+    for (auto& u : ctx->gptq_u) u.clear();   // (factors of an earlier weight set)
     rc = upload_tc_image(ctx, w, cen);
     if (rc == WANN_OK && ctx->mode == WANN_MODE_FP16C) {
       rc = calibrate_centering(ctx, &cen);
@@ -1782,6 +1907,27 @@ int wann_debug_centering(wann_ctx* ctx, float offsets[96], uint8_t position_of[7
   return WANN_OK;
 }
 
+int wann_debug_effective_weights(wann_ctx* ctx, int layer, float* out) {
+  if (ctx == nullptr || out == nullptr) return fail(WANN_E_INVALID, "null argument");
+  if (layer < 2 || layer > 4) return fail(WANN_E_INVALID, "layer must be 2..4");
+  if (ctx->mode == WANN_MODE_FP32 || ctx->mode == WANN_MODE_FP32_TC) return fail(WANN_E_INVALID, "16-bit tensor-core modes only");
+  ReaderScope weights_scope(&ctx->weights_gate);
+  const std::vector<float>& we = ctx->w_eff[layer - 2];
+  if (we.empty()) return fail(WANN_E_INVALID, "no weights uploaded");
+  memcpy(out, we.data(), we.size() * sizeof(float));
+  return WANN_OK;
+}
+
+int wann_gptq_round(const float* H, int n, float* W, int rows, const uint8_t* exact, double damp) {
+  if (H == nullptr || W == nullptr || n <= 0 || rows <= 0) return fail(WANN_E_INVALID, "null argument");
+  std::vector<double> U;
+  if (!wann_gptq::inverse_factor(H, n, damp, U)) return fail(WANN_E_INVALID, "matrix not positive definite");
+  std::vector<double> Wd(W, W + static_cast<size_t>(rows) * n);
+  wann_gptq::round_rows(U.data(), n, Wd.data(), rows, exact);
+  for (size_t i = 0; i < Wd.size(); ++i) W[i] = static_cast<float>(Wd[i]);
+  return WANN_OK;
+}
+
 // CRC-32C (Castagnoli), the checksum of TF-V2 checkpoint bundles (model.index entries).
 uint32_t wann_crc32c(const void* data, uint64_t bytes, uint32_t seed) {
   static uint32_t table[8][256];
@@ -1850,6 +1996,23 @@ int wann_set_option(wann_ctx* ctx, const char* key, int64_t value) {
     return WANN_OK;
   }
   if (strcmp(key, "time_kernels") == 0) { ctx->time_kernels = value != 0; return WANN_OK; }
+  if (strcmp(key, "gptq") == 0) {
+    // centred mode: data-aware rounding of the 192->192 layers' weights (gptq.hpp) on / off; re-calibrates
+    if (ctx->mode != WANN_MODE_FP16C) return fail(WANN_E_INVALID, "gptq applies to the fp16c mode");
+    if ((value != 0) == ctx->gptq.load()) return WANN_OK;
+    DeviceGuard dev_guard(ctx->device);
+    CU(dev_guard.status);
+    ctx->weights_gate.writer_enter();
+    int rc = WANN_OK;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = fail(WANN_E_CUDA, "device synchronise: %s", cudaGetErrorString(e));
+    else {
+      ctx->gptq = value != 0;
+      rc = upload_weights(ctx, host_weights_view(ctx));
+    }
+    ctx->weights_gate.writer_exit();
+    return rc;
+  }
   if (strcmp(key, "split_layers") == 0 || strcmp(key, "lo_n") == 0 || strcmp(key, "lo_kgroups") == 0) {
     // centred mode, partial hi/lo weight split: in the conv layers of "split_layers" (bit l = conv(l+1), l = 1..3)
     // every K-block (tap, j < "lo_kgroups") streams a lo stage w - fp16(w) for the output positions [0, "lo_n")

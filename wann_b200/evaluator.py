@@ -88,6 +88,17 @@ class PolicyEvaluator(object):
         L.check(self._lib.wann_debug_centering(self._ctx, off.ctypes.data, pos.ctypes.data, kap.ctypes.data))
         return off, pos, kap
 
+    def effective_weights(self):
+        """bf16 / fp16 / fp16c modes: {layer: float32 [3,3,192,192] HWIO} for hidden_layer/2..4 -- the weights exactly as
+        the tensor-core kernel multiplies them (16-bit values; hi + lo where a lo stage covers the entry; with
+        the fp16c mode's data-aware rounding applied)."""
+        out = {}
+        for layer in (2, 3, 4):
+            w = np.zeros((3, 3, 192, 192), np.float32)
+            L.check(self._lib.wann_debug_effective_weights(self._ctx, layer, w.ctypes.data))
+            out[layer] = w
+        return out
+
     def stats(self):
         arr = (ctypes.c_uint64 * 8)()
         L.check(self._lib.wann_get_stats(self._ctx, ctypes.byref(arr)))
