@@ -24,7 +24,7 @@ for variant in [int(v) for v in os.environ.get("VARIANTS", "0").split(",")]:
   k = int((st[0] > 0).sum())
   print("layer-steps recorded", k, "(times relative to first stamp, cycles)")
   print("step L |  H0: mma_start  mma_issue  epi_wait  epi   |  H1: mma_start  mma_issue  epi_wait  epi  | lag(H1-H0 mma_start)")
-  for i in range(5, min(k, 20)):
+  for i in range(5 if k > 10 else 0, min(k, 20)):
       a = st[0:4, i]; b = st[4:8, i]
       print("%3d  %d | %9d %9d %8d %6d | %9d %9d %8d %6d | %6d" % (
           i, i % 5, a[0] - t0, a[1] - a[0], a[2] - a[1], a[3] - a[2],

@@ -99,9 +99,12 @@ constexpr int kThreads = 32 * (kFirstEpiWarp + kNumEpiWarps + kNumTailWarps);   
 constexpr int kBiasFloats = 4 * kC + 4;
 
 // shared memory carve-up (bytes from the 128-aligned base)
-constexpr int kOffA = 0;
-constexpr int kOffB = (kOffA + kABytes + 15) / 16 * 16;    // SWIZZLE_NONE operands and bulk copies need 16-byte alignment only
-constexpr int kOffBias = kOffB + kStages * kStageBytes;
+// (the weight ring first: its 128-byte core matrices then sit on 128-byte lines; the activation cells are read at
+// tap offsets anyway and need 16-byte alignment only)
+constexpr int kOffB = 0;
+constexpr int kOffA = kOffB + kStages * kStageBytes;
+constexpr int kOffBias = kOffA + kABytes;
+static_assert(kOffA % 128 == 0 && kOffBias % 16 == 0, "shared memory carve-up alignment");
 constexpr int kOffBar = kOffBias + kBiasFloats * 4;
 constexpr int kNumBars = 3 * kStages + 8;
 constexpr int kOffTmemSlot = kOffBar + kNumBars * 8;
@@ -169,6 +172,7 @@ struct TcParams {
   // a' = a - cen[l][(q / 64) * 8 + q % 8]; the halo holds -cen (so that a' + cen == 0 there) and the next
   // layer's bias absorbs sum(w * cen).  kappa[t] = sum_k w5[t][k] * cen[3][..] corrects conv5's tap products.
   float cen[4][kCenBuckets] = {};
+  uint32_t cen_neg16[4][kGroups][4] = {};   // the same offsets, negated and packed as fp16 pairs (what the epilogue needs)
   float kappa[9] = {};
   const uint8_t* dbg_unperm = nullptr;   // [4][192] channel position -> TF channel (debug dump of a permuted net)
 };
@@ -581,20 +585,20 @@ conv_stack_tc_kernel(const TcParams p) {
             // channel % 8); bias_s already holds b' - c.
             // -c as packed 16-bit pairs: rounding is monotonic and -c is exact in the operand format, so
             // fp16(max(t, -c)) == max(fp16(t), -c): one packed max per PAIR after the conversion
-            auto packed_neg_offsets = [&](int g) {
-              const float* c = p.cen[layer] + 8 * g;
-              return make_uint4(ptx::pack_sat<kF16>(-c[0], -c[1]), ptx::pack_sat<kF16>(-c[2], -c[3]),
-                                ptx::pack_sat<kF16>(-c[4], -c[5]), ptx::pack_sat<kF16>(-c[6], -c[7]));
-            };
+            uint4 hneg[kGroups];            // -c of the three chunk groups, packed (host-made: TcParams::cen_neg16)
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g)
+              hneg[g] = kCen ? make_uint4(p.cen_neg16[layer][g][0], p.cen_neg16[layer][g][1], p.cen_neg16[layer][g][2],
+                                          p.cen_neg16[layer][g][3])
+                             : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
             for (int ch = 0; ch < 3; ++ch) {
               const int qc0 = chalf * 12 + ch * 4;              // this pass writes chunks qc0..qc0+3: one group
               const int grp = qc0 / kGroupChunks;
               const uint32_t cell_q0 = cell0 + qc0 * kChunkStride + grp * kGroupGap;
-              uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+              const uint4 hv = grp == 0 ? hneg[0] : (grp == 1 ? hneg[1] : hneg[2]);
               float nc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               if (kCen) {
-                hv = packed_neg_offsets(grp);
                 if (dbg != nullptr) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) nc[j] = -p.cen[layer][8 * grp + j];
@@ -647,7 +651,7 @@ conv_stack_tc_kernel(const TcParams p) {
               const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
               uint4 hz[kGroups];
 #pragma unroll
-              for (int g = 0; g < kGroups; ++g) hz[g] = (layer < 3) ? packed_neg_offsets(g) : zero4;
+              for (int g = 0; g < kGroups; ++g) hz[g] = (layer < 3) ? hneg[g] : zero4;
               const uint32_t tile0 = a_base + h * kATileStride;
 #pragma unroll
               for (int i = 0; i < 4; ++i)

@@ -623,6 +623,13 @@ void fill_tc_params(const wann_ctx* ctx, TcParams& p) {
     p.lo_kgroups = ctx->img_lo_kgroups;
     static_assert(sizeof p.cen == sizeof ctx->cen.c, "centring tables");
     memcpy(p.cen, ctx->cen.c, sizeof p.cen);
+    for (int l = 0; l < 4; ++l)
+      for (int g = 0; g < kGroups; ++g)
+        for (int i = 0; i < 4; ++i) {
+          const float c0 = ctx->cen.c[l][8 * g + 2 * i], c1 = ctx->cen.c[l][8 * g + 2 * i + 1];
+          const uint32_t lo = c0 != 0.f ? f32_to_f16(-c0) : 0u, hi = c1 != 0.f ? f32_to_f16(-c1) : 0u;   // +0, not -0
+          p.cen_neg16[l][g][i] = lo | (hi << 16);
+        }
     memcpy(p.kappa, ctx->kappa, sizeof p.kappa);
     p.dbg_unperm = ctx->d_unperm;
   }
