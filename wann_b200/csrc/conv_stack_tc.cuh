@@ -597,15 +597,22 @@ conv_stack_tc_kernel(const TcParams p) {
               const int grp = qc0 / kGroupChunks;
               const uint32_t cell_q0 = cell0 + qc0 * kChunkStride + grp * kGroupGap;
               const uint4 hv = grp == 0 ? hneg[0] : (grp == 1 ? hneg[1] : hneg[2]);
-              float nc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              if (kCen) {
-                if (dbg != nullptr) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) nc[j] = -p.cen[layer][8 * grp + j];
-                }
-              }
               uint32_t v[32];
               ptx::tmem_ld_x32(taddr + chalf * 96 + ch * 32, v);
+              if (kCen && ch == 0) {
+                // (under the latency of the first accumulator load) the tile's halo must read as "activation 0" for
+                // the NEXT layer: -c of this layer's output (conv4's output: zeros -- conv5 uses the centre tap
+                // only, its stencil scratch and the next supertile's conv1 need a zero halo)
+                const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t tile0 = a_base + h * kATileStride;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (i < 3 || halo_off[3] != 0xFFFFFFFFu) {
+                    const uint32_t g = halo_off[i] & 3u;
+                    ptx::st_shared_v4(tile0 + (halo_off[i] & ~15u),
+                                      layer < 3 ? (g == 0 ? hneg[0] : (g == 1 ? hneg[1] : hneg[2])) : zero4);
+                  }
+              }
               ptx::tmem_ld_wait();
 #pragma unroll
               for (int kc = 0; kc < 4; ++kc) {
@@ -632,33 +639,21 @@ conv_stack_tc_kernel(const TcParams p) {
                                              __uint_as_float(v[kc * 8 + 7]) + b1.w);
                 }
                 ptx::st_shared_v4(cell_q0 + kc * kChunkStride, o);
-                if (dbg != nullptr) {
-                  const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-                  const int q0 = chalf * 96 + ch * 32 + kc * 8;     // channel position of w[0]'s low half
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const int q = q0 + i;
-                    const int c_tf = p.dbg_unperm != nullptr ? p.dbg_unperm[layer * kC + q] : q;
-                    dbg[c_tf] = ptx::unpack16<kF16>((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu) - nc[i];
-                  }
-                }
               }
             }
-            if (kCen) {
-              // the tile's halo must read as "activation 0" for the NEXT layer: -c of this layer's output
-              // (conv4's output: zeros -- conv5 uses the centre tap only, its stencil scratch and the next
-              // supertile's conv1 need a zero halo)
-              const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-              uint4 hz[kGroups];
-#pragma unroll
-              for (int g = 0; g < kGroups; ++g) hz[g] = (layer < 3) ? hneg[g] : zero4;
-              const uint32_t tile0 = a_base + h * kATileStride;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (i < 3 || halo_off[3] != 0xFFFFFFFFu) {
-                  const uint32_t g = halo_off[i] & 3u;
-                  ptx::st_shared_v4(tile0 + (halo_off[i] & ~15u), g == 0 ? hz[0] : (g == 1 ? hz[1] : hz[2]));
+            if (dbg != nullptr) {
+              // debug / calibration dump (kept OUT of the loop above: a branch per store would split it into
+              // basic blocks and serialise the bias loads): read this thread's 12 cells back, TF channel order
+              for (int qc = chalf * 12; qc < chalf * 12 + 12; ++qc) {
+                const uint4 o = ptx::ld_shared_v4(cell0 + chunk_off(qc));
+                const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+                for (int i = 0; i < 8; ++i) {
+                  const int q = qc * 8 + i;                        // channel position
+                  const int c_tf = p.dbg_unperm != nullptr ? p.dbg_unperm[layer * kC + q] : q;
+                  const float c = kCen ? p.cen[layer][8 * (qc / kGroupChunks) + i] : 0.f;
+                  dbg[c_tf] = ptx::unpack16<kF16>((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu) + c;
                 }
+              }
             }
           } else if (chalf == 0) {
             // conv5: column t of the accumulator is P[pixel][tap t]; out = 9-point stencil sum.
