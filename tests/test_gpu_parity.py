@@ -205,6 +205,26 @@ def test_centred_fp16_mode_matches_the_emulation_of_its_roundings(split, lo_n, l
                 assert np.array_equal(ev.eval_probs(sq[:300], bl[:300]), ev0.eval_probs(sq[:300], bl[:300]))
 
 
+def test_centred_mode_calibrates_on_degenerate_weights(weights, suite):
+    """A net whose hidden layers are dead (all-zero conv weights: every activation 0, the calibration's second-moment
+    matrices singular) still creates, calibrates and evaluates in the fp16c mode -- the affected layers fall back
+    to round-to-nearest -- and gives the fp32 mode's answer (softmax of the FC bias row)."""
+    import wann_b200
+    sq, bl = suite
+    w = {k: (np.zeros_like(v) if k.startswith("hidden_layer") else v.copy()) for k, v in weights.items()}
+    with wann_b200.PolicyEvaluator(w, mode="fp32") as ev32, wann_b200.PolicyEvaluator(w, mode="fp16c") as ev:
+        p32, p = ev32.eval_probs(sq[:64], bl[:64]), ev.eval_probs(sq[:64], bl[:64])
+        assert np.isfinite(p).all() and np.abs(p - p32).max() < 1e-6
+        off, pos, _ = ev.centering()
+        assert (off == 0).all()
+    w2 = {k: v.copy() for k, v in weights.items()}
+    w2["hidden_layer/3/weights"][:] = 0                    # dead from hidden_layer/3 on: its inputs are alive
+    w2["hidden_layer/3/bias"][:] = 0
+    with wann_b200.PolicyEvaluator(w2, mode="fp32") as ev32, wann_b200.PolicyEvaluator(w2, mode="fp16c") as ev:
+        p32, p = ev32.eval_probs(sq[:64], bl[:64]), ev.eval_probs(sq[:64], bl[:64])
+        assert np.isfinite(p).all() and nerr(p, p32) < 1e-3
+
+
 def test_centred_fp16_mode_meets_the_north_star_gates_on_100k_positions(weights):
     """north_star: logits and probabilities within 1e-3 relative of the fp32 graph, top-1 >= 99.9 % on a
     fixed suite of random legal positions -- measured on 100,000 positions against the fp32 mode (itself

@@ -853,8 +853,9 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
         CU(cudaMemcpyAsync(H.data(), d_gram, H.size() * 4, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         CU(cudaGetLastError());
-        if (!wann_gptq::inverse_factor(H.data(), kGramDim, 0.01, ctx->gptq_u[l]))
-          return fail(WANN_E_INVALID, "calibration: the second-moment matrix of hidden_layer/%d's inputs is not positive definite", l + 2);
+        // (a degenerate H -- e.g. a layer whose inputs are all zero -- leaves the factor empty: that layer's
+        // weights are then rounded to nearest, which is always correct)
+        if (!wann_gptq::inverse_factor(H.data(), kGramDim, 0.01, ctx->gptq_u[l])) ctx->gptq_u[l].clear();
       }
     }
     *out = cen;
