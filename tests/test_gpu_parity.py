@@ -121,7 +121,10 @@ def test_tensor_core_modes(mode, tol_emu, tol_fp32, ev_bf16, ev_fp16, suite, ref
     n = 256                                                    # BASELINE config 3 size
     lg_e, pr_e, acts_e = O.forward_16bit_emulated(ref1k["planes"][:n], weights, mode, return_all=True)
     a1 = ev.debug_activations(sq[:n], bl[:n], 1)
-    assert np.array_equal(a1, acts_e[0])                       # conv1 of 0/1 planes is exact
+    # conv1 of 0/1 planes: the products are exact; the bias enters the fp32 accumulator FIRST (the layer's opening
+    # MMA), the emulation adds it last, so a stored value may differ by one ulp of the operand format -- rarely
+    ulp = np.spacing(np.abs(acts_e[0]).astype(np.float16)).astype(np.float32) * (8 if mode == "bf16" else 1)
+    assert (np.abs(a1 - acts_e[0]) <= ulp).all() and (a1 != acts_e[0]).mean() < 1e-3
     for layer in (2, 4, 5):
         a = ev.debug_activations(sq[:n], bl[:n], layer)
         assert nerr(a, acts_e[layer - 1]) < tol_emu            # 1 ulp rounding flips at most

@@ -82,6 +82,7 @@ constexpr int kBoardsPerPair = 8;
 
 constexpr int kStageBytes = 96 * 64 * 2;      // 12288 B: half of [192 x 64] 16-bit
 constexpr int kStageBytesL5 = 16 * 64 * 2;    // 2048 B: half of [32 x 64] 16-bit (rows 0-15 = taps, 16-31 = their lo parts)
+constexpr int kStageBytesBias = 96 * 16 * 2;  // 3072 B: the bias stage of a layer, half of [192 x 16] (k = 0..2: the bias in three 16-bit parts)
 constexpr int kStages = 8;
 constexpr int kLboB = 96 / 8 * 128;           // 1536 B between K-chunks of a stage
 constexpr int kLboB5 = 16 / 8 * 128;          // 256 B
@@ -321,8 +322,16 @@ conv_stack_tc_kernel(const TcParams p) {
   // zero the activation tiles (the halo cells stay zero for the whole kernel)
   for (int i = tid; i < kABytes / 16; i += kThreads)
     ptx::st_shared_v4(a_base + 16u * i, make_uint4(0u, 0u, 0u, 0u));
-  for (int i = tid; i < kBiasFloats; i += kThreads)
-    reinterpret_cast<float*>(smem_gen + kOffBias)[i] = (i < 4 * kC + 1) ? p.bias[i] : 0.f;
+  // bias region: the first 128 bytes are the ONES tile -- one 8 x 16-byte core matrix whose rows are
+  // {1, 1, 1, 0, 0, 0, 0, 0}: operand A of the bias MMA that opens every layer conv1..4 (descriptor strides 0: all
+  // 128 rows and both K chunks read this one matrix; the bias stage holds the bias in three parts at k = 0..2 and
+  // zeros at k = 8..10).  The conv1..4 biases themselves are not needed here any more; b5 is (bias_s[4 * kC]).
+  for (int i = tid; i < kBiasFloats; i += kThreads) {
+    constexpr uint32_t one = kF16 ? 0x3C00u : 0x3F80u;
+    uint32_t bits = (i < 4 * kC + 1) ? __float_as_uint(p.bias[i]) : 0u;
+    if (i < 32) bits = (i % 4 == 0) ? (one | (one << 16)) : ((i % 4 == 1) ? one : 0u);
+    reinterpret_cast<uint32_t*>(smem_gen + kOffBias)[i] = bits;
+  }
   ptx::fence_proxy_async_smem();
   if (warp == 0) {
     ptx::tmem_alloc<2>(slot_addr, 512);
@@ -360,8 +369,10 @@ conv_stack_tc_kernel(const TcParams p) {
       const uint32_t bps = lo_blocks_per_stage(p.lo_n);
       for (long long st = pair; st < total_st && ok; st += npairs) {
         off = 0;
+        stage(kStageBytesBias);
         for (int kb = 0; kb < kKbL1; ++kb) stage(kStageBytes);
         for (int layer = 1; layer <= 3; ++layer) {
+          stage(kStageBytesBias);
           const int lo_j = ((p.split_mask >> layer) & 1) ? p.lo_kgroups : 0;
           uint32_t pend = 0;
           for (int tap = 0; tap < 9; ++tap)
@@ -404,6 +415,8 @@ conv_stack_tc_kernel(const TcParams p) {
       const uint32_t a_lo = ((a_base + h * kATileStride) >> 4) | ((kChunkStride >> 4) << 16);
       const uint32_t b_lo_mid = (b_base >> 4) | ((kLboB >> 4) << 16);
       const uint32_t b_lo_l5 = (b_base >> 4) | ((kLboB5 >> 4) << 16);
+      const uint32_t ones_lo = (smem_base + kOffBias) >> 4;       // LBO = 0
+      const uint32_t ones_hi = 1u << 14;                          // SBO = 0
       // lo stages: [lo_n / 2 rows x 64 k] per CTA, LBO = 8 * lo_n bytes, K-step = 2 LBO = lo_n sixteen-byte units
       const uint32_t lo_n = static_cast<uint32_t>(p.lo_n);
       const uint32_t b_lo_lo = (b_base >> 4) | (((8u * lo_n) >> 4) << 16);
@@ -449,6 +462,12 @@ conv_stack_tc_kernel(const TcParams p) {
             ptx::umma_bf16_2cta(tmem_d, a_lo + ao, a_hi, blo + ks * (B_KS16), b_hi, (IDESC), acc); \
         }                                                                                         \
       WANN_STAGE_END
+      // the layer's first MMA: accumulator = ones x bias stage (no accumulate), i.e. the bias in every row
+#define WANN_BIAS_BLOCK                                                                           \
+      WANN_STAGE_BEGIN                                                                            \
+        if (issuer && !skip_mma)                                                                  \
+          ptx::umma_bf16_2cta(tmem_d, ones_lo, ones_hi, b_lo_mid + s * kStage16, b_hi, kIdescN192, 0u); \
+      WANN_STAGE_END
       for (long long st = pair; st < total_st && ok; st += npairs) {
         // ---- conv1: 9 taps x K=16 (4 real planes); K-block kb holds taps 4kb..4kb+3
         do {
@@ -456,7 +475,8 @@ conv_stack_tc_kernel(const TcParams p) {
           ptx::tc_fence_after();
           if (prof && lstep < kProfSteps && issuer) prof[lstep] = clock64();
           constexpr uint32_t kTap16[12] = {0, 1, 2, 18, 19, 20, 36, 37, 38, 0, 0, 0};
-          WANN_KBLOCK(4, kTap16[ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, true)
+          WANN_BIAS_BLOCK
+          WANN_KBLOCK(4, kTap16[ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
           WANN_KBLOCK(4, kTap16[4 + ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
           WANN_KBLOCK(1, kTap16[8 + ks], b_lo_mid, (2 * kLboB) >> 4, kIdescN192, false)
           if (issuer) ptx::umma_commit<2>(acc_bar, 3);
@@ -468,7 +488,8 @@ conv_stack_tc_kernel(const TcParams p) {
           if (!wait_bar(ready_bar, lstep & 1u, true, p.err, 200 + 10 * h + layer)) { ok = false; break; }
           ptx::tc_fence_after();
           if (prof && lstep < kProfSteps && issuer) prof[lstep] = clock64();
-          uint32_t first = 1;
+          WANN_BIAS_BLOCK
+          const uint32_t first = 0;
           // hi/lo split: the blocks (tap, j < lo_j) also have lo weights; they arrive lo_bps blocks per stage,
           // right after the hi stage of the last block, and run with N = lo_n against the same A descriptors
           const uint32_t lo_j = ((p.split_mask >> layer) & 1) ? static_cast<uint32_t>(p.lo_kgroups) : 0u;
@@ -479,7 +500,6 @@ conv_stack_tc_kernel(const TcParams p) {
               for (uint32_t j = 0; j < 3; ++j) {
                 const uint32_t ao0 = j * kGroup16 + tap16;
                 WANN_KBLOCK(4, ao0 + ks * 2 * kChunk16, b_lo_mid, (2 * kLboB) >> 4, kIdescN192, first)
-                first = 0;
                 if (j < lo_j && (++pend == lo_bps || (ty == 2 && tx == 2 && j == lo_j - 1))) {
                   // one lo stage = the blocks first_blk .. first_blk + pend - 1 (block index = tap * lo_j + j)
                   WANN_STAGE_BEGIN
@@ -521,6 +541,7 @@ conv_stack_tc_kernel(const TcParams p) {
         } while (false);
       }
 #undef WANN_KBLOCK
+#undef WANN_BIAS_BLOCK
 #undef WANN_STAGE_BEGIN
 #undef WANN_STAGE_END
     }
@@ -578,7 +599,6 @@ conv_stack_tc_kernel(const TcParams p) {
           if (layer < 4) {
             if (layer == 3 && chalf == 0 && st + npairs < total_st)   // prefetch next supertile's input
               next_in[h] = load_input_cell<kF16>(p, n_tot, board_of(st + npairs, h), y, x);
-            const float* bs = bias_s + layer * kC + chalf * 96;
             float* dbg = (p.dbg != nullptr && p.dbg_layer == layer + 1 && board < n_tot)
                              ? p.dbg + (board * 64 + y * 8 + x) * kC : nullptr;
             // centred mode: store a' = max(acc + (b' - c), -c) = relu(acc + b') - c   (c by chunk group and
@@ -616,27 +636,25 @@ conv_stack_tc_kernel(const TcParams p) {
               ptx::tmem_ld_wait();
 #pragma unroll
               for (int kc = 0; kc < 4; ++kc) {
-                const float4 b0 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8);
-                const float4 b1 = *reinterpret_cast<const float4*>(bs + ch * 32 + kc * 8 + 4);
                 uint4 o;
                 if (kCen) {
-                  o.x = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 0]) + b0.x,
-                                                               __uint_as_float(v[kc * 8 + 1]) + b0.y), hv.x);
-                  o.y = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 2]) + b0.z,
-                                                               __uint_as_float(v[kc * 8 + 3]) + b0.w), hv.y);
-                  o.z = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 4]) + b1.x,
-                                                               __uint_as_float(v[kc * 8 + 5]) + b1.y), hv.z);
-                  o.w = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
-                                                               __uint_as_float(v[kc * 8 + 7]) + b1.w), hv.w);
+                  o.x = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 0]),
+                                                               __uint_as_float(v[kc * 8 + 1])), hv.x);
+                  o.y = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 2]),
+                                                               __uint_as_float(v[kc * 8 + 3])), hv.y);
+                  o.z = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 4]),
+                                                               __uint_as_float(v[kc * 8 + 5])), hv.z);
+                  o.w = ptx::max16x2<kF16>(ptx::pack_sat<kF16>(__uint_as_float(v[kc * 8 + 6]),
+                                                               __uint_as_float(v[kc * 8 + 7])), hv.w);
                 } else {
-                  o.x = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 0]) + b0.x,
-                                             __uint_as_float(v[kc * 8 + 1]) + b0.y);
-                  o.y = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 2]) + b0.z,
-                                             __uint_as_float(v[kc * 8 + 3]) + b0.w);
-                  o.z = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 4]) + b1.x,
-                                             __uint_as_float(v[kc * 8 + 5]) + b1.y);
-                  o.w = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 6]) + b1.z,
-                                             __uint_as_float(v[kc * 8 + 7]) + b1.w);
+                  o.x = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 0]),
+                                             __uint_as_float(v[kc * 8 + 1]));
+                  o.y = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 2]),
+                                             __uint_as_float(v[kc * 8 + 3]));
+                  o.z = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 4]),
+                                             __uint_as_float(v[kc * 8 + 5]));
+                  o.w = ptx::pack_relu<kF16>(__uint_as_float(v[kc * 8 + 6]),
+                                             __uint_as_float(v[kc * 8 + 7]));
                 }
                 ptx::st_shared_v4(cell_q0 + kc * kChunkStride, o);
               }

@@ -225,7 +225,7 @@ struct wann_ctx {
   std::atomic<int> split_mask{0};  // option "split_layers": conv layers (bits 1..3) whose weights stream as hi + lo
   std::atomic<int> lo_n{64};       // option "lo_n": the lo stages cover output positions [0, lo_n) ...
   std::atomic<int> lo_kgroups{1};  // option "lo_kgroups": ... and the first lo_kgroups 64-channel input groups of every tap
-  int img_lo_n = 192, img_lo_kgroups = 3;   // what the uploaded stage image was built with
+  int img_lo_n = 192, img_lo_kgroups = 3, img_split_mask = 0;   // what the uploaded stage image was built with
   // data-aware weight rounding (gptq.hpp; option "gptq", fp16c mode, default on): per 192->192 layer the
   // factor U of the inverse second-moment matrix of its calibration inputs (kept: re-rounding after a change
   // of the split options needs no new calibration), and the weights the kernel actually multiplies
@@ -276,20 +276,27 @@ struct ImageOpts {
   int lo_n = 192;
   int lo_kgroups = 3;
   const Centering* cen = nullptr;
+  // conv_stack_tc_kernel only: every layer conv1..4 starts with a BIAS stage [96 rows x 16 k]: k = 0..2 hold the
+  // bias of the output position as three 16-bit parts (hi + mid + lo); the kernel multiplies it with a tile of
+  // ones as the layer's first MMA (accumulate = 0), so the epilogue has no bias to load or add.
+  // [4][192] by output position (centred mode: b' - c), or null = no bias stages
+  const float* bias = nullptr;
 };
+constexpr int kBiasStageBytes = 96 * 16 * 2;
 
 int split_layer_count(int split_mask) {
   int n = 0;
   for (int l = 1; l <= 3; ++l) n += (split_mask >> l) & 1;
   return n;
 }
-int stages_per_supertile(int split_mask, int lo_n, int lo_kgroups) {
+int stages_per_supertile(int split_mask, int lo_n, int lo_kgroups, bool bias_stages) {
   const int bps = static_cast<int>(lo_blocks_per_stage(lo_n));        // (tap, j) lo blocks per stage
-  return kKbPerSupertile + split_layer_count(split_mask) * ((9 * lo_kgroups + bps - 1) / bps);
+  return kKbPerSupertile + split_layer_count(split_mask) * ((9 * lo_kgroups + bps - 1) / bps) + (bias_stages ? 4 : 0);
 }
-size_t image_bytes_per_rank(int split_mask, int lo_n, int lo_kgroups) {
+size_t image_bytes_per_rank(int split_mask, int lo_n, int lo_kgroups, bool bias_stages) {
   return static_cast<size_t>(kKbPerSupertile - kKbL5) * kStageBytes + kKbL5 * kStageBytesL5 +
-         static_cast<size_t>(split_layer_count(split_mask)) * 9 * lo_kgroups * 64 * lo_n;
+         static_cast<size_t>(split_layer_count(split_mask)) * 9 * lo_kgroups * 64 * lo_n +
+         (bias_stages ? 4 * kBiasStageBytes : 0);
 }
 
 // Build the shared-memory stage images of operand B (see conv_stack_tc.cuh).
@@ -297,7 +304,7 @@ size_t image_bytes_per_rank(int split_mask, int lo_n, int lo_kgroups) {
 void build_weight_image(const wann_weights& w, const ImageOpts& o, std::vector<uint8_t>& img) {
   static const Centering identity;
   const Centering& cen = o.cen ? *o.cen : identity;
-  const size_t per_rank = image_bytes_per_rank(o.split_mask, o.lo_n, o.lo_kgroups);
+  const size_t per_rank = image_bytes_per_rank(o.split_mask, o.lo_n, o.lo_kgroups, o.bias != nullptr);
   img.assign(2 * per_rank, 0);
   for (int rank = 0; rank < 2; ++rank) {
     uint8_t* base = img.data() + static_cast<size_t>(rank) * per_rank;
@@ -306,7 +313,23 @@ void build_weight_image(const wann_weights& w, const ImageOpts& o, std::vector<u
       const uint16_t h = o.f16 ? f32_to_f16(v) : f32_to_bf16(v);
       memcpy(stage + (k / 8) * lbo + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2, &h, 2);
     };
+    auto bias_stage = [&](int layer) {                // three 16-bit parts of the bias at k = 0, 1, 2
+      if (o.bias == nullptr) return;
+      for (int nl = 0; nl < 96; ++nl) {
+        float rest = o.bias[layer * 192 + rank * 96 + nl];
+        for (int k = 0; k < 3; ++k) {
+          put(base + off, kLboB, nl, k, rest);
+          uint16_t h = o.f16 ? f32_to_f16(rest) : f32_to_bf16(rest);
+          float part;
+          if (o.f16) part = f16_value(rest);
+          else { const uint32_t u = static_cast<uint32_t>(h) << 16; memcpy(&part, &u, 4); }
+          rest -= part;
+        }
+      }
+      off += kBiasStageBytes;
+    };
     // conv1: k-block kb holds taps 4kb..4kb+3, 16 k per tap (4 real input planes)
+    bias_stage(0);
     for (int kb = 0; kb < kKbL1; ++kb, off += kStageBytes)
       for (int ks = 0; ks < 4; ++ks) {
         const int tap = kb * 4 + ks;
@@ -321,6 +344,7 @@ void build_weight_image(const wann_weights& w, const ImageOpts& o, std::vector<u
       }
     // conv2..4: k-block kb = tap*3 + j holds input channel positions 64j..64j+63 of tap
     for (int layer = 1; layer <= 3; ++layer) {
+      bias_stage(layer);
       const int lo_j = ((o.split_mask >> layer) & 1) ? o.lo_kgroups : 0;
       const int bps = static_cast<int>(lo_blocks_per_stage(o.lo_n));
       int pend_tap[16], pend_j[16], pend = 0;
@@ -556,25 +580,6 @@ int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) 
         }
     }
   }
-  if (ctx->mode == WANN_MODE_FP32_TC) {
-    build_weight_image_split(w, img);
-  } else {
-    ImageOpts o;
-    o.f16 = ctx->mode != WANN_MODE_BF16;
-    o.exact15 = centred;
-    o.split_mask = split_mask;
-    o.lo_n = lo_n;
-    o.lo_kgroups = lo_kgroups;
-    o.cen = &cen;
-    build_weight_image(wi, o, img);
-  }
-  if (ctx->d_wimg != nullptr && ctx->wimg_capacity < img.size()) { cudaFree(ctx->d_wimg); ctx->d_wimg = nullptr; }
-  if (ctx->d_wimg == nullptr) { CU(cudaMalloc(&ctx->d_wimg, img.size())); ctx->wimg_capacity = img.size(); }
-  CU(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
-  ctx->stages_per_st = (ctx->mode == WANN_MODE_FP32_TC) ? kKbPerSupertile : stages_per_supertile(split_mask, lo_n, lo_kgroups);
-  ctx->img_stride = static_cast<long long>(img.size() / 2);
-  ctx->img_lo_n = lo_n;
-  ctx->img_lo_kgroups = lo_kgroups;
   // bias table: conv1..4 by channel POSITION, then b5.  Centred: b'[n] - c, where
   // b'[n] = b[n] + sum_{tap,k} W[tap][k][n] * c_prev[k] (true fp32 weights, summed in double) gives back
   // what subtracting c_prev from the layer's input took away (halo cells hold -c_prev, so the sum runs
@@ -592,6 +597,27 @@ int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) 
       bias[l * 192 + q] = static_cast<float>(b - (centred ? cen.c[l][cen_bucket(q)] : 0.f));
     }
   bias[4 * 192] = w.conv_b[4][0];
+  if (ctx->mode == WANN_MODE_FP32_TC) {
+    build_weight_image_split(w, img);
+  } else {
+    ImageOpts o;
+    o.bias = bias.data();
+    o.f16 = ctx->mode != WANN_MODE_BF16;
+    o.exact15 = centred;
+    o.split_mask = split_mask;
+    o.lo_n = lo_n;
+    o.lo_kgroups = lo_kgroups;
+    o.cen = &cen;
+    build_weight_image(wi, o, img);
+  }
+  if (ctx->d_wimg != nullptr && ctx->wimg_capacity < img.size()) { cudaFree(ctx->d_wimg); ctx->d_wimg = nullptr; }
+  if (ctx->d_wimg == nullptr) { CU(cudaMalloc(&ctx->d_wimg, img.size())); ctx->wimg_capacity = img.size(); }
+  CU(cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+  ctx->stages_per_st = (ctx->mode == WANN_MODE_FP32_TC) ? kKbPerSupertile : stages_per_supertile(split_mask, lo_n, lo_kgroups, true);
+  ctx->img_split_mask = split_mask;
+  ctx->img_stride = static_cast<long long>(img.size() / 2);
+  ctx->img_lo_n = lo_n;
+  ctx->img_lo_kgroups = lo_kgroups;
   for (int t = 0; t < 9; ++t) {
     double kp = 0;
     if (centred)
@@ -618,7 +644,7 @@ void fill_tc_params(const wann_ctx* ctx, TcParams& p) {
   p.stages_per_st = ctx->stages_per_st;
   p.img_stride = ctx->img_stride;
   if (ctx->mode == WANN_MODE_FP16C) {
-    p.split_mask = (ctx->stages_per_st == kKbPerSupertile) ? 0 : ctx->split_mask.load();
+    p.split_mask = ctx->img_split_mask;
     p.lo_n = ctx->img_lo_n;
     p.lo_kgroups = ctx->img_lo_kgroups;
     static_assert(sizeof p.cen == sizeof ctx->cen.c, "centring tables");
