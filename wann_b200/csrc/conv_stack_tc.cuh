@@ -185,8 +185,7 @@ __device__ __forceinline__ bool wait_bar(uint32_t bar, uint32_t parity, bool clu
     return true;
   long long t0 = clock64();
   while (true) {
-    if (cluster_scope ? ptx::mbar_try_wait_cluster(bar, parity) : ptx::mbar_try_wait(bar, parity))
-      return true;
+    if (ptx::mbar_try_wait_parked(bar, parity)) return true;
     if (clock64() - t0 > kWatchdogCycles) {
       if (atomicCAS(err, 0, code) == 0) {
         err[1] = static_cast<int>(blockIdx.x);

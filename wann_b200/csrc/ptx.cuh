@@ -71,6 +71,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// the same with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint, in ns,
+// expires) instead of returning at once -- a waiting warp then issues one instruction per wake-up, not a polling loop
+__device__ __forceinline__ uint32_t mbar_try_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok;
+}
 // cluster-scope acquire: for barriers another CTA arrives on
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
