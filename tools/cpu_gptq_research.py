@@ -1,6 +1,11 @@
+#!/usr/bin/env python
+"""Offline study of data-aware (GPTQ-style) rounding of the 192->192 layers' weights to fp16 (CPU, torch float64 with
+the centred mode's roundings): second moments of the calibration inputs, sequential rounding with error compensation,
+end-to-end error on HELD-OUT positions; variants (order, damping, calibration size, fp32 H, zero buckets).
+The numbers it printed are what the kernel later measured."""
 import os, sys, time
 import numpy as np, torch
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from wann_b200 import weights as W, synthetic
 from oracle import oracle as O

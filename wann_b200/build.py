@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libwann_b200.so")
 SOURCES = ["wann_api.cu"]
-DEPS = ["wann_api.cu", "conv_stack_tc.cuh", "conv_stack_split.cuh", "aux_kernels.cuh", "ptx.cuh", "array_tree.hpp",
+DEPS = ["wann_api.cu", "conv_stack_tc.cuh", "conv_stack_split.cuh", "aux_kernels.cuh", "ptx.cuh", "array_tree.hpp", "gptq.hpp",
         os.path.join("..", "..", "include", "wann_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-lgomp"]

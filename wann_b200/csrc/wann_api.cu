@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -230,7 +231,7 @@ struct wann_ctx {
   // factor U of the inverse second-moment matrix of its calibration inputs (kept: re-rounding after a change
   // of the split options needs no new calibration), and the weights the kernel actually multiplies
   std::atomic<bool> gptq{true};
-  std::vector<double> gptq_u[3];
+  std::shared_ptr<const std::vector<double>> gptq_u[3];   // (shared with the process-wide cache, wann_gptq::cached_inverse_factor)
   std::vector<float> w_eff[3];     // [9][192][192] HWIO: effective weights of hidden_layer/2..4 (wann_debug_effective_weights)
   int stages_per_st = wann::kKbPerSupertile;
   long long img_stride = wann::kImgBytesPerRank;
@@ -551,7 +552,7 @@ int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) 
     auto covered = [&](int ci, int co) {
       return lo_layer && cen.pos_of[l][ci] < 64 * lo_kgroups && cen.pos_of[l + 1][co] < lo_n;
     };
-    if (centred && ctx->gptq.load() && !ctx->gptq_u[l].empty()) {
+    if (centred && ctx->gptq.load() && ctx->gptq_u[l] != nullptr) {
       constexpr int K = 9 * 192;
       std::vector<double> W(static_cast<size_t>(192) * K);
       std::vector<uint8_t> exact(static_cast<size_t>(192) * K, 0);
@@ -560,7 +561,7 @@ int upload_tc_image(wann_ctx* ctx, const wann_weights& w, const Centering& cen) 
           W[static_cast<size_t>(co) * K + k] = src[static_cast<size_t>(k) * 192 + co];
           exact[static_cast<size_t>(co) * K + k] = covered(k % 192, co);
         }
-      wann_gptq::round_rows(ctx->gptq_u[l].data(), K, W.data(), 192, exact.data());
+      wann_gptq::round_rows(ctx->gptq_u[l]->data(), K, W.data(), 192, exact.data());
       for (int k = 0; k < K; ++k)
         for (int co = 0; co < 192; ++co) we[static_cast<size_t>(k) * 192 + co] = static_cast<float>(W[static_cast<size_t>(co) * K + k]);
       wi.conv_w[l + 1] = we.data();
@@ -869,7 +870,7 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
       for (int i = 0; i < zero_buckets && i < static_cast<int>(buckets.size()); ++i) cen.c[l][buckets[i].j] = 0.f;
       // data-aware weight rounding of the NEXT layer (hidden_layer/(l+2)): second moments of its centred inputs
       // on the device, the factor of their inverse on the host
-      if (l < 3) ctx->gptq_u[l].clear();
+      if (l < 3) ctx->gptq_u[l].reset();
       if (want_gptq && l < 3) {
         float off_tf[192];
         for (int c = 0; c < 192; ++c) off_tf[c] = cen.c[l][cen_bucket(cen.pos_of[l][c])];
@@ -881,7 +882,7 @@ int calibrate_centering(wann_ctx* ctx, Centering* out) {
         CU(cudaGetLastError());
         // (a degenerate H -- e.g. a layer whose inputs are all zero -- leaves the factor empty: that layer's
         // weights are then rounded to nearest, which is always correct)
-        if (!wann_gptq::inverse_factor(H.data(), kGramDim, 0.01, ctx->gptq_u[l])) ctx->gptq_u[l].clear();
+        ctx->gptq_u[l] = wann_gptq::cached_inverse_factor(H.data(), kGramDim, 0.01);   // null if H is degenerate
       }
     }
     *out = cen;
@@ -928,7 +929,7 @@ int upload_weights(wann_ctx* ctx, const wann_weights& w) {
   CU(cudaMemcpy(ctx->d_bias_plain, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   if (ctx->mode != WANN_MODE_FP32) {
     Centering cen;                       // identity: the plain layout
-    for (auto& u : ctx->gptq_u) u.clear();   // (factors of an earlier weight set)
+    for (auto& u : ctx->gptq_u) u.reset();   // (factors of an earlier weight set)
     rc = upload_tc_image(ctx, w, cen);
     if (rc == WANN_OK && ctx->mode == WANN_MODE_FP16C) {
       rc = calibrate_centering(ctx, &cen);
