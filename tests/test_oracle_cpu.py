@@ -832,6 +832,34 @@ def test_data_aware_weight_rounding_equals_its_restatement(lib_built):
     assert lib.wann_gptq_round(bad.ctypes.data, 4, w4.ctypes.data, 1, None, 0.0) != 0
 
 
+def test_concurrent_processes_do_not_live_lock_the_calibration(lib_built):
+    """The ranks of a multi-GPU job calibrate at the same moment on shared host cores.  Four processes running the
+    rounding (wann_gptq_round, n = 768) at once must take about as long as four runs one after the other -- an
+    earlier OpenMP version (a spinning barrier per Cholesky column) needed two orders of magnitude longer."""
+    import subprocess
+    import sys
+    import time
+    code = ("import sys, time, numpy as np\n"
+            "sys.path.insert(0, %r)\n"
+            "from wann_b200 import _lib as L\n"
+            "lib = L.load()\n"
+            "rng = np.random.default_rng(3)\n"
+            "n, rows = 768, 32\n"
+            "X = rng.normal(size=(2 * n, 12)) @ rng.normal(size=(12, n)) + 0.05 * rng.normal(size=(2 * n, n))\n"
+            "H = (X.T @ X / X.shape[0]).astype(np.float32)\n"
+            "W = (rng.normal(size=(rows, n)) * 0.03).astype(np.float32)\n"
+            "t0 = time.time()\n"
+            "L.check(lib.wann_gptq_round(H.ctypes.data, n, W.ctypes.data, rows, None, 0.01))\n"
+            "print(time.time() - t0)\n") % ROOT
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    alone = float(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout)
+    t0 = time.time()
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, text=True) for _ in range(4)]
+    times = [float(p.communicate()[0]) for p in procs]
+    assert all(p.returncode == 0 for p in procs)
+    assert max(times) < 20 * max(alone, 0.05) + 2.0, (alone, times)
+
+
 def test_shim_turns_valid_planes_back_into_boards():
     """sess.run(y_pred, {X: planes}) / evaluate(already_converted=True): valid P/O/E/1 planes take the
     boards path (refinement + coalescing apply), anything else is evaluated as planes."""

@@ -11,26 +11,33 @@
 //     tcgen05.mma covers M=256 (the same tile index in both CTAs = a "half") x N=192 x K=16.
 //   * Activations NEVER leave the SM: a layer's 16-bit output is written by the epilogue warps
 //     straight into the shared-memory layout the next layer's MMAs read as operand A.
-//     Layout per row tile ("A tile"):  [24 channel-chunks of 8][9 rows y=-1..7][2 boards]
-//     [9 cells x=-1..7][16 B], i.e. a zero-haloed board image whose 16-byte cells are the
-//     8x16B "core matrix" rows of a K-major SWIZZLE_NONE UMMA descriptor.  (The y=8 halo row of
-//     a chunk IS the y=-1 row of the next chunk, the x=8 halo cell of a row IS the x=-1 cell
-//     of the next row.)  MMA row m of a tile is square (y = m/16, board = (m/8)%2, x = m%8), so
+//     Layout per row tile ("A tile"):  3 groups x [8 channel-chunks of 8][9 rows y=-1..7][2 boards]
+//     [9 cells x=-1..7][16 B] (+ a trailing halo row per group), i.e. a haloed board image whose
+//     16-byte cells are the 8x16B "core matrix" rows of a K-major SWIZZLE_NONE UMMA descriptor.
+//     (Inside a group the y=8 halo row of a chunk IS the y=-1 row of the next chunk, the x=8 halo
+//     cell of a row IS the x=-1 cell of the next row; a group = the 64 channels of one K-block of
+//     the weight stream, and -- centred mode -- the unit that shares halo cells, hence offsets.)
+//     MMA row m of a tile is square (y = m/16, board = (m/8)%2, x = m%8), so
 //     an 8-row core-matrix group is one board row, the group stride (SBO) is one padded row =
 //     144 B and the K-chunk stride (LBO) is 2592 B.  The 3x3 taps are then nothing but nine
 //     descriptor START ADDRESSES ((dy+1)*288 + (dx+1)*16 bytes): implicit GEMM with zero im2col
-//     traffic, SAME padding supplied by the (never written) zero halo.
+//     traffic, SAME padding supplied by the halo (zero and never written in the bf16 / fp16 modes;
+//     minus the layer's offsets, rewritten per layer, in the centred mode).
 //   * Weights (operand B) stream from L2 through a ring of shared-memory stages via
 //     cp.async.bulk (TMA engine, 1-D).  They are pre-arranged on the host into the exact
 //     shared-memory image of each stage (K-major SWIZZLE_NONE core matrices; each CTA of the
-//     pair holds its half of the 192 output channels), so no tensor map is needed.
+//     pair holds its half of the 192 output channels), so no tensor map is needed.  Every layer
+//     conv1..4 opens with a BIAS stage (the bias in three 16-bit parts at k = 0..2) that is
+//     multiplied with a tile of ones as the layer's first MMA: the accumulator starts at the bias
+//     and the epilogue neither loads nor adds one.  Optional lo stages (w - fp16(w) of the leading
+//     input group x leading output positions, several taps per stage) follow their hi stages.
 //   * The two halves (row tile 0 / row tile 1) are issued by TWO MMA warps and consume every
 //     weight stage one after the other: a stage is freed when BOTH have used it.  Because the
 //     eight epilogue warps serve the halves alternately, half 1 settles a few K-blocks behind
-//     half 0, and each half's epilogue (TMEM -> +bias, ReLU, 16-bit -> shared memory) runs while
-//     the tensor core works on the other half: the epilogue is off the critical path.
+//     half 0, and each half's epilogue (TMEM -> ReLU (centred: max with -offset), 16-bit -> shared
+//     memory) runs while the tensor core works on the other half.
 //   * conv1 (4->192) runs as 9 taps x K=16 (4 real channels), conv2-4 as 9 taps x 3 x K=64,
-//     conv5 (192->1, 3x3) as a 1x1 GEMM with N=16 whose columns are the 9 TAPS
+//     conv5 (192->1, 3x3) as a 1x1 GEMM with N=32 whose columns are the 9 TAPS (and their lo parts)
 //     (P[pixel][tap] = <act4[pixel], w5[tap]>) followed by a 9-point stencil sum in the epilogue.
 //   * Warp roles per CTA (416 threads): warp 0 = weight producer, warps 1/2 = MMA issuers of
 //     half 0/1 (leader CTA; in the peer CTA warp 1 relays "my half of the stage has landed"),
@@ -157,7 +164,7 @@ struct TcParams {
   int fuse_tail = 0;
   TailParams tail;
   int* err_mirror = nullptr;   // host-mapped copy of err[0..5], written by the last CTA to finish
-  // weight stream geometry: stages per supertile (kKbPerSupertile + 27 per hi/lo-split layer) and the
+  // weight stream geometry: stages per supertile (kKbPerSupertile + 4 bias stages + the lo stages of the split layers) and the
   // byte distance between the stage images of CTA rank 0 and 1
   int stages_per_st = kKbPerSupertile;
   long long img_stride = kImgBytesPerRank;
