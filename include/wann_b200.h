@@ -58,13 +58,16 @@ enum wann_mode {
   WANN_MODE_FP32_TC = 3, /* fp32-class accuracy ON the tensor cores: operands split into fp16
                          hi + lo/4096 pairs, 3 MMAs per K-step, fp32 accumulate (about a third
                          of the BF16 throughput, ~20x the CUDA-core FP32 mode) */
-  WANN_MODE_FP16C = 4   /* "centred" fp16: the FP16 kernel at the same MMA count with its rounding error
-                         roughly halved -- activations are stored as a - c (c = calibrated per-bucket mean,
-                         the sign bit of fp16 is no longer wasted on non-negative ReLU outputs; the halo
-                         holds -c and the next bias absorbs sum(w*c)), conv1 and conv5 see their weights
-                         as fp16 hi + lo pairs in spare K / N slots.  Options "split_layers", "lo_n" and
-                         "lo_kgroups" add lo weight stages for the block of chosen 192->192 layers whose
-                         rounding error matters most (wann_set_option). */
+  WANN_MODE_FP16C = 4   /* "centred" fp16: the FP16 kernel at the same MMA count with a third of its error
+                         (logits and probabilities within 1e-3 of the fp32 graph, north_star's gate) --
+                         activations are stored as a - c (c = calibrated per-bucket mean: the sign bit of fp16
+                         is no longer wasted on non-negative ReLU outputs; the halo holds -c and the next bias
+                         absorbs sum(w*c)), conv1 and conv5 see their weights as fp16 hi + lo pairs in spare
+                         K / N slots, and the weights of the 192->192 layers are rounded to fp16 with error
+                         compensation against their inputs' second moments (option "gptq", default on).
+                         Calibrated at wann_create / wann_set_weights on built-in positions (+0.1 s).  Options
+                         "split_layers", "lo_n" and "lo_kgroups" add lo weight stages for the block of chosen
+                         192->192 layers whose rounding error matters most (wann_set_option). */
 };
 
 enum wann_mem { WANN_MEM_HOST = 0, WANN_MEM_DEVICE = 1 };
