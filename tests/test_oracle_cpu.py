@@ -797,6 +797,29 @@ def test_centred_fp16_emulation_halves_the_fp16_error():
     assert e_zero < e_plain and e_cen < 0.65 * e_plain and e_split < 0.8 * e_cen, (e_plain, e_zero, e_cen, e_split)
     assert e_split < e_part < 0.93 * e_cen, (e_cen, e_part, e_split)
     assert e_cen < 1e-3
+    # the data-aware rounding of the 192->192 layers' weights (wann_b200/csrc/gptq.hpp, restated in
+    # oracle.gptq_round): second moments of each layer's centred 3x3 input windows on HALF of the positions,
+    # error measured on the OTHER half -- it removes more than the partial split does, without any lo stage
+    cal = slice(0, 96)
+    w_eff = {}
+    for layer in (2, 3, 4):
+        q = pos[layer - 2].astype(np.int64)
+        c = off[layer - 2][(q // 64) * 8 + q % 8]                       # per TF channel
+        a = acts[layer - 2][cal].astype(np.float64) - c
+        xp = np.empty((a.shape[0], 10, 10, 192))
+        xp[:] = -c
+        xp[:, 1:-1, 1:-1, :] = a
+        X = np.concatenate([xp[:, dy:dy + 8, dx:dx + 8, :] for dy in range(3) for dx in range(3)], axis=-1).reshape(-1, 1728)
+        H = X.T @ X / X.shape[0]
+        wt = w["hidden_layer/%d/weights" % layer].reshape(1728, 192).T    # [out, (tap, in)]
+        w_eff[layer] = O.gptq_round(H, wt, 0.01).T.reshape(3, 3, 192, 192).astype(np.float32)
+        assert np.array_equal(w_eff[layer], w_eff[layer].astype(np.float16).astype(np.float32))
+    test_half = slice(96, 192)
+    rms2 = lambda d: float(np.sqrt((d.astype(np.float64) ** 2).mean()) / lg[test_half].std())   # noqa: E731
+    e_rtn = rms2(O.forward_fp16c_emulated(planes[test_half], w, off, pos)[0] - lg[test_half])
+    e_gptq = rms2(O.forward_fp16c_emulated(planes[test_half], w, off, pos, w_eff=w_eff)[0] - lg[test_half])
+    assert e_gptq < 0.9 * e_rtn, (e_rtn, e_gptq)
+    print("fp16c emulation, held-out half: rel-RMS round-to-nearest %.3e, data-aware %.3e" % (e_rtn, e_gptq))
 
 
 def test_data_aware_weight_rounding_equals_its_restatement(lib_built):
