@@ -28,8 +28,9 @@ graph's on all 100,000 positions -- are extra keys under `modes`.
            priors D2H inside the timed region.
 `roofline`: conv_stack_tc kernel, ALGORITHMIC FLOPs per launch (the extra MMAs of a split layer are
            overhead, not counted) / CUDA-event time of the launch, against the measured cuBLAS bf16
-           peak in MEASURED_PEAKS.json: the burst figure when the timed region is shorter than 1 s,
-           else the sustained one; `sustained` repeats the measurement over >= 3 s.
+           BURST peak in MEASURED_PEAKS.json (the conservative denominator: over >= 1 s this kernel runs
+           above cuBLAS's own sustained figure, which is shown beside it as `frac_of_sustained_peak`);
+           `sustained` repeats the measurement over >= 3 s.
 """
 import argparse
 import json
@@ -639,12 +640,15 @@ def main():
 
         def roof(run):
             ach, per_launch = roofline_of(run, None, None)
-            short = run["ms"] < 1000.0
-            peak = burst if short else sustained
+            # `frac` is ALWAYS against the burst figure, the higher of the two measured peaks: in a region of
+            # >= 1 s this kernel runs above cuBLAS's own sustained rate under the same power cap (a fraction
+            # above 1 says the denominator is not a ceiling), so the sustained figure is only shown beside it
+            peak = burst
             return {"bound": "tensor", "kernel": "conv_stack_tc_kernel<%s>" % args.mode, "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak,
-                    "peak_kind": "%s cuBLAS bf16 %s" % (src, "burst (timed region %.2f s < 1 s)" % (run["ms"] * 1e-3) if short
-                                                        else "sustained (timed region %.2f s)" % (run["ms"] * 1e-3)),
+                    "peak_kind": "%s cuBLAS bf16 burst, the conservative denominator (timed region %.2f s; cuBLAS itself "
+                                 "sustains %.1f TFLOP/s over 4 s under the same power cap: frac_of_sustained_peak)" % (
+                                     src, run["ms"] * 1e-3, sustained),
                     "frac_of_burst_peak": ach / burst, "frac_of_sustained_peak": ach / sustained,
                     "burst_peak": burst, "sustained_peak": sustained,
                     "flop_per_position": FLOP_PER_POS_CONV,
@@ -673,7 +677,7 @@ def main():
                        "mode": args.mode, "split_layers": split_layers, "lo_n": args.lo_n if split_layers else 0,
                        "lo_kgroups": args.lo_kgroups if split_layers else 0, "refine_margin_logits": refine_margin,
                        "arithmetic": arithmetic,
-                       "accuracy": "this configuration on 100,000 positions vs the fp32 graph: see profiles/r02_accuracy_gptq.json "
+                       "accuracy": "this configuration on 100,000 positions vs the fp32 graph: see profiles/r02_accuracy_gptq_seed{1,2,3}.json "
                                    "and tests/test_gpu_parity.py::test_centred_fp16_mode_meets_the_north_star_gates_on_100k_positions",
                        "weights": "synthetic trained_like seed 1 (reference weight shard absent)",
                        "positions": "seeded random legal play-out positions",
