@@ -205,6 +205,8 @@ def run_reference(args, rank):
     sample = ""
     # the whole run stays within ~2.5 minutes whatever K and W are
     per_step = max(0.25, min(15.0, 150.0 / (args.warmup + args.steps)))
+    if os.environ.get("WANN_B200_BENCH_CPU_SECONDS"):          # tests: a shorter sample per step
+        per_step = float(os.environ["WANN_B200_BENCH_CPU_SECONDS"])
     for i in range(args.warmup + args.steps):
         v, cores, kind, sample = cpu_arm(sample_seconds=per_step)
         if i >= args.warmup:

@@ -935,3 +935,26 @@ def test_forest_play_refuses_mid_expansion_and_restarts_unsearched_trees(lib_bui
         forest.run(_CpuSeeds(), 2)
         moves, fin = forest.play()
         assert (moves != 255).all()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs WITHOUT a GPU (the oracle port on the host cores) and prints exactly one
+    JSON line on stdout with the keys the driver reads; the metric, unit and direction are the ones of the GPU arm."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, WANN_B200_BENCH_CPU_SECONDS="0.2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1"], env=env, capture_output=True, timeout=300, check=True).stdout.decode()
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1, out
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "policy_net_leaf_evals_per_sec"
+    assert line["unit"] == "positions/s" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 1 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "positions/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
