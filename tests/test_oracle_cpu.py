@@ -958,3 +958,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "positions/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_any_fp32_implementation_of_the_graph_is_the_same_reference_for_the_gates():
+    """The reference's logits are unpinned (TensorFlow 1.0 and the weight shard are absent), so the question is how
+    much the choice of fp32 IMPLEMENTATION can matter for north_star's 1e-3 gates.  Three fp32 implementations with
+    three different summation orders (numpy/OpenBLAS, plain C, torch/oneDNN) are compared with the graph evaluated
+    in float64: all sit within a few 1e-6 of it -- more than two orders of magnitude below the gate, so a result
+    within 1e-3 of one fp32 implementation is within 1.01e-3 of any other, Eigen's included."""
+    from oracle import torch_oracle as T
+    w = O.synthetic_weights("trained_like", 1)
+    sq, bl = O.random_positions_fast(512, seed=5)
+    planes = O.encode_planes(sq, bl)
+    l64, p64 = O.forward_fp32(planes, w, dtype=np.float64)
+    for name, (lg, pr) in (("numpy", O.forward_fp32(planes, w)), ("C", C.forward(planes, w)),
+                           ("torch", T.forward(planes, w, threads=4))):
+        d = np.abs(lg - l64)
+        rel = np.abs(pr - p64) / p64
+        assert d.max() / np.abs(l64).max() < 1e-5, name
+        assert np.median(rel) < 1e-5 and rel.max() < 1e-4, name
